@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Krylov hot path (BASELINE.json).
+
+Workload (N = 1 and N > 1): BASELINE.json configs[4], the configuration the metric's target is quoted on --
+ConjugateGradient, float, 3D 7-point Poisson 512^3 (134,217,728 rows, 937,951,232 stored entries), b = A*1, x0 = 0,
+row-sharded over the N GPUs of one box (strong scaling: the total problem is fixed).  A "step" is one solver call
+that executes exactly --iters CG iterations (eps = 0 never passes the stopping test, maxIterations = --iters), so
+metric = Krylov iterations per second = K * iters / time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--grid 512] [--iters 50]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "krylov_iterations_per_sec"
+UNIT = "it/s"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def stencil_nnz(n):
+    return 7 * n ** 3 - 6 * n ** 2
+
+
+def bytes_cg_iteration(rows, nnz):
+    """fused minimum of one CG iteration."""
+    return 8 * nnz + 48 * rows + 4
+
+
+def bytes_spmv_dot(rows, nnz):
+    """The dominant kernel: Ap = A p with p.Ap in its epilogue: values+positions, start, p (gathered once), Ap."""
+    return 8 * nnz + 4 * (rows + 1) + 4 * rows + 4 * rows
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                if t0 - 0.1 <= ts <= t1 + 0.3:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                    for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref, SMM_MULTITHREADING build) on the host cores
+# ----------------------------------------------------------------------------------------------------------
+def _cpu_libs():
+    import oracle_lib as ol
+    if ol.ref_available():
+        return ol, ol.ref(1), "reference"
+    return ol, None, "port"
+
+
+def cpu_problem(grid):
+    """Build the grid^3 Poisson CSR on the host inside the reference library (no std::map); returns closures."""
+    import oracle_lib as ol
+    olib = ol.oracle()
+    olib.smm_oracle_stencil_nnz.restype = C.c_int64
+    olib.smm_oracle_stencil_nnz.argtypes = [C.c_int] * 4
+    olib.smm_oracle_gen_stencil.argtypes = [C.c_int] * 4 + [C.c_float] * 3 + [C.c_void_p] * 3
+    rows = grid ** 3
+    nnz = olib.smm_oracle_stencil_nnz(grid, grid, grid, 1)
+    _, rlib, kind = _cpu_libs()
+    if rlib is not None:
+        rlib.smm_ref_alloc_int.restype = C.c_void_p
+        rlib.smm_ref_alloc_int.argtypes = [C.c_int64]
+        rlib.smm_ref_alloc_float.restype = C.c_void_p
+        rlib.smm_ref_alloc_float.argtypes = [C.c_int64]
+        rlib.smm_ref_csr_adopt.restype = C.c_void_p
+        rlib.smm_ref_csr_adopt.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        start = rlib.smm_ref_alloc_int(rows + 1)
+        pos = rlib.smm_ref_alloc_int(nnz)
+        val = rlib.smm_ref_alloc_float(nnz)
+        olib.smm_oracle_gen_stencil(grid, grid, grid, 1, -1.0, 6.0, -1.0, start, pos, val)
+        h = rlib.smm_ref_csr_adopt(rows, rows, start, pos, val)
+        ones = np.ones(rows, np.float32)
+        b = np.zeros(rows, np.float32)
+        rlib.smm_ref_spmv(h, 0, None, ones, b)
+        del ones
+
+        def run(iters):
+            x = np.zeros(rows, np.float32)
+            t = time.perf_counter()
+            st = rlib.smm_ref_cg(h, b, x, x, iters, 0.0)
+            dt = time.perf_counter() - t
+            assert st == 2, st       # MAX_ITERATIONS_REACHED: exactly `iters` iterations ran
+            return dt
+
+        threads = rlib.smm_ref_threads()
+        return run, threads, kind, lambda: rlib.smm_ref_csr_destroy(h)
+    # port: the C restatement (OpenMP)
+    start = np.zeros(rows + 1, np.int32); pos = np.zeros(nnz, np.int32); val = np.zeros(nnz, np.float32)
+    olib.smm_oracle_gen_stencil(grid, grid, grid, 1, -1.0, 6.0, -1.0, start.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p))
+    m = ol.CSR(rows, rows, start, pos, val, 0)
+    b = ol.spmv(m, 0, None, np.ones(rows, np.float32))
+
+    def run(iters):
+        t = time.perf_counter()
+        o = ol.solve("cg", m, b, np.zeros(rows, np.float32), iters, 0.0, 1)
+        dt = time.perf_counter() - t
+        assert o["status"] == 2
+        return dt
+
+    return run, olib.smm_oracle_threads(), kind, lambda: None
+
+
+def pick_cpu_grid(grid):
+    """The full problem needs ~12 GB of host memory per 512^3; fall back to a smaller cube if the box is small."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    need = lambda g: 8 * stencil_nnz(g) + 4 * 10 * g ** 3
+    g = grid
+    while g > 64 and need(g) * 1.3 > avail:
+        g //= 2
+    return g
+
+
+def cpu_baseline(grid, budget_s=15.0):
+    g = pick_cpu_grid(grid)
+    run, threads, kind, free = cpu_problem(g)
+    t2 = run(2)                                   # includes r0 = b - A x0 and the first dot
+    t1 = run(1)
+    per_it = max(t2 - t1, 1e-9)
+    k = int(max(3, min(40, budget_s / per_it)))
+    tk = run(k)
+    rate = (k - 1) / max(tk - t1, 1e-9)           # marginal iterations: start-up cost excluded, as on the GPU side
+    free()
+    scale = (g ** 3) / float(grid ** 3)
+    sample = f"CG {g}^3 Poisson, {k} iterations (marginal rate over iterations 2..{k})"
+    if g != grid:
+        sample += f"; host memory too small for {grid}^3: rate scaled by rows ratio {scale:.4f}"
+    return {"value": rate * scale, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g = pick_cpu_grid(args.grid)
+    run, threads, kind, free = cpu_problem(g)
+    iters = max(2, min(args.iters, 5))
+    for _ in range(args.warmup):
+        run(iters)
+    t0 = time.perf_counter()
+    total = 0.0
+    for _ in range(args.steps):
+        total += run(iters)
+    wall = time.perf_counter() - t0
+    free()
+    scale = (g ** 3) / float(args.grid ** 3)
+    value = args.steps * iters / total * scale
+    sample = f"CG {g}^3 Poisson, {iters} iterations per step (each step includes r0 = b - A x0), {threads} host threads"
+    if g != args.grid:
+        sample += f"; rate scaled by rows ratio {scale:.4f}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ConjugateGradient float, 3D 7-point Poisson {args.grid}^3, b=A*1, x0=0 (BASELINE configs[4])",
+                   "grid": args.grid, "rows": args.grid ** 3, "nnz": stencil_nnz(args.grid), "iterations_per_step": iters,
+                   "cpu_grid": g},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+
+    import sparse_matrix_math_b200 as smm
+    from sparse_matrix_math_b200 import binding as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
+    torch.cuda.set_device(local)
+    L = smm.lib()
+    B._check(L.smm_set_device(local), "smm_set_device")
+    if world > 1:
+        from sparse_matrix_math_b200 import dist
+        return dist.bench(args, METRIC, UNIT)
+
+    grid, iters = args.grid, args.iters
+    rows, nnz = grid ** 3, stencil_nnz(grid)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    t_setup = time.perf_counter()
+    A = smm.CSRMatrix.generate(B.GEN_CONVDIFF3D, grid, grid, grid, 0.0)
+    assert (A.rows, A.nnz) == (rows, nnz)
+    ones = torch.ones(rows, dtype=torch.float32, device="cuda")
+    b = torch.empty(rows, dtype=torch.float32, device="cuda")
+    x = torch.zeros(rows, dtype=torch.float32, device="cuda")
+    A.spmv_dev(B.OP_ASSIGN, None, ones.data_ptr(), b.data_ptr(), stream=sp)     # b = A * 1
+    del ones
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+
+    opts = B._Options()
+    opts.reduction_mode = B.REDUCE_FAST
+    opts.driver_mode = {"auto": B.DRIVER_AUTO, "chunked": B.DRIVER_GRAPH_CHUNKED, "while": B.DRIVER_GRAPH_WHILE, "stream": B.DRIVER_STREAM}[args.driver]
+    opts.check_every = max(iters, 1)
+    info = B._Info()
+
+    def step_dev():
+        x.zero_()
+        B._check(L.smm_solve_cg_dev(A.handle, b.data_ptr(), x.data_ptr(), x.data_ptr(), iters, 0.0, C.byref(opts), C.byref(info), sp), "smm_solve_cg_dev")
+        assert info.iterations == iters and info.status == 2, (info.iterations, info.status)
+
+    for _ in range(args.warmup):
+        step_dev()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = smm.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tm0 = sampler.mark()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    tm1 = sampler.mark()
+    dev_ms = e0.elapsed_time(e1)
+    launches = smm.kernel_launch_count() - launches0
+    solve_ms = dev_ms / args.steps
+    value = args.steps * iters / (dev_ms * 1e-3)
+    final_rr = float(info.residual)
+
+    # --- per-kernel times of the fused CG iteration (same kernels, same arguments), CUDA events on this stream
+    ms = [C.c_float(), C.c_float(), C.c_float()]
+    B._check(L.smm_profile_cg_iteration(A.handle, max(10, min(50, iters)), C.byref(ms[0]), C.byref(ms[1]), C.byref(ms[2]), sp), "smm_profile_cg_iteration")
+    ms_spmv, ms_xr, ms_p = (m.value for m in ms)
+    clocks = sampler.stop(tm0, tm1)
+
+    # --- end to end through the host-pointer C ABI call (what the drop-in header's ConjugateGradient makes):
+    # pinned host b, x0, x; H2D of b and x0 and D2H of x inside the timed region, every step
+    hb = torch.empty(rows, dtype=torch.float32, pin_memory=True)
+    hx = torch.zeros(rows, dtype=torch.float32, pin_memory=True)
+    hb.copy_(b)
+    torch.cuda.synchronize()
+    hb_p, hx_p = C.c_void_p(hb.data_ptr()), C.c_void_p(hx.data_ptr())
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def step_host():
+        hx.zero_()
+        B._check(L.smm_solve_cg(A.handle, hb_p, hx_p, hx_p, iters, 0.0, C.byref(opts), C.byref(info)), "smm_solve_cg")
+        assert info.iterations == iters
+
+    step_host()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_value = e2e_steps * iters / e2e_s
+    x_host_check = float(hx[rows // 2])
+
+    peak, peak_src = measured_peak_gbs()
+    spmv_bytes = bytes_spmv_dot(rows, nnz)
+    achieved = spmv_bytes / (ms_spmv * 1e-3) / 1e9
+    iter_bytes = bytes_cg_iteration(rows, nnz)
+    iter_gbs = iter_bytes * value / 1e9
+    kernel_sum = ms_spmv + ms_xr + ms_p
+
+    cpu = None
+    if not args.no_cpu:
+        del hb, hx
+        cpu = cpu_baseline(grid, args.cpu_budget)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": solve_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ConjugateGradient float, 3D 7-point Poisson {grid}^3, b=A*1, x0=0 (BASELINE configs[4])",
+                   "grid": grid, "rows": rows, "nnz": nnz, "iterations_per_step": iters, "eps": 0.0,
+                   "parallelism": "1 GPU", "driver": args.driver, "reductions": "fast (fused, deterministic two-stage)",
+                   "l2": f"working set {(8 * nnz + 24 * rows) / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
+                   "setup_s": round(setup_s, 3)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * rows, "d2h_bytes_per_step": 4 * rows,
+                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "smm_solve_cg (host pointers, pinned)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "spmv_kernel (Ap = A p, p.Ap fused)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": ms_spmv,
+                     "share_of_iteration": ms_spmv / kernel_sum if kernel_sum > 0 else None},
+        "iteration": {"algorithmic_bytes": iter_bytes, "achieved_gbs": iter_gbs, "frac_of_peak": iter_gbs / peak,
+                      "ms_spmv_dot": ms_spmv, "ms_xr_update": ms_xr, "ms_p_update": ms_p,
+                      "ms_per_iteration": solve_ms / iters, "final_rr": final_rr, "x_mid": x_host_check},
+        "spmv_effective_gbs": achieved,
+        "cpu_baseline": cpu,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=512)
+    ap.add_argument("--iters", type=int, default=50, help="CG iterations per step")
+    ap.add_argument("--driver", default="auto", choices=["auto", "chunked", "while", "stream"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,178 @@
+/*
+ * smm_b200.h -- C ABI of the B200-native Krylov hot path (libsmm_b200.so).
+ *
+ * The reference (vasil-pashov/sparse_matrix_math) is a header-only C++17 template library with no FFI
+ * layer; its hot path is reached through the inline members / free functions of
+ * include/sparse_matrix_math.h ("H:n" = line n of that header).  This ABI is what the drop-in header of
+ * this repository (include/sparse_matrix_math.h, namespace SMM) binds for T = float; each entry point
+ * names the reference interface it replaces.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SMM_E_* code on failure (never throws, never falls
+ *     back to the CPU: without a CUDA device the calls fail with SMM_E_CUDA); smm_last_error() gives text.
+ *   - pointers are HOST pointers unless the function name ends in _dev; *_dev entry points take device
+ *     pointers and a cudaStream_t passed as void* (NULL = the library's own stream).
+ *   - a handle is bound to the CUDA device that was current when it was created.
+ *   - handles may be used from one thread at a time.
+ */
+#ifndef SMM_B200_H
+#define SMM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMM_B200_ABI_VERSION 1
+
+/* error codes */
+enum {
+    SMM_OK = 0,
+    SMM_E_INVALID = -1,   /* bad argument */
+    SMM_E_CUDA = -2,      /* CUDA runtime error (no device, launch failure, out of memory ...) */
+    SMM_E_ALIAS = -3,     /* forbidden aliasing (rMult: mult == out, H:1503; SGS apply: rhs == x, H:1667) */
+    SMM_E_STATE = -4,     /* handle in the wrong state */
+    SMM_E_TIMEOUT = -5    /* device-side wait exceeded its bound (sync-free triangular solve, halo wait) */
+};
+
+/* SMM::SolverStatus, H:2010-2014 */
+enum { SMM_SOLVER_SUCCESS = 0, SMM_SOLVER_DIVERGED = 1, SMM_SOLVER_MAX_ITERATIONS_REACHED = 2 };
+
+/* rMultOp functor, H:1501-1515 */
+enum { SMM_OP_ASSIGN = 0 /* rMult */, SMM_OP_ADD = 1 /* rMultAdd */, SMM_OP_SUB = 2 /* rMultSub */ };
+
+/* How dot products / norms are summed (Vector::operator*, H:305-328).
+ *   FAST            two-stage deterministic GPU tree, fused into the producing kernel (throughput mode)
+ *   REFERENCE_TREE  bit-for-bit the SMM_MULTITHREADING build: tbb::parallel_deterministic_reduce, grain 8192
+ *                   (and sequential row sums in SpMV), so iteration counts equal the reference's exactly
+ *   REFERENCE_SERIAL bit-for-bit the serial build: left-to-right (slow; parity runs on small inputs only) */
+enum { SMM_REDUCE_FAST = 0, SMM_REDUCE_REFERENCE_TREE = 1, SMM_REDUCE_REFERENCE_SERIAL = 2 };
+
+/* How the iteration loop is driven.
+ *   GRAPH_CHUNKED  one CUDA graph per iteration, enqueued `check_every` at a time; kernels no-op once the
+ *                  device-side convergence flag is set; host polls the flag once per chunk
+ *   GRAPH_WHILE    one launch: a conditional WHILE graph node loops on the device until the convergence test
+ *   STREAM         plain stream launches, flag polled every check_every iterations (debug) */
+enum { SMM_DRIVER_AUTO = 0, SMM_DRIVER_GRAPH_CHUNKED = 1, SMM_DRIVER_GRAPH_WHILE = 2, SMM_DRIVER_STREAM = 3 };
+
+typedef struct smm_csr smm_csr_t;          /* device-resident CSRMatrix<float> (H:1243-1259) + analysis */
+typedef struct smm_precond smm_precond_t;  /* CSRMatrix::SGSPreconditioner (H:1172-1186) + level analysis */
+
+typedef struct {
+    int reduction_mode;   /* SMM_REDUCE_* (default FAST) */
+    int driver_mode;      /* SMM_DRIVER_* (default AUTO) */
+    int check_every;      /* iterations between host polls, 0 = library default */
+    int history_cap;      /* entries available in `history` (0 = none) */
+    float* history;       /* HOST buffer: the residual quantity after every iteration (as the solver compares it) */
+    int reserved[4];
+} smm_solve_options;
+
+typedef struct {
+    int status;             /* SMM_SOLVER_* exactly as the reference function would return */
+    int iterations;         /* loop trips executed (= SpMV A*p calls) */
+    float residual;         /* last value compared with eps: ||r||^2 (CG, BiCGSymmetric, CGS), ||r||_2 (BiCGStab) */
+    int precond_error;      /* OR of non-zero preconditioner apply codes (the reference only asserts on them) */
+    double seconds_solve;   /* device time of the solve (CUDA events), vectors already resident */
+    double seconds_total;   /* wall time of the call including host<->device copies of b, x0, x */
+    int reduction_mode;     /* what was actually used */
+    int driver_mode;
+    long long kernel_launches; /* kernels launched inside the timed region */
+    int reserved[4];
+} smm_solve_info;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int smm_abi_version(void);
+const char* smm_last_error(void);
+int smm_device_count(int* count);
+int smm_set_device(int device);
+int smm_device_info(int* sm_count, size_t* l2_bytes, size_t* total_mem, size_t* free_mem);
+/* total kernels launched by this library in this process (bench.py's gpu_launches) */
+long long smm_kernel_launch_count(void);
+int smm_sync(void);
+
+/* ---- CSRMatrix<float>: storage, H:1243-1259; construction CSRMatrix(const TripletMatrix&) H:1314-1349 ----
+ * The triplet -> CSR conversion stays on the host (include/sparse_matrix_math.h of this repo, bit-exact);
+ * this uploads the three arrays and analyses row lengths for the SpMV kernels. */
+int smm_csr_create(int rows, int cols, const int32_t* start, const int32_t* positions, const float* values,
+                   smm_csr_t** out);
+/* same, from DEVICE arrays; copy != 0 copies them, copy == 0 adopts them (freed with cudaFree on destroy) */
+int smm_csr_create_dev(int rows, int cols, int32_t* start_dev, int32_t* positions_dev, float* values_dev,
+                       int copy, smm_csr_t** out);
+/* values changed on the host (operator*=, inplaceAdd, updateEntry, setValue ... H:1525-1604, H:846-849) */
+int smm_csr_update_values(smm_csr_t* m, const float* values);
+int smm_csr_destroy(smm_csr_t* m);
+int smm_csr_shape(const smm_csr_t* m, int* rows, int* cols, int64_t* nnz, int* first_active_start);
+/* device -> host copy of the arrays (for parity checks of device-generated matrices) */
+int smm_csr_download(const smm_csr_t* m, int32_t* start, int32_t* positions, float* values);
+/* raw device pointers of the resident arrays */
+int smm_csr_device_arrays(const smm_csr_t* m, const int32_t** start_dev, const int32_t** positions_dev,
+                          const float** values_dev);
+
+/* ---- CSRMatrix::rMult / rMultAdd / rMultSub, H:1458-1515 ----
+ * out[row] = op(lhs[row], sum_k values[k] * mult[positions[k]]); out may alias lhs; lhs ignored for ASSIGN.
+ * exact != 0 forces left-to-right accumulation in every row (bit-identical to the reference). */
+int smm_spmv(const smm_csr_t* m, int op, const float* lhs, const float* mult, float* out);
+int smm_spmv_dev(const smm_csr_t* m, int op, const float* lhs_dev, const float* mult_dev, float* out_dev,
+                 int exact, void* stream);
+
+/* ---- Vector::operator* and secondNorm[Squared], H:287-328 ---- */
+int smm_dot(int64_t n, const float* a, const float* b, int reduction_mode, float* out);
+int smm_dot_dev(int64_t n, const float* a_dev, const float* b_dev, int reduction_mode, float* out_host, void* stream);
+
+/* ---- CSRMatrix::getPreconditioner<SYMMETRIC_GAUS_SEIDEL>() H:1643-1651; SGSPreconditioner::apply H:1658-1713 ----
+ * create analyses the dependency levels of the lower and upper triangles once; apply returns the reference's
+ * int code through *rc (0 ok, 1 = empty row / missing or tiny diagonal / leading empty rows). */
+int smm_precond_sgs_create(const smm_csr_t* m, smm_precond_t** out);
+int smm_precond_apply(const smm_precond_t* p, const float* rhs, float* x, int* rc);
+int smm_precond_apply_dev(const smm_precond_t* p, const float* rhs_dev, float* x_dev, int* rc, void* stream);
+int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backward_levels);
+int smm_precond_destroy(smm_precond_t* p);
+
+/* ---- solvers ----
+ * ConjugateGradient H:2316-2398; BiCGSymmetric H:2021-2102; ConjugateGradientSquared H:2109-2178;
+ * BiCGStab H:2191-2303 (precond == NULL: the 5-argument overload / IDPreconditioner).
+ * Argument meaning, clamping of maxIterations, status codes and stopping tests follow the reference
+ * function exactly; opts may be NULL (defaults); info may be NULL. */
+int smm_solve_cg(const smm_csr_t* a, const float* b, const float* x0, float* x, int maxIterations, float eps,
+                 const smm_solve_options* opts, smm_solve_info* info);
+int smm_solve_bicgsym(const smm_csr_t* a, const float* b, float* x, int maxIterations, float eps,
+                      const smm_solve_options* opts, smm_solve_info* info);
+int smm_solve_cgs(const smm_csr_t* a, const float* b, float* x, int maxIterations, float eps,
+                  const smm_solve_options* opts, smm_solve_info* info);
+int smm_solve_bicgstab(const smm_csr_t* a, const smm_precond_t* precond, const float* b, float* x,
+                       int maxIterations, float eps, const smm_solve_options* opts, smm_solve_info* info);
+/* device-resident variants: b/x0/x already in HBM (x0 may equal x) */
+int smm_solve_cg_dev(const smm_csr_t* a, const float* b_dev, const float* x0_dev, float* x_dev, int maxIterations,
+                     float eps, const smm_solve_options* opts, smm_solve_info* info, void* stream);
+int smm_solve_bicgsym_dev(const smm_csr_t* a, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                          const smm_solve_options* opts, smm_solve_info* info, void* stream);
+int smm_solve_cgs_dev(const smm_csr_t* a, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                      const smm_solve_options* opts, smm_solve_info* info, void* stream);
+int smm_solve_bicgstab_dev(const smm_csr_t* a, const smm_precond_t* precond, const float* b_dev, float* x_dev,
+                           int maxIterations, float eps, const smm_solve_options* opts, smm_solve_info* info,
+                           void* stream);
+
+/* ---- benchmark inputs generated in HBM (additive; the reference can only ingest through std::map) ----
+ * bit-identical to tests/matgen.py: stencil7 = convdiff3d(nx,ny,nz,c) (c = 0: Poisson; nz = 1 and the y/z
+ * couplings of a 5-point 2D Poisson are selected with kind) */
+enum { SMM_GEN_POISSON2D = 0, SMM_GEN_CONVDIFF3D = 1, SMM_GEN_POWERLAW = 2 };
+int smm_gen_csr(int kind, int nx, int ny, int nz, float c, uint64_t seed, smm_csr_t** out);
+/* x*_i = (splitmix64(seed, i + offset) >> 40) / 2^24 written to a device vector */
+int smm_gen_xstar_dev(int64_t n, int64_t offset, uint64_t seed, float* x_dev, void* stream);
+
+/* ---- measurement hook (bench.py): average device time, in ms, of each of the three kernels of one fused CG
+ * iteration (SpMV + p.Ap | x,r update + r.r | p update), `reps` launches each, CUDA events on `stream` ---- */
+int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_spmv, float* ms_xr, float* ms_p, void* stream);
+
+/* ---- device memory helpers for hosts without their own allocator ---- */
+int smm_malloc_dev(size_t bytes, void** ptr_dev);
+int smm_free_dev(void* ptr_dev);
+int smm_memcpy_h2d(void* dst_dev, const void* src, size_t bytes);
+int smm_memcpy_d2h(void* dst, const void* src_dev, size_t bytes);
+int smm_memset_dev(void* dst_dev, int byte, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMM_B200_H */

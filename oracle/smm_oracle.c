@@ -634,3 +634,55 @@ out:
     fclose(f);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * benchmark inputs (not part of the reference: its only ingest path is the std::map TripletMatrix)
+ * ---------------------------------------------------------------------------------------------- */
+int64_t smm_oracle_stencil_nnz(int nx, int ny, int nz, int use_z) {
+    const int64_t rows = (int64_t)nx * ny * nz;
+    const int full = use_z ? 7 : 5;
+    return rows * full - 2ll * ny * nz - 2ll * nx * nz - (use_z ? 2ll * nx * ny : 0);
+}
+
+static int64_t stencil_start(int64_t r, int64_t nx, int64_t ny, int64_t nz, int use_z) {
+    const int64_t plane = nx * ny, k = r / plane, rem = r % plane, lines = r / nx, i = r % nx;
+    const int full = use_z ? 7 : 5;
+    int64_t miss = lines + (i > 0 ? 1 : 0) + lines;
+    miss += k * nx + (rem < nx ? rem : nx);
+    { const int64_t last = rem - (ny - 1) * nx; miss += k * nx + (last > 0 ? last : 0); }
+    if (use_z) {
+        miss += (r < plane ? r : plane);
+        { const int64_t last = r - (nz - 1) * plane; miss += (last > 0 ? last : 0); }
+    }
+    return r * full - miss;
+}
+
+void smm_oracle_gen_stencil(int nx, int ny, int nz, int use_z, float lo, float diag, float hi,
+                            int *start, int *positions, float *values) {
+    const int64_t rows = (int64_t)nx * ny * nz, plane = (int64_t)nx * ny;
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r <= rows; ++r) {
+        int64_t o = stencil_start(r, nx, ny, nz, use_z);
+        start[r] = (int)o;
+        if (r == rows) continue;
+        const int64_t k = r / plane, j = (r % plane) / nx, i = r % nx;
+        if (use_z && k > 0) { positions[o] = (int)(r - plane); values[o] = lo; ++o; }
+        if (j > 0) { positions[o] = (int)(r - nx); values[o] = lo; ++o; }
+        if (i > 0) { positions[o] = (int)(r - 1); values[o] = lo; ++o; }
+        positions[o] = (int)r; values[o] = diag; ++o;
+        if (i < nx - 1) { positions[o] = (int)(r + 1); values[o] = hi; ++o; }
+        if (j < ny - 1) { positions[o] = (int)(r + nx); values[o] = hi; ++o; }
+        if (use_z && k < nz - 1) { positions[o] = (int)(r + plane); values[o] = hi; ++o; }
+    }
+}
+
+void smm_oracle_gen_xstar(int64_t n, uint64_t seed, float *x) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t z = seed + ((uint64_t)i + 1ull) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        x[i] = (float)(z >> 40) / 16777216.0f;
+    }
+}

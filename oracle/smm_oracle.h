@@ -98,6 +98,15 @@ int smm_oracle_load_mtx(const char *path, int *rows, int *cols, int64_t *n_tripl
                         int **trow, int **tcol, float **tval);
 void smm_oracle_free(void *p);
 
+/* Benchmark inputs on the host (same bits as tests/matgen.py and the device generators): 7-point
+ * convection-diffusion / Poisson stencil on an nx*ny*nz grid (use_z = 0: the 5-point 2D Poisson with diag 4).
+ * start has rows+1 entries; positions/values hold smm_oracle_stencil_nnz() entries.  OpenMP-parallel. */
+int64_t smm_oracle_stencil_nnz(int nx, int ny, int nz, int use_z);
+void smm_oracle_gen_stencil(int nx, int ny, int nz, int use_z, float lo, float diag, float hi,
+                            int *start, int *positions, float *values);
+/* x*_i = (splitmix64(seed, i) >> 40) / 2^24 */
+void smm_oracle_gen_xstar(int64_t n, uint64_t seed, float *x);
+
 /* Number of OpenMP threads the row/vector loops use (1 if built without OpenMP). */
 int smm_oracle_threads(void);
 

@@ -1,0 +1,276 @@
+// sgs.cu -- Symmetric Gauss-Seidel preconditioner apply, the one preconditioner CSRMatrix::getPreconditioner()
+// hands to BiCGStab in the reference (H:1643-1651, class H:1172-1186, apply H:1658-1713):
+//     (D + L) y = rhs            forward substitution, rows ascending,  cols ascending inside a row
+//     x_i = y_i - (sum_{j>i} a_ij x_j) / a_ii   backward, rows descending, cols DESCENDING inside a row
+// on A's own CSR arrays (no factor storage).  The reference runs both sweeps serially; here they are
+// level-scheduled and sync-free:
+//   * create: one host pass over the structure computes the dependency level of every row in the lower and in the
+//     upper triangle (level = 1 + max level of the rows it reads) and the two row orders sorted by level, each level
+//     padded to a warp so that no lane ever waits on a lane of its own warp;
+//   * apply: ONE launch per sweep, one thread per row in level order.  A thread accumulates its row in the
+//     reference's order and, for every x[col] it needs, spins until the value has been published.  The output
+//     vector doubles as the ready flag: it is pre-filled with a NaN payload no arithmetic instruction can produce.
+//     CTAs take their logical index from an atomic ticket, so every producer a thread waits for belongs to a CTA
+//     that has already started -- no deadlock whatever order the hardware dispatches CTAs in.  Levels overlap
+//     freely (no grid barrier): the sweep is bounded by the dependency chain (levels x L2 round trip), not by
+//     launch or barrier latency.  A poll bound turns a would-be hang into SMM_E_TIMEOUT.
+// Per-row arithmetic is identical to the reference (two roundings per multiply-add, one division per sweep), so the
+// result is bit-identical to SGSPreconditioner::apply for any schedule.
+// Algorithmic bytes per apply: each stored entry once over the two sweeps (8 nnz) + start/diag index/order
+// (about 24 n) + rhs, y, x traffic (about 20 n).
+#include <algorithm>
+#include <vector>
+
+#include "smm_internal.cuh"
+
+struct smm_precond {
+    const smm_csr* m = nullptr;
+    int rows = 0;
+    bool valid = true;               // structure admits the sweeps (else apply returns the reference's code 1)
+    int levels_fwd = 0, levels_bwd = 0;
+    long long threads_fwd = 0, threads_bwd = 0;   // padded launch sizes
+    int32_t* order_fwd = nullptr;    // [threads_fwd] row index or -1 (padding)
+    int32_t* order_bwd = nullptr;    // [threads_bwd]
+    int32_t* diag_pos = nullptr;     // [rows] index of a_ii in positions/values
+    float* y = nullptr;              // [rows] forward result
+    unsigned int* tickets = nullptr; // [2] logical CTA counters, [2] = abort flag, [3] = error bits
+    float* io[2] = {nullptr, nullptr};   // staging for the host-pointer apply
+};
+
+namespace {
+
+constexpr unsigned int SENTINEL = 0x7FC0DEADu;   // quiet NaN with a payload; GPU arithmetic only produces 0x7FFFFFFF
+constexpr int SGS_THREADS = 128;
+constexpr unsigned int POLL_LIMIT = 1u << 23;
+
+__global__ void sgs_fill_kernel(float* __restrict__ y, float* __restrict__ x, long long n, unsigned int* tickets, const SolveState* st) {
+    if (st != nullptr && st->done) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        y[i] = __uint_as_float(SENTINEL);
+        x[i] = __uint_as_float(SENTINEL);
+    }
+    if (i == 0) { tickets[0] = 0u; tickets[1] = 0u; tickets[2] = 0u; tickets[3] = 0u; }
+}
+
+__device__ __forceinline__ float wait_value(const float* p, unsigned int* abort_flag) {
+    unsigned int bits;
+    unsigned int polls = 0;
+    for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bits) : "l"(p));
+        if (bits != SENTINEL) break;
+        if ((++polls & 1023u) == 0u) {
+            unsigned int a;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(a) : "l"(abort_flag));
+            if (a != 0u || polls >= POLL_LIMIT) { atomicExch(abort_flag, 1u); break; }
+        }
+    }
+    return __uint_as_float(bits);
+}
+
+__device__ __forceinline__ void publish(float* p, float v) {
+    // a computed value can never equal the sentinel payload, so the store itself is the ready flag
+    asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+template <bool FORWARD>
+__global__ void __launch_bounds__(SGS_THREADS) sgs_sweep_kernel(const int32_t* __restrict__ start, const int32_t* __restrict__ positions,
+                                                               const float* __restrict__ values, const int32_t* __restrict__ order,
+                                                               const int32_t* __restrict__ diag_pos, long long nthreads,
+                                                               const float* __restrict__ rhs, float* y, float* x,
+                                                               unsigned int* tickets, const SolveState* st) {
+    if (st != nullptr && st->done) return;
+    __shared__ unsigned int sh_bid;
+    if (threadIdx.x == 0) sh_bid = atomicAdd(&tickets[FORWARD ? 0 : 1], 1u);
+    __syncthreads();
+    const long long t = (long long)sh_bid * SGS_THREADS + threadIdx.x;
+    if (t >= nthreads) return;
+    const int row = order[t];
+    if (row < 0) return;
+    unsigned int* abort_flag = tickets + 2;
+    const int dp = diag_pos[row];
+    const float d = values[dp];
+    if (FORWARD) {
+        if (fabsf(d) < 1e-5) atomicOr(tickets + 3, 1u);                       // H:1691-1693 (reported, not fatal here)
+        float lhs = rhs[row];                                                 // H:1683
+        for (int k = start[row]; k < dp; ++k) {                               // cols ascending, H:1684-1689
+            const float xv = wait_value(y + positions[k], abort_flag);
+            lhs = __fadd_rn(__fmul_rn(-values[k], xv), lhs);                  // _smm_fma(-value, x[col], lhs)
+        }
+        publish(y + row, __fdiv_rn(lhs, d));                                  // H:1694
+    } else {
+        float lhs = 0.0f;                                                     // H:1702
+        for (int k = start[row + 1] - 1; k > dp; --k) {                       // cols descending, H:1703-1708
+            const float xv = wait_value(x + positions[k], abort_flag);
+            lhs = __fadd_rn(__fmul_rn(values[k], xv), lhs);                   // _smm_fma(value, x[col], lhs)
+        }
+        const float yr = wait_value(y + row, abort_flag);                     // own forward result (already published)
+        publish(x + row, __fsub_rn(yr, __fdiv_rn(lhs, d)));                   // H:1710
+    }
+}
+
+__global__ void sgs_status_kernel(const unsigned int* tickets, SolveState* st, int* rc_out) {
+    // fold the apply's status into the solve (the reference only asserts on it, H:2235-2238) / report it to the caller
+    const unsigned int aborted = tickets[2], bad_diag = tickets[3];
+    int rc = 0;
+    if (bad_diag) rc |= 1;
+    if (aborted) rc |= 4;
+    if (st != nullptr && !st->done && rc) st->precond_error |= rc;
+    if (rc_out) *rc_out = rc;
+}
+
+// level analysis on the host: one pass per triangle
+void analyse(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int first_active_start, bool* valid,
+             std::vector<int32_t>* diag, std::vector<int32_t>* order_f, std::vector<int32_t>* order_b, int* lf, int* lb) {
+    *valid = first_active_start == 0 || rows == 0;                            // H:1668-1670
+    diag->assign((size_t)rows, 0);
+    std::vector<int32_t> lev((size_t)rows, 0);
+    int maxl = -1;
+    for (int r = 0; r < rows && *valid; ++r) {
+        int k = start[r];
+        const int e = start[r + 1];
+        if (e == k) { *valid = false; break; }                               // H:1678-1680
+        int l = 0;
+        while (k < e && pos[k] < r) { l = std::max(l, lev[pos[k]] + 1); ++k; }
+        if (k >= e || pos[k] != r) { *valid = false; break; }                 // H:1691 (col != row)
+        (*diag)[r] = k;
+        lev[r] = l;
+        maxl = std::max(maxl, l);
+    }
+    if (!*valid) { *lf = *lb = 0; order_f->clear(); order_b->clear(); return; }
+    auto build_order = [&](const std::vector<int32_t>& level, int nlev, bool descending, std::vector<int32_t>* out) {
+        std::vector<long long> count((size_t)nlev + 1, 0);
+        for (int r = 0; r < rows; ++r) count[(size_t)level[r] + 1]++;
+        std::vector<long long> off((size_t)nlev + 1, 0);
+        for (int l = 0; l < nlev; ++l) off[(size_t)l + 1] = off[l] + ((count[(size_t)l + 1] + 31) / 32) * 32;   // pad each level to a warp
+        out->assign((size_t)off[nlev], -1);
+        std::vector<long long> cur(off.begin(), off.end() - 1);
+        if (!descending) { for (int r = 0; r < rows; ++r) (*out)[(size_t)cur[level[r]]++] = r; }
+        else { for (int r = rows - 1; r >= 0; --r) (*out)[(size_t)cur[level[r]]++] = r; }
+    };
+    *lf = maxl + 1;
+    build_order(lev, *lf, false, order_f);
+    maxl = -1;
+    for (int r = rows - 1; r >= 0; --r) {
+        int l = 0;
+        for (int k = start[r + 1] - 1; k > (*diag)[r]; --k) l = std::max(l, lev[pos[k]] + 1);   // lev[] of rows > r already hold backward levels
+        lev[r] = l;
+        maxl = std::max(maxl, l);
+    }
+    *lb = maxl + 1;
+    build_order(lev, *lb, true, order_b);
+}
+
+}  // namespace
+
+int smm_sgs_kernels_per_apply(const smm_precond* p) { return p && p->valid ? 4 : 1; }
+
+// rhs_dev -> x_dev on stream s.  With `state` (inside a solve) the kernels no-op once state->done is set.
+int smm_sgs_apply_async(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, cudaStream_t s) {
+    return smm_sgs_apply_async_rc(p, rhs_dev, x_dev, state, nullptr, s);
+}
+
+int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, int* rc_dev, cudaStream_t s) {
+    if (!p) return SMM_E_INVALID;
+    if (rhs_dev == x_dev) { smm_set_error("SGS apply: rhs must not alias x (H:1667)"); return SMM_E_ALIAS; }
+    const smm_csr* m = p->m;
+    if (p->rows == 0) return SMM_OK;
+    if (!p->valid) {
+        // SGSPreconditioner::apply returns 1 here (H:1668, 1678, 1691) and BiCGStab only asserts on it (H:2235-2238),
+        // continuing on an unspecified vector; this build refuses instead of iterating on garbage
+        smm_set_error("SGS preconditioner unusable for this matrix (leading empty rows, an empty row or a missing diagonal): apply() returns 1");
+        return SMM_E_STATE;
+    }
+    const long long n = p->rows;
+    sgs_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->y, x_dev, n, p->tickets, state);
+    sgs_sweep_kernel<true><<<(unsigned)((p->threads_fwd + SGS_THREADS - 1) / SGS_THREADS), SGS_THREADS, 0, s>>>(
+        m->start, m->positions, m->values, p->order_fwd, p->diag_pos, p->threads_fwd, rhs_dev, p->y, x_dev, p->tickets, state);
+    sgs_sweep_kernel<false><<<(unsigned)((p->threads_bwd + SGS_THREADS - 1) / SGS_THREADS), SGS_THREADS, 0, s>>>(
+        m->start, m->positions, m->values, p->order_bwd, p->diag_pos, p->threads_bwd, rhs_dev, p->y, x_dev, p->tickets, state);
+    sgs_status_kernel<<<1, 1, 0, s>>>(p->tickets, state, rc_dev);
+    SMM_COUNT_LAUNCH(4);
+    SMM_CUDA(cudaGetLastError());
+    return SMM_OK;
+}
+
+extern "C" {
+
+int smm_precond_sgs_create(const smm_csr_t* m, smm_precond_t** out) {
+    if (!m || !out) return SMM_E_INVALID;
+    if (m->rows != m->cols) { smm_set_error("SGS: matrix must be square"); return SMM_E_INVALID; }
+    SMM_CUDA(cudaSetDevice(m->device));
+    smm_precond* p = new smm_precond();
+    p->m = m;
+    p->rows = m->rows;
+    std::vector<int32_t> start((size_t)m->rows + 1), pos((size_t)m->nnz);
+    SMM_CUDA(cudaDeviceSynchronize());
+    SMM_CUDA(cudaMemcpy(start.data(), m->start, sizeof(int32_t) * start.size(), cudaMemcpyDeviceToHost));
+    if (m->nnz) SMM_CUDA(cudaMemcpy(pos.data(), m->positions, sizeof(int32_t) * pos.size(), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> diag, of, ob;
+    analyse(m->rows, start, pos, m->first_active_start, &p->valid, &diag, &of, &ob, &p->levels_fwd, &p->levels_bwd);
+    SMM_CUDA(cudaMalloc(&p->tickets, 4 * sizeof(unsigned int)));
+    SMM_CUDA(cudaMemset(p->tickets, 0, 4 * sizeof(unsigned int)));
+    if (p->valid && m->rows > 0) {
+        p->threads_fwd = (long long)of.size();
+        p->threads_bwd = (long long)ob.size();
+        SMM_CUDA(cudaMalloc(&p->order_fwd, sizeof(int32_t) * of.size()));
+        SMM_CUDA(cudaMalloc(&p->order_bwd, sizeof(int32_t) * ob.size()));
+        SMM_CUDA(cudaMalloc(&p->diag_pos, sizeof(int32_t) * diag.size()));
+        SMM_CUDA(cudaMalloc(&p->y, sizeof(float) * (size_t)m->rows));
+        SMM_CUDA(cudaMemcpy(p->order_fwd, of.data(), sizeof(int32_t) * of.size(), cudaMemcpyHostToDevice));
+        SMM_CUDA(cudaMemcpy(p->order_bwd, ob.data(), sizeof(int32_t) * ob.size(), cudaMemcpyHostToDevice));
+        SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
+    }
+    *out = p;
+    return SMM_OK;
+}
+
+int smm_precond_apply_dev(const smm_precond_t* p, const float* rhs_dev, float* x_dev, int* rc, void* stream) {
+    if (!p || (p->rows && (!rhs_dev || !x_dev))) return SMM_E_INVALID;
+    if (rc) *rc = 0;
+    if (!p->valid) { if (rc) *rc = 1; return SMM_OK; }       // the reference's error exits (H:1668, 1678, 1691): x is not produced
+    if (p->rows == 0) return SMM_OK;
+    SMM_CUDA(cudaSetDevice(p->m->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : smm_default_stream();
+    int* rc_dev = reinterpret_cast<int*>(p->tickets) + 3;      // reuse: the status kernel writes the code over the error bits
+    SMM_TRY(smm_sgs_apply_async_rc(p, rhs_dev, x_dev, nullptr, rc_dev, s));
+    int code = 0;
+    SMM_CUDA(cudaMemcpyAsync(&code, rc_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SMM_CUDA(cudaStreamSynchronize(s));
+    if (code & 4) { smm_set_error("SGS apply: device-side wait exceeded its bound"); return SMM_E_TIMEOUT; }
+    if (rc) *rc = code & 1;
+    return SMM_OK;
+}
+
+int smm_precond_apply(const smm_precond_t* pc, const float* rhs, float* x, int* rc) {
+    smm_precond* p = const_cast<smm_precond*>(pc);
+    if (!p || (p->rows && (!rhs || !x))) return SMM_E_INVALID;
+    if (rhs == x && p->rows) { smm_set_error("SGS apply: rhs must not alias x (H:1667)"); return SMM_E_ALIAS; }
+    if (rc) *rc = 0;
+    if (!p->valid) { if (rc) *rc = 1; return SMM_OK; }
+    if (p->rows == 0) return SMM_OK;
+    SMM_CUDA(cudaSetDevice(p->m->device));
+    const size_t bytes = sizeof(float) * (size_t)p->rows;
+    for (int i = 0; i < 2; ++i) if (!p->io[i]) SMM_CUDA(cudaMalloc(&p->io[i], bytes));
+    SMM_CUDA(cudaMemcpy(p->io[0], rhs, bytes, cudaMemcpyHostToDevice));
+    SMM_TRY(smm_precond_apply_dev(p, p->io[0], p->io[1], rc, nullptr));
+    SMM_CUDA(cudaMemcpy(x, p->io[1], bytes, cudaMemcpyDeviceToHost));
+    return SMM_OK;
+}
+
+int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backward_levels) {
+    if (!p) return SMM_E_INVALID;
+    if (forward_levels) *forward_levels = p->levels_fwd;
+    if (backward_levels) *backward_levels = p->levels_bwd;
+    return SMM_OK;
+}
+
+int smm_precond_destroy(smm_precond_t* p) {
+    if (!p) return SMM_OK;
+    cudaFree(p->order_fwd); cudaFree(p->order_bwd); cudaFree(p->diag_pos); cudaFree(p->y); cudaFree(p->tickets);
+    cudaFree(p->io[0]); cudaFree(p->io[1]);
+    delete p;
+    return SMM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,547 @@
+// solvers.cu -- iteration drivers of the four Krylov solvers.
+//
+//   smm_solve_cg        <- SMM::ConjugateGradient        H:2316-2398
+//   smm_solve_bicgsym   <- SMM::BiCGSymmetric            H:2021-2102
+//   smm_solve_cgs       <- SMM::ConjugateGradientSquared H:2109-2178
+//   smm_solve_bicgstab  <- SMM::BiCGStab                 H:2191-2303
+//
+// Every scalar of the recurrences (alpha, beta, omega, the residual norms), the iteration counter and the
+// stopping / DIVERGED tests live in a SolveState block in HBM and are updated by the last CTA of the kernel that
+// produced the reduction (epilogue.cuh), so the host never reads a dot product.  One iteration is a fixed
+// sequence of kernels; every kernel starts with `if (state->done) return`, which makes the iterations enqueued
+// after convergence free of side effects.  The loop itself is
+//   GRAPH_WHILE    a CUDA-graph conditional WHILE node: one launch, the device decides when to stop;
+//   GRAPH_CHUNKED  the captured iteration graph launched `check_every` times between polls of the done flag;
+//   STREAM         plain launches (debug).
+//
+// Fused kernel sequence per iteration (FAST reductions) and algorithmic bytes (n rows, nnz entries):
+//   CG        SpMV[Ap=A p; p.Ap->alpha] | x,r update + r.r -> beta, stop | p update            8 nnz + 48 n
+//   BiCGSym   same shape (different rounding and tests)                                         8 nnz + 48 n
+//   CGS       SpMV[ap; ap.r0->alpha] | q,auq,x | SpMV[r-=A auq; r.r0, r.r->beta, stop] | u,p    16 nnz + 80 n
+//   BiCGStab  SpMV[ap; ap.r0->alpha] | s | SpMV[as; as.s, as.as->omega] | x,r + r.r, r.r0 | p   16 nnz + 84 n
+// In the REFERENCE_* reduction modes the reductions are un-fused and use dots.cu so that every float operation
+// happens in the reference's order.
+#include <chrono>
+#include <string.h>
+
+#include "epilogue.cuh"
+#include "smm_internal.cuh"
+
+namespace {
+
+struct Ctx {
+    const smm_csr* a = nullptr;
+    const smm_precond* precond = nullptr;
+    smm_workspace* ws = nullptr;
+    cudaStream_t s = nullptr;
+    SolveState* st = nullptr;
+    long long n = 0;
+    int mode = SMM_REDUCE_FAST;      // reduction mode
+    bool exact = false;              // mode != FAST
+    const float* b = nullptr;
+    float* x = nullptr;
+    float *r = nullptr, *p = nullptr, *ap = nullptr, *r0 = nullptr, *u = nullptr, *q = nullptr, *auq = nullptr,
+          *sv = nullptr, *as = nullptr, *scratch = nullptr;
+    int kernels_per_iteration = 0;
+};
+
+int spmv(Ctx& c, int op, const float* lhs, const float* mult, float* out, int reduce, int finish, const float* aux,
+         float* c1 = nullptr, float* c2 = nullptr, float* c3 = nullptr) {
+    SpmvArgs a;
+    a.m = c.a; a.op = op; a.lhs = lhs; a.mult = mult; a.out = out; a.exact = c.exact ? 1 : 0;
+    a.reduce = reduce; a.finish = finish; a.slot = 0; a.aux = aux; a.state = c.st;
+    a.copy1 = c1; a.copy2 = c2; a.copy3 = c3;
+    return smm_launch_spmv(a, c.s);
+}
+
+int vec(Ctx& c, int kind, int finish, std::initializer_list<const float*> in, std::initializer_list<float*> out) {
+    VecArgs v;
+    v.n = c.n; v.state = c.st; v.finish = finish; v.slot = 1; v.ws = c.ws;
+    int i = 0;
+    for (const float* p : in) v.in[i++] = p;
+    i = 0;
+    for (float* p : out) v.out[i++] = p;
+    return smm_launch_vec(kind, v, c.s);
+}
+
+// a dot product (or two) whose totals feed `finish`; FAST: fused two-stage kernel, otherwise the reference order
+int dots(Ctx& c, int finish, const float* a0, const float* b0, const float* a1 = nullptr, const float* b1 = nullptr) {
+    if (c.mode == SMM_REDUCE_FAST) {
+        // VEC_DOT2 computes (a.b, a.a): callers in FAST mode only use shapes it covers
+        return vec(c, VEC_DOT2, finish, {a0, b0}, {});
+    }
+    return smm_launch_dot_ref(c.mode, c.n, a1 ? 2 : 1, a0, b0, a1 ? a1 : a0, b1 ? b1 : b0, c.st, finish, nullptr, c.s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-solver: start-up sequence and one iteration
+// ---------------------------------------------------------------------------------------------------
+int cg_init(Ctx& c, const float* x0) {
+    // r = b - A x0 ; p = r ; rr = r.r ; early SUCCESS if eps^2 > rr          H:2336-2347
+    if (!c.exact) return spmv(c, SMM_OP_SUB, c.b, x0, c.r, RED_OUT_OUT, FIN_CG_INIT, nullptr, c.p);
+    SMM_TRY(spmv(c, SMM_OP_SUB, c.b, x0, c.r, RED_NONE, FIN_NONE, nullptr, c.p));
+    return dots(c, FIN_CG_INIT, c.r, c.r);
+}
+int cg_iter(Ctx& c) {
+    if (!c.exact) {
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));        // H:2353-2358
+        SMM_TRY(vec(c, VEC_CG_XR, FIN_CG_UPDATE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));              // H:2363-2382
+        SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}));                                    // H:2385-2393
+        c.kernels_per_iteration = 3;
+        return SMM_OK;
+    }
+    SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_NONE, FIN_NONE, nullptr));
+    SMM_TRY(dots(c, FIN_CG_ALPHA, c.ap, c.p));
+    SMM_TRY(vec(c, VEC_CG_XR, FIN_NONE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
+    SMM_TRY(dots(c, FIN_CG_UPDATE, c.r, c.r));
+    SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}));
+    c.kernels_per_iteration = 5;
+    return SMM_OK;
+}
+
+int bicgsym_init(Ctx& c) {
+    if (!c.exact) return spmv(c, SMM_OP_SUB, c.b, c.x, c.r, RED_OUT_OUT, FIN_RR_INIT, nullptr, c.p);   // H:2035-2043
+    SMM_TRY(spmv(c, SMM_OP_SUB, c.b, c.x, c.r, RED_NONE, FIN_NONE, nullptr, c.p));
+    return dots(c, FIN_RR_INIT, c.r, c.r);
+}
+int bicgsym_iter(Ctx& c) {
+    if (!c.exact) {
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_OUT_AUX, FIN_BICGSYM_ALPHA, c.p));   // H:2048-2059
+        SMM_TRY(vec(c, VEC_BICGSYM_XR, FIN_BICGSYM_UPDATE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));    // H:2061-2082, 2094-2096
+        SMM_TRY(vec(c, VEC_BICGSYM_P, FIN_NONE, {c.p, c.r}, {c.p}));                               // H:2084-2092
+        c.kernels_per_iteration = 3;
+        return SMM_OK;
+    }
+    SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_NONE, FIN_NONE, nullptr));
+    SMM_TRY(dots(c, FIN_BICGSYM_ALPHA, c.ap, c.p));
+    SMM_TRY(vec(c, VEC_BICGSYM_XR, FIN_NONE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
+    SMM_TRY(dots(c, FIN_BICGSYM_UPDATE, c.r, c.r));
+    SMM_TRY(vec(c, VEC_BICGSYM_P, FIN_NONE, {c.p, c.r}, {c.p}));
+    c.kernels_per_iteration = 5;
+    return SMM_OK;
+}
+
+int cgs_init(Ctx& c) {
+    // r = b - A x ; p = u = r0 = r ; rr0 = r.r0                                 H:2117-2128
+    if (!c.exact) return spmv(c, SMM_OP_SUB, c.b, c.x, c.r, RED_OUT_OUT, FIN_RR_INIT, nullptr, c.p, c.u, c.r0);
+    SMM_TRY(spmv(c, SMM_OP_SUB, c.b, c.x, c.r, RED_NONE, FIN_NONE, nullptr, c.p, c.u, c.r0));
+    return dots(c, FIN_RR_INIT, c.r, c.r0);
+}
+int cgs_iter(Ctx& c) {
+    if (!c.exact) {
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_OUT_AUX, FIN_ALPHA_R0, c.r0));       // H:2132-2135
+        SMM_TRY(vec(c, VEC_CGS_QX, FIN_NONE, {c.ap, c.u, c.x}, {c.q, c.auq, c.x}));                // H:2137-2149
+        SMM_TRY(spmv(c, SMM_OP_SUB, c.r, c.auq, c.r, RED_OUT_AUX_OUT_OUT, FIN_CGS_UPDATE, c.r0));   // H:2151-2154, 2169-2172
+        SMM_TRY(vec(c, VEC_CGS_UP, FIN_NONE, {c.q, c.r, c.p}, {c.u, c.p}));                        // H:2157-2167
+        c.kernels_per_iteration = 4;
+        return SMM_OK;
+    }
+    SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_NONE, FIN_NONE, nullptr));
+    SMM_TRY(dots(c, FIN_ALPHA_R0, c.ap, c.r0));
+    SMM_TRY(vec(c, VEC_CGS_QX, FIN_NONE, {c.ap, c.u, c.x}, {c.q, c.auq, c.x}));
+    SMM_TRY(spmv(c, SMM_OP_SUB, c.r, c.auq, c.r, RED_NONE, FIN_NONE, nullptr));
+    SMM_TRY(dots(c, FIN_CGS_UPDATE, c.r, c.r0, c.r, c.r));
+    SMM_TRY(vec(c, VEC_CGS_UP, FIN_NONE, {c.q, c.r, c.p}, {c.u, c.p}));
+    c.kernels_per_iteration = 6;
+    return SMM_OK;
+}
+
+int stab_init(Ctx& c) {
+    // r = b - A x ; [r = M^-1 r] ; r0 = p = r ; rr0 = r.r0                       H:2214-2231
+    if (!c.precond) {
+        if (!c.exact) return spmv(c, SMM_OP_SUB, c.b, c.x, c.r, RED_OUT_OUT, FIN_RR_INIT, nullptr, c.p, c.r0);
+        SMM_TRY(spmv(c, SMM_OP_SUB, c.b, c.x, c.r, RED_NONE, FIN_NONE, nullptr, c.p, c.r0));
+        return dots(c, FIN_RR_INIT, c.r, c.r0);
+    }
+    SMM_TRY(spmv(c, SMM_OP_SUB, c.b, c.x, c.scratch, RED_NONE, FIN_NONE, nullptr));
+    SMM_TRY(smm_sgs_apply_async(c.precond, c.scratch, c.r, c.st, c.s));
+    SMM_TRY(vec(c, VEC_COPY3, FIN_NONE, {c.r}, {c.r0, c.p, c.r0}));
+    return dots(c, FIN_RR_INIT, c.r, c.r0);
+}
+int stab_iter(Ctx& c) {
+    int k = 0;
+    if (!c.precond && !c.exact) {
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_OUT_AUX, FIN_ALPHA_R0, c.r0));       // H:2240-2244
+        SMM_TRY(vec(c, VEC_STAB_S, FIN_NONE, {c.ap, c.r}, {c.sv}));                                // H:2245-2247
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.sv, c.as, RED_OUT_AUX_OUT_OUT, FIN_BICGSTAB_OMEGA, c.sv));   // H:2256-2261
+        SMM_TRY(vec(c, VEC_STAB_XR, FIN_BICGSTAB_UPDATE, {c.x, c.p, c.sv, c.as, c.r0}, {c.x, c.r})); // H:2262-2271, 2275-2277
+        SMM_TRY(vec(c, VEC_STAB_P, FIN_NONE, {c.p, c.ap, c.r}, {c.p}));                            // H:2272-2274
+        c.kernels_per_iteration = 5;
+        return SMM_OK;
+    }
+    // ap = [M^-1] A p                                                             H:2233-2241
+    if (c.precond) {
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.scratch, RED_NONE, FIN_NONE, nullptr));
+        SMM_TRY(smm_sgs_apply_async(c.precond, c.scratch, c.ap, c.st, c.s));
+        k += 1 + smm_sgs_kernels_per_apply(c.precond);
+    } else {
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_NONE, FIN_NONE, nullptr));
+        k += 1;
+    }
+    SMM_TRY(dots(c, FIN_ALPHA_R0, c.ap, c.r0));
+    SMM_TRY(vec(c, VEC_STAB_S, FIN_NONE, {c.ap, c.r}, {c.sv}));
+    // as = [M^-1] A s                                                             H:2249-2257
+    if (c.precond) {
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.sv, c.scratch, RED_NONE, FIN_NONE, nullptr));
+        SMM_TRY(smm_sgs_apply_async(c.precond, c.scratch, c.as, c.st, c.s));
+        k += 1 + smm_sgs_kernels_per_apply(c.precond);
+    } else {
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.sv, c.as, RED_NONE, FIN_NONE, nullptr));
+        k += 1;
+    }
+    if (c.mode == SMM_REDUCE_FAST) {
+        SMM_TRY(dots(c, FIN_BICGSTAB_OMEGA, c.as, c.sv));                                          // (as.s, as.as)
+        SMM_TRY(vec(c, VEC_STAB_XR, FIN_BICGSTAB_UPDATE, {c.x, c.p, c.sv, c.as, c.r0}, {c.x, c.r}));
+        k += 4;
+    } else {
+        SMM_TRY(dots(c, FIN_BICGSTAB_OMEGA, c.as, c.sv, c.as, c.as));
+        SMM_TRY(vec(c, VEC_STAB_XR, FIN_NONE, {c.x, c.p, c.sv, c.as, c.r0}, {c.x, c.r}));
+        // resL2Norm is a serial left-to-right sum in BOTH builds of the reference (H:2262-2267); r.r0 follows the build
+        SMM_TRY(smm_launch_dot_ref(SMM_REDUCE_REFERENCE_SERIAL, c.n, 1, c.r, c.r, c.r, c.r, c.st, FIN_STASH0, nullptr, c.s));
+        SMM_TRY(dots(c, FIN_BICGSTAB_UPDATE_STASHED, c.r, c.r0));
+        k += 6;
+    }
+    SMM_TRY(vec(c, VEC_STAB_P, FIN_NONE, {c.p, c.ap, c.r}, {c.p}));
+    c.kernels_per_iteration = k + 1;
+    return SMM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// loop drivers
+// ---------------------------------------------------------------------------------------------------
+__global__ void while_condition_kernel(const SolveState* st, cudaGraphConditionalHandle h) {
+    cudaGraphSetConditional(h, st->done ? 0u : 1u);
+}
+
+typedef int (*IterFn)(Ctx&);
+
+int poll_state(Ctx& c) {
+    SMM_CUDA(cudaMemcpyAsync(c.ws->state_host, c.st, sizeof(SolveState), cudaMemcpyDeviceToHost, c.s));
+    SMM_CUDA(cudaStreamSynchronize(c.s));
+    return SMM_OK;
+}
+
+int run_stream(Ctx& c, IterFn iter, long long budget, int check_every, long long* launches) {
+    long long done_iters = 0;
+    while (done_iters < budget) {
+        const long long m = (budget - done_iters < check_every) ? budget - done_iters : check_every;
+        for (long long i = 0; i < m; ++i) SMM_TRY(iter(c));
+        *launches += m * c.kernels_per_iteration;
+        done_iters += m;
+        SMM_TRY(poll_state(c));
+        if (c.ws->state_host->done) break;
+    }
+    return SMM_OK;
+}
+
+int capture_iteration(Ctx& c, IterFn iter, cudaGraph_t* graph) {
+    SMM_CUDA(cudaStreamBeginCapture(c.s, cudaStreamCaptureModeThreadLocal));
+    const long long before = g_smm_launches;
+    int rc = iter(c);
+    g_smm_launches = before;                                  // captured, not launched: counted per graph launch
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c.s, &g);
+    if (rc != SMM_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return smm_cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+    *graph = g;
+    return SMM_OK;
+}
+
+int run_graph_chunked(Ctx& c, IterFn iter, long long budget, int check_every, long long* launches) {
+    cudaGraph_t g = nullptr;
+    SMM_TRY(capture_iteration(c, iter, &g));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return smm_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+    int rc = SMM_OK;
+    long long done_iters = 0;
+    while (done_iters < budget && rc == SMM_OK) {
+        const long long m = (budget - done_iters < check_every) ? budget - done_iters : check_every;
+        for (long long i = 0; i < m && rc == SMM_OK; ++i) {
+            e = cudaGraphLaunch(exec, c.s);
+            if (e != cudaSuccess) rc = smm_cuda_fail(e, "cudaGraphLaunch", __FILE__, __LINE__);
+        }
+        *launches += m * c.kernels_per_iteration;
+        g_smm_launches += m * c.kernels_per_iteration;
+        done_iters += m;
+        if (rc == SMM_OK) rc = poll_state(c);
+        if (rc == SMM_OK && c.ws->state_host->done) break;
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(g);
+    return rc;
+}
+
+int run_graph_while(Ctx& c, IterFn iter, long long* launches) {
+    cudaGraph_t g = nullptr;
+    SMM_CUDA(cudaGraphCreate(&g, 0));
+    cudaGraphConditionalHandle h;
+    cudaError_t e = cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return smm_cuda_fail(e, "cudaGraphConditionalHandleCreate", __FILE__, __LINE__); }
+    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = h;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    e = cudaGraphAddNode(&node, g, nullptr, 0, &np);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return smm_cuda_fail(e, "cudaGraphAddNode(conditional)", __FILE__, __LINE__); }
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    e = cudaStreamBeginCaptureToGraph(c.s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return smm_cuda_fail(e, "cudaStreamBeginCaptureToGraph", __FILE__, __LINE__); }
+    const long long before = g_smm_launches;
+    int rc = iter(c);
+    if (rc == SMM_OK) {
+        while_condition_kernel<<<1, 1, 0, c.s>>>(c.st, h);
+        if (cudaGetLastError() != cudaSuccess) rc = SMM_E_CUDA;
+    }
+    g_smm_launches = before;
+    e = cudaStreamEndCapture(c.s, nullptr);
+    if (rc != SMM_OK || e != cudaSuccess) {
+        cudaGraphDestroy(g);
+        return rc != SMM_OK ? rc : smm_cuda_fail(e, "cudaStreamEndCapture(body)", __FILE__, __LINE__);
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return smm_cuda_fail(e, "cudaGraphInstantiate(while)", __FILE__, __LINE__); }
+    e = cudaGraphLaunch(exec, c.s);
+    if (e != cudaSuccess) rc = smm_cuda_fail(e, "cudaGraphLaunch(while)", __FILE__, __LINE__);
+    if (rc == SMM_OK) rc = poll_state(c);
+    if (rc == SMM_OK) {
+        // the body ran once per iteration plus possibly one no-op pass
+        const long long it = c.ws->state_host->iterations;
+        *launches += (it + 1) * (c.kernels_per_iteration + 1);
+        g_smm_launches += (it + 1) * (c.kernels_per_iteration + 1);
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(g);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// common front end
+// ---------------------------------------------------------------------------------------------------
+enum Solver { S_CG, S_BICGSYM, S_CGS, S_BICGSTAB };
+
+int clamp_iterations(int solver, int max_iterations, int rows) {
+    if (solver == S_CG) return max_iterations == -1 ? rows : max_iterations;                       // H:2345-2347
+    int m = max_iterations < rows ? max_iterations : rows;                                          // H:2030, 2111, 2200
+    if (m == -1) m = rows;                                                                          // H:2031-2033
+    return m;
+}
+
+int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const float* b_dev, const float* x0_dev, float* x_dev,
+              int max_iterations, float eps, const smm_solve_options* opts, smm_solve_info* info, cudaStream_t s) {
+    if (!a || (a->rows && (!b_dev || !x_dev || !x0_dev))) { smm_set_error("solve: bad arguments"); return SMM_E_INVALID; }
+    if (a->rows != a->cols) { smm_set_error("solve: matrix must be square"); return SMM_E_INVALID; }
+    SMM_CUDA(cudaSetDevice(a->device));
+    smm_workspace* ws = nullptr;
+    SMM_TRY(smm_workspace_get(a, &ws));
+    Ctx c;
+    c.a = a; c.precond = precond; c.ws = ws; c.s = s; c.st = ws->state; c.n = a->rows;
+    c.mode = opts ? opts->reduction_mode : SMM_REDUCE_FAST;
+    if (c.mode < 0 || c.mode > 2) { smm_set_error("solve: unknown reduction mode"); return SMM_E_INVALID; }
+    c.exact = c.mode != SMM_REDUCE_FAST;
+    c.b = b_dev; c.x = x_dev;
+    const int nvec = solver == S_CG || solver == S_BICGSYM ? 3 : (solver == S_CGS ? 7 : 7);
+    // work vectors live behind the three host-I/O staging slots (vec[0..2])
+    SMM_TRY(smm_workspace_vectors(ws, 3 + nvec, (size_t)a->rows));
+    float** w = ws->vec + 3;
+    c.r = w[0]; c.p = w[1]; c.ap = w[2];
+    if (solver == S_CGS) { c.r0 = w[3]; c.u = w[4]; c.q = w[5]; c.auq = w[6]; }
+    if (solver == S_BICGSTAB) { c.r0 = w[3]; c.sv = w[4]; c.as = w[5]; c.scratch = w[6]; }
+
+    const int driver_req = opts ? opts->driver_mode : SMM_DRIVER_AUTO;
+    int driver = driver_req == SMM_DRIVER_AUTO ? SMM_DRIVER_GRAPH_CHUNKED : driver_req;
+    int check_every = opts && opts->check_every > 0 ? opts->check_every : 32;
+    const int hist_cap = opts && opts->history && opts->history_cap > 0 ? opts->history_cap : 0;
+    if (hist_cap > ws->history_cap) {
+        cudaFree(ws->history);
+        ws->history = nullptr;
+        SMM_CUDA(cudaMalloc(&ws->history, sizeof(float) * (size_t)hist_cap));
+        ws->history_cap = hist_cap;
+    }
+
+    SolveState* h = ws->state_host;
+    memset(h, 0, sizeof *h);
+    h->max_iterations = clamp_iterations(solver, max_iterations, a->rows);
+    h->eps = eps;
+    h->eps2 = eps * eps;                                       // H:2045, H:2130, H:2335 (float product)
+    h->history = hist_cap ? ws->history : nullptr;
+    h->history_cap = hist_cap;
+    const int max_it = h->max_iterations;
+    SMM_CUDA(cudaMemcpyAsync(c.st, h, sizeof *h, cudaMemcpyHostToDevice, s));
+
+    long long launches = 0;
+    const long long launches_before = g_smm_launches;
+    SMM_CUDA(cudaEventRecord(ws->ev0, s));
+    IterFn iter = nullptr;
+    long long budget = 0;
+    if (a->rows > 0) {
+        switch (solver) {
+            case S_CG:
+                if (x_dev != x0_dev) SMM_CUDA(cudaMemcpyAsync(x_dev, x0_dev, sizeof(float) * (size_t)a->rows, cudaMemcpyDeviceToDevice, s));
+                SMM_TRY(cg_init(c, x0_dev));
+                iter = cg_iter;
+                budget = max_it > 0 ? max_it : 0;                                                  // for-loop, H:2352
+                break;
+            case S_BICGSYM:
+                SMM_TRY(bicgsym_init(c)); iter = bicgsym_iter; budget = max_it > 1 ? max_it : 1;   // do-while, H:2047/2096
+                break;
+            case S_CGS:
+                SMM_TRY(cgs_init(c)); iter = cgs_iter; budget = max_it > 1 ? max_it : 1;           // H:2131/2172
+                break;
+            case S_BICGSTAB:
+                SMM_TRY(stab_init(c)); iter = stab_iter; budget = max_it > 1 ? max_it : 1;         // H:2232/2277
+                break;
+        }
+        launches += g_smm_launches - launches_before;
+        int rc = SMM_OK;
+        if (budget > 0) {
+            if (driver == SMM_DRIVER_GRAPH_WHILE) rc = run_graph_while(c, iter, &launches);
+            else if (driver == SMM_DRIVER_GRAPH_CHUNKED) rc = run_graph_chunked(c, iter, budget, check_every, &launches);
+            else rc = run_stream(c, iter, budget, check_every, &launches);
+        } else {
+            rc = poll_state(c);
+        }
+        if (rc != SMM_OK) return rc;
+    } else {
+        SMM_TRY(poll_state(c));
+    }
+    SMM_CUDA(cudaEventRecord(ws->ev1, s));
+    SMM_CUDA(cudaEventSynchronize(ws->ev1));
+    float ms = 0.f;
+    SMM_CUDA(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+
+    const SolveState* r = ws->state_host;
+    int status = r->status;
+    if (a->rows == 0) status = solver == S_CG ? SMM_SOLVER_SUCCESS : SMM_SOLVER_SUCCESS;
+    if (hist_cap) {
+        const int m = r->iterations < hist_cap ? r->iterations : hist_cap;
+        if (m > 0) SMM_CUDA(cudaMemcpy(opts->history, ws->history, sizeof(float) * (size_t)m, cudaMemcpyDeviceToHost));
+    }
+    if (info) {
+        memset(info, 0, sizeof *info);
+        info->status = status;
+        info->iterations = r->iterations;
+        info->residual = r->residual;
+        info->precond_error = r->precond_error;
+        info->seconds_solve = ms * 1e-3;
+        info->seconds_total = ms * 1e-3;
+        info->reduction_mode = c.mode;
+        info->driver_mode = driver;
+        info->kernel_launches = launches;
+    }
+    return SMM_OK;
+}
+
+// host-pointer front end: stage b, x0 in HBM, solve, copy x back
+int solve_host(int solver, const smm_csr* a, const smm_precond* precond, const float* b, const float* x0, float* x,
+               int max_iterations, float eps, const smm_solve_options* opts, smm_solve_info* info) {
+    if (!a || (a->rows && (!b || !x || !x0))) { smm_set_error("solve: bad arguments"); return SMM_E_INVALID; }
+    const auto t0 = std::chrono::steady_clock::now();
+    SMM_CUDA(cudaSetDevice(a->device));
+    smm_workspace* ws = nullptr;
+    SMM_TRY(smm_workspace_get(a, &ws));
+    SMM_TRY(smm_workspace_vectors(ws, 10, (size_t)a->rows));
+    cudaStream_t s = smm_default_stream();
+    const size_t bytes = sizeof(float) * (size_t)a->rows;
+    float* d_b = ws->vec[0];
+    float* d_x = ws->vec[1];
+    float* d_x0 = d_x;
+    if (a->rows) {
+        SMM_CUDA(cudaMemcpyAsync(d_b, b, bytes, cudaMemcpyHostToDevice, s));
+        SMM_CUDA(cudaMemcpyAsync(d_x, x0, bytes, cudaMemcpyHostToDevice, s));
+    }
+    smm_solve_info local;
+    SMM_TRY(solve_dev(solver, a, precond, d_b, d_x0, d_x, max_iterations, eps, opts, &local, s));
+    // ConjugateGradient returns before touching x when the initial residual already passes (H:2342-2344)
+    const bool x_written = !(solver == S_CG && local.iterations == 0) || x == x0;
+    if (a->rows && x_written) {
+        SMM_CUDA(cudaMemcpyAsync(x, d_x, bytes, cudaMemcpyDeviceToHost, s));
+        SMM_CUDA(cudaStreamSynchronize(s));
+    }
+    local.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (info) *info = local;
+    return SMM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smm_solve_cg(const smm_csr_t* a, const float* b, const float* x0, float* x, int maxIterations, float eps,
+                 const smm_solve_options* opts, smm_solve_info* info) {
+    return solve_host(S_CG, a, nullptr, b, x0, x, maxIterations, eps, opts, info);
+}
+int smm_solve_bicgsym(const smm_csr_t* a, const float* b, float* x, int maxIterations, float eps,
+                      const smm_solve_options* opts, smm_solve_info* info) {
+    return solve_host(S_BICGSYM, a, nullptr, b, x, x, maxIterations, eps, opts, info);
+}
+int smm_solve_cgs(const smm_csr_t* a, const float* b, float* x, int maxIterations, float eps,
+                  const smm_solve_options* opts, smm_solve_info* info) {
+    return solve_host(S_CGS, a, nullptr, b, x, x, maxIterations, eps, opts, info);
+}
+int smm_solve_bicgstab(const smm_csr_t* a, const smm_precond_t* precond, const float* b, float* x, int maxIterations,
+                       float eps, const smm_solve_options* opts, smm_solve_info* info) {
+    return solve_host(S_BICGSTAB, a, precond, b, x, x, maxIterations, eps, opts, info);
+}
+
+static inline cudaStream_t pick_stream(void* stream) { return stream ? (cudaStream_t)stream : smm_default_stream(); }
+
+int smm_solve_cg_dev(const smm_csr_t* a, const float* b_dev, const float* x0_dev, float* x_dev, int maxIterations,
+                     float eps, const smm_solve_options* opts, smm_solve_info* info, void* stream) {
+    return solve_dev(S_CG, a, nullptr, b_dev, x0_dev, x_dev, maxIterations, eps, opts, info, pick_stream(stream));
+}
+int smm_solve_bicgsym_dev(const smm_csr_t* a, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                          const smm_solve_options* opts, smm_solve_info* info, void* stream) {
+    return solve_dev(S_BICGSYM, a, nullptr, b_dev, x_dev, x_dev, maxIterations, eps, opts, info, pick_stream(stream));
+}
+int smm_solve_cgs_dev(const smm_csr_t* a, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                      const smm_solve_options* opts, smm_solve_info* info, void* stream) {
+    return solve_dev(S_CGS, a, nullptr, b_dev, x_dev, x_dev, maxIterations, eps, opts, info, pick_stream(stream));
+}
+int smm_solve_bicgstab_dev(const smm_csr_t* a, const smm_precond_t* precond, const float* b_dev, float* x_dev,
+                           int maxIterations, float eps, const smm_solve_options* opts, smm_solve_info* info, void* stream) {
+    return solve_dev(S_BICGSTAB, a, precond, b_dev, x_dev, x_dev, maxIterations, eps, opts, info, pick_stream(stream));
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// measurement hook: per-kernel device times of one fused CG iteration (bench.py's roofline line).
+// Launches the SAME three kernels the solver's iteration graph holds, `reps` times each, on `stream`, bracketed
+// by CUDA events.  Vectors are the handle's own work vectors (contents irrelevant for timing, kept finite).
+// ---------------------------------------------------------------------------------------------------
+extern "C" int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_spmv, float* ms_xr, float* ms_p, void* stream) {
+    if (!a || reps < 1) return SMM_E_INVALID;
+    SMM_CUDA(cudaSetDevice(a->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : smm_default_stream();
+    smm_workspace* ws = nullptr;
+    SMM_TRY(smm_workspace_get(a, &ws));
+    SMM_TRY(smm_workspace_vectors(ws, 7, (size_t)a->rows));
+    Ctx c;
+    c.a = a; c.ws = ws; c.s = s; c.st = ws->state; c.n = a->rows;
+    float** w = ws->vec + 3;
+    c.x = ws->vec[1]; c.r = w[0]; c.p = w[1]; c.ap = w[2];
+    const size_t bytes = sizeof(float) * (size_t)a->rows;
+    SMM_CUDA(cudaMemsetAsync(c.x, 0, bytes, s));
+    SMM_CUDA(cudaMemsetAsync(c.r, 0, bytes, s));
+    SMM_CUDA(cudaMemsetAsync(c.p, 0, bytes, s));
+    SMM_CUDA(cudaMemsetAsync(c.st, 0, sizeof(SolveState), s));
+    float* outs[3] = {ms_spmv, ms_xr, ms_p};
+    for (int k = 0; k < 3; ++k) {
+        for (int rep = -2; rep < reps; ++rep) {                // two untimed warm-up launches
+            if (rep == 0) SMM_CUDA(cudaEventRecord(ws->ev0, s));
+            if (k == 0) SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));
+            else if (k == 1) SMM_TRY(vec(c, VEC_CG_XR, FIN_STORE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
+            else SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}));
+        }
+        SMM_CUDA(cudaEventRecord(ws->ev1, s));
+        SMM_CUDA(cudaEventSynchronize(ws->ev1));
+        float ms = 0.f;
+        SMM_CUDA(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+        if (outs[k]) *outs[k] = ms / reps;
+    }
+    return SMM_OK;
+}

@@ -229,3 +229,16 @@ def test_live_dot_tree(n):
     b = rng.uniform(-1, 1, n).astype(np.float32)
     for mt in (0, 1):
         assert np.float32(ol.dot(a, b, mt)) == np.float32(ol.ref(mt).smm_ref_dot(n, a, b))
+
+
+@needs_ref
+@pytest.mark.parametrize("solver", ["cg", "bicgsym", "cgs", "bicgstab"])
+@pytest.mark.parametrize("maxit", [0, 1, 3, -7])
+def test_live_iteration_cap_quirks(solver, maxit):
+    # do-while solvers run the body once even for maxIterations <= 0 and then report MAX_ITERATIONS_REACHED (H:2098)
+    m = matgen.poisson2d(20, 20)
+    b = ol.spmv(m, 0, None, matgen.xstar(m.rows))
+    for mt in (0, 1):
+        o = ol.solve(solver, m, b, np.zeros(m.rows, np.float32), maxit, 1e-6, mt)
+        st, x = ol.RefCSR(m, mt).solve(solver, b, np.zeros(m.rows, np.float32), maxit, 1e-6)
+        assert st == o["status"] and x.tobytes() == o["x"].tobytes()
