@@ -229,12 +229,15 @@ def test_dot_modes(smm, n):
 # ---------------------------------------------------------------------------------------------
 def _solver_cases():
     names = [k[: -len("/status_iterations_eps")] for k in np.load(os.path.join(GOLD, "golden_v1.npz")).files if k.endswith("/status_iterations_eps")]
-    return sorted(n for n in names if "cg_ic0" not in n and "_sgs" not in n)
+    return sorted(n for n in names if "cg_ic0" not in n)
 
 
 def run_solver(smm, solver, m, b, x0, maxit, eps, **kw):
     x = x0.copy()
-    if solver == "cg":
+    if solver == "bicgstab_sgs":
+        M = m.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
+        info = smm.BiCGStab(m, b, x, maxit, eps, preconditioner=M, **kw)
+    elif solver == "cg":
         info = smm.ConjugateGradient(m, b, x, x, maxit, eps, **kw)
     elif solver == "bicgsym":
         info = smm.BiCGSymmetric(m, b, x, maxit, eps, **kw)
@@ -273,13 +276,13 @@ def test_solvers_fast_mode(smm, golden, name):
     st, it, eps = golden[name + "/status_iterations_eps"]
     it_st = golden[name.replace("/mt/", "/st/") + "/status_iterations_eps"][1]
     b = golden[f"{key}/b"]
-    if key == "sherman1" and solver in ("cgs", "bicgstab"):
+    if key == "sherman1" and solver in ("cgs", "bicgstab", "bicgstab_sgs"):
         pytest.skip("indefinite, ill-conditioned: CGS/BiCGStab wander chaotically with the summation order (no breakdown "
                     "checks in the reference, H:2134,2153); covered by the bit-exact modes only")
     info, x = run_solver(smm, solver, m, b, np.zeros(g.rows, np.float32), -1, np.float32(eps), history_cap=4096)
     assert int(info.status) == int(st)
     # the solver's own residual quantity passed its test (squared recurrence residual, or L2 for BiCGStab)
-    assert info.residual <= (eps if solver == "bicgstab" else np.float32(eps) * np.float32(eps))
+    assert info.residual <= (eps if solver.startswith("bicgstab") else np.float32(eps) * np.float32(eps))
     lo, hi = min(it, it_st), max(it, it_st)
     assert 0.95 * lo - 1 <= info.iterations <= 1.05 * hi + 1, (info.iterations, it, it_st)
     if solver in ("cg", "bicgsym") and key != "sherman1":
@@ -369,3 +372,74 @@ def test_bicgsym_diverged_and_nan_paths(smm):
     o = ol.solve("bicgstab", g2, bb, xs, -1, 1e-6, 1)
     assert int(info.status) == o["status"] == 0 and info.iterations == o["iterations"] == 1
     assert np.array_equal(np.isnan(x), np.isnan(o["x"]))
+
+
+# ---------------------------------------------------------------------------------------------
+# SGS preconditioner (getPreconditioner<SYMMETRIC_GAUS_SEIDEL>(), H:1643-1713)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", ASSETS + GENERATED)
+def test_sgs_apply_bit_exact(smm, golden, key):
+    g = gold_csr(golden, key)
+    m = upload(smm, g)
+    M = m.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
+    b = golden[f"{key}/b"]
+    rc, x = M.apply(b)
+    assert rc == int(golden[f"{key}/mt/sgs_rc"]) == 0
+    assert x.tobytes() == golden[f"{key}/mt/sgs_b"].tobytes()          # same bits as SGSPreconditioner::apply
+    rc2, x2 = M.apply(b)                                                # reusable, deterministic
+    assert rc2 == 0 and x2.tobytes() == x.tobytes()
+    with pytest.raises(smm.SmmError):
+        M.apply(b, b)                                                   # assert(rhs != x), H:1667
+
+
+def test_sgs_levels_and_large_grid(smm):
+    # natural-order 7-point grid: hyperplane wavefronts i+j+k = const -> nx+ny+nz-2 levels in each sweep
+    g = matgen.convdiff3d(20, 0.5, 17, 13)
+    m = upload(smm, g)
+    M = m.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
+    assert M.levels() == (20 + 17 + 13 - 2, 20 + 17 + 13 - 2)
+    rng = np.random.default_rng(2)
+    rhs = rng.uniform(-1, 1, g.rows).astype(np.float32)
+    rc, x = M.apply(rhs)
+    rc_o, x_o = ol.sgs_apply(g, rhs)
+    assert rc == rc_o == 0 and x.tobytes() == x_o.tobytes()
+    # a chain (tridiagonal): every row is its own level -- the worst case for level scheduling still terminates
+    t = matgen.poisson3d(3000, 1, 1)
+    mt_ = upload(smm, t)
+    Mt = mt_.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
+    assert Mt.levels() == (3000, 3000)
+    rhs = rng.uniform(-1, 1, 3000).astype(np.float32)
+    assert Mt.apply(rhs)[1].tobytes() == ol.sgs_apply(t, rhs)[1].tobytes()
+
+
+def test_sgs_error_codes(smm):
+    # missing diagonal / empty row / leading empty row / tiny diagonal -> apply returns 1 (H:1668, 1678, 1691)
+    rhs = np.ones(4, np.float32)
+    cases = {
+        "missing_diag": ol.triplets_to_csr(4, 4, [0, 1, 1, 2, 3], [0, 0, 2, 2, 3], [1, 1, 1, 1, 1]),
+        "empty_row": ol.triplets_to_csr(4, 4, [0, 1, 3], [0, 1, 3], [1, 1, 1]),
+        "leading_empty": ol.triplets_to_csr(4, 4, [1, 2, 3], [1, 2, 3], [1, 1, 1]),
+        "tiny_diag": ol.triplets_to_csr(4, 4, [0, 1, 2, 3], [0, 1, 2, 3], [1, 1e-7, 1, 1]),
+    }
+    for name, g in cases.items():
+        M = upload(smm, g).getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
+        rc, _ = M.apply(rhs)
+        assert rc == ol.sgs_apply(g, rhs)[0] == 1, name
+
+
+def test_bicgstab_sgs_large_parity(smm):
+    # config 2' shape at a size the oracle finishes in seconds: 3D convection-diffusion 48^3, b = A x*
+    g = matgen.convdiff3d(48)
+    m = upload(smm, g)
+    xs = matgen.xstar(g.rows)
+    b = ol.spmv(g, 0, None, xs)
+    M = m.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
+    o = ol.solve("bicgstab", g, b, np.zeros(g.rows, np.float32), -1, 1e-5, 1, precond=1)
+    x = np.zeros(g.rows, np.float32)
+    info = smm.BiCGStab(m, b, x, -1, 1e-5, preconditioner=M, reduction_mode=smm.REDUCE_REFERENCE_TREE)
+    assert info.iterations == o["iterations"] and x.tobytes() == o["x"].tobytes() and info.precond_error == 0
+    x = np.zeros(g.rows, np.float32)
+    info = smm.BiCGStab(m, b, x, -1, 1e-5, preconditioner=M)
+    assert int(info.status) == 0 and info.residual <= 1e-5
+    assert abs(info.iterations - o["iterations"]) <= max(1, round(0.05 * o["iterations"]) + 1)
+    assert np.max(np.abs(x - xs)) < 1e-4
