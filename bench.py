@@ -41,6 +41,23 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_bytes(kernel_prefix, grid):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
+    same command (profiles/r01b_spmv_rows_kernel_full.txt, 512^3); None for any other problem size."""
+    p = os.path.join(ROOT, "profiles", "r01b_spmv_rows_kernel_full.txt")
+    if grid != 512 or not os.path.exists(p):
+        return None
+    rd = wr = None
+    unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    for line in open(p):
+        f = line.split()
+        if len(f) >= 3 and f[0] == "dram__bytes_read.sum" and rd is None:
+            rd = float(f[1]) * unit.get(f[2], 1.0)
+        if len(f) >= 3 and f[0] == "dram__bytes_write.sum" and wr is None:
+            wr = float(f[1]) * unit.get(f[2], 1.0)
+    return None if rd is None or wr is None else rd + wr
+
+
 def stencil_nnz(n):
     return 7 * n ** 3 - 6 * n ** 2
 
@@ -356,8 +373,8 @@ def run_b200(args):
                 "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "smm_solve_cg (host pointers, pinned)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "spmv_kernel (Ap = A p, p.Ap fused)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "spmv_rows_kernel<1> (Ap = A p, p.Ap fused; TMA-staged, 1 lane per row)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes("spmv_rows", grid), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": ms_spmv,
                      "share_of_iteration": ms_spmv / kernel_sum if kernel_sum > 0 else None},
         "iteration": {"algorithmic_bytes": iter_bytes, "achieved_gbs": iter_gbs, "frac_of_peak": iter_gbs / peak,

@@ -38,6 +38,7 @@ constexpr int SPMV_CAP = 6144;             // products staged in shared memory (
 constexpr int SPMV_MIN_STREAM_ROWS = 48;   // fewer rows than this in a CTA's range -> warp/CTA-per-row path
 constexpr int SPMV_LONG_IN_STREAM = 192;   // rows longer than this inside a streamed range are summed by a warp
 constexpr int SPMV_CTA_ROW = 4096;         // rows longer than this are reduced by the whole CTA
+constexpr int SPMV_ROWS_CAP = 2560;        // rows kernel: upper bound of the entries per TMA stage
 
 // ---------------------------------------------------------------------------------------------------
 // handles
@@ -55,6 +56,9 @@ struct smm_csr {
     int num_blocks = 0;
     int32_t* block_row = nullptr;   // [num_blocks+1]
     int max_row_len = 0;
+    int rows_kernel_lanes = 0;      // 0: product-staging kernel; V > 0: TMA rows kernel with V lanes per row
+    int sm_count = 148;
+    int rows_kernel_cap = 0;        // entries per TMA stage of the rows kernel (sized to the matrix)
     // reduction scratch shared by every kernel launched for this matrix (one solve at a time per handle)
     struct smm_workspace* ws = nullptr;
 };

@@ -16,8 +16,19 @@
 //   * row path (few long rows): warp per row with coalesced strided loads and a shuffle reduction; rows longer
 //     than SPMV_CTA_ROW are reduced by the whole CTA.
 //   * exact mode: every row is accumulated left to right by one thread (parity runs).
+//
+// Matrices whose rows are all short and of similar length (stencils: BASELINE configs 1, 2, 3, 5) take a second,
+// Blackwell-specific kernel instead (spmv_rows_kernel): a persistent CTA per SM slot streams fixed groups of rows;
+// the TMA engine (cp.async.bulk + mbarrier, 3 stages) copies each group's values/positions window into shared
+// memory while the previous groups are being multiplied, and V lanes per row (V = 1, 2, 4, 8 chosen from the mean
+// row length; V = 1 for stencils) walk their row out of shared memory, so that consecutive lanes gather CONSECUTIVE
+// entries of mult[] (one or two 128-byte lines per warp-wide gather instead of one line per distinct stencil
+// offset), and accumulate in registers -- for V = 1 in the reference's left-to-right order, bit-identical.
 // Algorithmic bytes per launch: 8*nnz (values+positions) + 4*(rows+1) (start) + 4*cols (mult, gathered once)
 // + 4*rows (out) [+ 4*rows lhs for ADD/SUB] [+ 4*rows per fused-dot operand].
+#include <stdlib.h>
+#include <string.h>
+
 #include "smm_internal.cuh"
 
 namespace {
@@ -76,6 +87,68 @@ struct RowWriter {
         }
     }
 };
+
+// Rows [r0, r1) straight from global memory: exact mode = one thread per row, left to right; otherwise warp per row
+// (coalesced strided loads + shuffle reduction) and the whole CTA for rows longer than SPMV_CTA_ROW.
+// Must be called by every thread of the CTA (it contains block-wide barriers).
+template <class Writer>
+__device__ __forceinline__ void row_path(const SpmvParams& P, int r0, int r1, Writer& write, float* red_sh) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwarps = blockDim.x >> 5;
+    if (P.exact) {
+        for (int r = r0 + tid; r < r1; r += nthreads) {
+            const int s = P.start[r], e = P.start[r + 1];
+            float dot = 0.0f;
+            for (int k = s; k < e; ++k) dot = __fadd_rn(__fmul_rn(P.values[k], __ldg(P.mult + P.positions[k])), dot);
+            write(r, dot);
+        }
+        return;
+    }
+    bool any_cta_row = false;
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+        const int s = P.start[r], e = P.start[r + 1];
+        if (e - s > SPMV_CTA_ROW) { any_cta_row = true; continue; }
+        float acc = 0.0f;
+        int k = s + lane;
+        for (; k + 32 < e; k += 64) {                         // two independent gathers in flight
+            const int c0 = ldg_stream_i(P.positions + k), c1 = ldg_stream_i(P.positions + k + 32);
+            const float a0v = ldg_stream_f(P.values + k), a1v = ldg_stream_f(P.values + k + 32);
+            acc = fmaf(a0v, __ldg(P.mult + c0), acc);
+            acc = fmaf(a1v, __ldg(P.mult + c1), acc);
+        }
+        if (k < e) acc = fmaf(ldg_stream_f(P.values + k), __ldg(P.mult + ldg_stream_i(P.positions + k)), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) write(r, acc);
+    }
+    if (__syncthreads_or(any_cta_row)) {                      // uniform: rescan for CTA-wide rows
+        for (int r = r0; r < r1; ++r) {
+            const int s = P.start[r], e = P.start[r + 1];
+            if (e - s <= SPMV_CTA_ROW) continue;
+            float acc = 0.0f;
+            const int sa = (s + 3) & ~3;                      // aligned body, scalar head/tail
+            const int ea = e & ~3;
+            if (tid < sa - s) acc = fmaf(P.values[s + tid], __ldg(P.mult + P.positions[s + tid]), acc);
+            if (tid < e - ea) acc = fmaf(P.values[ea + tid], __ldg(P.mult + P.positions[ea + tid]), acc);
+            const int4* pos4 = reinterpret_cast<const int4*>(P.positions + sa);
+            const float4* val4 = reinterpret_cast<const float4*>(P.values + sa);
+            const int nvec = (ea - sa) >> 2;
+            for (int v = tid; v < nvec; v += nthreads) {
+                const int4 c = ldg_stream_i4(pos4 + v);
+                const float4 a = ldg_stream_f4(val4 + v);
+                acc = fmaf(a.x, __ldg(P.mult + c.x), acc);
+                acc = fmaf(a.y, __ldg(P.mult + c.y), acc);
+                acc = fmaf(a.z, __ldg(P.mult + c.z), acc);
+                acc = fmaf(a.w, __ldg(P.mult + c.w), acc);
+            }
+            float v1[1] = {acc};
+            __syncthreads();
+            block_sum<1>(v1, red_sh);
+            if (tid == 0) write(r, v1[0]);
+            __syncthreads();
+        }
+    }
+}
 
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const SpmvParams P) {
     if (P.state != nullptr && P.state->done) return;
@@ -145,60 +218,8 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const SpmvParams P) 
                     if (lane == 0) write(r, acc);
                 }
             }
-        } else if (P.exact) {
-            // ---------------- exact row path: one thread per row, left to right from global memory ----------------
-            for (int r = r0 + tid; r < r1; r += SPMV_THREADS) {
-                const int s = P.start[r], e = P.start[r + 1];
-                float dot = 0.0f;
-                for (int k = s; k < e; ++k) dot = __fadd_rn(__fmul_rn(P.values[k], __ldg(P.mult + P.positions[k])), dot);
-                write(r, dot);
-            }
         } else {
-            // ---------------- row path: warp per row, CTA per very long row ----------------
-            bool any_cta_row = false;
-            for (int r = r0 + warp; r < r1; r += NWARPS) {
-                const int s = P.start[r], e = P.start[r + 1];
-                if (e - s > SPMV_CTA_ROW) { any_cta_row = true; continue; }
-                float acc = 0.0f;
-                int k = s + lane;
-                for (; k + 32 < e; k += 64) {                 // two independent gathers in flight
-                    const int c0 = ldg_stream_i(P.positions + k), c1 = ldg_stream_i(P.positions + k + 32);
-                    const float a0v = ldg_stream_f(P.values + k), a1v = ldg_stream_f(P.values + k + 32);
-                    acc = fmaf(a0v, __ldg(P.mult + c0), acc);
-                    acc = fmaf(a1v, __ldg(P.mult + c1), acc);
-                }
-                if (k < e) acc = fmaf(ldg_stream_f(P.values + k), __ldg(P.mult + ldg_stream_i(P.positions + k)), acc);
-                acc = warp_sum(acc);
-                if (lane == 0) write(r, acc);
-            }
-            // nrows < SPMV_MIN_STREAM_ROWS or a row longer than the window: rescan for CTA-wide rows (uniform branch)
-            if (__syncthreads_or(any_cta_row)) {
-                for (int r = r0; r < r1; ++r) {
-                    const int s = P.start[r], e = P.start[r + 1];
-                    if (e - s <= SPMV_CTA_ROW) continue;
-                    float acc = 0.0f;
-                    const int sa = (s + 3) & ~3;              // aligned body, scalar head/tail
-                    const int ea = e & ~3;
-                    if (tid < sa - s) acc = fmaf(P.values[s + tid], __ldg(P.mult + P.positions[s + tid]), acc);
-                    if (tid < e - ea) acc = fmaf(P.values[ea + tid], __ldg(P.mult + P.positions[ea + tid]), acc);
-                    const int4* pos4 = reinterpret_cast<const int4*>(P.positions + sa);
-                    const float4* val4 = reinterpret_cast<const float4*>(P.values + sa);
-                    const int nvec = (ea - sa) >> 2;
-                    for (int v = tid; v < nvec; v += SPMV_THREADS) {
-                        const int4 c = ldg_stream_i4(pos4 + v);
-                        const float4 a = ldg_stream_f4(val4 + v);
-                        acc = fmaf(a.x, __ldg(P.mult + c.x), acc);
-                        acc = fmaf(a.y, __ldg(P.mult + c.y), acc);
-                        acc = fmaf(a.z, __ldg(P.mult + c.z), acc);
-                        acc = fmaf(a.w, __ldg(P.mult + c.w), acc);
-                    }
-                    float v1[1] = {acc};
-                    __syncthreads();
-                    block_sum<1>(v1, red_sh);
-                    if (tid == 0) write(r, v1[0]);
-                    __syncthreads();
-                }
-            }
+            row_path(P, r0, r1, write, red_sh);
         }
     }
 
@@ -209,6 +230,187 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const SpmvParams P) 
             if (tid == 0) smm_finish(P.finish, P.state, v[0], v[1]);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// spmv_rows_kernel: persistent, TMA-staged, V lanes per row (see the file header)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion is signalled on the mbarrier in bytes
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int ROWS_MAX_STAGES = 4;
+constexpr int ROWS_CONSUMERS = SPMV_THREADS;                      // 8 consumer warps
+constexpr int ROWS_THREADS = SPMV_THREADS + 32;                   // + 1 producer warp
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One row (or a V-lane slice of it) out of a values/positions window; four independent gathers in flight,
+// added in the order of the entries (V = 1: the reference's left-to-right sum, H:1484-1489).
+template <int V, class VP, class CP>
+__device__ __forceinline__ float row_dot(const VP vs, const CP cs, const float* __restrict__ mult, int j, const int e) {
+    float dot = 0.0f;
+    for (; j + 3 * V < e; j += 4 * V) {
+        const int c0 = cs[j], c1 = cs[j + V], c2 = cs[j + 2 * V], c3 = cs[j + 3 * V];
+        const float v0 = vs[j], v1 = vs[j + V], v2 = vs[j + 2 * V], v3 = vs[j + 3 * V];
+        const float x0 = __ldg(mult + c0), x1 = __ldg(mult + c1), x2 = __ldg(mult + c2), x3 = __ldg(mult + c3);
+        dot = __fadd_rn(__fmul_rn(v0, x0), dot);
+        dot = __fadd_rn(__fmul_rn(v1, x1), dot);
+        dot = __fadd_rn(__fmul_rn(v2, x2), dot);
+        dot = __fadd_rn(__fmul_rn(v3, x3), dot);
+    }
+    if (j + V < e) {                                              // two or three entries left
+        const int c0 = cs[j], c1 = cs[j + V];
+        const float v0 = vs[j], v1 = vs[j + V];
+        const bool three = j + 2 * V < e;
+        const int c2 = three ? cs[j + 2 * V] : c0;
+        const float v2 = three ? vs[j + 2 * V] : 0.0f;
+        const float x0 = __ldg(mult + c0), x1 = __ldg(mult + c1), x2 = __ldg(mult + c2);
+        dot = __fadd_rn(__fmul_rn(v0, x0), dot);
+        dot = __fadd_rn(__fmul_rn(v1, x1), dot);
+        if (three) dot = __fadd_rn(__fmul_rn(v2, x2), dot);
+    } else if (j < e) {
+        dot = __fadd_rn(__fmul_rn(vs[j], __ldg(mult + cs[j])), dot);
+    }
+    return dot;
+}
+
+// Warp-specialised persistent kernel.  Warp 8 is the producer: for each of this CTA's row groups it waits until
+// the slot is free (empty barrier), then has the TMA engine copy the group's values/positions window into the
+// slot, completion counted in bytes on the slot's full barrier.  Warps 0..7 are consumers: wait for the slot, take
+// one row per V lanes out of shared memory, release the slot.  No CTA-wide barrier inside the loop.
+template <int V>   // lanes per row
+__global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParams P, const int cap, const int nchunks, const int stages) {
+    if (P.state != nullptr && P.state->done) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: vals[stages][cap] | cols[stages][cap] | full[4] | empty[4] | win[4][2]
+    float* vals_s = reinterpret_cast<float*>(smem_raw);
+    int* cols_s = reinterpret_cast<int*>(smem_raw + (size_t)stages * cap * sizeof(float));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * cap * 8);
+    uint64_t* empty = full + ROWS_MAX_STAGES;
+    int* win = reinterpret_cast<int*>(empty + ROWS_MAX_STAGES);   // [stage][2]: window start a0, staged flag
+    __shared__ float red_sh[96];
+    __shared__ int sh_flag;
+
+    constexpr int R = ROWS_CONSUMERS / V;                         // rows per group
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    RowWriter write(P);
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ROWS_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int G = gridDim.x;
+    const int first = blockIdx.x;
+    const int my_chunks = first < nchunks ? (nchunks - first + G - 1) / G : 0;
+
+    if (warp == ROWS_CONSUMERS / 32) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            int k0 = 0, k1 = 0;
+            if (my_chunks > 0) {
+                const int rb = first * R, re = min(rb + R, P.rows);
+                k0 = P.start[rb]; k1 = P.start[re];
+            }
+            for (int it = 0; it < my_chunks; ++it) {
+                const int s = it % stages;
+                int n0 = 0, n1 = 0;                                // next group's window, fetched ahead of the wait
+                if (it + 1 < my_chunks) {
+                    const int rb = (first + (it + 1) * G) * R, re = min(rb + R, P.rows);
+                    n0 = P.start[rb]; n1 = P.start[re];
+                }
+                if (it >= stages) mbar_wait(&empty[s], (uint32_t)(((it / stages) - 1) & 1));
+                const int a0 = k0 & ~3;
+                const int span = k1 - a0;
+                const bool staged = span > 0 && span <= cap;
+                win[2 * s] = a0;
+                win[2 * s + 1] = staged ? 1 : 0;
+                if (staged) {
+                    const uint32_t bytes = (uint32_t)(((span + 3) & ~3) * 4);
+                    mbar_expect_tx(&full[s], 2 * bytes);
+                    tma_load_1d(vals_s + (size_t)s * cap, P.values + a0, bytes, &full[s]);
+                    tma_load_1d(cols_s + (size_t)s * cap, P.positions + a0, bytes, &full[s]);
+                } else {
+                    mbar_arrive(&full[s]);                         // nothing to copy: consumers read global memory
+                }
+                k0 = n0; k1 = n1;
+            }
+        }
+    } else {
+        // ---------------- consumers ----------------
+        const int sub = tid % V;                                  // lane inside the row's lane group
+        const int rloc = tid / V;                                 // row inside the group
+        int my_s = 0, my_e = 0;
+        if (my_chunks > 0) {
+            const int r = first * R + rloc;
+            if (r < P.rows) { my_s = P.start[r]; my_e = P.start[r + 1]; }
+        }
+        for (int it = 0; it < my_chunks; ++it) {
+            const int q = first + it * G;
+            const int s = it % stages;
+            int nx_s = 0, nx_e = 0;                               // next group's row bounds, fetched ahead
+            if (it + 1 < my_chunks) {
+                const int rn = (q + G) * R + rloc;
+                if (rn < P.rows) { nx_s = P.start[rn]; nx_e = P.start[rn + 1]; }
+            }
+            const int row = q * R + rloc;
+            mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
+            const int a0 = win[2 * s];
+            float dot;
+            // rows past the end have my_s == my_e == 0: their lanes fall through and only join the shuffles
+            if (win[2 * s + 1]) dot = row_dot<V>(vals_s + (size_t)s * cap - a0, cols_s + (size_t)s * cap - a0, P.mult, my_s + sub, my_e);
+            else dot = row_dot<V>(P.values, P.positions, P.mult, my_s + sub, my_e);
+            if (V > 1) {
+#pragma unroll
+                for (int o = V / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            }
+            if (sub == 0 && row < P.rows) write(row, dot);        // the store depends on every shared-memory read above
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);                // this warp is done with the slot
+            my_s = nx_s; my_e = nx_e;
+        }
+    }
+
+    if (P.reduce != RED_NONE) {
+        float v[2] = {write.acc0, write.acc1};
+        __syncthreads();
+        if (grid_sum_last_block<2>(v, P.partials, P.partials_stride, P.ticket, red_sh, &sh_flag)) {
+            if (tid == 0) smm_finish(P.finish, P.state, v[0], v[1]);
+        }
+    }
+}
+
+__global__ void row_stats_kernel(const int32_t* __restrict__ start, int rows, int* __restrict__ max_len) {
+    int m = 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) m = max(m, start[r + 1] - start[r]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_len, m);
 }
 
 __global__ void block_row_kernel(const int32_t* __restrict__ start, int rows, int num_blocks, int32_t* __restrict__ block_row) {
@@ -233,6 +435,38 @@ __global__ void first_active_kernel(const int32_t* __restrict__ start, int rows,
 }  // namespace
 
 int smm_csr_analyse(smm_csr* m, cudaStream_t s) {
+    // row-length statistics -> kernel choice
+    {
+        int* d = nullptr;
+        SMM_CUDA(cudaMalloc(&d, sizeof(int)));
+        SMM_CUDA(cudaMemsetAsync(d, 0, sizeof(int), s));
+        if (m->rows > 0) {
+            row_stats_kernel<<<1184, 256, 0, s>>>(m->start, m->rows, d);
+            SMM_COUNT_LAUNCH(1);
+        }
+        SMM_CUDA(cudaMemcpyAsync(&m->max_row_len, d, sizeof(int), cudaMemcpyDeviceToHost, s));
+        SMM_CUDA(cudaStreamSynchronize(s));
+        cudaFree(d);
+        const double mean = m->rows ? (double)m->nnz / m->rows : 0.0;
+        // lanes per row (V) so that a group of 256/V rows fits a staging window of at most SPMV_ROWS_CAP entries; the
+        // window itself is then sized to the matrix (mean group size + 3 % + alignment slack): a smaller window
+        // means more resident CTAs per SM, which is what the kernel's latency hiding lives on
+        int v = 1;
+        while (v < 8 && mean * (SPMV_THREADS / v) > 0.9 * SPMV_ROWS_CAP) v *= 2;
+        const bool regular = m->rows >= 4096 && m->max_row_len <= 64 && m->max_row_len <= 4 * mean + 8 &&
+                             mean * (SPMV_THREADS / v) <= 0.9 * SPMV_ROWS_CAP;
+        m->rows_kernel_lanes = regular ? v : 0;
+        int cap = ((int)(mean * (SPMV_THREADS / v) * 1.03) + 8 + 63) & ~63;
+        if (cap < 512) cap = 512;
+        if (cap > SPMV_ROWS_CAP) cap = SPMV_ROWS_CAP;
+        m->rows_kernel_cap = cap;
+        const char* env = getenv("SMM_B200_SPMV_KERNEL");           // benchmarking override: "stage" | "rows"
+        if (env && !strcmp(env, "stage")) m->rows_kernel_lanes = 0;
+        if (env && !strcmp(env, "rows") && m->rows_kernel_lanes == 0) m->rows_kernel_lanes = v;
+        cudaDeviceProp prop;
+        SMM_CUDA(cudaGetDeviceProperties(&prop, m->device));
+        m->sm_count = prop.multiProcessorCount;
+    }
     m->num_blocks = (int)(m->nnz / SPMV_CHUNK) + 1;
     if (m->block_row) { cudaFree(m->block_row); m->block_row = nullptr; }
     SMM_CUDA(cudaMalloc(&m->block_row, sizeof(int32_t) * (size_t)(m->num_blocks + 1)));
@@ -275,7 +509,43 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
         P.partials_stride = ws->partials_cap;
         P.ticket = ws->tickets + a.slot;
     }
-    spmv_kernel<<<m->num_blocks, SPMV_THREADS, 0, s>>>(P);
+    const int V = (a.exact && m->rows_kernel_lanes > 1) ? 0 : m->rows_kernel_lanes;   // exact mode needs one lane per row
+    if (V > 0) {
+        static int stages = 0, cap_env = 0;
+        if (!stages) {
+            const char* e1 = getenv("SMM_B200_ROWS_STAGES");
+            const char* e2 = getenv("SMM_B200_ROWS_CAP");
+            stages = e1 ? atoi(e1) : 3;
+            if (stages < 2) stages = 2;
+            if (stages > ROWS_MAX_STAGES) stages = ROWS_MAX_STAGES;
+            cap_env = e2 ? (atoi(e2) & ~3) : 0;                          // 0: per-matrix window from the analysis
+        }
+        const int cap = cap_env ? cap_env : m->rows_kernel_cap;
+        const size_t smem = (size_t)stages * cap * 8 + ROWS_MAX_STAGES * 8 * 2 + ROWS_MAX_STAGES * 8;
+        const int R = ROWS_CONSUMERS / V;
+        const int nchunks = (m->rows + R - 1) / R;
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm > 2048 / ROWS_THREADS) per_sm = 2048 / ROWS_THREADS;
+        int grid = m->sm_count * per_sm;
+        if (grid > nchunks) grid = nchunks;
+        if (a.reduce != RED_NONE && m->ws->partials_cap < (size_t)grid) { smm_set_error("spmv: reduction workspace too small"); return SMM_E_STATE; }
+        static size_t attr_smem = 0;
+        if (attr_smem != smem) {
+            SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem = smem;
+        }
+        switch (V) {
+            case 1: spmv_rows_kernel<1><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); break;
+            case 2: spmv_rows_kernel<2><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); break;
+            case 4: spmv_rows_kernel<4><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); break;
+            default: spmv_rows_kernel<8><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); break;
+        }
+    } else {
+        spmv_kernel<<<m->num_blocks, SPMV_THREADS, 0, s>>>(P);
+    }
     SMM_COUNT_LAUNCH(1);
     SMM_CUDA(cudaGetLastError());
     return SMM_OK;
