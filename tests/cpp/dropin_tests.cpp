@@ -1,0 +1,295 @@
+// dropin_tests.cpp -- the reference's own test scenarios (test/cpp/{triplet,csr,cg,cgsquared,bicgstab,bicgsymmetric}.cpp)
+// re-hosted against this repository's drop-in header, T = float.  Same call forms, same tolerances
+// (l2Eps<float>() = infEps<float>() = 1e-4, test/include/test_common.h:28-50).  Built and run by tests/test_cpp_dropin.py.
+#include <string>
+#include <vector>
+
+#include "mini_test.h"
+#include "sparse_matrix_math.h"
+
+#ifndef ASSET_PATH
+#define ASSET_PATH "tests/golden/"
+#endif
+
+using T = float;
+static constexpr T kL2Eps = 1e-4f;
+static constexpr T kInfEps = 1e-4f;
+
+static SMM::Vector<T> sumColumsPerRow(const SMM::CSRMatrix<T>& m) {   // test/include/test_common.h:13-22
+    SMM::Vector<T> v(m.getDenseRowCount(), 0);
+    for (const auto& el : m) v[el.getRow()] += el.getValue();
+    return v;
+}
+
+static const std::vector<std::string> kMeshes = {"mesh1e1.mtx", "mesh1em1.mtx", "mesh1em6.mtx"};
+
+// ---- triplet.cpp ---------------------------------------------------------------------------------------------
+TEST_CASE("TripletMatrix: constructor, duplicates, getValue/updateEntry") {
+    SMM::TripletMatrix<T> m(4, 5);
+    CHECK_EQ(m.getDenseRowCount(), 4);
+    CHECK_EQ(m.getDenseColCount(), 5);
+    CHECK_EQ(m.getNonZeroCount(), 0);
+    m.addEntry(1, 2, 1.5f);
+    m.addEntry(1, 2, 2.5f);            // summed, nnz does not grow (triplet.cpp:24-62)
+    m.addEntry(3, 4, -1.0f);
+    m.addEntry(0, 0, 0.0f);            // explicit zero is a stored entry
+    CHECK_EQ(m.getNonZeroCount(), 3);
+    CHECK_EQ(m.getValue(1, 2), 4.0f);
+    CHECK_EQ(m.getValue(2, 2), 0.0f);
+    CHECK(m.updateEntry(3, 4, 7.0f));
+    CHECK(!m.updateEntry(2, 2, 7.0f));
+    CHECK_EQ(m.getValue(3, 4), 7.0f);
+    std::vector<T> dense(20, 0);
+    SMM::toLinearDenseRowMajor(m, dense.data());
+    CHECK_EQ(dense[1 * 5 + 2], 4.0f);
+    CHECK_EQ(dense[3 * 5 + 4], 7.0f);
+    int seen = 0, lastRow = -1;
+    for (const auto& el : m) { CHECK(el.getRow() >= lastRow); lastRow = el.getRow(); ++seen; }
+    CHECK_EQ(seen, 3);
+}
+
+// ---- csr.cpp: construction, element access, iterators --------------------------------------------------------
+TEST_CASE("CSRMatrix: empty and zero-nnz construction") {
+    SMM::CSRMatrix<T> e;
+    CHECK_EQ(e.getNonZeroCount(), 0);
+    CHECK_EQ(e.getDenseRowCount(), 0);
+    SMM::TripletMatrix<T> t(10, 12);
+    SMM::CSRMatrix m(t);               // CTAD as in csr.cpp:17
+    CHECK_EQ(m.getNonZeroCount(), 0);
+    CHECK_EQ(m.getDenseRowCount(), 10);
+    CHECK_EQ(m.getDenseColCount(), 12);
+    CHECK(m.begin() == m.end());
+    SMM::CSRMatrix<T> m2;
+    CHECK_EQ(m2.init(t), 0);
+    CHECK_EQ(m2.getNonZeroCount(), 0);
+}
+
+static SMM::CSRMatrix<T> make5x4() {  // csr.cpp:263-275
+    SMM::TripletMatrix<T> t(5, 4, 10);
+    t.addEntry(0, 0, 4.5); t.addEntry(0, 2, 3.2); t.addEntry(1, 0, 3.1); t.addEntry(1, 1, 2.9); t.addEntry(1, 3, 0.9);
+    t.addEntry(2, 1, 1.7); t.addEntry(2, 2, 3.0); t.addEntry(3, 0, 3.5); t.addEntry(3, 1, 0.4); t.addEntry(3, 3, 1.0);
+    SMM::CSRMatrix<T> m;
+    m.init(t);
+    return m;
+}
+
+TEST_CASE("CSRMatrix: element access and iterators") {
+    SMM::CSRMatrix<T> m = make5x4();
+    CHECK_EQ(m.getNonZeroCount(), 10);
+    CHECK_EQ(m.getValue(1, 3), 0.9f);
+    CHECK_EQ(m.getValue(4, 0), 0.0f);
+    CHECK(m.updateEntry(2, 2, 5.0f));
+    CHECK(!m.updateEntry(4, 3, 5.0f));
+    CHECK(m.addEntry(2, 2, -2.0f));
+    CHECK_EQ(m.getValue(2, 2), 3.0f);
+    int count = 0, lastRow = 0;
+    for (SMM::CSRMatrix<T>::ConstIterator it = m.cbegin(); it != m.cend(); ++it) { CHECK(it->getRow() >= lastRow); lastRow = it->getRow(); ++count; }
+    CHECK_EQ(count, 10);
+    int rowCount = 0;
+    for (auto it = m.rowBegin(1); it != m.rowEnd(1); ++it) { CHECK_EQ(it->getRow(), 1); ++rowCount; }
+    CHECK_EQ(rowCount, 3);
+    CHECK(m.rowBegin(4) == m.rowEnd(4));   // empty last row
+    for (auto it = m.begin(); it != m.end(); ++it) it->setValue(it->getValue() * 2);   // csr.cpp:214-219
+    CHECK_EQ(m.getValue(0, 0), 9.0f);
+    SMM::CSRMatrix<T>::ConstIterator cit = m.begin();   // non-const -> const conversion
+    CHECK_EQ(cit->getCol(), 0);
+}
+
+// ---- csr.cpp: A*x + b and b - A*x known answers (csr.cpp:258-523) ---------------------------------------------
+TEST_CASE("CSRMatrix A * x + b") {
+    SMM::CSRMatrix<T> m = make5x4();
+    {
+        T mult[5] = {1, 2, 3, 4, 5}, add[5] = {5, 6, 7, 8, 9}, res[5] = {};
+        SMM::TripletMatrix<T> emptyTriplet(5, 4, 10);
+        SMM::CSRMatrix emptyMatrix(emptyTriplet);
+        emptyMatrix.rMultAdd(add, mult, res);
+        for (int i = 0; i < 5; ++i) CHECK_EQ(res[i], add[i]);
+    }
+    {
+        T mult[5] = {1, 2, 3, 4, 5}, add[5] = {};
+        const T ref[5] = {14.1f, 12.5f, 12.4f, 8.3f, 0};
+        T res[5] = {};
+        m.rMultAdd(add, mult, res);
+        for (int i = 0; i < 5; ++i) CHECK_APPROX(ref[i], res[i], 1e-6);
+        m.rMultAdd(add, mult, add);     // in place
+        for (int i = 0; i < 5; ++i) CHECK_APPROX(ref[i], add[i], 1e-6);
+    }
+    {
+        T mult[5] = {1, 0, 3, 4}, add[5] = {5, 6, 7, 8, 10};
+        const T ref[5] = {19.1f, 12.7f, 16.f, 15.5f, 10};
+        T res[5] = {};
+        m.rMultAdd(add, mult, res);
+        for (int i = 0; i < 5; ++i) CHECK_APPROX(ref[i], res[i], 1e-6);
+        CHECK_EQ(add[0], 5.0f);         // lhs not modified
+    }
+}
+
+TEST_CASE("CSRMatrix b - A * x") {
+    SMM::CSRMatrix<T> m = make5x4();
+    T mult[5] = {1, 0, 3, 4}, lhs[5] = {5, 6, 7, 8, 10};
+    const T ref[5] = {-9.1f, -0.7f, -2.f, 0.5f, 10};
+    T res[5] = {};
+    m.rMultSub(lhs, mult, res);
+    for (int i = 0; i < 5; ++i) CHECK_APPROX(ref[i], res[i], 1e-5);
+    m.rMultSub(lhs, mult, lhs);
+    for (int i = 0; i < 5; ++i) CHECK_APPROX(ref[i], lhs[i], 1e-5);
+    T x[4] = {1, 2, 3, 4};
+    T y[5] = {};
+    m.rMult(x, y);
+    const T ref2[5] = {14.1f, 12.5f, 12.4f, 8.3f, 0};
+    for (int i = 0; i < 5; ++i) CHECK_APPROX(ref2[i], y[i], 1e-6);
+}
+
+TEST_CASE("CSRMatrix arithmetic keeps the device copy coherent") {   // csr.cpp:525-785 + SURVEY f3
+    SMM::CSRMatrix<T> m = make5x4();
+    T x[4] = {1, 2, 3, 4}, y[5] = {}, y2[5] = {};
+    m.rMult(x, y);
+    m *= 2.0f;
+    m.rMult(x, y2);
+    for (int i = 0; i < 5; ++i) CHECK_EQ(y2[i], 2 * y[i]);
+    SMM::CSRMatrix<T> o = make5x4();
+    m.inplaceSubtract(o);
+    m.rMult(x, y2);
+    for (int i = 0; i < 5; ++i) CHECK_APPROX(y2[i], y[i], 1e-6);
+    m.inplaceAdd(o);
+    m.zeroValues();
+    m.rMult(x, y2);
+    for (int i = 0; i < 5; ++i) CHECK_EQ(y2[i], 0.0f);
+}
+
+// ---- csr.cpp: file I/O ------------------------------------------------------------------------------------------
+TEST_CASE("Load symmetric matrix market") {    // csr.cpp:788-826
+    SMM::CSRMatrix<T> csr;
+    REQUIRE_EQ(SMM::loadMatrix((std::string(ASSET_PATH) + "load_symmetric_test.mtx").c_str(), csr), SMM::MatrixLoadStatus::SUCCESS);
+    CHECK_EQ(csr.getDenseRowCount(), 5);
+    CHECK_EQ(csr.getDenseColCount(), 5);
+    CHECK_EQ(csr.getNonZeroCount(), 8);
+    CHECK_EQ(csr.getValue(0, 0), 3.0f);
+    CHECK_EQ(csr.getValue(1, 1), 12.0f);
+    CHECK_EQ(csr.getValue(1, 4), 34.0f);
+    CHECK_EQ(csr.getValue(4, 1), 34.0f);
+    CHECK_EQ(csr.getValue(2, 2), -0.3f);
+    CHECK_EQ(csr.getValue(4, 4), -4.0f);
+    CHECK_EQ(csr.getValue(3, 2), 0.0f);
+    SMM::CSRMatrix<T> none;
+    CHECK(SMM::loadMatrix("does_not_exist.mtx", none) == SMM::MatrixLoadStatus::FAILED_TO_OPEN_FILE);
+    CHECK(SMM::loadMatrix("file.unknown", none) == SMM::MatrixLoadStatus::FAILED_TO_OPEN_FILE_UNKNOWN_FORMAT);
+}
+
+TEST_CASE("Save as dense text and load back") {  // csr.cpp:828-865
+    SMM::CSRMatrix<T> m = make5x4();
+    const char* path = "/tmp/smm_b200_dense_test.smmdt";
+    SMM::saveDenseText(path, m);
+    SMM::CSRMatrix<T> back;
+    REQUIRE_EQ(SMM::loadMatrix(path, back), SMM::MatrixLoadStatus::SUCCESS);
+    CHECK_EQ(back.getDenseRowCount(), 5);
+    CHECK_EQ(back.getDenseColCount(), 4);
+    for (int r = 0; r < 5; ++r) for (int c = 0; c < 4; ++c) CHECK_APPROX(m.getValue(r, c), back.getValue(r, c), 1e-6);
+    std::remove(path);
+}
+
+// ---- solvers: file -> CSR -> solve -> x ~ 1 (cg.cpp:7-26, bicgsymmetric.cpp:7-25, cgsquared.cpp:7-25, bicgstab.cpp:124-167)
+TEST_CASE("Conjugate Gradient method") {
+    for (const auto& name : kMeshes) {
+        SMM::CSRMatrix<T> m;
+        REQUIRE_EQ(SMM::loadMatrix((std::string(ASSET_PATH) + name).c_str(), m), SMM::MatrixLoadStatus::SUCCESS);
+        SMM::Vector<T> rhs = sumColumsPerRow(m);
+        SMM::Vector<T> x(m.getDenseRowCount(), 0);
+        REQUIRE_EQ(SMM::ConjugateGradient<T>(m, rhs, x, x, -1, kL2Eps), SMM::SolverStatus::SUCCESS);
+        for (const T ri : x) CHECK_APPROX(T(1), ri, kInfEps);
+    }
+}
+
+TEST_CASE("BiConjugate Gradient Symmetric method") {
+    for (const auto& name : kMeshes) {
+        SMM::CSRMatrix<T> m;
+        REQUIRE_EQ(SMM::loadMatrix((std::string(ASSET_PATH) + name).c_str(), m), SMM::MatrixLoadStatus::SUCCESS);
+        SMM::Vector<T> rhs = sumColumsPerRow(m);
+        SMM::Vector<T> x(m.getDenseRowCount(), 0);
+        REQUIRE_EQ(SMM::BiCGSymmetric<T>(m, rhs, x, -1, kL2Eps), SMM::SolverStatus::SUCCESS);
+        for (const T ri : x) CHECK_APPROX(T(1), ri, kInfEps);
+    }
+}
+
+TEST_CASE("Conjugate Gradient Squared method (both spellings)") {
+    for (const auto& name : kMeshes) {
+        SMM::CSRMatrix<T> m;
+        REQUIRE_EQ(SMM::loadMatrix((std::string(ASSET_PATH) + name).c_str(), m), SMM::MatrixLoadStatus::SUCCESS);
+        SMM::Vector<T> rhs = sumColumsPerRow(m);
+        SMM::Vector<T> x(m.getDenseRowCount(), 0);
+        REQUIRE_EQ(SMM::ConjugateGradientSquared<T>(m, rhs, x, -1, kL2Eps), SMM::SolverStatus::SUCCESS);
+        for (const T ri : x) CHECK_APPROX(T(1), ri, kInfEps);
+        SMM::Vector<T> x2(m.getDenseRowCount(), 0);
+        REQUIRE_EQ(SMM::ConjugateGradientSqared<T>(m, rhs, x2, -1, kL2Eps), SMM::SolverStatus::SUCCESS);
+    }
+}
+
+TEST_CASE("BiConjugate Gradient Stabilized method") {
+    for (const auto& name : kMeshes) {
+        SMM::CSRMatrix<T> m;
+        REQUIRE_EQ(SMM::loadMatrix((std::string(ASSET_PATH) + name).c_str(), m), SMM::MatrixLoadStatus::SUCCESS);
+        SMM::Vector<T> rhs = sumColumsPerRow(m);
+        SMM::Vector<T> x(m.getDenseRowCount(), 0);
+        REQUIRE_EQ(SMM::BiCGStab<T>(m, rhs, x, -1, kL2Eps), SMM::SolverStatus::SUCCESS);
+        for (const T ri : x) CHECK_APPROX(T(1), ri, kInfEps);
+    }
+}
+
+TEST_CASE("Preconditioned BiCGStab. Symmetric Gauss Seidel Preconditioner") {
+    for (const auto& name : kMeshes) {
+        SMM::CSRMatrix<T> m;
+        REQUIRE_EQ(SMM::loadMatrix((std::string(ASSET_PATH) + name).c_str(), m), SMM::MatrixLoadStatus::SUCCESS);
+        SMM::Vector<T> rhs = sumColumsPerRow(m);
+        SMM::Vector<T> x(m.getDenseRowCount(), 0);
+        using SGSPreconditioner = SMM::CSRMatrix<T>::SGSPreconditioner;
+        const SGSPreconditioner& M = m.template getPreconditioner<SMM::SolverPreconditioner::SYMMETRIC_GAUS_SEIDEL>();
+        REQUIRE_EQ((SMM::BiCGStab<SGSPreconditioner, T>(m, rhs, x, -1, kL2Eps, M)), SMM::SolverStatus::SUCCESS);
+        for (const T ri : x) CHECK_APPROX(T(1), ri, kInfEps);
+        // README spelling of the enum value
+        const auto& M2 = m.template getPreconditioner<SMM::SolverPreconditioner::SYMMETRIC_GAUSS_SEIDEL>();
+        SMM::Vector<T> y(m.getDenseRowCount(), 0);
+        CHECK_EQ(M2.apply(rhs, y), 0);
+    }
+}
+
+// ---- iteration counts of the reference on its own assets, in the reference's summation order --
+TEST_CASE("Iteration counts equal the reference's (reference-order reductions)") {
+    SMM::b200::options().reduction_mode = SMM_REDUCE_REFERENCE_TREE;
+    const int expected[3][5] = {{13, 13, 7, 8, 3}, {24, 24, 15, 17, 5}, {13, 13, 8, 8, 3}};
+    for (int k = 0; k < 3; ++k) {
+        SMM::CSRMatrix<T> m;
+        REQUIRE_EQ(SMM::loadMatrix((std::string(ASSET_PATH) + kMeshes[k]).c_str(), m), SMM::MatrixLoadStatus::SUCCESS);
+        SMM::Vector<T> rhs = sumColumsPerRow(m);
+        const int n = m.getDenseRowCount();
+        { SMM::Vector<T> x(n, 0); SMM::ConjugateGradient<T>(m, rhs, x, x, -1, kL2Eps); CHECK_EQ(SMM::b200::lastSolveInfo().iterations, expected[k][0]); }
+        { SMM::Vector<T> x(n, 0); SMM::BiCGSymmetric<T>(m, rhs, x, -1, kL2Eps); CHECK_EQ(SMM::b200::lastSolveInfo().iterations, expected[k][1]); }
+        { SMM::Vector<T> x(n, 0); SMM::ConjugateGradientSquared<T>(m, rhs, x, -1, kL2Eps); CHECK_EQ(SMM::b200::lastSolveInfo().iterations, expected[k][2]); }
+        { SMM::Vector<T> x(n, 0); SMM::BiCGStab<T>(m, rhs, x, -1, kL2Eps); CHECK_EQ(SMM::b200::lastSolveInfo().iterations, expected[k][3]); }
+        {
+            SMM::Vector<T> x(n, 0);
+            const auto& M = m.template getPreconditioner<SMM::SolverPreconditioner::SYMMETRIC_GAUS_SEIDEL>();
+            SMM::BiCGStab<SMM::CSRMatrix<T>::SGSPreconditioner, T>(m, rhs, x, -1, kL2Eps, M);
+            CHECK_EQ(SMM::b200::lastSolveInfo().iterations, expected[k][4]);
+        }
+    }
+    SMM::b200::options().reduction_mode = SMM_REDUCE_FAST;
+}
+
+TEST_CASE("Vector: dot product and norms run on the device") {
+    SMM::Vector<T> a({1.f, 2.f, 3.f, 4.f}), b({4.f, 3.f, 2.f, 1.f});
+    CHECK_EQ(a * b, 20.0f);
+    CHECK_EQ(a.secondNormSquared(), 30.0f);
+    CHECK_APPROX(a.secondNorm(), std::sqrt(30.0f), 1e-7);
+    a += b;
+    CHECK_EQ(a[0], 5.0f);
+    a -= b;
+    CHECK_EQ(a[3], 4.0f);
+    SMM::Vector<T> c(3, 2.5f);
+    CHECK_EQ(c.getSize(), 3);
+    CHECK_EQ(c[2], 2.5f);
+    SMM::Vector<T> d(std::move(c));
+    CHECK_EQ(c.getSize(), 0);
+    CHECK_EQ(d[1], 2.5f);
+}
+
+int main() { return mini_main(); }

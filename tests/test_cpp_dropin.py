@@ -1,0 +1,80 @@
+"""The drop-in C++17 header (include/sparse_matrix_math.h -> smm_b200.hpp): builds against libsmm_b200.so, refuses
+non-float scalar types on the hot path at compile time, and (on a GPU) passes the reference's own test scenarios
+re-hosted in tests/cpp/dropin_tests.cpp."""
+import os
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BUILD = os.path.join(HERE, "cpp", "build")
+CXX = "/usr/bin/g++"
+LIBDIR = os.path.join(ROOT, "sparse_matrix_math_b200")
+
+
+def compile_cpp(src, out, extra=()):
+    os.makedirs(BUILD, exist_ok=True)
+    cmd = [CXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", f"-I{ROOT}/include", f"-I{HERE}/cpp",
+           f'-DASSET_PATH="{HERE}/golden/"', src, "-o", out, f"-L{LIBDIR}", "-lsmm_b200", f"-Wl,-rpath,{LIBDIR}",
+           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", *extra]
+    return subprocess.run(cmd, capture_output=True, text=True)
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from sparse_matrix_math_b200 import build
+    return build.build()
+
+
+def test_dropin_tests_compile_and_link(built_lib):
+    r = compile_cpp(os.path.join(HERE, "cpp", "dropin_tests.cpp"), os.path.join(BUILD, "dropin_tests"))
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_host_containers_are_scalar_generic(built_lib, tmp_path):
+    # containers, iterators and loaders are templates usable with double (as in the reference's TEST_CASE_TEMPLATEs)
+    src = tmp_path / "generic.cpp"
+    src.write_text('''
+#include "sparse_matrix_math.h"
+int main() {
+    SMM::TripletMatrix<double> t(3, 3);
+    t.addEntry(0, 0, 1.0); t.addEntry(2, 1, 2.0); t.addEntry(2, 1, 0.5);
+    SMM::CSRMatrix<double> m(t);
+    double sum = 0;
+    for (const auto& el : m) sum += el.getValue();
+    SMM::Vector<double> v(3, 1.0);
+    v += v;
+    return (m.getNonZeroCount() == 2 && sum == 3.5 && m.getValue(2, 1) == 2.5 && v[0] == 2.0) ? 0 : 1;
+}
+''')
+    out = str(tmp_path / "generic")
+    r = compile_cpp(str(src), out)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert subprocess.run([out]).returncode == 0        # host-only code: runs without a GPU
+
+
+def test_hot_path_refuses_other_scalars_at_compile_time(built_lib, tmp_path):
+    src = tmp_path / "dbl.cpp"
+    src.write_text('''
+#include "sparse_matrix_math.h"
+int main() {
+    SMM::TripletMatrix<double> t(2, 2);
+    SMM::CSRMatrix<double> m(t);
+    double b[2] = {1, 1}, x[2] = {0, 0};
+    return (int)SMM::ConjugateGradient<double>(m, b, x, x, -1, 1e-8);
+}
+''')
+    r = compile_cpp(str(src), str(tmp_path / "dbl"))
+    assert r.returncode != 0 and "float only (no CPU fallback)" in r.stderr
+
+
+@pytest.mark.gpu
+def test_dropin_tests_run_on_gpu(built_lib):
+    exe = os.path.join(BUILD, "dropin_tests")
+    r = compile_cpp(os.path.join(HERE, "cpp", "dropin_tests.cpp"), exe)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert " 0 failures" in r.stdout
