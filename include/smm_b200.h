@@ -161,6 +161,30 @@ int smm_gen_csr(int kind, int nx, int ny, int nz, float c, uint64_t seed, smm_cs
 /* x*_i = (splitmix64(seed, i + offset) >> 40) / 2^24 written to a device vector */
 int smm_gen_xstar_dev(int64_t n, int64_t offset, uint64_t seed, float* x_dev, void* stream);
 
+/* ---- multi-GPU: one process per GPU, contiguous row blocks (additive; the reference is single-process) ----
+ * Each rank builds the CSR of its rows [row_begin,row_end) with GLOBAL column indices (smm_csr_create /
+ * smm_gen_csr_rows), then
+ *   smm_dist_create   finds the window of the global vector those rows read and re-indexes the columns into it,
+ *                     allocates the extended vector + reduction mailboxes + halo flags in one IPC-exported block;
+ *   smm_dist_info     returns {row_begin,row_end,lo,hi} and the 64-byte CUDA IPC handle of that block, which the host
+ *                     program all-gathers over its own transport (torch.distributed, MPI ...);
+ *   smm_dist_connect  maps every peer's block and derives the halo send plan.
+ * smm_dist_solve_cg then runs ConjugateGradient (H:2316-2398) on the partitioned system: b, x0, x are this rank's
+ * DEVICE slices; halo exchange by P2P stores + flags, scalar reductions by a P2P all-reduce fused into the kernels'
+ * epilogues (summed in rank order: identical bits, identical branches on every rank).  No NCCL inside the loop. */
+typedef struct smm_dist smm_dist_t;
+int smm_dist_create(int rank, int nranks, int64_t global_rows, int64_t row_begin, int64_t row_end, smm_csr_t* local,
+                    smm_dist_t** out);
+int smm_dist_info(const smm_dist_t* d, int64_t* ranges4, void* ipc_handle64);
+int smm_dist_connect(smm_dist_t* d, const int64_t* all_ranges /* [nranks][4] */, const void* all_handles /* [nranks][64] */);
+int smm_dist_spmv_dev(smm_dist_t* d, const float* x_local_dev, float* y_local_dev, void* stream);
+int smm_dist_solve_cg(smm_dist_t* d, const float* b_dev, const float* x0_dev, float* x_dev, int maxIterations, float eps,
+                      const smm_solve_options* opts, smm_solve_info* info, void* stream);
+int smm_dist_error(const smm_dist_t* d, int* error);
+int smm_dist_destroy(smm_dist_t* d);
+/* rows [row_begin,row_end) of a generated stencil matrix, global column indices (kinds POISSON2D / CONVDIFF3D) */
+int smm_gen_csr_rows(int kind, int nx, int ny, int nz, float c, int64_t row_begin, int64_t row_end, smm_csr_t** out);
+
 /* ---- measurement hook (bench.py): average device time, in ms, of each of the three kernels of one fused CG
  * iteration (SpMV + p.Ap | x,r update + r.r | p update), `reps` launches each, CUDA events on `stream` ---- */
 int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_spmv, float* ms_xr, float* ms_p, void* stream);

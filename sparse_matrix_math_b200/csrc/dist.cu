@@ -1,0 +1,274 @@
+// dist.cu -- multi-GPU layer: one process per GPU, rows partitioned in contiguous blocks.
+//
+// Rank r owns rows [row_begin, row_end) of the global matrix and stores them as a local CSR whose columns index an
+// EXTENDED vector: the contiguous window [lo, hi) of the global vector that its rows touch (owned entries in the
+// middle, halo entries on both sides; lo is rounded so the owned part stays 16-byte aligned).  The extended vector,
+// the reduction mailboxes and the halo flags live in one cudaMalloc block exported with CUDA IPC; peers map it and
+// write into it directly over NVLink (dist_device.cuh).  There is no NCCL call and no host synchronisation inside an
+// iteration: the scalar all-reduces are fused into the epilogues of the kernels that produce the partial sums, the
+// halo exchange is one push kernel (P2P stores + release flags) and one wait kernel (acquire spin).
+#include <string.h>
+
+#include <vector>
+
+#include "dist.h"
+#include "epilogue.cuh"
+
+namespace {
+
+struct SegDev { float* dst; const float* src; long long len; long long first_block; };
+
+__global__ void minmax_col_kernel(const int32_t* __restrict__ positions, long long nnz, int* __restrict__ mn, int* __restrict__ mx) {
+    int lo = 0x7fffffff, hi = -1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x) {
+        const int c = positions[i];
+        lo = min(lo, c); hi = max(hi, c);
+    }
+    for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(mn, lo); atomicMax(mx, hi); }
+}
+
+__global__ void shift_cols_kernel(int32_t* __restrict__ positions, long long nnz, int shift) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x) positions[i] -= shift;
+}
+
+constexpr int PUSH_THREADS = 256;
+constexpr int PUSH_ELEMS_PER_BLOCK = PUSH_THREADS * 4;
+
+// copies every send segment into the peers' extended vectors, then raises this rank's flag on every destination
+__global__ void __launch_bounds__(PUSH_THREADS) halo_push_kernel(const SegDev* __restrict__ segs, int nsegs, DistComm* comm, unsigned int* ticket,
+                                                                 const int* __restrict__ dests, int ndests, const SolveState* st) {
+    if (st != nullptr && st->done) return;
+    __shared__ int last;
+    for (int s = 0; s < nsegs; ++s) {
+        const SegDev sg = segs[s];
+        const long long b = (long long)blockIdx.x - sg.first_block;
+        if (b < 0) continue;
+        const long long base = b * PUSH_ELEMS_PER_BLOCK;
+        if (base >= sg.len) continue;
+        for (int k = threadIdx.x; k < PUSH_ELEMS_PER_BLOCK; k += PUSH_THREADS) {
+            const long long i = base + k;
+            if (i < sg.len) sg.dst[i] = sg.src[i];                 // peer-mapped store over NVLink
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int seq = comm->push_seq + 1u;
+        for (int k = 0; k < ndests; ++k) st_release_sys_u32(comm->flags[dests[k]] + comm->rank, seq);
+        comm->push_seq = seq;
+        *ticket = 0u;
+    }
+}
+
+// a launch with nothing to send still has to advance the exchange counter
+__global__ void halo_push_empty_kernel(DistComm* comm, const SolveState* st) {
+    if (st != nullptr && st->done) return;
+    comm->push_seq = comm->push_seq + 1u;
+}
+
+__global__ void halo_wait_kernel(DistComm* comm, const int* __restrict__ sources, int nsources, SolveState* st) {
+    if (st != nullptr && st->done) return;
+    const int k = threadIdx.x;
+    if (k >= nsources) return;
+    const unsigned int want = comm->push_seq;                       // my own push of this exchange is already counted
+    const unsigned int* f = comm->flags[comm->rank] + sources[k];
+    unsigned int polls = 0;
+    while ((int)(ld_acquire_sys_u32(f) - want) < 0) {
+        if (++polls >= SMM_DIST_POLL_LIMIT) { comm->error = 1; if (st) { st->done = 1; st->precond_error |= 8; } break; }
+    }
+}
+
+}  // namespace
+
+// ---- used by solvers.cu --------------------------------------------------------------------------------------
+int smm_dist_exchange_async(smm_dist* d, SolveState* st, cudaStream_t s) {
+    if (d->nranks == 1) return SMM_OK;
+    if (!d->send.empty()) {
+        long long blocks = 0;
+        for (auto& sg : d->send) blocks += (sg.len + PUSH_ELEMS_PER_BLOCK - 1) / PUSH_ELEMS_PER_BLOCK;
+        halo_push_kernel<<<(unsigned)blocks, PUSH_THREADS, 0, s>>>((const SegDev*)d->seg_dev, (int)d->send.size(), d->comm_dev, d->ticket,
+                                                                   d->dests_dev, (int)d->dests.size(), st);
+    } else {
+        halo_push_empty_kernel<<<1, 1, 0, s>>>(d->comm_dev, st);
+    }
+    halo_wait_kernel<<<1, 32, 0, s>>>(d->comm_dev, d->sources_dev, (int)d->sources.size(), st);
+    SMM_COUNT_LAUNCH(2);
+    SMM_CUDA(cudaGetLastError());
+    return SMM_OK;
+}
+
+// ---- C ABI ---------------------------------------------------------------------------------------------------
+int smm_solve_dist_cg_impl(smm_dist* d, const float* b_dev, const float* x0_dev, float* x_dev, int maxIterations, float eps,
+                           const smm_solve_options* opts, smm_solve_info* info, cudaStream_t s);   // solvers.cu
+
+extern "C" {
+
+int smm_dist_create(int rank, int nranks, int64_t global_rows, int64_t row_begin, int64_t row_end, smm_csr_t* local, smm_dist_t** out) {
+    if (!out || !local || nranks < 1 || nranks > SMM_MAX_RANKS || rank < 0 || rank >= nranks || row_begin < 0 || row_end < row_begin ||
+        row_end > global_rows || local->rows != row_end - row_begin) {
+        smm_set_error("smm_dist_create: bad arguments");
+        return SMM_E_INVALID;
+    }
+    SMM_CUDA(cudaSetDevice(local->device));
+    cudaStream_t s = smm_default_stream();
+    smm_dist* d = new smm_dist();
+    d->rank = rank; d->nranks = nranks; d->device = local->device; d->local = local;
+    d->global_rows = global_rows; d->row_begin = row_begin; d->row_end = row_end;
+    // window of the global vector the local rows read
+    int mm[2] = {0x7fffffff, -1};
+    int* mm_dev = nullptr;
+    SMM_CUDA(cudaMalloc(&mm_dev, 2 * sizeof(int)));
+    SMM_CUDA(cudaMemcpyAsync(mm_dev, mm, sizeof mm, cudaMemcpyHostToDevice, s));
+    if (local->nnz > 0) {
+        minmax_col_kernel<<<1184, 256, 0, s>>>(local->positions, local->nnz, mm_dev, mm_dev + 1);
+        SMM_COUNT_LAUNCH(1);
+    }
+    SMM_CUDA(cudaMemcpyAsync(mm, mm_dev, sizeof mm, cudaMemcpyDeviceToHost, s));
+    SMM_CUDA(cudaStreamSynchronize(s));
+    cudaFree(mm_dev);
+    long long lo = row_begin, hi = row_end;
+    if (local->nnz > 0) { if (mm[0] < lo) lo = mm[0]; if ((long long)mm[1] + 1 > hi) hi = (long long)mm[1] + 1; }
+    if (hi > global_rows || lo < 0) { delete d; smm_set_error("smm_dist_create: column index outside the global vector"); return SMM_E_INVALID; }
+    lo = row_begin - (((row_begin - lo) + 3) / 4) * 4;            // keep the owned part 16-byte aligned (may dip below 0: unused pad)
+    d->lo = lo; d->hi = hi; d->own_off = row_begin - lo;
+    if (local->nnz > 0 && lo != 0) {
+        shift_cols_kernel<<<1184, 256, 0, s>>>(local->positions, local->nnz, (int)lo);
+        SMM_COUNT_LAUNCH(1);
+    }
+    local->cols = (int)(hi - lo);
+    // shared block
+    const size_t ext_bytes = (((size_t)(hi - lo) * sizeof(float)) + 255) & ~(size_t)255;
+    const size_t mail_bytes = (size_t)4 * nranks * 2 * sizeof(unsigned long long);
+    const size_t flag_bytes = 256;
+    d->mail_off = ext_bytes; d->flag_off = ext_bytes + ((mail_bytes + 255) & ~(size_t)255);
+    d->shared_bytes = d->flag_off + flag_bytes;
+    SMM_CUDA(cudaMalloc(&d->shared, d->shared_bytes));
+    SMM_CUDA(cudaMemsetAsync(d->shared, 0, d->shared_bytes, s));
+    d->ext = reinterpret_cast<float*>(d->shared);
+    SMM_CUDA(cudaMalloc(&d->comm_dev, sizeof(DistComm)));
+    SMM_CUDA(cudaMalloc(&d->ticket, sizeof(unsigned int)));
+    SMM_CUDA(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned int), s));
+    SMM_CUDA(cudaStreamSynchronize(s));
+    if (nranks == 1) d->connected = true;
+    *out = d;
+    return SMM_OK;
+}
+
+int smm_dist_info(const smm_dist_t* d, int64_t* ranges4, void* ipc_handle64) {
+    if (!d) return SMM_E_INVALID;
+    if (ranges4) { ranges4[0] = d->row_begin; ranges4[1] = d->row_end; ranges4[2] = d->lo; ranges4[3] = d->hi; }
+    if (ipc_handle64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        SMM_CUDA(cudaSetDevice(d->device));
+        SMM_CUDA(cudaIpcGetMemHandle(&h, d->shared));
+        memcpy(ipc_handle64, &h, 64);
+    }
+    return SMM_OK;
+}
+
+int smm_dist_connect(smm_dist_t* d, const int64_t* all_ranges, const void* all_handles) {
+    if (!d || !all_ranges || !all_handles) return SMM_E_INVALID;
+    SMM_CUDA(cudaSetDevice(d->device));
+    const int P = d->nranks, me = d->rank;
+    DistComm c;
+    memset(&c, 0, sizeof c);
+    c.rank = me; c.nranks = P;
+    for (int r = 0; r < P; ++r) {
+        if (r == me) { d->peer_base[r] = d->shared; }
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)all_handles + 64 * r, 64);
+            SMM_CUDA(cudaIpcOpenMemHandle(&d->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    // every rank lays its block out as [ext | mail | flags] with its own window length
+    d->send.clear(); d->dests.clear(); d->sources.clear();
+    std::vector<SegDev> segs;
+    long long first_block = 0;
+    for (int r = 0; r < P; ++r) {
+        const long long rb = all_ranges[4 * r], re = all_ranges[4 * r + 1], lo = all_ranges[4 * r + 2], hi = all_ranges[4 * r + 3];
+        const size_t ext_bytes = (((size_t)(hi - lo) * sizeof(float)) + 255) & ~(size_t)255;
+        const size_t mail_bytes = (size_t)4 * P * 2 * sizeof(unsigned long long);
+        char* base = (char*)d->peer_base[r];
+        c.mail[r] = reinterpret_cast<unsigned long long*>(base + ext_bytes);
+        c.flags[r] = reinterpret_cast<unsigned int*>(base + ext_bytes + ((mail_bytes + 255) & ~(size_t)255));
+        if (r == me) continue;
+        (void)rb; (void)re;
+        // what rank r needs from me: my owned rows inside its window
+        const long long a = d->row_begin > lo ? d->row_begin : lo;
+        const long long b = d->row_end < hi ? d->row_end : hi;
+        if (b > a) {
+            d->send.push_back({r, a - d->lo, a - lo, b - a});
+            d->dests.push_back(r);
+            SegDev sg;
+            sg.dst = reinterpret_cast<float*>(base) + (a - lo);
+            sg.src = d->ext + (a - d->lo);
+            sg.len = b - a;
+            sg.first_block = first_block;
+            first_block += (sg.len + PUSH_ELEMS_PER_BLOCK - 1) / PUSH_ELEMS_PER_BLOCK;
+            segs.push_back(sg);
+        }
+        // what I need from rank r: its owned rows inside my window
+        const long long a2 = rb > d->lo ? rb : d->lo;
+        const long long b2 = re < d->hi ? re : d->hi;
+        if (b2 > a2) d->sources.push_back(r);
+    }
+    if (!segs.empty()) {
+        SMM_CUDA(cudaMalloc(&d->seg_dev, sizeof(SegDev) * segs.size()));
+        SMM_CUDA(cudaMemcpy(d->seg_dev, segs.data(), sizeof(SegDev) * segs.size(), cudaMemcpyHostToDevice));
+    }
+    SMM_CUDA(cudaMalloc(&d->dests_dev, sizeof(int) * SMM_MAX_RANKS));
+    SMM_CUDA(cudaMalloc(&d->sources_dev, sizeof(int) * SMM_MAX_RANKS));
+    if (!d->dests.empty()) SMM_CUDA(cudaMemcpy(d->dests_dev, d->dests.data(), sizeof(int) * d->dests.size(), cudaMemcpyHostToDevice));
+    if (!d->sources.empty()) SMM_CUDA(cudaMemcpy(d->sources_dev, d->sources.data(), sizeof(int) * d->sources.size(), cudaMemcpyHostToDevice));
+    SMM_CUDA(cudaMemcpy(d->comm_dev, &c, sizeof c, cudaMemcpyHostToDevice));
+    d->connected = true;
+    return SMM_OK;
+}
+
+// y_local = A_local * x (exchange of x's halo included); x_local_dev, y_local_dev hold this rank's owned rows
+int smm_dist_spmv_dev(smm_dist_t* d, const float* x_local_dev, float* y_local_dev, void* stream) {
+    if (!d || !d->connected) { smm_set_error("smm_dist_spmv_dev: not connected"); return SMM_E_STATE; }
+    SMM_CUDA(cudaSetDevice(d->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : smm_default_stream();
+    const long long n = d->row_end - d->row_begin;
+    if (n) SMM_CUDA(cudaMemcpyAsync(d->ext + d->own_off, x_local_dev, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    SMM_TRY(smm_dist_exchange_async(d, nullptr, s));
+    SpmvArgs a;
+    a.m = d->local; a.op = SMM_OP_ASSIGN; a.mult = d->ext; a.out = y_local_dev;
+    SMM_TRY(smm_launch_spmv(a, s));
+    return SMM_OK;
+}
+
+int smm_dist_solve_cg(smm_dist_t* d, const float* b_dev, const float* x0_dev, float* x_dev, int maxIterations, float eps,
+                      const smm_solve_options* opts, smm_solve_info* info, void* stream) {
+    if (!d || !d->connected) { smm_set_error("smm_dist_solve_cg: not connected"); return SMM_E_STATE; }
+    cudaStream_t s = stream ? (cudaStream_t)stream : smm_default_stream();
+    return smm_solve_dist_cg_impl(d, b_dev, x0_dev, x_dev, maxIterations, eps, opts, info, s);
+}
+
+int smm_dist_error(const smm_dist_t* d, int* error) {
+    if (!d || !error) return SMM_E_INVALID;
+    DistComm c;
+    SMM_CUDA(cudaDeviceSynchronize());
+    SMM_CUDA(cudaMemcpy(&c, d->comm_dev, sizeof c, cudaMemcpyDeviceToHost));
+    *error = c.error;
+    return SMM_OK;
+}
+
+int smm_dist_destroy(smm_dist_t* d) {
+    if (!d) return SMM_OK;
+    cudaSetDevice(d->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < d->nranks; ++r) if (r != d->rank && d->peer_base[r]) cudaIpcCloseMemHandle(d->peer_base[r]);
+    cudaFree(d->shared); cudaFree(d->comm_dev); cudaFree(d->ticket); cudaFree(d->seg_dev); cudaFree(d->dests_dev); cudaFree(d->sources_dev);
+    delete d;
+    return SMM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// dist.h -- host-side state of the multi-GPU layer (shared by dist.cu and solvers.cu)
+#pragma once
+#include <vector>
+
+#include "dist_device.cuh"
+#include "smm_internal.cuh"
+
+struct smm_dist {
+    int rank = 0, nranks = 1, device = 0;
+    smm_csr* local = nullptr;            // rows = owned rows, cols = window length, columns remapped into the window
+    long long global_rows = 0, row_begin = 0, row_end = 0;
+    long long lo = 0, hi = 0;            // window [lo, hi) of the global vector this rank's rows read
+    long long own_off = 0;               // row_begin - lo (multiple of 4: the owned part stays 16-byte aligned)
+    // one IPC-exported block: [extended vector | mailboxes | halo flags]
+    void* shared = nullptr;
+    size_t shared_bytes = 0, mail_off = 0, flag_off = 0;
+    float* ext = nullptr;
+    void* peer_base[SMM_MAX_RANKS] = {nullptr};
+    DistComm* comm_dev = nullptr;
+    // halo plan
+    struct Seg { int peer; long long src_off, dst_off, len; };
+    std::vector<Seg> send;               // my owned entries -> a peer's extended vector
+    std::vector<int> dests;              // ranks I push to
+    std::vector<int> sources;            // ranks that push to me
+    void* seg_dev = nullptr;
+    int* dests_dev = nullptr;
+    int* sources_dev = nullptr;
+    unsigned int* ticket = nullptr;
+    bool connected = false;
+};
+
+// push this rank's boundary entries of d->ext to the peers and wait for theirs (two launches on s)
+int smm_dist_exchange_async(smm_dist* d, SolveState* st, cudaStream_t s);

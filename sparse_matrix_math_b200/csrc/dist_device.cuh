@@ -1,0 +1,78 @@
+// dist_device.cuh -- device-side communication primitives of the multi-GPU solvers (one process per GPU).
+//
+// All traffic is direct peer-to-peer loads/stores over NVLink into buffers every rank exports with CUDA IPC:
+//   * scalar all-reduce, fused into the epilogue of the kernel that produced the partial sum: the last CTA of every
+//     rank writes (value, sequence tag) as ONE 64-bit word into its slot of every peer's mailbox, then waits until
+//     its own mailbox holds the current tag from every rank and adds the values in rank order -- every rank gets
+//     the same bits, so all ranks take the same branches without any further agreement.  Four mailbox sets cycle,
+//     and a rank cannot run two reductions ahead of a peer (it needs that peer's contribution), so a set is never
+//     overwritten before it has been read.
+//   * halo exchange: a push kernel stores the boundary entries of the local vector straight into the peers'
+//     extended vectors and then raises a per-source flag (release, system scope); a wait kernel spins on the flags
+//     (acquire, system scope) before the SpMV that gathers the halo.
+// Every spin is bounded; on expiry the error flag is set and the solve is marked done so nothing can hang.
+#pragma once
+#include <stdint.h>
+
+constexpr int SMM_MAX_RANKS = 8;
+constexpr unsigned int SMM_DIST_POLL_LIMIT = 1u << 27;
+
+struct DistComm {
+    int rank, nranks;
+    unsigned int red_seq;                       // reductions completed (same on every rank)
+    unsigned int push_seq;                      // halo exchanges completed
+    int error;                                  // 1: a bounded wait expired
+    int pad;
+    unsigned long long* mail[SMM_MAX_RANKS];    // mail[d]: rank d's mailbox [4 sets][nranks][2] (mail[rank] is local)
+    unsigned int* flags[SMM_MAX_RANKS];         // flags[d]: rank d's flag array [nranks]; this rank writes flags[d][rank]
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Called by ONE thread per rank.  Sums t0 and t1 over all ranks, in rank order.
+__device__ __forceinline__ void dist_allreduce2(DistComm* c, float& t0, float& t1) {
+    const unsigned int seq = c->red_seq + 1u;
+    const int P = c->nranks, me = c->rank;
+    const size_t set = (size_t)(seq & 3u) * P * 2;
+    const unsigned long long w0 = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(t0);
+    const unsigned long long w1 = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(t1);
+    for (int k = 0; k < P; ++k) {                           // start with the next rank: spread the NVLink writes
+        const int d = (me + 1 + k) % P;
+        st_sys_u64(c->mail[d] + set + 2 * me, w0);
+        st_sys_u64(c->mail[d] + set + 2 * me + 1, w1);
+    }
+    float s0 = 0.0f, s1 = 0.0f;
+    const unsigned long long* mine = c->mail[me] + set;
+    for (int s = 0; s < P; ++s) {
+        unsigned long long a = 0, b = 0;
+        unsigned int polls = 0;
+        for (;;) {
+            a = ld_sys_u64(mine + 2 * s);
+            b = ld_sys_u64(mine + 2 * s + 1);
+            if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) break;
+            if (++polls >= SMM_DIST_POLL_LIMIT) { c->error = 1; break; }
+        }
+        s0 += __uint_as_float((unsigned int)a);
+        s1 += __uint_as_float((unsigned int)b);
+    }
+    t0 = s0;
+    t1 = s1;
+    c->red_seq = seq;
+}
+#endif

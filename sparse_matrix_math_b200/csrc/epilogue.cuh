@@ -5,6 +5,7 @@
 //
 // All float ops use the round-to-nearest intrinsics so nvcc cannot contract or reassociate them.
 #pragma once
+#include "dist_device.cuh"
 #include "smm_internal.cuh"
 
 enum ReduceShape {
@@ -43,6 +44,11 @@ __device__ __forceinline__ int smm_do_while_status(const SolveState* st) {
 }
 
 __device__ __forceinline__ void smm_finish(int kind, SolveState* st, float t0, float t1) {
+    if (kind == FIN_NONE) return;
+    if (st->comm != nullptr) {
+        dist_allreduce2(st->comm, t0, t1);                     // every rank now holds the same totals
+        if (st->comm->error) { st->done = 1; st->precond_error |= 8; return; }
+    }
     switch (kind) {
         case FIN_STORE:
             st->scratch[0] = t0;

@@ -48,13 +48,15 @@ __device__ __forceinline__ long long stencil_start(const StencilDesc& d, long lo
     return r * full - miss;
 }
 
-__global__ void stencil_kernel(const StencilDesc d, long long rows, int32_t* __restrict__ start, int32_t* __restrict__ positions,
-                               float* __restrict__ values) {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > rows) return;
-    const long long s = stencil_start(d, r);
-    start[r] = (int32_t)s;
-    if (r == rows) return;
+// rows [row0, row0 + rows) of the global operator; start[] is relative to the first generated row
+__global__ void stencil_kernel(const StencilDesc d, long long row0, long long rows, int32_t* __restrict__ start,
+                               int32_t* __restrict__ positions, float* __restrict__ values) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > rows) return;
+    const long long r = row0 + t;
+    const long long s = stencil_start(d, r) - stencil_start(d, row0);
+    start[t] = (int32_t)s;
+    if (t == rows) return;
     const long long nx = d.nx, ny = d.ny, plane = nx * ny;
     const int k = (int)(r / plane), j = (int)((r % plane) / nx), i = (int)(r % nx);
     long long o = s;
@@ -185,6 +187,40 @@ __global__ void xstar_kernel(uint64_t seed, long long n, long long offset, float
 
 extern "C" {
 
+static int gen_stencil_rows(int kind, int nx, int ny, int nz, float c, long long row0, long long row1, smm_csr_t** out) {
+    cudaStream_t s = smm_default_stream();
+    StencilDesc d;
+    d.nx = nx; d.ny = ny; d.nz = kind == SMM_GEN_POISSON2D ? 1 : nz;
+    if (d.nx < 1 || d.ny < 1 || d.nz < 1) { smm_set_error("smm_gen_csr: bad grid"); return SMM_E_INVALID; }
+    d.use_y = 1; d.use_z = kind == SMM_GEN_CONVDIFF3D;
+    if (kind == SMM_GEN_POISSON2D) { d.lo = -1.0f; d.hi = -1.0f; d.diag = 4.0f; }
+    else { d.lo = -1.0f - c; d.hi = -1.0f + c; d.diag = 6.0f; }
+    const long long total = (long long)d.nx * d.ny * d.nz;
+    if (row0 < 0 || row1 < row0 || row1 > total) { smm_set_error("smm_gen_csr_rows: bad row range"); return SMM_E_INVALID; }
+    const long long rows = row1 - row0;
+    if (total > 0x7fffffffll - 1) { smm_set_error("smm_gen_csr: exceeds 32-bit indices"); return SMM_E_INVALID; }
+    int32_t* start = nullptr;
+    SMM_CUDA(cudaMalloc(&start, sizeof(int32_t) * (size_t)(rows + 1)));
+    // two passes: row offsets first (to learn nnz), then the entries
+    const int full = 3 + 2 * d.use_y + 2 * d.use_z;
+    const size_t nmax = (((size_t)rows * full) + 3) & ~(size_t)3;
+    int32_t* positions = nullptr;
+    float* values = nullptr;
+    SMM_CUDA(cudaMalloc(&positions, sizeof(int32_t) * (nmax ? nmax : 4)));
+    SMM_CUDA(cudaMalloc(&values, sizeof(float) * (nmax ? nmax : 4)));
+    stencil_kernel<<<(unsigned)((rows + 1 + 255) / 256), 256, 0, s>>>(d, row0, rows, start, positions, values);
+    SMM_COUNT_LAUNCH(1);
+    SMM_CUDA(cudaGetLastError());
+    SMM_CUDA(cudaStreamSynchronize(s));
+    int rc = smm_csr_create_dev((int)rows, (int)total, start, positions, values, 0, out);
+    return rc;
+}
+
+int smm_gen_csr_rows(int kind, int nx, int ny, int nz, float c, int64_t row_begin, int64_t row_end, smm_csr_t** out) {
+    if (!out || (kind != SMM_GEN_POISSON2D && kind != SMM_GEN_CONVDIFF3D)) return SMM_E_INVALID;
+    return gen_stencil_rows(kind, nx, ny, nz, c, row_begin, row_end, out);
+}
+
 int smm_gen_csr(int kind, int nx, int ny, int nz, float c, uint64_t seed, smm_csr_t** out) {
     if (!out) return SMM_E_INVALID;
     cudaStream_t s = smm_default_stream();
@@ -192,23 +228,8 @@ int smm_gen_csr(int kind, int nx, int ny, int nz, float c, uint64_t seed, smm_cs
     float* values = nullptr;
     long long rows = 0, nnz = 0;
     if (kind == SMM_GEN_POISSON2D || kind == SMM_GEN_CONVDIFF3D) {
-        StencilDesc d;
-        d.nx = nx; d.ny = ny; d.nz = kind == SMM_GEN_POISSON2D ? 1 : nz;
-        if (d.nx < 1 || d.ny < 1 || d.nz < 1) { smm_set_error("smm_gen_csr: bad grid"); return SMM_E_INVALID; }
-        d.use_y = 1; d.use_z = kind == SMM_GEN_CONVDIFF3D;
-        if (kind == SMM_GEN_POISSON2D) { d.lo = -1.0f; d.hi = -1.0f; d.diag = 4.0f; }
-        else { d.lo = -1.0f - c; d.hi = -1.0f + c; d.diag = 6.0f; }
-        rows = (long long)d.nx * d.ny * d.nz;
-        const int full = 3 + 2 * d.use_y + 2 * d.use_z;
-        nnz = rows * full - 2ll * d.ny * d.nz - (d.use_y ? 2ll * d.nx * d.nz : 0) - (d.use_z ? 2ll * d.nx * d.ny : 0);
-        if (rows > 0x7fffffffll - 1 || nnz > 0x7fffffffll) { smm_set_error("smm_gen_csr: exceeds 32-bit indices"); return SMM_E_INVALID; }
-        const size_t npad = ((size_t)nnz + 3) & ~(size_t)3;
-        SMM_CUDA(cudaMalloc(&start, sizeof(int32_t) * (size_t)(rows + 1)));
-        SMM_CUDA(cudaMalloc(&positions, sizeof(int32_t) * npad));
-        SMM_CUDA(cudaMalloc(&values, sizeof(float) * npad));
-        stencil_kernel<<<(unsigned)((rows + 1 + 255) / 256), 256, 0, s>>>(d, rows, start, positions, values);
-        SMM_COUNT_LAUNCH(1);
-        SMM_CUDA(cudaGetLastError());
+        const long long total = (long long)nx * ny * (kind == SMM_GEN_POISSON2D ? 1 : nz);
+        return gen_stencil_rows(kind, nx, ny, nz, c, 0, total, out);
     } else if (kind == SMM_GEN_POWERLAW) {
         rows = nx;
         const int cap = ny > 1 ? ny : 131072;          // ny = optional row-length cap

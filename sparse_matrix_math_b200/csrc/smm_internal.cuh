@@ -83,7 +83,8 @@ struct SolveState {
     int pad0;
     float* history;      // device residual history (may be null)
     unsigned long long cond_handle;   // cudaGraphConditionalHandle of the WHILE driver (0 = none)
-    int pad[8];
+    struct DistComm* comm;            // multi-GPU: reductions are summed over ranks before the scalar step (null: one GPU)
+    int pad[6];
 };
 
 struct smm_workspace {

@@ -24,12 +24,15 @@
 #include <chrono>
 #include <string.h>
 
+#include "dist.h"
 #include "epilogue.cuh"
 #include "smm_internal.cuh"
 
 namespace {
 
 struct Ctx {
+    smm_dist* dist = nullptr;        // multi-GPU: rows of this rank, extended vector, peer mailboxes
+
     const smm_csr* a = nullptr;
     const smm_precond* precond = nullptr;
     smm_workspace* ws = nullptr;
@@ -76,6 +79,27 @@ int dots(Ctx& c, int finish, const float* a0, const float* b0, const float* a1 =
 // ---------------------------------------------------------------------------------------------------
 // per-solver: start-up sequence and one iteration
 // ---------------------------------------------------------------------------------------------------
+// Multi-GPU CG: p lives inside the extended vector (owned part + halo); every SpMV operand is exchanged first.
+// The reductions are summed over the ranks inside the kernels' epilogues (dist_device.cuh), so the scalar state --
+// and with it every branch -- is bit-identical on all ranks.
+int cg_init_dist(Ctx& c, const float* x0) {
+    smm_dist* d = c.dist;
+    SMM_CUDA(cudaMemcpyAsync(d->ext + d->own_off, x0, sizeof(float) * (size_t)c.n, cudaMemcpyDeviceToDevice, c.s));
+    SMM_TRY(smm_dist_exchange_async(d, c.st, c.s));
+    SMM_TRY(spmv(c, SMM_OP_SUB, c.b, d->ext, c.r, RED_OUT_OUT, FIN_CG_INIT, nullptr));
+    SMM_TRY(vec(c, VEC_COPY3, FIN_NONE, {c.r}, {c.p, c.p, c.p}));
+    return smm_dist_exchange_async(d, c.st, c.s);
+}
+int cg_iter_dist(Ctx& c) {
+    smm_dist* d = c.dist;
+    SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, d->ext, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));
+    SMM_TRY(vec(c, VEC_CG_XR, FIN_CG_UPDATE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
+    SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}));
+    SMM_TRY(smm_dist_exchange_async(d, c.st, c.s));
+    c.kernels_per_iteration = 5;
+    return SMM_OK;
+}
+
 int cg_init(Ctx& c, const float* x0) {
     // r = b - A x0 ; p = r ; rr = r.r ; early SUCCESS if eps^2 > rr          H:2336-2347
     if (!c.exact) return spmv(c, SMM_OP_SUB, c.b, x0, c.r, RED_OUT_OUT, FIN_CG_INIT, nullptr, c.p);
@@ -331,16 +355,18 @@ int clamp_iterations(int solver, int max_iterations, int rows) {
 }
 
 int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const float* b_dev, const float* x0_dev, float* x_dev,
-              int max_iterations, float eps, const smm_solve_options* opts, smm_solve_info* info, cudaStream_t s) {
+              int max_iterations, float eps, const smm_solve_options* opts, smm_solve_info* info, cudaStream_t s,
+              smm_dist* dist = nullptr) {
     if (!a || (a->rows && (!b_dev || !x_dev || !x0_dev))) { smm_set_error("solve: bad arguments"); return SMM_E_INVALID; }
-    if (a->rows != a->cols) { smm_set_error("solve: matrix must be square"); return SMM_E_INVALID; }
+    if (!dist && a->rows != a->cols) { smm_set_error("solve: matrix must be square"); return SMM_E_INVALID; }
     SMM_CUDA(cudaSetDevice(a->device));
     smm_workspace* ws = nullptr;
     SMM_TRY(smm_workspace_get(a, &ws));
     Ctx c;
-    c.a = a; c.precond = precond; c.ws = ws; c.s = s; c.st = ws->state; c.n = a->rows;
+    c.a = a; c.precond = precond; c.ws = ws; c.s = s; c.st = ws->state; c.n = a->rows; c.dist = dist;
     c.mode = opts ? opts->reduction_mode : SMM_REDUCE_FAST;
     if (c.mode < 0 || c.mode > 2) { smm_set_error("solve: unknown reduction mode"); return SMM_E_INVALID; }
+    if (dist && c.mode != SMM_REDUCE_FAST) { smm_set_error("multi-GPU solve: only the FAST reduction mode is distributed"); return SMM_E_INVALID; }
     c.exact = c.mode != SMM_REDUCE_FAST;
     c.b = b_dev; c.x = x_dev;
     const int nvec = solver == S_CG || solver == S_BICGSYM ? 3 : (solver == S_CGS ? 7 : 7);
@@ -348,6 +374,7 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
     SMM_TRY(smm_workspace_vectors(ws, 3 + nvec, (size_t)a->rows));
     float** w = ws->vec + 3;
     c.r = w[0]; c.p = w[1]; c.ap = w[2];
+    if (dist) c.p = dist->ext + dist->own_off;                  // p is the owned part of the extended vector
     if (solver == S_CGS) { c.r0 = w[3]; c.u = w[4]; c.q = w[5]; c.auq = w[6]; }
     if (solver == S_BICGSTAB) { c.r0 = w[3]; c.sv = w[4]; c.as = w[5]; c.scratch = w[6]; }
 
@@ -369,6 +396,9 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
     h->eps2 = eps * eps;                                       // H:2045, H:2130, H:2335 (float product)
     h->history = hist_cap ? ws->history : nullptr;
     h->history_cap = hist_cap;
+    h->comm = (dist && dist->nranks > 1) ? dist->comm_dev : nullptr;
+    // the iteration cap refers to the GLOBAL system (H:2345-2347: -1 means rows)
+    if (dist && solver == S_CG && max_iterations == -1) h->max_iterations = (int)dist->global_rows;
     const int max_it = h->max_iterations;
     SMM_CUDA(cudaMemcpyAsync(c.st, h, sizeof *h, cudaMemcpyHostToDevice, s));
 
@@ -381,8 +411,8 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
         switch (solver) {
             case S_CG:
                 if (x_dev != x0_dev) SMM_CUDA(cudaMemcpyAsync(x_dev, x0_dev, sizeof(float) * (size_t)a->rows, cudaMemcpyDeviceToDevice, s));
-                SMM_TRY(cg_init(c, x0_dev));
-                iter = cg_iter;
+                if (dist) { SMM_TRY(cg_init_dist(c, x0_dev)); iter = cg_iter_dist; }
+                else { SMM_TRY(cg_init(c, x0_dev)); iter = cg_iter; }
                 budget = max_it > 0 ? max_it : 0;                                                  // for-loop, H:2352
                 break;
             case S_BICGSYM:
@@ -467,6 +497,11 @@ int solve_host(int solver, const smm_csr* a, const smm_precond* precond, const f
 }
 
 }  // namespace
+
+int smm_solve_dist_cg_impl(smm_dist* d, const float* b_dev, const float* x0_dev, float* x_dev, int maxIterations, float eps,
+                           const smm_solve_options* opts, smm_solve_info* info, cudaStream_t s) {
+    return solve_dev(S_CG, d->local, nullptr, b_dev, x0_dev, x_dev, maxIterations, eps, opts, info, s, d);
+}
 
 extern "C" {
 

@@ -1,0 +1,88 @@
+"""Multi-GPU parity check, launched under torchrun (one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py
+Every rank slices the same global matrix, runs the distributed SpMV and CG through the C ABI and compares with the
+oracle on the global problem."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import matgen  # noqa: E402
+import oracle_lib as ol  # noqa: E402
+import sparse_matrix_math_b200 as smm  # noqa: E402
+from sparse_matrix_math_b200 import binding as B  # noqa: E402
+from sparse_matrix_math_b200 import dist as smd  # noqa: E402
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = smd.init_process_group()
+    fails = []
+
+    def check(cond, what):
+        if not cond:
+            fails.append(what)
+            print(f"[rank {rank}] FAILED: {what}", flush=True)
+
+    for name, g, part in [("poisson3d 12x10x16", matgen.poisson3d(12, 10, 16), "rows"),
+                          ("poisson2d 64x50", matgen.poisson2d(64, 50), "nnz"),
+                          ("poisson3d 40x40x48", matgen.poisson3d(40, 40, 48), "planes")]:
+        if part == "rows":
+            parts = smd.row_partition(g.rows, world)
+        elif part == "nnz":
+            parts = smd.nnz_partition(g.start, world)
+        else:
+            parts = smd.row_partition(g.rows, world, 1600)
+        rb, re = parts[rank]
+        start, pos, val = smd.slice_rows(g.start, g.positions, g.values, rb, re)
+        A = smm.CSRMatrix.from_arrays(re - rb, g.cols, start, pos, val)
+        D = smd.DistMatrix(A, g.rows, rb, re, rank, world, smd.all_gather_object)
+        xs = matgen.xstar(g.rows)
+        dx, dy = smm.DeviceVector(re - rb, xs[rb:re]), smm.DeviceVector(re - rb)
+        dist.barrier()
+        D.spmv_dev(dx.ptr, dy.ptr)
+        y = dy.download()
+        b_glob = ol.spmv(g, 0, None, xs)
+        check(y.tobytes() == b_glob[rb:re].tobytes(), f"{name}: distributed SpMV differs from the oracle")
+        # CG to convergence; compare with the oracle's multithreaded build on the global problem
+        o = ol.solve("cg", g, b_glob, np.zeros(g.rows, np.float32), -1, 1e-5, 1)
+        db, dxx = smm.DeviceVector(re - rb, b_glob[rb:re]), smm.DeviceVector(re - rb, np.zeros(re - rb, np.float32))
+        dist.barrier()
+        for drv in (B.DRIVER_GRAPH_CHUNKED, B.DRIVER_GRAPH_WHILE, B.DRIVER_STREAM):
+            dxx.zero()
+            info = D.solve_cg_dev(db.ptr, dxx.ptr, dxx.ptr, -1, 1e-5, driver_mode=drv, check_every=8)
+            x = dxx.download()
+            its = [None] * world
+            dist.all_gather_object(its, (info.iterations, int(info.status), info.residual))
+            check(len(set(its)) == 1, f"{name}: ranks disagree on the scalar state {its}")
+            check(int(info.status) == o["status"] == 0, f"{name}: status {info.status}")
+            check(abs(info.iterations - o["iterations"]) <= max(1, round(0.05 * o["iterations"])),
+                  f"{name}: iterations {info.iterations} vs reference {o['iterations']}")
+            check(info.residual <= 1e-10, f"{name}: residual {info.residual}")
+            check(np.max(np.abs(x - xs[rb:re])) < 2e-4, f"{name}: x error {np.max(np.abs(x - xs[rb:re]))}")
+        # capped run: MAX_ITERATIONS_REACHED with exactly maxIterations iterations
+        dxx.zero()
+        info = D.solve_cg_dev(db.ptr, dxx.ptr, dxx.ptr, 7, 0.0)
+        check(info.iterations == 7 and int(info.status) == 2, f"{name}: capped run {info.iterations} {info.status}")
+        check(D.error() == 0, f"{name}: communication error flag")
+        if rank == 0:
+            print(f"{name}: ok={not fails} (CG {info.iterations} capped; converged run vs reference {o['iterations']} iterations)", flush=True)
+        dist.barrier()
+        D.close()
+    total = [None] * world
+    dist.all_gather_object(total, len(fails))
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DIST CHECK", "PASSED" if sum(total) == 0 else f"FAILED ({sum(total)} failures)", flush=True)
+    sys.exit(1 if sum(total) else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -447,3 +447,21 @@ def test_bicgstab_sgs_large_parity(smm):
     assert int(info.status) == 0 and info.residual <= 1e-5
     assert abs(info.iterations - o["iterations"]) <= max(1, round(0.05 * o["iterations"]) + 1)
     assert np.max(np.abs(x - xs)) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU (needs >= 2 GPUs on the box; single-GPU boxes skip)
+# ---------------------------------------------------------------------------------------------
+def test_multi_gpu_cg_parity(smm):
+    import ctypes as C
+    import subprocess
+    import sys
+    n = C.c_int()
+    smm.lib().smm_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29511", os.path.join(here, "dist_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "DIST CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
