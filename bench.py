@@ -221,7 +221,10 @@ def run_reference(args):
         return
     g = pick_cpu_grid(args.grid)
     run, threads, kind, free = cpu_problem(g)
-    iters = max(2, min(args.iters, 5))
+    # same iterations per step as the GPU arm unless that would take more than ~2.5 minutes in total
+    t2, t1 = run(2), run(1)
+    per_it = max(t2 - t1, 1e-6)
+    iters = int(max(2, min(args.iters, 150.0 / ((args.steps + args.warmup) * per_it))))
     for _ in range(args.warmup):
         run(iters)
     t0 = time.perf_counter()

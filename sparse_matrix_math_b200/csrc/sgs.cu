@@ -18,6 +18,8 @@
 // result is bit-identical to SGSPreconditioner::apply for any schedule.
 // Algorithmic bytes per apply: each stored entry once over the two sweeps (8 nnz) + start/diag index/order
 // (about 24 n) + rhs, y, x traffic (about 20 n).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -41,7 +43,7 @@ namespace {
 
 constexpr unsigned int SENTINEL = 0x7FC0DEADu;   // quiet NaN with a payload; GPU arithmetic only produces 0x7FFFFFFF
 constexpr int SGS_THREADS = 128;
-constexpr unsigned int POLL_LIMIT = 1u << 23;
+constexpr unsigned int POLL_LIMIT = 1u << 22;
 
 __global__ void sgs_fill_kernel(float* __restrict__ y, float* __restrict__ x, long long n, unsigned int* tickets, const SolveState* st) {
     if (st != nullptr && st->done) return;
@@ -59,7 +61,8 @@ __device__ __forceinline__ float wait_value(const float* p, unsigned int* abort_
     for (;;) {
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bits) : "l"(p));
         if (bits != SENTINEL) break;
-        if ((++polls & 1023u) == 0u) {
+        __nanosleep(polls < 16u ? 32u : 128u);                // back off: thousands of lanes may be waiting on L2
+        if ((++polls & 255u) == 0u) {
             unsigned int a;
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(a) : "l"(abort_flag));
             if (a != 0u || polls >= POLL_LIMIT) { atomicExch(abort_flag, 1u); break; }
@@ -81,31 +84,40 @@ __global__ void __launch_bounds__(SGS_THREADS) sgs_sweep_kernel(const int32_t* _
                                                                unsigned int* tickets, const SolveState* st) {
     if (st != nullptr && st->done) return;
     __shared__ unsigned int sh_bid;
-    if (threadIdx.x == 0) sh_bid = atomicAdd(&tickets[FORWARD ? 0 : 1], 1u);
-    __syncthreads();
-    const long long t = (long long)sh_bid * SGS_THREADS + threadIdx.x;
-    if (t >= nthreads) return;
-    const int row = order[t];
-    if (row < 0) return;
     unsigned int* abort_flag = tickets + 2;
-    const int dp = diag_pos[row];
-    const float d = values[dp];
-    if (FORWARD) {
-        if (fabsf(d) < 1e-5) atomicOr(tickets + 3, 1u);                       // H:1691-1693 (reported, not fatal here)
-        float lhs = rhs[row];                                                 // H:1683
-        for (int k = start[row]; k < dp; ++k) {                               // cols ascending, H:1684-1689
-            const float xv = wait_value(y + positions[k], abort_flag);
-            lhs = __fadd_rn(__fmul_rn(-values[k], xv), lhs);                  // _smm_fma(-value, x[col], lhs)
+    // persistent CTAs: logical blocks are handed out in order by an atomic ticket, so (a) every row a thread waits for
+    // belongs to a block that has already been claimed by a running CTA, and (b) the number of lanes that can be
+    // spinning at any time is bounded by the grid, which is sized to stay a few levels deep at most
+    const long long nblocks = (nthreads + SGS_THREADS - 1) / SGS_THREADS;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh_bid = atomicAdd(&tickets[FORWARD ? 0 : 1], 1u);
+        __syncthreads();
+        const long long bid = sh_bid;
+        if (bid >= nblocks) break;
+        const long long t = bid * SGS_THREADS + threadIdx.x;
+        if (t >= nthreads) continue;
+        const int row = order[t];
+        if (row < 0) continue;
+        const int dp = diag_pos[row];
+        const float d = values[dp];
+        if (FORWARD) {
+            if (fabsf(d) < 1e-5) atomicOr(tickets + 3, 1u);                       // H:1691-1693 (reported, not fatal here)
+            float lhs = rhs[row];                                                 // H:1683
+            for (int k = start[row]; k < dp; ++k) {                               // cols ascending, H:1684-1689
+                const float xv = wait_value(y + positions[k], abort_flag);
+                lhs = __fadd_rn(__fmul_rn(-values[k], xv), lhs);                  // _smm_fma(-value, x[col], lhs)
+            }
+            publish(y + row, __fdiv_rn(lhs, d));                                  // H:1694
+        } else {
+            float lhs = 0.0f;                                                     // H:1702
+            for (int k = start[row + 1] - 1; k > dp; --k) {                       // cols descending, H:1703-1708
+                const float xv = wait_value(x + positions[k], abort_flag);
+                lhs = __fadd_rn(__fmul_rn(values[k], xv), lhs);                   // _smm_fma(value, x[col], lhs)
+            }
+            const float yr = wait_value(y + row, abort_flag);                     // own forward result (already published)
+            publish(x + row, __fsub_rn(yr, __fdiv_rn(lhs, d)));                   // H:1710
         }
-        publish(y + row, __fdiv_rn(lhs, d));                                  // H:1694
-    } else {
-        float lhs = 0.0f;                                                     // H:1702
-        for (int k = start[row + 1] - 1; k > dp; --k) {                       // cols descending, H:1703-1708
-            const float xv = wait_value(x + positions[k], abort_flag);
-            lhs = __fadd_rn(__fmul_rn(values[k], xv), lhs);                   // _smm_fma(value, x[col], lhs)
-        }
-        const float yr = wait_value(y + row, abort_flag);                     // own forward result (already published)
-        publish(x + row, __fsub_rn(yr, __fdiv_rn(lhs, d)));                   // H:1710
     }
 }
 
@@ -183,9 +195,13 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
     }
     const long long n = p->rows;
     sgs_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->y, x_dev, n, p->tickets, state);
-    sgs_sweep_kernel<true><<<(unsigned)((p->threads_fwd + SGS_THREADS - 1) / SGS_THREADS), SGS_THREADS, 0, s>>>(
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) { const char* e = getenv("SMM_B200_SGS_CTAS_PER_SM"); ctas_per_sm = e ? atoi(e) : 4; if (ctas_per_sm < 1) ctas_per_sm = 1; }
+    const long long cap = (long long)m->sm_count * ctas_per_sm;
+    const long long bf = (p->threads_fwd + SGS_THREADS - 1) / SGS_THREADS, bb = (p->threads_bwd + SGS_THREADS - 1) / SGS_THREADS;
+    sgs_sweep_kernel<true><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(
         m->start, m->positions, m->values, p->order_fwd, p->diag_pos, p->threads_fwd, rhs_dev, p->y, x_dev, p->tickets, state);
-    sgs_sweep_kernel<false><<<(unsigned)((p->threads_bwd + SGS_THREADS - 1) / SGS_THREADS), SGS_THREADS, 0, s>>>(
+    sgs_sweep_kernel<false><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(
         m->start, m->positions, m->values, p->order_bwd, p->diag_pos, p->threads_bwd, rhs_dev, p->y, x_dev, p->tickets, state);
     sgs_status_kernel<<<1, 1, 0, s>>>(p->tickets, state, rc_dev);
     SMM_COUNT_LAUNCH(4);
