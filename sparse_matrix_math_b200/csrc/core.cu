@@ -228,6 +228,7 @@ int smm_csr_update_values(smm_csr_t* m, const float* values) {
     if (!m || (m->nnz && !values)) return SMM_E_INVALID;
     SMM_CUDA(cudaSetDevice(m->device));
     if (m->nnz) SMM_CUDA(cudaMemcpy(m->values, values, sizeof(float) * (size_t)m->nnz, cudaMemcpyHostToDevice));
+    m->values_version++;
     return SMM_OK;
 }
 

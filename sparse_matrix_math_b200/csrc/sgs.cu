@@ -7,6 +7,9 @@
 //   * create: one host pass over the structure computes the dependency level of every row in the lower and in the
 //     upper triangle (level = 1 + max level of the rows it reads) and the two row orders sorted by level, each level
 //     padded to a warp so that no lane ever waits on a lane of its own warp;
+//     for each sweep the off-diagonal entries are also re-packed in that order as 32-row slices (sliced ELL: entry k
+//     of lane l of slice s sits at slice_ptr[s] + 32 k + l), so a warp reads its rows' entries with coalesced loads
+//     that depend on nothing but the thread index -- the only dependent accesses left are rhs[row] and x[col];
 //   * apply: ONE launch per sweep, one thread per row in level order.  A thread accumulates its row in the
 //     reference's order and, for every x[col] it needs, spins until the value has been published.  The output
 //     vector doubles as the ready flag: it is pre-filled with a NaN payload no arithmetic instruction can produce.
@@ -34,6 +37,14 @@ struct smm_precond {
     int32_t* order_fwd = nullptr;    // [threads_fwd] row index or -1 (padding)
     int32_t* order_bwd = nullptr;    // [threads_bwd]
     int32_t* diag_pos = nullptr;     // [rows] index of a_ii in positions/values
+    // sliced-ELL copies of the strict lower / upper triangles in sweep order (index 0: forward, 1: backward)
+    long long* slice_ptr[2] = {nullptr, nullptr};   // [threads/32 + 1]
+    int32_t* ecol[2] = {nullptr, nullptr};          // column or -1 (padding)
+    int32_t* eidx[2] = {nullptr, nullptr};          // index into the CSR values (to refresh eval after value updates)
+    float* eval[2] = {nullptr, nullptr};
+    float* dval[2] = {nullptr, nullptr};            // [threads] a_ii of the thread's row
+    long long esize[2] = {0, 0};
+    unsigned long long values_version = ~0ull;      // version of m->values the packed copies were gathered from
     float* y = nullptr;              // [rows] forward result
     unsigned int* tickets = nullptr; // [2] logical CTA counters, [2] = abort flag, [3] = error bits
     float* io[2] = {nullptr, nullptr};   // staging for the host-pointer apply
@@ -76,11 +87,24 @@ __device__ __forceinline__ void publish(float* p, float v) {
     asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+struct SweepArgs {
+    const int32_t* order;        // [nthreads] row or -1
+    const long long* slice_ptr;  // [nthreads/32 + 1]
+    const int32_t* ecol;
+    const float* eval;
+    const float* dval;           // [nthreads]
+    long long nthreads;
+};
+
+__global__ void sgs_gather_values_kernel(const float* __restrict__ values, const int32_t* __restrict__ eidx, float* __restrict__ eval, long long n,
+                                         const int32_t* __restrict__ order, const int32_t* __restrict__ diag_pos, float* __restrict__ dval, long long nthreads) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const int k = eidx[i]; eval[i] = k >= 0 ? values[k] : 0.0f; }
+    if (i < nthreads) { const int r = order[i]; dval[i] = r >= 0 ? values[diag_pos[r]] : 1.0f; }
+}
+
 template <bool FORWARD>
-__global__ void __launch_bounds__(SGS_THREADS) sgs_sweep_kernel(const int32_t* __restrict__ start, const int32_t* __restrict__ positions,
-                                                               const float* __restrict__ values, const int32_t* __restrict__ order,
-                                                               const int32_t* __restrict__ diag_pos, long long nthreads,
-                                                               const float* __restrict__ rhs, float* y, float* x,
+__global__ void __launch_bounds__(SGS_THREADS) sgs_sweep_kernel(const SweepArgs A, const float* __restrict__ rhs, float* y, float* x,
                                                                unsigned int* tickets, const SolveState* st) {
     if (st != nullptr && st->done) return;
     __shared__ unsigned int sh_bid;
@@ -88,35 +112,53 @@ __global__ void __launch_bounds__(SGS_THREADS) sgs_sweep_kernel(const int32_t* _
     // persistent CTAs: logical blocks are handed out in order by an atomic ticket, so (a) every row a thread waits for
     // belongs to a block that has already been claimed by a running CTA, and (b) the number of lanes that can be
     // spinning at any time is bounded by the grid, which is sized to stay a few levels deep at most
-    const long long nblocks = (nthreads + SGS_THREADS - 1) / SGS_THREADS;
+    const long long nblocks = (A.nthreads + SGS_THREADS - 1) / SGS_THREADS;
+    const int lane = threadIdx.x & 31;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) sh_bid = atomicAdd(&tickets[FORWARD ? 0 : 1], 1u);
         __syncthreads();
         const long long bid = sh_bid;
         if (bid >= nblocks) break;
-        const long long t = bid * SGS_THREADS + threadIdx.x;
-        if (t >= nthreads) continue;
-        const int row = order[t];
-        if (row < 0) continue;
-        const int dp = diag_pos[row];
-        const float d = values[dp];
+        const long long t = bid * SGS_THREADS + threadIdx.x;      // nthreads is a multiple of 32: whole warps in or out
+        if (t >= A.nthreads) continue;
+        const long long slice = t >> 5;
+        const long long e0 = A.slice_ptr[slice], e1 = A.slice_ptr[slice + 1];
+        const int width = (int)((e1 - e0) >> 5);
+        const int row = A.order[t];
+        const float d = A.dval[t];
+        float acc;
+        const float* src = FORWARD ? y : x;
         if (FORWARD) {
-            if (fabsf(d) < 1e-5) atomicOr(tickets + 3, 1u);                       // H:1691-1693 (reported, not fatal here)
-            float lhs = rhs[row];                                                 // H:1683
-            for (int k = start[row]; k < dp; ++k) {                               // cols ascending, H:1684-1689
-                const float xv = wait_value(y + positions[k], abort_flag);
-                lhs = __fadd_rn(__fmul_rn(-values[k], xv), lhs);                  // _smm_fma(-value, x[col], lhs)
-            }
-            publish(y + row, __fdiv_rn(lhs, d));                                  // H:1694
+            if (row >= 0 && fabsf(d) < 1e-5) atomicOr(tickets + 3, 1u);          // H:1691-1693 (reported, not fatal here)
+            acc = row >= 0 ? rhs[row] : 0.0f;                                     // H:1683
         } else {
-            float lhs = 0.0f;                                                     // H:1702
-            for (int k = start[row + 1] - 1; k > dp; --k) {                       // cols descending, H:1703-1708
-                const float xv = wait_value(x + positions[k], abort_flag);
-                lhs = __fadd_rn(__fmul_rn(values[k], xv), lhs);                   // _smm_fma(value, x[col], lhs)
+            acc = 0.0f;                                                           // H:1702
+        }
+        for (int k = 0; k < width; k += 4) {
+            int c[4];
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                                         // coalesced, independent of any other row
+                const bool in = k + j < width;
+                c[j] = in ? A.ecol[e0 + (long long)(k + j) * 32 + lane] : -1;
+                v[j] = in ? A.eval[e0 + (long long)(k + j) * 32 + lane] : 0.0f;
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c[j] >= 0) {
+                    const float xv = wait_value(src + c[j], abort_flag);
+                    // forward: _smm_fma(-value, x[col], lhs) cols ascending (H:1685); backward: _smm_fma(value, x[col], lhs) cols descending (H:1704)
+                    acc = __fadd_rn(__fmul_rn(FORWARD ? -v[j] : v[j], xv), acc);
+                }
+            }
+        }
+        if (row < 0) continue;
+        if (FORWARD) {
+            publish(y + row, __fdiv_rn(acc, d));                                  // H:1694
+        } else {
             const float yr = wait_value(y + row, abort_flag);                     // own forward result (already published)
-            publish(x + row, __fsub_rn(yr, __fdiv_rn(lhs, d)));                   // H:1710
+            publish(x + row, __fsub_rn(yr, __fdiv_rn(acc, d)));                   // H:1710
         }
     }
 }
@@ -132,6 +174,38 @@ __global__ void sgs_status_kernel(const unsigned int* tickets, SolveState* st, i
 }
 
 // level analysis on the host: one pass per triangle
+// pack the strict triangle of every row, in sweep order, as 32-row slices in thread order
+void build_sell(bool forward, const std::vector<int32_t>& order, const std::vector<int32_t>& start, const std::vector<int32_t>& pos,
+                const std::vector<int32_t>& diag, std::vector<long long>* slice_ptr, std::vector<int32_t>* ecol, std::vector<int32_t>* eidx) {
+    const size_t nslices = order.size() / 32;
+    slice_ptr->assign(nslices + 1, 0);
+    for (size_t s = 0; s < nslices; ++s) {
+        int w = 0;
+        for (int l = 0; l < 32; ++l) {
+            const int r = order[s * 32 + l];
+            if (r < 0) continue;
+            const int cnt = forward ? diag[r] - start[r] : start[r + 1] - 1 - diag[r];
+            w = std::max(w, cnt);
+        }
+        (*slice_ptr)[s + 1] = (*slice_ptr)[s] + (long long)w * 32;
+    }
+    ecol->assign((size_t)(*slice_ptr)[nslices], -1);
+    eidx->assign((size_t)(*slice_ptr)[nslices], -1);
+    for (size_t s = 0; s < nslices; ++s) {
+        const long long base = (*slice_ptr)[s];
+        for (int l = 0; l < 32; ++l) {
+            const int r = order[s * 32 + l];
+            if (r < 0) continue;
+            const int cnt = forward ? diag[r] - start[r] : start[r + 1] - 1 - diag[r];
+            for (int k = 0; k < cnt; ++k) {
+                const int src = forward ? start[r] + k : start[r + 1] - 1 - k;   // ascending / descending columns
+                (*ecol)[(size_t)(base + (long long)k * 32 + l)] = pos[src];
+                (*eidx)[(size_t)(base + (long long)k * 32 + l)] = src;
+            }
+        }
+    }
+}
+
 void analyse(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int first_active_start, bool* valid,
              std::vector<int32_t>* diag, std::vector<int32_t>* order_f, std::vector<int32_t>* order_b, int* lf, int* lb) {
     *valid = first_active_start == 0 || rows == 0;                            // H:1668-1670
@@ -177,6 +251,7 @@ void analyse(int rows, const std::vector<int32_t>& start, const std::vector<int3
 
 int smm_sgs_kernels_per_apply(const smm_precond* p) { return p && p->valid ? 4 : 1; }
 
+
 // rhs_dev -> x_dev on stream s.  With `state` (inside a solve) the kernels no-op once state->done is set.
 int smm_sgs_apply_async(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, cudaStream_t s) {
     return smm_sgs_apply_async_rc(p, rhs_dev, x_dev, state, nullptr, s);
@@ -197,12 +272,23 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
     sgs_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->y, x_dev, n, p->tickets, state);
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) { const char* e = getenv("SMM_B200_SGS_CTAS_PER_SM"); ctas_per_sm = e ? atoi(e) : 4; if (ctas_per_sm < 1) ctas_per_sm = 1; }
+    if (p->values_version != m->values_version) {              // matrix values changed since the packed copies were gathered
+        smm_precond* pm = const_cast<smm_precond*>(p);
+        for (int w = 0; w < 2; ++w) {
+            const long long nt = w == 0 ? p->threads_fwd : p->threads_bwd;
+            const long long n = std::max(p->esize[w], nt);
+            sgs_gather_values_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m->values, p->eidx[w], p->eval[w], p->esize[w],
+                                                                                 w == 0 ? p->order_fwd : p->order_bwd, p->diag_pos, p->dval[w], nt);
+        }
+        SMM_COUNT_LAUNCH(2);
+        pm->values_version = m->values_version;
+    }
     const long long cap = (long long)m->sm_count * ctas_per_sm;
     const long long bf = (p->threads_fwd + SGS_THREADS - 1) / SGS_THREADS, bb = (p->threads_bwd + SGS_THREADS - 1) / SGS_THREADS;
-    sgs_sweep_kernel<true><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(
-        m->start, m->positions, m->values, p->order_fwd, p->diag_pos, p->threads_fwd, rhs_dev, p->y, x_dev, p->tickets, state);
-    sgs_sweep_kernel<false><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(
-        m->start, m->positions, m->values, p->order_bwd, p->diag_pos, p->threads_bwd, rhs_dev, p->y, x_dev, p->tickets, state);
+    SweepArgs F{p->order_fwd, p->slice_ptr[0], p->ecol[0], p->eval[0], p->dval[0], p->threads_fwd};
+    SweepArgs Bk{p->order_bwd, p->slice_ptr[1], p->ecol[1], p->eval[1], p->dval[1], p->threads_bwd};
+    sgs_sweep_kernel<true><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->y, x_dev, p->tickets, state);
+    sgs_sweep_kernel<false><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->y, x_dev, p->tickets, state);
     sgs_status_kernel<<<1, 1, 0, s>>>(p->tickets, state, rc_dev);
     SMM_COUNT_LAUNCH(4);
     SMM_CUDA(cudaGetLastError());
@@ -236,6 +322,24 @@ int smm_precond_sgs_create(const smm_csr_t* m, smm_precond_t** out) {
         SMM_CUDA(cudaMemcpy(p->order_fwd, of.data(), sizeof(int32_t) * of.size(), cudaMemcpyHostToDevice));
         SMM_CUDA(cudaMemcpy(p->order_bwd, ob.data(), sizeof(int32_t) * ob.size(), cudaMemcpyHostToDevice));
         SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
+        for (int w = 0; w < 2; ++w) {
+            std::vector<long long> sp;
+            std::vector<int32_t> ec, ei;
+            build_sell(w == 0, w == 0 ? of : ob, start, pos, diag, &sp, &ec, &ei);
+            const size_t n = ec.size() ? ec.size() : 1;
+            const size_t nt = (w == 0 ? of : ob).size();
+            p->esize[w] = (long long)ec.size();
+            SMM_CUDA(cudaMalloc(&p->slice_ptr[w], sizeof(long long) * sp.size()));
+            SMM_CUDA(cudaMalloc(&p->ecol[w], sizeof(int32_t) * n));
+            SMM_CUDA(cudaMalloc(&p->eidx[w], sizeof(int32_t) * n));
+            SMM_CUDA(cudaMalloc(&p->eval[w], sizeof(float) * n));
+            SMM_CUDA(cudaMalloc(&p->dval[w], sizeof(float) * (nt ? nt : 1)));
+            SMM_CUDA(cudaMemcpy(p->slice_ptr[w], sp.data(), sizeof(long long) * sp.size(), cudaMemcpyHostToDevice));
+            if (!ec.empty()) {
+                SMM_CUDA(cudaMemcpy(p->ecol[w], ec.data(), sizeof(int32_t) * ec.size(), cudaMemcpyHostToDevice));
+                SMM_CUDA(cudaMemcpy(p->eidx[w], ei.data(), sizeof(int32_t) * ei.size(), cudaMemcpyHostToDevice));
+            }
+        }
     }
     *out = p;
     return SMM_OK;
@@ -284,6 +388,7 @@ int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backwar
 int smm_precond_destroy(smm_precond_t* p) {
     if (!p) return SMM_OK;
     cudaFree(p->order_fwd); cudaFree(p->order_bwd); cudaFree(p->diag_pos); cudaFree(p->y); cudaFree(p->tickets);
+    for (int w = 0; w < 2; ++w) { cudaFree(p->slice_ptr[w]); cudaFree(p->ecol[w]); cudaFree(p->eidx[w]); cudaFree(p->eval[w]); cudaFree(p->dval[w]); }
     cudaFree(p->io[0]); cudaFree(p->io[1]);
     delete p;
     return SMM_OK;

@@ -52,6 +52,7 @@ struct smm_csr {
     int32_t* positions = nullptr;   // [nnz]
     float* values = nullptr;        // [nnz]
     bool owns_arrays = true;
+    unsigned long long values_version = 1;   // bumped by smm_csr_update_values (packed copies refresh lazily)
     // SpMV analysis: CTA q handles rows [block_row[q], block_row[q+1])
     int num_blocks = 0;
     int32_t* block_row = nullptr;   // [num_blocks+1]
