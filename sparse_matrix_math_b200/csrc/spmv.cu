@@ -268,32 +268,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// One row (or a V-lane slice of it) out of a values/positions window; four independent gathers in flight,
-// added in the order of the entries (V = 1: the reference's left-to-right sum, H:1484-1489).
+// One row (or a V-lane slice of it) out of a values/positions window.  Up to eight entries are fetched and their
+// mult[] gathers issued together (one latency round for a stencil row), then added in the order of the entries
+// (V = 1: the reference's left-to-right sum with two roundings per term, H:1484-1489).
 template <int V, class VP, class CP>
 __device__ __forceinline__ float row_dot(const VP vs, const CP cs, const float* __restrict__ mult, int j, const int e) {
     float dot = 0.0f;
-    for (; j + 3 * V < e; j += 4 * V) {
-        const int c0 = cs[j], c1 = cs[j + V], c2 = cs[j + 2 * V], c3 = cs[j + 3 * V];
-        const float v0 = vs[j], v1 = vs[j + V], v2 = vs[j + 2 * V], v3 = vs[j + 3 * V];
-        const float x0 = __ldg(mult + c0), x1 = __ldg(mult + c1), x2 = __ldg(mult + c2), x3 = __ldg(mult + c3);
-        dot = __fadd_rn(__fmul_rn(v0, x0), dot);
-        dot = __fadd_rn(__fmul_rn(v1, x1), dot);
-        dot = __fadd_rn(__fmul_rn(v2, x2), dot);
-        dot = __fadd_rn(__fmul_rn(v3, x3), dot);
-    }
-    if (j + V < e) {                                              // two or three entries left
-        const int c0 = cs[j], c1 = cs[j + V];
-        const float v0 = vs[j], v1 = vs[j + V];
-        const bool three = j + 2 * V < e;
-        const int c2 = three ? cs[j + 2 * V] : c0;
-        const float v2 = three ? vs[j + 2 * V] : 0.0f;
-        const float x0 = __ldg(mult + c0), x1 = __ldg(mult + c1), x2 = __ldg(mult + c2);
-        dot = __fadd_rn(__fmul_rn(v0, x0), dot);
-        dot = __fadd_rn(__fmul_rn(v1, x1), dot);
-        if (three) dot = __fadd_rn(__fmul_rn(v2, x2), dot);
-    } else if (j < e) {
-        dot = __fadd_rn(__fmul_rn(vs[j], __ldg(mult + cs[j])), dot);
+    while (j < e) {
+        int c[8];
+        float v[8], x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool in = j + k * V < e;
+            c[k] = in ? cs[j + k * V] : -1;
+            v[k] = in ? vs[j + k * V] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = c[k] >= 0 ? __ldg(mult + c[k]) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (c[k] >= 0) dot = __fadd_rn(__fmul_rn(v[k], x[k]), dot);
+        }
+        j += 8 * V;
     }
     return dot;
 }
@@ -338,14 +334,15 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
                 const int rb = first * R, re = min(rb + R, P.rows);
                 k0 = P.start[rb]; k1 = P.start[re];
             }
+            int s = 0;                                             // ring slot and how often it has been used before
+            uint32_t use = 0;
             for (int it = 0; it < my_chunks; ++it) {
-                const int s = it % stages;
                 int n0 = 0, n1 = 0;                                // next group's window, fetched ahead of the wait
                 if (it + 1 < my_chunks) {
                     const int rb = (first + (it + 1) * G) * R, re = min(rb + R, P.rows);
                     n0 = P.start[rb]; n1 = P.start[re];
                 }
-                if (it >= stages) mbar_wait(&empty[s], (uint32_t)(((it / stages) - 1) & 1));
+                if (use > 0) mbar_wait(&empty[s], (use - 1) & 1u);
                 const int a0 = k0 & ~3;
                 const int span = k1 - a0;
                 const bool staged = span > 0 && span <= cap;
@@ -360,6 +357,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
                     mbar_arrive(&full[s]);                         // nothing to copy: consumers read global memory
                 }
                 k0 = n0; k1 = n1;
+                if (++s == stages) { s = 0; ++use; }
             }
         }
     } else {
@@ -371,16 +369,17 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
             const int r = first * R + rloc;
             if (r < P.rows) { my_s = P.start[r]; my_e = P.start[r + 1]; }
         }
-        for (int it = 0; it < my_chunks; ++it) {
-            const int q = first + it * G;
-            const int s = it % stages;
+        int s = 0;
+        uint32_t phase = 0;
+        int q = first;
+        for (int it = 0; it < my_chunks; ++it, q += G) {
             int nx_s = 0, nx_e = 0;                               // next group's row bounds, fetched ahead
             if (it + 1 < my_chunks) {
                 const int rn = (q + G) * R + rloc;
                 if (rn < P.rows) { nx_s = P.start[rn]; nx_e = P.start[rn + 1]; }
             }
             const int row = q * R + rloc;
-            mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
+            mbar_wait(&full[s], phase);
             const int a0 = win[2 * s];
             float dot;
             // rows past the end have my_s == my_e == 0: their lanes fall through and only join the shuffles
@@ -394,6 +393,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);                // this warp is done with the slot
             my_s = nx_s; my_e = nx_e;
+            if (++s == stages) { s = 0; phase ^= 1u; }
         }
     }
 
