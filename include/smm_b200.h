@@ -180,6 +180,14 @@ int smm_dist_connect(smm_dist_t* d, const int64_t* all_ranges /* [nranks][4] */,
 int smm_dist_spmv_dev(smm_dist_t* d, const float* x_local_dev, float* y_local_dev, void* stream);
 int smm_dist_solve_cg(smm_dist_t* d, const float* b_dev, const float* x0_dev, float* x_dev, int maxIterations, float eps,
                       const smm_solve_options* opts, smm_solve_info* info, void* stream);
+/* the other unpreconditioned solvers on the partitioned system (BiCGSymmetric H:2021, ConjugateGradientSquared H:2109,
+ * BiCGStab H:2294): every SpMV operand is staged into the extended vector and its halo exchanged first */
+int smm_dist_solve_bicgsym(smm_dist_t* d, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                           const smm_solve_options* opts, smm_solve_info* info, void* stream);
+int smm_dist_solve_cgs(smm_dist_t* d, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                       const smm_solve_options* opts, smm_solve_info* info, void* stream);
+int smm_dist_solve_bicgstab(smm_dist_t* d, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                            const smm_solve_options* opts, smm_solve_info* info, void* stream);
 int smm_dist_error(const smm_dist_t* d, int* error);
 int smm_dist_destroy(smm_dist_t* d);
 /* rows [row_begin,row_end) of a generated stencil matrix, global column indices (kinds POISSON2D / CONVDIFF3D) */

@@ -105,6 +105,9 @@ int smm_dist_exchange_async(smm_dist* d, SolveState* st, cudaStream_t s) {
 int smm_solve_dist_cg_impl(smm_dist* d, const float* b_dev, const float* x0_dev, float* x_dev, int maxIterations, float eps,
                            const smm_solve_options* opts, smm_solve_info* info, cudaStream_t s);   // solvers.cu
 
+int smm_solve_dist_impl(smm_dist* d, int solver, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                        const smm_solve_options* opts, smm_solve_info* info, cudaStream_t s);   // solvers.cu
+
 extern "C" {
 
 int smm_dist_create(int rank, int nranks, int64_t global_rows, int64_t row_begin, int64_t row_end, smm_csr_t* local, smm_dist_t** out) {
@@ -250,6 +253,25 @@ int smm_dist_solve_cg(smm_dist_t* d, const float* b_dev, const float* x0_dev, fl
     if (!d || !d->connected) { smm_set_error("smm_dist_solve_cg: not connected"); return SMM_E_STATE; }
     cudaStream_t s = stream ? (cudaStream_t)stream : smm_default_stream();
     return smm_solve_dist_cg_impl(d, b_dev, x0_dev, x_dev, maxIterations, eps, opts, info, s);
+}
+
+static int dist_solve_other(smm_dist_t* d, int solver, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                            const smm_solve_options* opts, smm_solve_info* info, void* stream) {
+    if (!d || !d->connected) { smm_set_error("smm_dist_solve: not connected"); return SMM_E_STATE; }
+    cudaStream_t s = stream ? (cudaStream_t)stream : smm_default_stream();
+    return smm_solve_dist_impl(d, solver, b_dev, x_dev, maxIterations, eps, opts, info, s);
+}
+int smm_dist_solve_bicgsym(smm_dist_t* d, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                           const smm_solve_options* opts, smm_solve_info* info, void* stream) {
+    return dist_solve_other(d, 1, b_dev, x_dev, maxIterations, eps, opts, info, stream);
+}
+int smm_dist_solve_cgs(smm_dist_t* d, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                       const smm_solve_options* opts, smm_solve_info* info, void* stream) {
+    return dist_solve_other(d, 2, b_dev, x_dev, maxIterations, eps, opts, info, stream);
+}
+int smm_dist_solve_bicgstab(smm_dist_t* d, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                            const smm_solve_options* opts, smm_solve_info* info, void* stream) {
+    return dist_solve_other(d, 3, b_dev, x_dev, maxIterations, eps, opts, info, stream);
 }
 
 int smm_dist_error(const smm_dist_t* d, int* error) {

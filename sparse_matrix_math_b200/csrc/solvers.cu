@@ -50,6 +50,14 @@ struct Ctx {
 
 int spmv(Ctx& c, int op, const float* lhs, const float* mult, float* out, int reduce, int finish, const float* aux,
          float* c1 = nullptr, float* c2 = nullptr, float* c3 = nullptr) {
+    if (c.dist && mult != c.dist->ext) {
+        // multi-GPU: the operand's owned entries go into the extended vector, the halo comes from the peers
+        smm_dist* d = c.dist;
+        if (mult != d->ext + d->own_off)
+            SMM_CUDA(cudaMemcpyAsync(d->ext + d->own_off, mult, sizeof(float) * (size_t)c.n, cudaMemcpyDeviceToDevice, c.s));
+        SMM_TRY(smm_dist_exchange_async(d, c.st, c.s));
+        mult = d->ext;
+    }
     SpmvArgs a;
     a.m = c.a; a.op = op; a.lhs = lhs; a.mult = mult; a.out = out; a.exact = c.exact ? 1 : 0;
     a.reduce = reduce; a.finish = finish; a.slot = 0; a.aux = aux; a.state = c.st;
@@ -374,7 +382,7 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
     SMM_TRY(smm_workspace_vectors(ws, 3 + nvec, (size_t)a->rows));
     float** w = ws->vec + 3;
     c.r = w[0]; c.p = w[1]; c.ap = w[2];
-    if (dist) c.p = dist->ext + dist->own_off;                  // p is the owned part of the extended vector
+    if (dist && solver == S_CG) c.p = dist->ext + dist->own_off;   // CG keeps p inside the extended vector (no staging copy)
     if (solver == S_CGS) { c.r0 = w[3]; c.u = w[4]; c.q = w[5]; c.auq = w[6]; }
     if (solver == S_BICGSTAB) { c.r0 = w[3]; c.sv = w[4]; c.as = w[5]; c.scratch = w[6]; }
 
@@ -398,7 +406,7 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
     h->history_cap = hist_cap;
     h->comm = (dist && dist->nranks > 1) ? dist->comm_dev : nullptr;
     // the iteration cap refers to the GLOBAL system (H:2345-2347: -1 means rows)
-    if (dist && solver == S_CG && max_iterations == -1) h->max_iterations = (int)dist->global_rows;
+    if (dist) h->max_iterations = clamp_iterations(solver, max_iterations, (int)dist->global_rows);
     const int max_it = h->max_iterations;
     SMM_CUDA(cudaMemcpyAsync(c.st, h, sizeof *h, cudaMemcpyHostToDevice, s));
 
@@ -501,6 +509,12 @@ int solve_host(int solver, const smm_csr* a, const smm_precond* precond, const f
 int smm_solve_dist_cg_impl(smm_dist* d, const float* b_dev, const float* x0_dev, float* x_dev, int maxIterations, float eps,
                            const smm_solve_options* opts, smm_solve_info* info, cudaStream_t s) {
     return solve_dev(S_CG, d->local, nullptr, b_dev, x0_dev, x_dev, maxIterations, eps, opts, info, s, d);
+}
+// solver: 1 BiCGSymmetric, 2 ConjugateGradientSquared, 3 BiCGStab (unpreconditioned); x is initial guess and result
+int smm_solve_dist_impl(smm_dist* d, int solver, const float* b_dev, float* x_dev, int maxIterations, float eps,
+                        const smm_solve_options* opts, smm_solve_info* info, cudaStream_t s) {
+    const int kind = solver == 1 ? S_BICGSYM : (solver == 2 ? S_CGS : S_BICGSTAB);
+    return solve_dev(kind, d->local, nullptr, b_dev, x_dev, x_dev, maxIterations, eps, opts, info, s, d);
 }
 
 extern "C" {

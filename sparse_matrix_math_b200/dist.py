@@ -84,6 +84,8 @@ def _bind(L):
     L.smm_dist_connect.argtypes = [vp, C.POINTER(i64), vp]
     L.smm_dist_spmv_dev.argtypes = [vp, vp, vp, vp]
     L.smm_dist_solve_cg.argtypes = [vp, vp, vp, vp, i32, C.c_float, C.POINTER(B._Options), C.POINTER(B._Info), vp]
+    for name in ("smm_dist_solve_bicgsym", "smm_dist_solve_cgs", "smm_dist_solve_bicgstab"):
+        getattr(L, name).argtypes = [vp, vp, vp, i32, C.c_float, C.POINTER(B._Options), C.POINTER(B._Info), vp]
     L.smm_dist_error.argtypes = [vp, C.POINTER(i32)]
     L.smm_dist_destroy.argtypes = [vp]
     L.smm_gen_csr_rows.argtypes = [i32, i32, i32, i32, C.c_float, i64, i64, C.POINTER(vp)]
@@ -129,6 +131,15 @@ class DistMatrix:
         info = B._Info()
         B._check(self.L.smm_dist_solve_cg(self.handle, b_ptr, x0_ptr, x_ptr, int(max_iterations), float(eps), C.byref(o), C.byref(info), stream),
                  "smm_dist_solve_cg")
+        return B.SolveInfo(info)
+
+    def solve_dev(self, solver, b_ptr, x_ptr, max_iterations, eps, stream=None, driver_mode=B.DRIVER_AUTO, check_every=0):
+        """solver in {"bicgsym", "cgs", "bicgstab"}; x is initial guess and result (device slices of this rank)."""
+        o = B._Options()
+        o.reduction_mode, o.driver_mode, o.check_every = B.REDUCE_FAST, driver_mode, check_every
+        info = B._Info()
+        fn = getattr(self.L, "smm_dist_solve_" + solver)
+        B._check(fn(self.handle, b_ptr, x_ptr, int(max_iterations), float(eps), C.byref(o), C.byref(info), stream), "smm_dist_solve_" + solver)
         return B.SolveInfo(info)
 
     def error(self):

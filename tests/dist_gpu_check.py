@@ -66,6 +66,19 @@ def main():
                   f"{name}: iterations {info.iterations} vs reference {o['iterations']}")
             check(info.residual <= 1e-10, f"{name}: residual {info.residual}")
             check(np.max(np.abs(x - xs[rb:re])) < 2e-4, f"{name}: x error {np.max(np.abs(x - xs[rb:re]))}")
+        # the other unpreconditioned solvers (operands staged into the extended vector)
+        for solver in ("bicgsym", "cgs", "bicgstab"):
+            oo = ol.solve(solver, g, b_glob, np.zeros(g.rows, np.float32), -1, 1e-5, 1)
+            dxx.zero()
+            info = D.solve_dev(solver, db.ptr, dxx.ptr, -1, 1e-5)
+            x = dxx.download()
+            st = [None] * world
+            dist.all_gather_object(st, (info.iterations, int(info.status), info.residual))
+            check(len(set(st)) == 1, f"{name}/{solver}: ranks disagree {st}")
+            check(int(info.status) == oo["status"] == 0, f"{name}/{solver}: status {info.status}")
+            lo_it, hi_it = 0.8 * oo["iterations"] - 2, 1.25 * oo["iterations"] + 2
+            check(lo_it <= info.iterations <= hi_it, f"{name}/{solver}: iterations {info.iterations} vs reference {oo['iterations']}")
+            check(np.max(np.abs(x - xs[rb:re])) < 5e-4, f"{name}/{solver}: x error {np.max(np.abs(x - xs[rb:re]))}")
         # capped run: MAX_ITERATIONS_REACHED with exactly maxIterations iterations
         dxx.zero()
         info = D.solve_cg_dev(db.ptr, dxx.ptr, dxx.ptr, 7, 0.0)
