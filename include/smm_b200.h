@@ -127,6 +127,13 @@ int smm_precond_sgs_create(const smm_csr_t* m, smm_precond_t** out);
 int smm_precond_apply(const smm_precond_t* p, const float* rhs, float* x, int* rc);
 int smm_precond_apply_dev(const smm_precond_t* p, const float* rhs_dev, float* x_dev, int* rc, void* stream);
 int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backward_levels);
+/* CSRMatrix::IC0Preconditioner (H:1214-1235): construction + init() (factorize, H:1839-1928; *rc = its return code) and
+ * apply (H:1802-1837, through smm_precond_apply[_dev]).  The factorisation is set-up code and runs on the host, row by
+ * row instead of the reference's O(rows^2) scan, with bit-identical values; the two triangular solves of every apply
+ * run on the GPU with the same level-scheduled sweeps as SGS. */
+int smm_precond_ic0_create(const smm_csr_t* m, int* rc, smm_precond_t** out);
+int smm_precond_ic0_factor(const smm_precond_t* p, float* factor_host);
+int smm_precond_kind(const smm_precond_t* p);
 int smm_precond_destroy(smm_precond_t* p);
 
 /* ---- solvers ----
@@ -136,6 +143,11 @@ int smm_precond_destroy(smm_precond_t* p);
  * function exactly; opts may be NULL (defaults); info may be NULL. */
 int smm_solve_cg(const smm_csr_t* a, const float* b, const float* x0, float* x, int maxIterations, float eps,
                  const smm_solve_options* opts, smm_solve_info* info);
+/* ConjugateGradient(a, b, x0, x, maxIterations, eps, IC0Preconditioner) H:2414-2505 */
+int smm_solve_cg_ic0(const smm_csr_t* a, const smm_precond_t* ic0, const float* b, const float* x0, float* x, int maxIterations,
+                     float eps, const smm_solve_options* opts, smm_solve_info* info);
+int smm_solve_cg_ic0_dev(const smm_csr_t* a, const smm_precond_t* ic0, const float* b_dev, const float* x0_dev, float* x_dev,
+                         int maxIterations, float eps, const smm_solve_options* opts, smm_solve_info* info, void* stream);
 int smm_solve_bicgsym(const smm_csr_t* a, const float* b, float* x, int maxIterations, float eps,
                       const smm_solve_options* opts, smm_solve_info* info);
 int smm_solve_cgs(const smm_csr_t* a, const float* b, float* x, int maxIterations, float eps,

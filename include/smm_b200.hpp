@@ -576,6 +576,35 @@ public:
         const CSRMatrix& m;
     };
 
+    // Zero-fill incomplete Cholesky (ref H:1214-1235): IC0Preconditioner M(m); M.init(); M.apply(rhs, x) and the
+    // ConjugateGradient overload taking it.  init() factorises on the host (set-up), the solves run on the GPU.
+    class IC0Preconditioner {
+    public:
+        IC0Preconditioner(const CSRMatrix& matrix) noexcept : m(matrix) {}
+        IC0Preconditioner(const IC0Preconditioner&) = delete;
+        IC0Preconditioner& operator=(const IC0Preconditioner&) = delete;
+        IC0Preconditioner(IC0Preconditioner&& o) noexcept : m(o.m), handle(o.handle) { o.handle = nullptr; }
+        ~IC0Preconditioner() { if (handle) smm_precond_destroy(handle); }
+        int init() noexcept {
+            b200::requireFloat<T>();
+            if (handle) { smm_precond_destroy(handle); handle = nullptr; }
+            int rc = 0;
+            b200::check(smm_precond_ic0_create(m.device(), &rc, &handle), "smm_precond_ic0_create");
+            return rc;
+        }
+        int apply(const T* rhs, T* x) const noexcept {
+            b200::requireFloat<T>();
+            int rc = 0;
+            b200::check(smm_precond_apply(handle, rhs, x, &rc), "smm_precond_apply");
+            return rc;
+        }
+        const smm_precond_t* device() const { return handle; }
+        const CSRMatrix& matrix() const { return m; }
+    private:
+        const CSRMatrix& m;
+        smm_precond_t* handle = nullptr;
+    };
+
     template <SolverPreconditioner precond>
     decltype(auto) getPreconditioner() const noexcept {
         if constexpr (precond == SolverPreconditioner::NONE) return IDPreconditioner();
@@ -716,6 +745,17 @@ inline SolverStatus ConjugateGradient(const CSRMatrix<T>& a, const T* const b, c
     b200::requireFloat<T>();
     smm_solve_info info;
     b200::check(smm_solve_cg(a.device(), b, x0, x, maxIterations, eps, &b200::options(), &info), "smm_solve_cg");
+    b200::record(info);
+    return static_cast<SolverStatus>(info.status);
+}
+
+// preconditioned CG with the IC(0) object (ref H:2414-2505)
+template <typename T>
+inline SolverStatus ConjugateGradient(const CSRMatrix<T>& a, const T* const b, const T* const x0, T* const x, int maxIterations, T eps,
+                                      const typename CSRMatrix<T>::IC0Preconditioner& M) {
+    b200::requireFloat<T>();
+    smm_solve_info info;
+    b200::check(smm_solve_cg_ic0(a.device(), M.device(), b, x0, x, maxIterations, eps, &b200::options(), &info), "smm_solve_cg_ic0");
     b200::record(info);
     return static_cast<SolverStatus>(info.status);
 }

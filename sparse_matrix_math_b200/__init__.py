@@ -16,6 +16,7 @@ from .binding import (  # noqa: F401
     ConjugateGradientSquared,
     CSRMatrix,
     DeviceVector,
+    IC0Preconditioner,
     MatrixLoadStatus,
     SGSPreconditioner,
     SmmError,

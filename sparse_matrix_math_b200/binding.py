@@ -117,8 +117,13 @@ def lib():
         L.smm_precond_apply_dev.argtypes = [_vp, _vp, _vp, C.POINTER(_i32), _vp]
         L.smm_precond_levels.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_i32)]
         L.smm_precond_destroy.argtypes = [_vp]
+        L.smm_precond_ic0_create.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_vp)]
+        L.smm_precond_ic0_factor.argtypes = [_vp, _vp]
+        L.smm_precond_kind.argtypes = [_vp]
         op, ip = C.POINTER(_Options), C.POINTER(_Info)
         L.smm_solve_cg.argtypes = [_vp, _vp, _vp, _vp, _i32, _f32, op, ip]
+        L.smm_solve_cg_ic0.argtypes = [_vp, _vp, _vp, _vp, _vp, _i32, _f32, op, ip]
+        L.smm_solve_cg_ic0_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, _i32, _f32, op, ip, _vp]
         L.smm_solve_bicgsym.argtypes = [_vp, _vp, _vp, _i32, _f32, op, ip]
         L.smm_solve_cgs.argtypes = [_vp, _vp, _vp, _i32, _f32, op, ip]
         L.smm_solve_bicgstab.argtypes = [_vp, _vp, _vp, _vp, _i32, _f32, op, ip]
@@ -304,6 +309,26 @@ class SGSPreconditioner:
             pass
 
 
+class IC0Preconditioner(SGSPreconditioner):
+    """CSRMatrix<float>::IC0Preconditioner (H:1214-1235): IC0Preconditioner(m); init(); apply(rhs, x)."""
+
+    def __init__(self, matrix):
+        self.matrix = matrix
+        self.handle = None
+        self.init_code = None
+
+    def init(self):
+        h, rc = _vp(), _i32()
+        _check(lib().smm_precond_ic0_create(self.matrix.handle, C.byref(rc), C.byref(h)), "smm_precond_ic0_create")
+        self.handle, self.init_code = h.value, rc.value
+        return rc.value
+
+    def factor(self):
+        out = np.zeros(max(self.matrix.nnz, 1), np.float32)
+        _check(lib().smm_precond_ic0_factor(self.handle, _ptr(out)), "smm_precond_ic0_factor")
+        return out[: self.matrix.nnz]
+
+
 class CSRMatrix:
     """SMM::CSRMatrix<float> (H:1011-1302) with its arrays resident in HBM."""
 
@@ -435,11 +460,15 @@ def _solve(fn, name, args, reduction_mode, driver_mode, check_every, history_cap
     return SolveInfo(info, hist)
 
 
-def ConjugateGradient(a, b, x0, x, maxIterations, eps, reduction_mode=REDUCE_FAST, driver_mode=DRIVER_AUTO,
+def ConjugateGradient(a, b, x0, x, maxIterations, eps, M=None, reduction_mode=REDUCE_FAST, driver_mode=DRIVER_AUTO,
                       check_every=0, history_cap=0):
-    """SMM::ConjugateGradient (H:2316-2398).  x may be x0.  Returns SolveInfo (status as the reference returns it)."""
+    """SMM::ConjugateGradient (H:2316-2398); with M = IC0Preconditioner the PCG overload (H:2414-2505).  x may be x0.
+    Returns SolveInfo (status as the reference returns it)."""
     b = _f32arr(b)
     assert x.dtype == np.float32 and x0.dtype == np.float32
+    if M is not None:
+        return _solve(lib().smm_solve_cg_ic0, "smm_solve_cg_ic0", (a.handle, M.handle, _ptr(b), _ptr(x0), _ptr(x), int(maxIterations), float(eps)),
+                      reduction_mode, driver_mode, check_every, history_cap)
     return _solve(lib().smm_solve_cg, "smm_solve_cg", (a.handle, _ptr(b), _ptr(x0), _ptr(x), int(maxIterations), float(eps)),
                   reduction_mode, driver_mode, check_every, history_cap)
 

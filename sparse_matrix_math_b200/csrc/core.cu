@@ -176,6 +176,7 @@ int smm_csr_create(int rows, int cols, const int32_t* start, const int32_t* posi
     m->nnz = start ? start[rows] : 0;
     if (m->nnz < 0 || (m->nnz > 0 && (!positions || !values))) { delete m; smm_set_error("smm_csr_create: bad arrays"); return SMM_E_INVALID; }
     const size_t npad = ((size_t)m->nnz + 3) & ~(size_t)3;
+    m->nnz_alloc = (int64_t)(npad ? npad : 4);
     int rc = SMM_OK;
     do {
         if (cudaMalloc(&m->start, sizeof(int32_t) * ((size_t)rows + 1)) != cudaSuccess ||
@@ -205,8 +206,10 @@ int smm_csr_create_dev(int rows, int cols, int32_t* start_dev, int32_t* position
     int32_t nnz32 = 0;
     SMM_CUDA(cudaMemcpy(&nnz32, start_dev + rows, sizeof(int32_t), cudaMemcpyDeviceToHost));
     m->nnz = nnz32;
+    m->nnz_alloc = m->nnz;                                     // adopted arrays: nothing is known beyond nnz entries
     if (copy) {
         const size_t npad = ((size_t)m->nnz + 3) & ~(size_t)3;
+        m->nnz_alloc = (int64_t)(npad ? npad : 4);
         SMM_CUDA(cudaMalloc(&m->start, sizeof(int32_t) * ((size_t)rows + 1)));
         SMM_CUDA(cudaMalloc(&m->positions, sizeof(int32_t) * (npad ? npad : 4)));
         SMM_CUDA(cudaMalloc(&m->values, sizeof(float) * (npad ? npad : 4)));

@@ -144,6 +144,9 @@ struct DotScratch {
     float* out = nullptr;        // 2 floats
 };
 DotScratch g_scratch[64];
+}  // namespace
+int smm_tree_depth(long long n);
+namespace {
 
 int scratch_for(long long nn, DotScratch** out) {
     int dev = 0;
@@ -165,6 +168,12 @@ int scratch_for(long long nn, DotScratch** out) {
 }
 
 }  // namespace
+
+// allocate the node scratch for vectors of length n now (cudaMalloc is not allowed while a stream is capturing)
+int smm_dot_ref_prepare(long long n) {
+    DotScratch* sc = nullptr;
+    return scratch_for(1ll << smm_tree_depth(n), &sc);
+}
 
 int smm_tree_depth(long long n) {
     int d = 0;

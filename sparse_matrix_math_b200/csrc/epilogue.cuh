@@ -30,6 +30,9 @@ enum FinishKind {
     FIN_BICGSTAB_UPDATE,        // H:2268-2277  (t0 = sum r^2, t1 = r.r0)
     FIN_STASH0,                 // scratch[0] = t0 (first half of a two-kernel reduction)
     FIN_BICGSTAB_UPDATE_STASHED,// as FIN_BICGSTAB_UPDATE with sum r^2 = scratch[0], r.r0 = t0
+    FIN_PCG_INIT,               // H:2442-2454  (t0 = r.z, t1 = r.r)
+    FIN_PCG_ALPHA,              // H:2462-2466
+    FIN_PCG_UPDATE,             // H:2483-2501  (t0 = r.z, t1 = r.r)
 };
 
 #ifdef __CUDACC__
@@ -140,6 +143,28 @@ __device__ __forceinline__ void smm_finish(int kind, SolveState* st, float t0, f
             if (!(res > st->eps && st->iterations < st->max_iterations)) {                     // H:2277
                 st->done = 1; st->status = smm_do_while_status(st);                            // H:2279-2282
             }
+            break;
+        }
+        case FIN_PCG_INIT:
+            st->rr = t0;                                       // rz
+            st->res2 = t1;                                     // residualNormSquared
+            st->residual = t1;
+            if (st->eps2 > t1) { st->done = 1; st->status = SMM_SOLVER_SUCCESS; }             // H:2449-2451
+            else if (st->iterations >= st->max_iterations) { st->done = 1; st->status = SMM_SOLVER_MAX_ITERATIONS_REACHED; }
+            break;
+        case FIN_PCG_ALPHA:
+            st->denom = t0;                                    // pAp
+            st->alpha = __fdiv_rn(st->rr, t0);                 // alpha = rz / pAp, H:2466
+            break;
+        case FIN_PCG_UPDATE: {
+            smm_push_history(st, t1);
+            st->iterations += 1;
+            st->res2 = t1;                                     // r * r, H:2484
+            st->residual = t1;
+            if (st->eps2 > t1) { st->done = 1; st->status = SMM_SOLVER_SUCCESS; break; }      // H:2485-2487
+            st->beta = __fdiv_rn(t0, st->rr);                  // newRZ / rz, H:2488
+            st->rr = t0;                                       // H:2501
+            if (st->iterations >= st->max_iterations) { st->done = 1; st->status = SMM_SOLVER_MAX_ITERATIONS_REACHED; }  // H:2504
             break;
         }
         default: break;

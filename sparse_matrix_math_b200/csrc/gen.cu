@@ -213,6 +213,7 @@ static int gen_stencil_rows(int kind, int nx, int ny, int nz, float c, long long
     SMM_CUDA(cudaGetLastError());
     SMM_CUDA(cudaStreamSynchronize(s));
     int rc = smm_csr_create_dev((int)rows, (int)total, start, positions, values, 0, out);
+    if (rc == SMM_OK) (*out)->nnz_alloc = (int64_t)(nmax ? nmax : 4);       // our own padded allocation
     return rc;
 }
 
@@ -262,7 +263,11 @@ int smm_gen_csr(int kind, int nx, int ny, int nz, float c, uint64_t seed, smm_cs
         return SMM_E_INVALID;
     }
     SMM_CUDA(cudaStreamSynchronize(s));
-    return smm_csr_create_dev((int)rows, (int)rows, start, positions, values, 0, out);
+    {
+        int rc = smm_csr_create_dev((int)rows, (int)rows, start, positions, values, 0, out);
+        if (rc == SMM_OK) (*out)->nnz_alloc = (int64_t)((((size_t)nnz + 3) & ~(size_t)3));
+        return rc;
+    }
 }
 
 int smm_gen_xstar_dev(int64_t n, int64_t offset, uint64_t seed, float* x_dev, void* stream) {

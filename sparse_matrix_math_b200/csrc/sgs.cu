@@ -24,11 +24,14 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "smm_internal.cuh"
 
 struct smm_precond {
+    int kind = 0;                    // 0: Symmetric Gauss-Seidel on A's values; 1: IC(0) on its own factor values
+    float* factor = nullptr;         // IC(0): [nnz] factor in A's pattern (L below and on the diagonal, L^T above), ref H:1233-1234
     const smm_csr* m = nullptr;
     int rows = 0;
     bool valid = true;               // structure admits the sweeps (else apply returns the reference's code 1)
@@ -103,7 +106,9 @@ __global__ void sgs_gather_values_kernel(const float* __restrict__ values, const
     if (i < nthreads) { const int r = order[i]; dval[i] = r >= 0 ? values[diag_pos[r]] : 1.0f; }
 }
 
-template <bool FORWARD>
+// IC0 = false: SGS sweeps (H:1658-1713).  IC0 = true: L y = rhs then L^T x = y (IC0Preconditioner::apply, H:1802-1837):
+// `sum -= ic0[j] * x[col]`, one division by the diagonal of the factor per row and sweep.
+template <bool FORWARD, bool IC0>
 __global__ void __launch_bounds__(SGS_THREADS) sgs_sweep_kernel(const SweepArgs A, const float* __restrict__ rhs, float* y, float* x,
                                                                unsigned int* tickets, const SolveState* st) {
     if (st != nullptr && st->done) return;
@@ -130,8 +135,10 @@ __global__ void __launch_bounds__(SGS_THREADS) sgs_sweep_kernel(const SweepArgs 
         float acc;
         const float* src = FORWARD ? y : x;
         if (FORWARD) {
-            if (row >= 0 && fabsf(d) < 1e-5) atomicOr(tickets + 3, 1u);          // H:1691-1693 (reported, not fatal here)
-            acc = row >= 0 ? rhs[row] : 0.0f;                                     // H:1683
+            if (!IC0 && row >= 0 && fabsf(d) < 1e-5) atomicOr(tickets + 3, 1u);  // H:1691-1693 (reported, not fatal here)
+            acc = row >= 0 ? rhs[row] : 0.0f;                                     // H:1683 / H:1807
+        } else if (IC0) {
+            acc = row >= 0 ? wait_value(y + row, abort_flag) : 0.0f;              // T sum = x[row], H:1823
         } else {
             acc = 0.0f;                                                           // H:1702
         }
@@ -149,13 +156,14 @@ __global__ void __launch_bounds__(SGS_THREADS) sgs_sweep_kernel(const SweepArgs 
                 if (c[j] >= 0) {
                     const float xv = wait_value(src + c[j], abort_flag);
                     // forward: _smm_fma(-value, x[col], lhs) cols ascending (H:1685); backward: _smm_fma(value, x[col], lhs) cols descending (H:1704)
-                    acc = __fadd_rn(__fmul_rn(FORWARD ? -v[j] : v[j], xv), acc);
+                    // IC0: sum -= ic0[j] * x[col] (H:1813, H:1829) -- the same bits as the forward SGS form
+                    acc = (FORWARD || IC0) ? __fsub_rn(acc, __fmul_rn(v[j], xv)) : __fadd_rn(__fmul_rn(v[j], xv), acc);
                 }
             }
         }
         if (row < 0) continue;
-        if (FORWARD) {
-            publish(y + row, __fdiv_rn(acc, d));                                  // H:1694
+        if (FORWARD || IC0) {
+            publish((FORWARD ? y : x) + row, __fdiv_rn(acc, d));                  // H:1694 / H:1818, H:1834
         } else {
             const float yr = wait_value(y + row, abort_flag);                     // own forward result (already published)
             publish(x + row, __fsub_rn(yr, __fdiv_rn(acc, d)));                   // H:1710
@@ -247,6 +255,49 @@ void analyse(int rows, const std::vector<int32_t>& start, const std::vector<int3
     build_order(lev, *lb, true, order_b);
 }
 
+// Zero-fill incomplete Cholesky in A's pattern, IC0Preconditioner::factorize (H:1839-1928), on the host (set-up code).
+// The reference walks column by column and scans every later row for each column (O(rows^2)); this walks row by row.
+// Every entry is computed from the same already-final entries with the same operations in the same order
+// (sum += l_ik * l_jk over row j's columns k < i in ascending order, l_ji = (a_ji - sum) * (1 / l_ii),
+// l_jj = sqrt(a_jj - sum of l_jk^2)), so the factor is bit-identical.  Returns 0, or 1 on a missing diagonal (H:1873-1876).
+int ic0_factorize_host(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag,
+                       const std::vector<float>& a, std::vector<float>* out) {
+    std::vector<float>& l = *out;
+    l.assign(a.size(), 0.0f);
+    std::vector<float> dinv((size_t)rows, 0.0f);
+    for (int j = 0; j < rows; ++j) {
+        const int rs = start[j], dj = diag[j];
+        for (int e = rs; e < dj; ++e) {
+            const int i = pos[e];                              // entry (j, i), i < j
+            float sum = 0.0f;
+            int ki = start[i];
+            const int di = diag[i];
+            for (int ek = rs; ek < e; ++ek) {                  // row j's columns k < i, ascending (H:1900-1907)
+                const int k = pos[ek];
+                while (ki < di && pos[ki] < k) ++ki;
+                if (ki < di && pos[ki] == k) sum += l[ki] * l[ek];
+            }
+            l[e] = (a[e] - sum) * dinv[i];                     // H:1914
+        }
+        float dsum = 0.0f;
+        for (int e = rs; e < dj; ++e) dsum += l[e] * l[e];    // H:1868-1872
+        const float d = std::sqrt(a[dj] - dsum);               // H:1879
+        l[dj] = d;
+        dinv[j] = 1.0f / d;                                    // H:1883
+    }
+    // the transpose goes into the upper triangle of the same pattern (H:1916-1917)
+    for (int j = 0; j < rows; ++j) {
+        for (int e = start[j]; e < diag[j]; ++e) {
+            const int i = pos[e];
+            const int32_t* b = pos.data() + diag[i] + 1;
+            const int32_t* en = pos.data() + start[i + 1];
+            const int32_t* it = std::lower_bound(b, en, j);
+            if (it != en && *it == j) l[(size_t)(it - pos.data())] = l[e];
+        }
+    }
+    return 0;
+}
+
 }  // namespace
 
 int smm_sgs_kernels_per_apply(const smm_precond* p) { return p && p->valid ? 4 : 1; }
@@ -272,23 +323,30 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
     sgs_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->y, x_dev, n, p->tickets, state);
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) { const char* e = getenv("SMM_B200_SGS_CTAS_PER_SM"); ctas_per_sm = e ? atoi(e) : 4; if (ctas_per_sm < 1) ctas_per_sm = 1; }
-    if (p->values_version != m->values_version) {              // matrix values changed since the packed copies were gathered
+    // SGS reads A's current values; an IC(0) factor is frozen at init() like the reference's ic0Val
+    const unsigned long long want_version = p->kind == 1 ? 0ull : m->values_version;
+    if (p->values_version != want_version) {                   // matrix values changed since the packed copies were gathered
         smm_precond* pm = const_cast<smm_precond*>(p);
         for (int w = 0; w < 2; ++w) {
             const long long nt = w == 0 ? p->threads_fwd : p->threads_bwd;
             const long long n = std::max(p->esize[w], nt);
-            sgs_gather_values_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m->values, p->eidx[w], p->eval[w], p->esize[w],
+            sgs_gather_values_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->kind == 1 ? p->factor : m->values, p->eidx[w], p->eval[w], p->esize[w],
                                                                                  w == 0 ? p->order_fwd : p->order_bwd, p->diag_pos, p->dval[w], nt);
         }
         SMM_COUNT_LAUNCH(2);
-        pm->values_version = m->values_version;
+        pm->values_version = want_version;
     }
     const long long cap = (long long)m->sm_count * ctas_per_sm;
     const long long bf = (p->threads_fwd + SGS_THREADS - 1) / SGS_THREADS, bb = (p->threads_bwd + SGS_THREADS - 1) / SGS_THREADS;
     SweepArgs F{p->order_fwd, p->slice_ptr[0], p->ecol[0], p->eval[0], p->dval[0], p->threads_fwd};
     SweepArgs Bk{p->order_bwd, p->slice_ptr[1], p->ecol[1], p->eval[1], p->dval[1], p->threads_bwd};
-    sgs_sweep_kernel<true><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->y, x_dev, p->tickets, state);
-    sgs_sweep_kernel<false><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->y, x_dev, p->tickets, state);
+    if (p->kind == 1) {
+        sgs_sweep_kernel<true, true><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->y, x_dev, p->tickets, state);
+        sgs_sweep_kernel<false, true><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->y, x_dev, p->tickets, state);
+    } else {
+        sgs_sweep_kernel<true, false><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->y, x_dev, p->tickets, state);
+        sgs_sweep_kernel<false, false><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->y, x_dev, p->tickets, state);
+    }
     sgs_status_kernel<<<1, 1, 0, s>>>(p->tickets, state, rc_dev);
     SMM_COUNT_LAUNCH(4);
     SMM_CUDA(cudaGetLastError());
@@ -297,12 +355,13 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
 
 extern "C" {
 
-int smm_precond_sgs_create(const smm_csr_t* m, smm_precond_t** out) {
+static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond_t** out) {
     if (!m || !out) return SMM_E_INVALID;
-    if (m->rows != m->cols) { smm_set_error("SGS: matrix must be square"); return SMM_E_INVALID; }
+    if (m->rows != m->cols) { smm_set_error("preconditioner: matrix must be square"); return SMM_E_INVALID; }
     SMM_CUDA(cudaSetDevice(m->device));
     smm_precond* p = new smm_precond();
     p->m = m;
+    p->kind = kind;
     p->rows = m->rows;
     std::vector<int32_t> start((size_t)m->rows + 1), pos((size_t)m->nnz);
     SMM_CUDA(cudaDeviceSynchronize());
@@ -310,6 +369,14 @@ int smm_precond_sgs_create(const smm_csr_t* m, smm_precond_t** out) {
     if (m->nnz) SMM_CUDA(cudaMemcpy(pos.data(), m->positions, sizeof(int32_t) * pos.size(), cudaMemcpyDeviceToHost));
     std::vector<int32_t> diag, of, ob;
     analyse(m->rows, start, pos, m->first_active_start, &p->valid, &diag, &of, &ob, &p->levels_fwd, &p->levels_bwd);
+    if (rc_out) *rc_out = p->valid ? 0 : 1;
+    if (kind == 1 && p->valid && m->nnz > 0) {
+        std::vector<float> a((size_t)m->nnz), l;
+        SMM_CUDA(cudaMemcpy(a.data(), m->values, sizeof(float) * a.size(), cudaMemcpyDeviceToHost));
+        ic0_factorize_host(m->rows, start, pos, diag, a, &l);
+        SMM_CUDA(cudaMalloc(&p->factor, sizeof(float) * l.size()));
+        SMM_CUDA(cudaMemcpy(p->factor, l.data(), sizeof(float) * l.size(), cudaMemcpyHostToDevice));
+    }
     SMM_CUDA(cudaMalloc(&p->tickets, 4 * sizeof(unsigned int)));
     SMM_CUDA(cudaMemset(p->tickets, 0, 4 * sizeof(unsigned int)));
     if (p->valid && m->rows > 0) {
@@ -344,6 +411,22 @@ int smm_precond_sgs_create(const smm_csr_t* m, smm_precond_t** out) {
     *out = p;
     return SMM_OK;
 }
+
+int smm_precond_sgs_create(const smm_csr_t* m, smm_precond_t** out) { return precond_create(m, 0, nullptr, out); }
+
+// IC0Preconditioner(m) + init() (H:1216-1235, 1798-1800): *rc receives init()'s code (0 ok, 1 = the matrix has no
+// usable diagonal / is not SPD structurally).  The factor is frozen at this point, like the reference's ic0Val.
+int smm_precond_ic0_create(const smm_csr_t* m, int* rc, smm_precond_t** out) { return precond_create(m, 1, rc, out); }
+
+// copy of the factor values (nnz floats, A's pattern) for parity checks
+int smm_precond_ic0_factor(const smm_precond_t* p, float* factor_host) {
+    if (!p || p->kind != 1 || !factor_host) return SMM_E_INVALID;
+    if (!p->factor) return SMM_E_STATE;
+    SMM_CUDA(cudaMemcpy(factor_host, p->factor, sizeof(float) * (size_t)p->m->nnz, cudaMemcpyDeviceToHost));
+    return SMM_OK;
+}
+
+int smm_precond_kind(const smm_precond_t* p) { return p ? p->kind : -1; }
 
 int smm_precond_apply_dev(const smm_precond_t* p, const float* rhs_dev, float* x_dev, int* rc, void* stream) {
     if (!p || (p->rows && (!rhs_dev || !x_dev))) return SMM_E_INVALID;
@@ -387,7 +470,7 @@ int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backwar
 
 int smm_precond_destroy(smm_precond_t* p) {
     if (!p) return SMM_OK;
-    cudaFree(p->order_fwd); cudaFree(p->order_bwd); cudaFree(p->diag_pos); cudaFree(p->y); cudaFree(p->tickets);
+    cudaFree(p->order_fwd); cudaFree(p->order_bwd); cudaFree(p->diag_pos); cudaFree(p->y); cudaFree(p->tickets); cudaFree(p->factor);
     for (int w = 0; w < 2; ++w) { cudaFree(p->slice_ptr[w]); cudaFree(p->ecol[w]); cudaFree(p->eidx[w]); cudaFree(p->eval[w]); cudaFree(p->dval[w]); }
     cudaFree(p->io[0]); cudaFree(p->io[1]);
     delete p;

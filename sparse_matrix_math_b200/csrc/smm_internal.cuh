@@ -47,6 +47,7 @@ struct smm_csr {
     int device = 0;
     int rows = 0, cols = 0;
     int64_t nnz = 0;
+    int64_t nnz_alloc = 0;          // entries the positions/values allocations really hold (>= nnz; padded to 4 when owned)
     int first_active_start = 0;
     int32_t* start = nullptr;       // [rows+1]
     int32_t* positions = nullptr;   // [nnz]
@@ -160,6 +161,7 @@ int smm_vec_max_grid(const smm_workspace* ws);
 
 // dot products in the reference's summation orders (dots.cu)
 int smm_tree_depth(long long n);
+int smm_dot_ref_prepare(long long n);
 int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const float* b0, const float* a1, const float* b1,
                        SolveState* state, int finish, float* out_dev, cudaStream_t s);
 
@@ -167,6 +169,7 @@ int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const 
 int smm_sgs_apply_async(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, cudaStream_t s);
 int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, int* rc_dev, cudaStream_t s);
 int smm_sgs_kernels_per_apply(const smm_precond* p);
+extern "C" int smm_precond_kind(const smm_precond* p);   // 0 SGS, 1 IC(0)
 int smm_csr_analyse(smm_csr* m, cudaStream_t s);
 int smm_first_active_start(const smm_csr* m, int* out_host, cudaStream_t s);
 

@@ -131,6 +131,31 @@ int cg_iter(Ctx& c) {
     return SMM_OK;
 }
 
+// ConjugateGradient with the IC(0) preconditioner, H:2414-2505.  z lives in c.sv.
+int pcg_init(Ctx& c, const float* x0) {
+    SMM_TRY(spmv(c, SMM_OP_SUB, c.b, x0, c.r, RED_NONE, FIN_NONE, nullptr));                        // H:2440
+    SMM_TRY(smm_sgs_apply_async(c.precond, c.r, c.sv, c.st, c.s));                                 // z = M^-1 r, H:2441
+    SMM_TRY(vec(c, VEC_COPY3, FIN_NONE, {c.sv}, {c.p, c.p, c.p}));                                 // p = z, H:2447
+    // rz and ||r||^2 are accumulated by a plain loop in BOTH builds of the reference (H:2444-2448)
+    if (c.mode == SMM_REDUCE_FAST) return vec(c, VEC_DOT2, FIN_PCG_INIT, {c.r, c.sv}, {});
+    return smm_launch_dot_ref(SMM_REDUCE_REFERENCE_SERIAL, c.n, 2, c.r, c.sv, c.r, c.r, c.st, FIN_PCG_INIT, nullptr, c.s);
+}
+int pcg_iter(Ctx& c) {
+    if (!c.exact) {
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_OUT_AUX, FIN_PCG_ALPHA, c.p));       // H:2461-2466
+    } else {
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_NONE, FIN_NONE, nullptr));
+        SMM_TRY(dots(c, FIN_PCG_ALPHA, c.ap, c.p));
+    }
+    SMM_TRY(vec(c, VEC_CG_XR, FIN_NONE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));                       // H:2470-2480
+    SMM_TRY(smm_sgs_apply_async(c.precond, c.r, c.sv, c.st, c.s));                                 // H:2482
+    if (!c.exact) SMM_TRY(vec(c, VEC_DOT2, FIN_PCG_UPDATE, {c.r, c.sv}, {}));                      // (r.z, r.r), H:2483-2488
+    else SMM_TRY(dots(c, FIN_PCG_UPDATE, c.r, c.sv, c.r, c.r));
+    SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.sv}, {c.p}));                                       // p = fma(beta, p, z), H:2490-2499
+    c.kernels_per_iteration = (c.exact ? 5 : 4) + smm_sgs_kernels_per_apply(c.precond);
+    return SMM_OK;
+}
+
 int bicgsym_init(Ctx& c) {
     if (!c.exact) return spmv(c, SMM_OP_SUB, c.b, c.x, c.r, RED_OUT_OUT, FIN_RR_INIT, nullptr, c.p);   // H:2035-2043
     SMM_TRY(spmv(c, SMM_OP_SUB, c.b, c.x, c.r, RED_NONE, FIN_NONE, nullptr, c.p));
@@ -353,10 +378,10 @@ int run_graph_while(Ctx& c, IterFn iter, long long* launches) {
 // ---------------------------------------------------------------------------------------------------
 // common front end
 // ---------------------------------------------------------------------------------------------------
-enum Solver { S_CG, S_BICGSYM, S_CGS, S_BICGSTAB };
+enum Solver { S_CG, S_BICGSYM, S_CGS, S_BICGSTAB, S_CG_IC0 };
 
 int clamp_iterations(int solver, int max_iterations, int rows) {
-    if (solver == S_CG) return max_iterations == -1 ? rows : max_iterations;                       // H:2345-2347
+    if (solver == S_CG || solver == S_CG_IC0) return max_iterations == -1 ? rows : max_iterations;   // H:2345-2347, H:2452-2454
     int m = max_iterations < rows ? max_iterations : rows;                                          // H:2030, 2111, 2200
     if (m == -1) m = rows;                                                                          // H:2031-2033
     return m;
@@ -376,6 +401,7 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
     if (c.mode < 0 || c.mode > 2) { smm_set_error("solve: unknown reduction mode"); return SMM_E_INVALID; }
     if (dist && c.mode != SMM_REDUCE_FAST) { smm_set_error("multi-GPU solve: only the FAST reduction mode is distributed"); return SMM_E_INVALID; }
     c.exact = c.mode != SMM_REDUCE_FAST;
+    if (c.exact) SMM_TRY(smm_dot_ref_prepare(a->rows));        // scratch must exist before the iteration graph is captured
     c.b = b_dev; c.x = x_dev;
     const int nvec = solver == S_CG || solver == S_BICGSYM ? 3 : (solver == S_CGS ? 7 : 7);
     // work vectors live behind the three host-I/O staging slots (vec[0..2])
@@ -385,6 +411,7 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
     if (dist && solver == S_CG) c.p = dist->ext + dist->own_off;   // CG keeps p inside the extended vector (no staging copy)
     if (solver == S_CGS) { c.r0 = w[3]; c.u = w[4]; c.q = w[5]; c.auq = w[6]; }
     if (solver == S_BICGSTAB) { c.r0 = w[3]; c.sv = w[4]; c.as = w[5]; c.scratch = w[6]; }
+    if (solver == S_CG_IC0) { c.sv = w[3]; }
 
     const int driver_req = opts ? opts->driver_mode : SMM_DRIVER_AUTO;
     int driver = driver_req == SMM_DRIVER_AUTO ? SMM_DRIVER_GRAPH_CHUNKED : driver_req;
@@ -423,6 +450,13 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
                 else { SMM_TRY(cg_init(c, x0_dev)); iter = cg_iter; }
                 budget = max_it > 0 ? max_it : 0;                                                  // for-loop, H:2352
                 break;
+            case S_CG_IC0:
+                if (!precond || smm_precond_kind(precond) != 1) { smm_set_error("ConjugateGradient(IC0): an IC0 preconditioner is required"); return SMM_E_INVALID; }
+                if (x_dev != x0_dev) SMM_CUDA(cudaMemcpyAsync(x_dev, x0_dev, sizeof(float) * (size_t)a->rows, cudaMemcpyDeviceToDevice, s));
+                SMM_TRY(pcg_init(c, x0_dev));
+                iter = pcg_iter;
+                budget = max_it > 0 ? max_it : 0;
+                break;
             case S_BICGSYM:
                 SMM_TRY(bicgsym_init(c)); iter = bicgsym_iter; budget = max_it > 1 ? max_it : 1;   // do-while, H:2047/2096
                 break;
@@ -430,6 +464,7 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
                 SMM_TRY(cgs_init(c)); iter = cgs_iter; budget = max_it > 1 ? max_it : 1;           // H:2131/2172
                 break;
             case S_BICGSTAB:
+                if (precond && smm_precond_kind(precond) != 0) { smm_set_error("BiCGStab takes the SGS preconditioner (getPreconditioner())"); return SMM_E_INVALID; }
                 SMM_TRY(stab_init(c)); iter = stab_iter; budget = max_it > 1 ? max_it : 1;         // H:2232/2277
                 break;
         }
@@ -494,7 +529,7 @@ int solve_host(int solver, const smm_csr* a, const smm_precond* precond, const f
     smm_solve_info local;
     SMM_TRY(solve_dev(solver, a, precond, d_b, d_x0, d_x, max_iterations, eps, opts, &local, s));
     // ConjugateGradient returns before touching x when the initial residual already passes (H:2342-2344)
-    const bool x_written = !(solver == S_CG && local.iterations == 0) || x == x0;
+    const bool x_written = !((solver == S_CG || solver == S_CG_IC0) && local.iterations == 0) || x == x0;
     if (a->rows && x_written) {
         SMM_CUDA(cudaMemcpyAsync(x, d_x, bytes, cudaMemcpyDeviceToHost, s));
         SMM_CUDA(cudaStreamSynchronize(s));
@@ -522,6 +557,14 @@ extern "C" {
 int smm_solve_cg(const smm_csr_t* a, const float* b, const float* x0, float* x, int maxIterations, float eps,
                  const smm_solve_options* opts, smm_solve_info* info) {
     return solve_host(S_CG, a, nullptr, b, x0, x, maxIterations, eps, opts, info);
+}
+int smm_solve_cg_ic0(const smm_csr_t* a, const smm_precond_t* ic0, const float* b, const float* x0, float* x, int maxIterations,
+                     float eps, const smm_solve_options* opts, smm_solve_info* info) {
+    return solve_host(S_CG_IC0, a, ic0, b, x0, x, maxIterations, eps, opts, info);
+}
+int smm_solve_cg_ic0_dev(const smm_csr_t* a, const smm_precond_t* ic0, const float* b_dev, const float* x0_dev, float* x_dev,
+                         int maxIterations, float eps, const smm_solve_options* opts, smm_solve_info* info, void* stream) {
+    return solve_dev(S_CG_IC0, a, ic0, b_dev, x0_dev, x_dev, maxIterations, eps, opts, info, stream ? (cudaStream_t)stream : smm_default_stream());
 }
 int smm_solve_bicgsym(const smm_csr_t* a, const float* b, float* x, int maxIterations, float eps,
                       const smm_solve_options* opts, smm_solve_info* info) {

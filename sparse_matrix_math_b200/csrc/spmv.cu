@@ -40,6 +40,7 @@ struct SpmvParams {
     const int32_t* __restrict__ block_row;
     int rows;
     int nnz;
+    int nnz_alloc;        // entries readable in positions/values (TMA windows are rounded up to 16 bytes)
     int op;
     int exact;
     const float* lhs;     // may alias out
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
                 if (use > 0) mbar_wait(&empty[s], (use - 1) & 1u);
                 const int a0 = k0 & ~3;
                 const int span = k1 - a0;
-                const bool staged = span > 0 && span <= cap;
+                // the copy is rounded up to 16 bytes: it must stay inside the allocation (adopted arrays may not be padded)
+                const bool staged = span > 0 && span <= cap && a0 + ((span + 3) & ~3) <= P.nnz_alloc;
                 win[2 * s] = a0;
                 win[2 * s + 1] = staged ? 1 : 0;
                 if (staged) {
@@ -497,7 +499,7 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
     if (m->rows == 0) return SMM_OK;
     SpmvParams P;
     P.start = m->start; P.positions = m->positions; P.values = m->values; P.block_row = m->block_row;
-    P.rows = m->rows; P.nnz = (int)m->nnz; P.op = a.op; P.exact = a.exact;
+    P.rows = m->rows; P.nnz = (int)m->nnz; P.nnz_alloc = (int)m->nnz_alloc; P.op = a.op; P.exact = a.exact;
     P.lhs = a.lhs; P.mult = a.mult; P.out = a.out;
     P.copy1 = a.copy1; P.copy2 = a.copy2; P.copy3 = a.copy3;
     P.aux = a.aux; P.reduce = a.reduce; P.finish = a.finish; P.state = a.state;

@@ -252,6 +252,39 @@ TEST_CASE("Preconditioned BiCGStab. Symmetric Gauss Seidel Preconditioner") {
     }
 }
 
+// ---- cg.cpp:28-84: IC0 known answer and PCG ------------------------------------------------------------------------
+TEST_CASE("Compute and apply IC0") {
+    SMM::TripletMatrix<T> triplet(5, 5);
+    triplet.addEntry(0, 3, 4); triplet.addEntry(0, 0, 10); triplet.addEntry(1, 1, 9); triplet.addEntry(1, 4, 5);
+    triplet.addEntry(2, 2, 12); triplet.addEntry(3, 0, 4); triplet.addEntry(3, 3, 15); triplet.addEntry(3, 4, 7);
+    triplet.addEntry(4, 1, 5); triplet.addEntry(4, 3, 7); triplet.addEntry(4, 4, 8);
+    SMM::CSRMatrix<T> m;
+    m.init(triplet);
+    SMM::CSRMatrix<T>::IC0Preconditioner ic0(m);
+    REQUIRE_EQ(ic0.init(), 0);
+    T rhs[5] = {1, 1, 1, 1, 1}, res[5];
+    const T ref[5] = {0.0995763f, 0.0646186f, 0.0833333f, 0.0010593f, 0.0836864f};
+    ic0.apply(rhs, res);
+    for (int i = 0; i < 5; ++i) CHECK_APPROX(res[i], ref[i], 1e-4);
+}
+
+TEST_CASE("Preconditioned Conjugate Gradient method. IC0 Preconditioner") {
+    const int expected[3] = {5, 8, 5};
+    for (int k = 0; k < 3; ++k) {
+        SMM::CSRMatrix<T> m;
+        REQUIRE_EQ(SMM::loadMatrix((std::string(ASSET_PATH) + kMeshes[k]).c_str(), m), SMM::MatrixLoadStatus::SUCCESS);
+        SMM::Vector<T> rhs = sumColumsPerRow(m);
+        SMM::Vector<T> x(m.getDenseRowCount(), 0);
+        typename SMM::CSRMatrix<T>::IC0Preconditioner M(m);
+        REQUIRE_EQ(M.init(), 0);
+        SMM::b200::options().reduction_mode = SMM_REDUCE_REFERENCE_TREE;
+        REQUIRE_EQ(SMM::ConjugateGradient<T>(m, rhs, x, x, -1, kL2Eps, M), SMM::SolverStatus::SUCCESS);
+        SMM::b200::options().reduction_mode = SMM_REDUCE_FAST;
+        CHECK_EQ(SMM::b200::lastSolveInfo().iterations, expected[k]);
+        for (const T ri : x) CHECK_APPROX(T(1), ri, kInfEps);
+    }
+}
+
 // ---- iteration counts of the reference on its own assets, in the reference's summation order --
 TEST_CASE("Iteration counts equal the reference's (reference-order reductions)") {
     SMM::b200::options().reduction_mode = SMM_REDUCE_REFERENCE_TREE;

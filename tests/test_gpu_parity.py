@@ -229,12 +229,16 @@ def test_dot_modes(smm, n):
 # ---------------------------------------------------------------------------------------------
 def _solver_cases():
     names = [k[: -len("/status_iterations_eps")] for k in np.load(os.path.join(GOLD, "golden_v1.npz")).files if k.endswith("/status_iterations_eps")]
-    return sorted(n for n in names if "cg_ic0" not in n)
+    return sorted(names)
 
 
 def run_solver(smm, solver, m, b, x0, maxit, eps, **kw):
     x = x0.copy()
-    if solver == "bicgstab_sgs":
+    if solver == "cg_ic0":
+        M = smm.IC0Preconditioner(m)
+        assert M.init() == 0
+        info = smm.ConjugateGradient(m, b, x, x, maxit, eps, M=M, **kw)
+    elif solver == "bicgstab_sgs":
         M = m.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
         info = smm.BiCGStab(m, b, x, maxit, eps, preconditioner=M, **kw)
     elif solver == "cg":
@@ -465,3 +469,54 @@ def test_multi_gpu_cg_parity(smm):
                         "--master-port", "29511", os.path.join(here, "dist_gpu_check.py")], capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:])
     assert r.returncode == 0 and "DIST CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+# ---------------------------------------------------------------------------------------------
+# IC(0) preconditioner and the PCG overload (H:1214-1235, 1792-1928, 2414-2505; reference tests cg.cpp:28-84)
+# ---------------------------------------------------------------------------------------------
+def test_ic0_known_answer_and_factor(smm, golden):
+    trow = [0, 0, 1, 1, 2, 3, 3, 3, 4, 4, 4]
+    tcol = [3, 0, 1, 4, 2, 0, 3, 4, 1, 3, 4]
+    tval = [4, 10, 9, 5, 12, 4, 15, 7, 5, 7, 8]
+    g = ol.triplets_to_csr(5, 5, trow, tcol, tval)
+    m = upload(smm, g)
+    M = smm.IC0Preconditioner(m)
+    assert M.init() == 0
+    rc, x = M.apply(np.ones(5, np.float32))
+    assert rc == 0
+    assert np.allclose(x, [0.0995763, 0.0646186, 0.0833333, 0.0010593, 0.0836864], rtol=1e-4)   # cg.cpp:55
+    assert x.tobytes() == golden["ic0_5x5/apply_ones"].tobytes()
+    assert M.factor().tobytes() == golden["ic0_5x5/factor"].tobytes()
+
+
+@pytest.mark.parametrize("key", ["mesh1e1", "mesh1em1", "mesh1em6", "poisson2d_96x100"])
+def test_ic0_factor_and_apply_bit_exact(smm, golden, key):
+    g = gold_csr(golden, key)
+    m = upload(smm, g)
+    M = smm.IC0Preconditioner(m)
+    assert M.init() == 0
+    rc, f = ol.ic0_factorize(g)                       # the reference's O(rows^2) algorithm restated (pinned against oracle/_ref)
+    assert rc == 0 and M.factor().tobytes() == f[: g.nnz].tobytes()
+    rhs = golden[f"{key}/b"]
+    assert M.apply(rhs)[1].tobytes() == ol.ic0_apply(g, f, rhs).tobytes()
+
+
+def test_pcg_ic0_larger_parity(smm):
+    g = matgen.poisson2d(60, 70)
+    m = upload(smm, g)
+    xs = matgen.xstar(g.rows)
+    b = ol.spmv(g, 0, None, xs)
+    M = smm.IC0Preconditioner(m)
+    assert M.init() == 0
+    f = ol.ic0_factorize(g)[1]
+    for mt, mode in ((1, smm.REDUCE_REFERENCE_TREE), (0, smm.REDUCE_REFERENCE_SERIAL)):
+        o = ol.solve("cg_ic0", g, b, np.zeros(g.rows, np.float32), -1, 1e-5, mt, ic0=f)
+        x = np.zeros(g.rows, np.float32)
+        info = smm.ConjugateGradient(m, b, x, x, -1, 1e-5, M=M, reduction_mode=mode)
+        assert int(info.status) == o["status"] == 0 and info.iterations == o["iterations"] and x.tobytes() == o["x"].tobytes()
+    x = np.zeros(g.rows, np.float32)
+    info = smm.ConjugateGradient(m, b, x, x, -1, 1e-5, M=M)
+    assert int(info.status) == 0 and abs(info.iterations - o["iterations"]) <= 2 and np.max(np.abs(x - xs)) < 1e-4
+    # a matrix without a usable diagonal: init() reports 1 as the reference's factorize does (H:1873-1876)
+    bad = upload(smm, ol.triplets_to_csr(3, 3, [0, 1, 1, 2], [0, 0, 2, 2], [1, 1, 1, 1]))
+    assert smm.IC0Preconditioner(bad).init() == 1
