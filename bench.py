@@ -43,8 +43,8 @@ def measured_peak_gbs():
 
 def ncu_traffic_bytes(kernel_prefix, grid):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
-    same command (profiles/r01b_spmv_rows_kernel_full.txt, 512^3); None for any other problem size."""
-    p = os.path.join(ROOT, "profiles", "r01b_spmv_rows_kernel_full.txt")
+    same command (profiles/r01d_spmv_rows_kernel_full.txt, 512^3); None for any other problem size."""
+    p = os.path.join(ROOT, "profiles", "r01d_spmv_rows_kernel_full.txt")
     if grid != 512 or not os.path.exists(p):
         return None
     rd = wr = None
@@ -397,7 +397,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=512)
-    ap.add_argument("--iters", type=int, default=50, help="CG iterations per step")
+    ap.add_argument("--iters", type=int, default=200, help="CG iterations per step")
     ap.add_argument("--driver", default="auto", choices=["auto", "chunked", "while", "stream"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=15.0)

@@ -29,6 +29,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "smm_internal.cuh"
 
 namespace {
@@ -86,6 +88,19 @@ struct RowWriter {
             case RED_OUT_AUX_OUT_OUT: acc0 = fmaf(o, P.aux[row], acc0); acc1 = fmaf(o, o, acc1); break;
             default: break;
         }
+    }
+};
+
+// out[row] = dot with no lhs and no extra copies: the SpMV of every Krylov iteration (rMult, H:1501-1505)
+struct PlainWriter {
+    const SpmvParams& P;
+    float acc0 = 0.0f, acc1 = 0.0f;
+    __device__ __forceinline__ explicit PlainWriter(const SpmvParams& p) : P(p) {}
+    __device__ __forceinline__ void operator()(int row, float o) {
+        P.out[row] = o;
+        if (P.reduce == RED_OUT_AUX) acc0 = fmaf(o, P.aux[row], acc0);
+        else if (P.reduce == RED_OUT_AUX_OUT_OUT) { acc0 = fmaf(o, P.aux[row], acc0); acc1 = fmaf(o, o, acc1); }
+        else if (P.reduce == RED_OUT_OUT) acc0 = fmaf(o, o, acc0);
     }
 };
 
@@ -272,8 +287,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // One row (or a V-lane slice of it) out of a values/positions window.  Up to eight entries are fetched and their
 // mult[] gathers issued together (one latency round for a stencil row), then added in the order of the entries
 // (V = 1: the reference's left-to-right sum with two roundings per term, H:1484-1489).
+// exactly L entries, no predicates (the interior rows of a stencil)
+template <int L, class VP, class CP>
+__device__ __forceinline__ float row_dot_fixed(const VP vs, const CP cs, const float* __restrict__ mult, const int j) {
+    int c[L];
+    float v[L], x[L];
+#pragma unroll
+    for (int k = 0; k < L; ++k) { c[k] = cs[j + k]; v[k] = vs[j + k]; }
+#pragma unroll
+    for (int k = 0; k < L; ++k) x[k] = __ldg(mult + c[k]);
+    float dot = 0.0f;
+#pragma unroll
+    for (int k = 0; k < L; ++k) dot = __fadd_rn(__fmul_rn(v[k], x[k]), dot);
+    return dot;
+}
+
 template <int V, class VP, class CP>
 __device__ __forceinline__ float row_dot(const VP vs, const CP cs, const float* __restrict__ mult, int j, const int e) {
+    if (V == 1) {                                                 // warp-uniform row length: same sum, fewer instructions
+        const int len = e - j;
+        if (__all_sync(0xffffffffu, len == 7)) return row_dot_fixed<7>(vs, cs, mult, j);
+        if (__all_sync(0xffffffffu, len == 5)) return row_dot_fixed<5>(vs, cs, mult, j);
+    }
     float dot = 0.0f;
     while (j < e) {
         int c[8];
@@ -299,7 +334,7 @@ __device__ __forceinline__ float row_dot(const VP vs, const CP cs, const float* 
 // the slot is free (empty barrier), then has the TMA engine copy the group's values/positions window into the
 // slot, completion counted in bytes on the slot's full barrier.  Warps 0..7 are consumers: wait for the slot, take
 // one row per V lanes out of shared memory, release the slot.  No CTA-wide barrier inside the loop.
-template <int V>   // lanes per row
+template <int V, bool PLAIN>   // lanes per row; PLAIN: op == ASSIGN and no extra copies of the result
 __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParams P, const int cap, const int nchunks, const int stages) {
     if (P.state != nullptr && P.state->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -315,7 +350,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
     constexpr int R = ROWS_CONSUMERS / V;                         // rows per group
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    RowWriter write(P);
+    typename std::conditional<PLAIN, PlainWriter, RowWriter>::type write(P);
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ROWS_CONSUMERS / 32); }
@@ -533,18 +568,23 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
         if (a.reduce != RED_NONE && m->ws->partials_cap < (size_t)grid) { smm_set_error("spmv: reduction workspace too small"); return SMM_E_STATE; }
         static size_t attr_smem = 0;
         if (attr_smem != smem) {
-            SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#define SMM_ROWS_ATTR(V_, PL_) SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<V_, PL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+            SMM_ROWS_ATTR(1, true); SMM_ROWS_ATTR(2, true); SMM_ROWS_ATTR(4, true); SMM_ROWS_ATTR(8, true);
+            SMM_ROWS_ATTR(1, false); SMM_ROWS_ATTR(2, false); SMM_ROWS_ATTR(4, false); SMM_ROWS_ATTR(8, false);
+#undef SMM_ROWS_ATTR
             attr_smem = smem;
         }
+        const bool plain = a.op == SMM_OP_ASSIGN && !a.copy1 && !a.copy2 && !a.copy3;
+#define SMM_ROWS_LAUNCH(V_) \
+    if (plain) spmv_rows_kernel<V_, true><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); \
+    else spmv_rows_kernel<V_, false><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages)
         switch (V) {
-            case 1: spmv_rows_kernel<1><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); break;
-            case 2: spmv_rows_kernel<2><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); break;
-            case 4: spmv_rows_kernel<4><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); break;
-            default: spmv_rows_kernel<8><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); break;
+            case 1: SMM_ROWS_LAUNCH(1); break;
+            case 2: SMM_ROWS_LAUNCH(2); break;
+            case 4: SMM_ROWS_LAUNCH(4); break;
+            default: SMM_ROWS_LAUNCH(8); break;
         }
+#undef SMM_ROWS_LAUNCH
     } else {
         spmv_kernel<<<m->num_blocks, SPMV_THREADS, 0, s>>>(P);
     }
