@@ -9,7 +9,9 @@ from sparse_matrix_math_b200 import binding as B
 
 grid = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-A = smm.CSRMatrix.generate(B.GEN_CONVDIFF3D, grid, grid, grid, 0.5)
+ny = int(sys.argv[3]) if len(sys.argv) > 3 else grid
+nz = int(sys.argv[4]) if len(sys.argv) > 4 else grid
+A = smm.CSRMatrix.generate(B.GEN_CONVDIFF3D, grid, ny, nz, 0.5)
 M = A.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
 n = A.rows
 rhs = smm.DeviceVector(n); x = smm.DeviceVector(n)
@@ -22,4 +24,4 @@ for _ in range(reps):
 smm.lib().smm_sync()
 dt = (time.perf_counter() - t) / reps
 bytes_apply = 8 * A.nnz + 44 * n
-print(f"grid {grid}^3 levels {M.levels()} apply {dt*1e3:.3f} ms  ({dt*1e6/(2*M.levels()[0]):.2f} us per level)  {bytes_apply/dt/1e9:.0f} GB/s  ctas_per_sm={os.environ.get('SMM_B200_SGS_CTAS_PER_SM','4')}")
+print(f"grid {grid}x{ny}x{nz} levels {M.levels()} apply {dt*1e3:.3f} ms  ({dt*1e6/(2*M.levels()[0]):.2f} us per level)  {bytes_apply/dt/1e9:.0f} GB/s  ctas_per_sm={os.environ.get('SMM_B200_SGS_CTAS_PER_SM','4')}")
