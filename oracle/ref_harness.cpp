@@ -4,7 +4,8 @@
 // compiled where it lies under /root/reference by oracle/Makefile into oracle/_ref/libsmm_ref_{st,mt}.so.
 // Nothing of the reference is copied into this repository: the Makefile writes a patched copy of the
 // header (2-line scope fix in ConjugateGradientSquared, H:2131/H:2171, without which GCC rejects the
-// header) into the git-ignored oracle/_ref/ directory and compiles this file against it.
+// header) to a scratch directory OUTSIDE the repository and compiles this file against it; only the
+// resulting shared libraries land in the git-ignored oracle/_ref/ directory.
 //
 // Used for (1) pinning oracle/smm_oracle.c (tests/test_oracle_pinned.py, tests/golden/make_golden.py),
 // (2) the CPU baseline / `bench.py --impl reference` arm.  Never linked into the product library.

@@ -63,7 +63,6 @@ int smm_workspace_get(const smm_csr* mc, smm_workspace** out) {
         SMM_CUDA(cudaMallocHost(&ws->state_host, sizeof(SolveState)));
         SMM_CUDA(cudaEventCreate(&ws->ev0));
         SMM_CUDA(cudaEventCreate(&ws->ev1));
-        SMM_CUDA(cudaEventCreateWithFlags(&ws->ev_poll, cudaEventDisableTiming));
         m->ws = ws;
     }
     *out = m->ws;
@@ -93,7 +92,6 @@ void smm_workspace_free(smm_workspace* ws) {
     for (int i = 0; i < 10; ++i) cudaFree(ws->vec[i]);
     if (ws->ev0) cudaEventDestroy(ws->ev0);
     if (ws->ev1) cudaEventDestroy(ws->ev1);
-    if (ws->ev_poll) cudaEventDestroy(ws->ev_poll);
     delete ws;
 }
 

@@ -92,7 +92,6 @@ struct SerialParams {
     SolveState* state;
     int finish;
     float* out_dev;
-    int mixed_tree_second;  // unused here (kept for symmetry)
 };
 
 constexpr int SER_THREADS = 256;
@@ -199,7 +198,7 @@ int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const 
         SerialParams P;
         P.n = n; P.ndots = ndots;
         P.a[0] = a0; P.b[0] = b0; P.a[1] = a1; P.b[1] = b1;
-        P.state = state; P.finish = finish; P.out_dev = out_dev; P.mixed_tree_second = 0;
+        P.state = state; P.finish = finish; P.out_dev = out_dev;
         dot_serial_kernel<<<1, SER_THREADS, 0, s>>>(P);
     }
     SMM_COUNT_LAUNCH(1);

@@ -103,7 +103,7 @@ struct smm_workspace {
     // work vectors of the solvers, grown on demand
     float* vec[10] = {nullptr};
     size_t vec_len = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 constexpr int RED_SLOTS = 4;
