@@ -4,9 +4,10 @@
 //       tbb::parallel_deterministic_reduce over blocked_range<int>(0,n,8192), identity 0.0f, std::plus.
 //       The range is halved at begin+(end-begin)/2 while its size exceeds the grain; each leaf is summed left to
 //       right from 0; joins are left+right.  All nodes at depth D' = min{d : floor(n/2^d) <= 8192} exist, and each
-//       is either a leaf or (size 8193) splits exactly once more, so: one thread per depth-D' node walks down from
-//       the root to find its range, sums its one or two leaves sequentially, and the 2^D' node values are then
-//       combined by a perfect pairwise tree -- the same additions in the same order as the reference.
+//       is either a leaf or (size 8193) splits exactly once more, so: one WARP per depth-D' node walks down from
+//       the root to find its range, sums its one or two leaves (coalesced loads by all lanes, the sequential adds by
+//       lane 0 out of shared memory), and the 2^D' node values are then combined by a perfect pairwise tree -- the
+//       same additions in the same order as the reference.
 //   SMM_REDUCE_REFERENCE_SERIAL the serial build (H:322-326): left to right.  One thread adds, the rest of its CTA
 //       streams products into shared memory ahead of it.
 //   SMM_REDUCE_FAST             vecops.cu's fused two-stage reduction (VEC_DOT2).
@@ -17,10 +18,45 @@ namespace {
 
 constexpr int TBB_GRAIN = 8192;
 
-__device__ __forceinline__ float leaf_sum(const float* __restrict__ a, const float* __restrict__ b, long long lo, long long hi) {
+constexpr int LEAF_CHUNK = 512;        // products staged per round: 16 per lane
+constexpr int TREE_WARPS = 4;
+
+// One warp sums one leaf: all lanes stream a[], b[] with coalesced loads (the next chunk is already in flight in
+// registers), multiply, and park the products in shared memory; lane 0 then adds them left to right from 0, which
+// is the order of the reference's leaf loop (H:312-316).  The 4-cycle FADD chain of lane 0 (8192 adds per leaf) is
+// the critical path; the loads hide under it.
+__device__ __forceinline__ float leaf_sum(const float* __restrict__ a, const float* __restrict__ b, long long lo, long long hi, float* buf) {
+    const int lane = threadIdx.x & 31;
     float cur = 0.0f;                                        // identity, H:312
-    for (long long j = lo; j < hi; ++j) cur = __fadd_rn(cur, __fmul_rn(a[j], b[j]));   // H:314-316
-    return cur;
+    float ra[LEAF_CHUNK / 32], rb[LEAF_CHUNK / 32];
+    auto fetch = [&](long long base) {
+#pragma unroll
+        for (int k = 0; k < LEAF_CHUNK / 32; ++k) {
+            const long long j = base + k * 32 + lane;
+            const bool in = j < hi;
+            ra[k] = in ? __ldg(a + j) : 0.0f;
+            rb[k] = in ? __ldg(b + j) : 0.0f;
+        }
+    };
+    fetch(lo);
+    for (long long base = lo; base < hi; base += LEAF_CHUNK) {
+#pragma unroll
+        for (int k = 0; k < LEAF_CHUNK / 32; ++k) buf[k * 32 + lane] = __fmul_rn(ra[k], rb[k]);
+        __syncwarp();
+        if (base + LEAF_CHUNK < hi) fetch(base + LEAF_CHUNK);
+        if (lane == 0) {
+            const long long left = hi - base;
+            const int m = left < LEAF_CHUNK ? (int)left : LEAF_CHUNK;
+            int t = 0;
+            for (; t + 4 <= m; t += 4) {
+                const float4 q = *reinterpret_cast<const float4*>(buf + t);
+                cur = __fadd_rn(cur, q.x); cur = __fadd_rn(cur, q.y); cur = __fadd_rn(cur, q.z); cur = __fadd_rn(cur, q.w);   // H:314-316
+            }
+            for (; t < m; ++t) cur = __fadd_rn(cur, buf[t]);
+        }
+        __syncwarp();
+    }
+    return cur;                                              // valid in lane 0
 }
 
 struct TreeParams {
@@ -36,27 +72,30 @@ struct TreeParams {
     float* out_dev;        // optional: totals written here too
 };
 
-__global__ void __launch_bounds__(128) dot_tree_kernel(const TreeParams P) {
+__global__ void __launch_bounds__(TREE_WARPS * 32) dot_tree_kernel(const TreeParams P) {
     if (P.state != nullptr && P.state->done) return;
     __shared__ int sh_last;
+    __shared__ __align__(16) float sh_buf[TREE_WARPS][LEAF_CHUNK];
     const long long nn = 1ll << P.depth;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nn) {
+    const int warp = threadIdx.x >> 5;
+    const long long job = (long long)blockIdx.x * TREE_WARPS + warp;     // (dot, depth-D' node)
+    if (job < nn * P.ndots) {
+        const int d = (int)(job / nn);
+        const long long i = job - (long long)d * nn;
         long long lo = 0, hi = P.n;
         for (int level = P.depth - 1; level >= 0; --level) {
             const long long mid = lo + (hi - lo) / 2;
             if ((i >> level) & 1) lo = mid; else hi = mid;
         }
-        for (int d = 0; d < P.ndots; ++d) {
-            float v;
-            if (hi - lo > TBB_GRAIN) {
-                const long long mid = lo + (hi - lo) / 2;
-                v = __fadd_rn(leaf_sum(P.a[d], P.b[d], lo, mid), leaf_sum(P.a[d], P.b[d], mid, hi));
-            } else {
-                v = leaf_sum(P.a[d], P.b[d], lo, hi);
-            }
-            P.nodes[(size_t)d * 2 * nn + i] = v;
+        float v;
+        if (hi - lo > TBB_GRAIN) {
+            const long long mid = lo + (hi - lo) / 2;
+            const float l = leaf_sum(P.a[d], P.b[d], lo, mid, sh_buf[warp]);
+            v = __fadd_rn(l, leaf_sum(P.a[d], P.b[d], mid, hi, sh_buf[warp]));
+        } else {
+            v = leaf_sum(P.a[d], P.b[d], lo, hi, sh_buf[warp]);
         }
+        if ((threadIdx.x & 31) == 0) P.nodes[(size_t)d * 2 * nn + i] = v;
     }
     __threadfence();
     __syncthreads();
@@ -70,7 +109,10 @@ __global__ void __launch_bounds__(128) dot_tree_kernel(const TreeParams P) {
         float* cur = P.nodes + (size_t)d * 2 * nn;
         float* nxt = cur + nn;
         for (long long w = nn >> 1; w >= 1; w >>= 1) {
-            for (long long k = threadIdx.x; k < w; k += blockDim.x) nxt[k] = __fadd_rn(__ldcg(cur + 2 * k), __ldcg(cur + 2 * k + 1));
+            for (long long k = threadIdx.x; k < w; k += blockDim.x) {
+                const float2 pr = __ldcg(reinterpret_cast<const float2*>(cur) + k);
+                nxt[k] = __fadd_rn(pr.x, pr.y);
+            }
             __threadfence_block();
             __syncthreads();
             float* t = cur; cur = nxt; nxt = t;
@@ -191,9 +233,8 @@ int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const 
         DotScratch* sc = nullptr;
         SMM_TRY(scratch_for(1ll << P.depth, &sc));
         P.nodes = sc->nodes; P.ticket = sc->ticket; P.state = state; P.finish = finish; P.out_dev = out_dev;
-        const long long nn = 1ll << P.depth;
-        const int threads = 128;
-        dot_tree_kernel<<<(unsigned)((nn + threads - 1) / threads), threads, 0, s>>>(P);
+        const long long jobs = (1ll << P.depth) * ndots;       // one warp per (dot, depth-D' node)
+        dot_tree_kernel<<<(unsigned)((jobs + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, 0, s>>>(P);
     } else {
         SerialParams P;
         P.n = n; P.ndots = ndots;

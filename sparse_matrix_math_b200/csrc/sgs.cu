@@ -11,12 +11,17 @@
 //     of lane l of slice s sits at slice_ptr[s] + 32 k + l), so a warp reads its rows' entries with coalesced loads
 //     that depend on nothing but the thread index -- the only dependent accesses left are rhs[row] and x[col];
 //   * apply: ONE launch per sweep, one thread per row in level order.  A thread accumulates its row in the
-//     reference's order and, for every x[col] it needs, spins until the value has been published.  The output
-//     vector doubles as the ready flag: it is pre-filled with a NaN payload no arithmetic instruction can produce.
-//     CTAs take their logical index from an atomic ticket, so every producer a thread waits for belongs to a CTA
-//     that has already started -- no deadlock whatever order the hardware dispatches CTAs in.  Levels overlap
-//     freely (no grid barrier): the sweep is bounded by the dependency chain (levels x L2 round trip), not by
-//     launch or barrier latency.  A poll bound turns a would-be hang into SMM_E_TIMEOUT.
+//     reference's order; the operands it needs are requested all at once and re-requested until every one has been
+//     published.  Intermediate vectors are stored BY SWEEP POSITION (yperm / xperm, columns of the packed triangles
+//     are remapped to positions at create time): the rows a warp waits for are neighbours in the previous level, so
+//     its polls and its publishes touch one or two 128-byte lines instead of one sector per lane.  The vector doubles
+//     as the ready flag: it is pre-filled with a NaN payload no arithmetic instruction can produce.
+//     CTAs take their logical blocks from an atomic ticket, three blocks ahead (entries, right-hand side and slice
+//     headers of the next blocks are in flight while the current one is solved), so every producer a thread waits
+//     for belongs to a CTA that has already started -- no deadlock whatever order the hardware dispatches CTAs in.
+//     Levels overlap freely (no grid barrier): the sweep is bounded by the dependency chain, levels x one
+//     producer->L2->consumer hand-off (340-530 ns on an idle B200, tools/hop_latency.cu), not by launch or barrier
+//     latency.  A poll bound turns a would-be hang into SMM_E_TIMEOUT.
 // Per-row arithmetic is identical to the reference (two roundings per multiply-add, one division per sweep), so the
 // result is bit-identical to SGSPreconditioner::apply for any schedule.
 // Algorithmic bytes per apply: each stored entry once over the two sweeps (8 nnz) + start/diag index/order
@@ -48,7 +53,9 @@ struct smm_precond {
     float* dval[2] = {nullptr, nullptr};            // [threads] a_ii of the thread's row
     long long esize[2] = {0, 0};
     unsigned long long values_version = ~0ull;      // version of m->values the packed copies were gathered from
-    float* y = nullptr;              // [rows] forward result
+    float* yperm = nullptr;          // [threads_fwd] forward result, stored in forward sweep order
+    float* xperm = nullptr;          // [threads_bwd] backward result in backward sweep order (x itself is also written in natural order)
+    int32_t* ypos = nullptr;         // [threads_bwd] where the backward thread's own row sits in yperm
     unsigned int* tickets = nullptr; // [2] logical CTA counters, [2] = abort flag, [3] = error bits
     float* io[2] = {nullptr, nullptr};   // staging for the host-pointer apply
 };
@@ -59,30 +66,28 @@ constexpr unsigned int SENTINEL = 0x7FC0DEADu;   // quiet NaN with a payload; GP
 constexpr int SGS_THREADS = 128;
 constexpr unsigned int POLL_LIMIT = 1u << 22;
 
-__global__ void sgs_fill_kernel(float* __restrict__ y, float* __restrict__ x, long long n, unsigned int* tickets, const SolveState* st) {
+__global__ void sgs_fill_kernel(float* __restrict__ yperm, long long nf, float* __restrict__ xperm, long long nb, unsigned int* tickets, const SolveState* st) {
     if (st != nullptr && st->done) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        y[i] = __uint_as_float(SENTINEL);
-        x[i] = __uint_as_float(SENTINEL);
-    }
+    if (i < nf) yperm[i] = __uint_as_float(SENTINEL);
+    if (i < nb) xperm[i] = __uint_as_float(SENTINEL);
     if (i == 0) { tickets[0] = 0u; tickets[1] = 0u; tickets[2] = 0u; tickets[3] = 0u; }
 }
 
-__device__ __forceinline__ float wait_value(const float* p, unsigned int* abort_flag) {
+__device__ __forceinline__ unsigned int peek(const float* p) {
     unsigned int bits;
-    unsigned int polls = 0;
-    for (;;) {
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bits) : "l"(p));
-        if (bits != SENTINEL) break;
-        __nanosleep(polls < 16u ? 32u : 128u);                // back off: thousands of lanes may be waiting on L2
-        if ((++polls & 255u) == 0u) {
-            unsigned int a;
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(a) : "l"(abort_flag));
-            if (a != 0u || polls >= POLL_LIMIT) { atomicExch(abort_flag, 1u); break; }
-        }
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bits) : "l"(p));
+    return bits;
+}
+
+// back off between polls: thousands of lanes may be waiting on L2.  Returns false when the wait must be abandoned.
+__device__ __forceinline__ bool poll_pause(unsigned int* polls, unsigned int* abort_flag, unsigned int sleep_first, unsigned int sleep_later) {
+    const unsigned int ns = *polls < 16u ? sleep_first : sleep_later;
+    if (ns) __nanosleep(ns);
+    if ((++*polls & 255u) == 0u) {
+        if (peek(reinterpret_cast<const float*>(abort_flag)) != 0u || *polls >= POLL_LIMIT) { atomicExch(abort_flag, 1u); return false; }
     }
-    return __uint_as_float(bits);
+    return true;
 }
 
 __device__ __forceinline__ void publish(float* p, float v) {
@@ -92,11 +97,13 @@ __device__ __forceinline__ void publish(float* p, float v) {
 
 struct SweepArgs {
     const int32_t* order;        // [nthreads] row or -1
+    const int32_t* ypos;         // backward only: [nthreads] position of the row in yperm
     const long long* slice_ptr;  // [nthreads/32 + 1]
     const int32_t* ecol;
     const float* eval;
     const float* dval;           // [nthreads]
     long long nthreads;
+    unsigned int sleep_first, sleep_later;   // ns between polls: the first 16 polls / afterwards
 };
 
 __global__ void sgs_gather_values_kernel(const float* __restrict__ values, const int32_t* __restrict__ eidx, float* __restrict__ eval, long long n,
@@ -108,66 +115,115 @@ __global__ void sgs_gather_values_kernel(const float* __restrict__ values, const
 
 // IC0 = false: SGS sweeps (H:1658-1713).  IC0 = true: L y = rhs then L^T x = y (IC0Preconditioner::apply, H:1802-1837):
 // `sum -= ic0[j] * x[col]`, one division by the diagonal of the factor per row and sweep.
+//
+// Persistent CTAs; logical blocks of SGS_THREADS consecutive sweep positions are handed out in order by an atomic
+// ticket, so every row a thread waits for belongs to a block that a running CTA has already claimed.  A CTA claims
+// THREE blocks ahead and software-pipelines them: while block i is being solved, the entries / right-hand side of
+// block i+1 and the slice header of block i+2 are already in flight (their addresses depend on nothing but the block
+// index), so the only latency left on a row's path is the L2 round trip to its operands.  Claims are processed in
+// increasing order, so the smallest unfinished block is always the current block of some running CTA: no deadlock.
+struct RowHead { long long e0; int width; int row; float d; int yp; };
+struct RowBody { int c[4]; float v[4]; float init; };
+
 template <bool FORWARD, bool IC0>
-__global__ void __launch_bounds__(SGS_THREADS) sgs_sweep_kernel(const SweepArgs A, const float* __restrict__ rhs, float* y, float* x,
-                                                               unsigned int* tickets, const SolveState* st) {
+__global__ void __launch_bounds__(SGS_THREADS) sgs_sweep_kernel(const SweepArgs A, const float* __restrict__ rhs, float* yperm, float* xperm,
+                                                               float* __restrict__ x, unsigned int* tickets, const SolveState* st) {
     if (st != nullptr && st->done) return;
-    __shared__ unsigned int sh_bid;
+    __shared__ unsigned int sh_bid[2];
     unsigned int* abort_flag = tickets + 2;
-    // persistent CTAs: logical blocks are handed out in order by an atomic ticket, so (a) every row a thread waits for
-    // belongs to a block that has already been claimed by a running CTA, and (b) the number of lanes that can be
-    // spinning at any time is bounded by the grid, which is sized to stay a few levels deep at most
+    unsigned int* ticket = tickets + (FORWARD ? 0 : 1);
     const long long nblocks = (A.nthreads + SGS_THREADS - 1) / SGS_THREADS;
     const int lane = threadIdx.x & 31;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) sh_bid = atomicAdd(&tickets[FORWARD ? 0 : 1], 1u);
-        __syncthreads();
-        const long long bid = sh_bid;
-        if (bid >= nblocks) break;
-        const long long t = bid * SGS_THREADS + threadIdx.x;      // nthreads is a multiple of 32: whole warps in or out
-        if (t >= A.nthreads) continue;
-        const long long slice = t >> 5;
-        const long long e0 = A.slice_ptr[slice], e1 = A.slice_ptr[slice + 1];
-        const int width = (int)((e1 - e0) >> 5);
-        const int row = A.order[t];
-        const float d = A.dval[t];
-        float acc;
-        const float* src = FORWARD ? y : x;
-        if (FORWARD) {
-            if (!IC0 && row >= 0 && fabsf(d) < 1e-5) atomicOr(tickets + 3, 1u);  // H:1691-1693 (reported, not fatal here)
-            acc = row >= 0 ? rhs[row] : 0.0f;                                     // H:1683 / H:1807
-        } else if (IC0) {
-            acc = row >= 0 ? wait_value(y + row, abort_flag) : 0.0f;              // T sum = x[row], H:1823
-        } else {
-            acc = 0.0f;                                                           // H:1702
+    const float* src = FORWARD ? yperm : xperm;                                   // operands are addressed by sweep position
+    float* dst = FORWARD ? yperm : xperm;
+
+    auto load_head = [&](long long bid) {
+        RowHead h;
+        h.e0 = 0; h.width = 0; h.row = -1; h.d = 1.0f; h.yp = 0;
+        const long long t = bid * SGS_THREADS + threadIdx.x;                      // nthreads is a multiple of 32: whole warps in or out
+        if (bid < nblocks && t < A.nthreads) {
+            const long long s0 = A.slice_ptr[t >> 5];
+            h.e0 = s0;
+            h.width = (int)((A.slice_ptr[(t >> 5) + 1] - s0) >> 5);
+            h.row = A.order[t];
+            h.d = A.dval[t];
+            if (!FORWARD) h.yp = A.ypos[t];
         }
-        for (int k = 0; k < width; k += 4) {
-            int c[4];
-            float v[4];
+        return h;
+    };
+    auto load_entries = [&](const RowHead& h, int k, int* c, float* v) {          // coalesced, independent of any other row
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {                                         // coalesced, independent of any other row
-                const bool in = k + j < width;
-                c[j] = in ? A.ecol[e0 + (long long)(k + j) * 32 + lane] : -1;
-                v[j] = in ? A.eval[e0 + (long long)(k + j) * 32 + lane] : 0.0f;
+        for (int j = 0; j < 4; ++j) {
+            const bool in = k + j < h.width;
+            c[j] = in ? A.ecol[h.e0 + (long long)(k + j) * 32 + lane] : -1;
+            v[j] = in ? A.eval[h.e0 + (long long)(k + j) * 32 + lane] : 0.0f;
+        }
+    };
+    auto load_body = [&](const RowHead& h) {
+        RowBody b;
+        load_entries(h, 0, b.c, b.v);
+        b.init = 0.0f;
+        // forward: the right-hand side (H:1683 / H:1807); backward: the row's own forward result, written by the forward launch
+        if (h.row >= 0) b.init = FORWARD ? rhs[h.row] : yperm[h.yp];
+        return b;
+    };
+    auto solve_block = [&](long long bid, const RowHead& h, const RowBody& r) {
+        if (FORWARD && !IC0 && h.row >= 0 && fabsf(h.d) < 1e-5) atomicOr(tickets + 3, 1u);   // H:1691-1693 (reported, not fatal here)
+        float acc = (FORWARD || IC0) ? r.init : 0.0f;                             // H:1683 / T sum = x[row], H:1823 / H:1702
+        int c[4];
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c[j] = r.c[j]; v[j] = r.v[j]; }
+        for (int k = 0; k < h.width; k += 4) {
+            if (k > 0) load_entries(h, k, c, v);
+            // every operand of the batch is requested at once and only the missing ones are asked for again: the wait
+            // costs one L2 round trip after the LAST producer has published, not one per operand
+            unsigned int xb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xb[j] = c[j] >= 0 ? peek(src + c[j]) : 0u;
+            unsigned int polls = 0;
+            while (xb[0] == SENTINEL || xb[1] == SENTINEL || xb[2] == SENTINEL || xb[3] == SENTINEL) {
+                if (!poll_pause(&polls, abort_flag, A.sleep_first, A.sleep_later)) break;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (xb[j] == SENTINEL) xb[j] = peek(src + c[j]);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (c[j] >= 0) {
-                    const float xv = wait_value(src + c[j], abort_flag);
+                    const float xv = __uint_as_float(xb[j]);
                     // forward: _smm_fma(-value, x[col], lhs) cols ascending (H:1685); backward: _smm_fma(value, x[col], lhs) cols descending (H:1704)
                     // IC0: sum -= ic0[j] * x[col] (H:1813, H:1829) -- the same bits as the forward SGS form
                     acc = (FORWARD || IC0) ? __fsub_rn(acc, __fmul_rn(v[j], xv)) : __fadd_rn(__fmul_rn(v[j], xv), acc);
                 }
             }
         }
-        if (row < 0) continue;
-        if (FORWARD || IC0) {
-            publish((FORWARD ? y : x) + row, __fdiv_rn(acc, d));                  // H:1694 / H:1818, H:1834
-        } else {
-            const float yr = wait_value(y + row, abort_flag);                     // own forward result (already published)
-            publish(x + row, __fsub_rn(yr, __fdiv_rn(acc, d)));                   // H:1710
-        }
+        if (h.row < 0) return;
+        const float res = (FORWARD || IC0) ? __fdiv_rn(acc, h.d)                  // H:1694 / H:1818, H:1834
+                                           : __fsub_rn(r.init, __fdiv_rn(acc, h.d));   // H:1710
+        publish(dst + (bid * SGS_THREADS + threadIdx.x), res);                    // coalesced: consumers poll by position
+        if (!FORWARD) x[h.row] = res;                                             // the caller's vector, natural order
+    };
+
+    unsigned int pending = 0u;
+    if (threadIdx.x == 0) {
+        sh_bid[0] = atomicAdd(ticket, 1u);
+        sh_bid[1] = atomicAdd(ticket, 1u);
+        pending = atomicAdd(ticket, 1u);
+    }
+    __syncthreads();
+    long long b0 = sh_bid[0], b1 = sh_bid[1];
+    __syncthreads();
+    RowHead h0 = load_head(b0), h1 = load_head(b1);
+    RowBody r0 = load_body(h0);
+    for (unsigned int it = 0; b0 < nblocks; ++it) {
+        if (threadIdx.x == 0) sh_bid[it & 1u] = pending;
+        __syncthreads();                                                          // one barrier per block: the slots alternate
+        const long long b2 = sh_bid[it & 1u];
+        if (threadIdx.x == 0) pending = atomicAdd(ticket, 1u);                    // consumed one block from now
+        const RowHead h2 = load_head(b2);
+        const RowBody r1 = load_body(h1);
+        solve_block(b0, h0, r0);
+        b0 = b1; b1 = b2; h0 = h1; h1 = h2; r0 = r1;
     }
 }
 
@@ -184,7 +240,8 @@ __global__ void sgs_status_kernel(const unsigned int* tickets, SolveState* st, i
 // level analysis on the host: one pass per triangle
 // pack the strict triangle of every row, in sweep order, as 32-row slices in thread order
 void build_sell(bool forward, const std::vector<int32_t>& order, const std::vector<int32_t>& start, const std::vector<int32_t>& pos,
-                const std::vector<int32_t>& diag, std::vector<long long>* slice_ptr, std::vector<int32_t>* ecol, std::vector<int32_t>* eidx) {
+                const std::vector<int32_t>& diag, const std::vector<int32_t>& where, std::vector<long long>* slice_ptr,
+                std::vector<int32_t>* ecol, std::vector<int32_t>* eidx) {
     const size_t nslices = order.size() / 32;
     slice_ptr->assign(nslices + 1, 0);
     for (size_t s = 0; s < nslices; ++s) {
@@ -207,7 +264,7 @@ void build_sell(bool forward, const std::vector<int32_t>& order, const std::vect
             const int cnt = forward ? diag[r] - start[r] : start[r + 1] - 1 - diag[r];
             for (int k = 0; k < cnt; ++k) {
                 const int src = forward ? start[r] + k : start[r + 1] - 1 - k;   // ascending / descending columns
-                (*ecol)[(size_t)(base + (long long)k * 32 + l)] = pos[src];
+                (*ecol)[(size_t)(base + (long long)k * 32 + l)] = where[pos[src]];   // the producer's position in this sweep's order
                 (*eidx)[(size_t)(base + (long long)k * 32 + l)] = src;
             }
         }
@@ -320,9 +377,10 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
         return SMM_E_STATE;
     }
     const long long n = p->rows;
-    sgs_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->y, x_dev, n, p->tickets, state);
+    const long long nfill = std::max(p->threads_fwd, p->threads_bwd);
+    sgs_fill_kernel<<<(unsigned)((nfill + 255) / 256), 256, 0, s>>>(p->yperm, p->threads_fwd, p->xperm, p->threads_bwd, p->tickets, state);
     static int ctas_per_sm = 0;
-    if (!ctas_per_sm) { const char* e = getenv("SMM_B200_SGS_CTAS_PER_SM"); ctas_per_sm = e ? atoi(e) : 4; if (ctas_per_sm < 1) ctas_per_sm = 1; }
+    if (!ctas_per_sm) { const char* e = getenv("SMM_B200_SGS_CTAS_PER_SM"); ctas_per_sm = e ? atoi(e) : 8; if (ctas_per_sm < 1) ctas_per_sm = 1; }
     // SGS reads A's current values; an IC(0) factor is frozen at init() like the reference's ic0Val
     const unsigned long long want_version = p->kind == 1 ? 0ull : m->values_version;
     if (p->values_version != want_version) {                   // matrix values changed since the packed copies were gathered
@@ -338,14 +396,21 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
     }
     const long long cap = (long long)m->sm_count * ctas_per_sm;
     const long long bf = (p->threads_fwd + SGS_THREADS - 1) / SGS_THREADS, bb = (p->threads_bwd + SGS_THREADS - 1) / SGS_THREADS;
-    SweepArgs F{p->order_fwd, p->slice_ptr[0], p->ecol[0], p->eval[0], p->dval[0], p->threads_fwd};
-    SweepArgs Bk{p->order_bwd, p->slice_ptr[1], p->ecol[1], p->eval[1], p->dval[1], p->threads_bwd};
+    static unsigned int sleep_first = 0u, sleep_later = 64u;
+    static bool sleeps_read = false;
+    if (!sleeps_read) {                                        // tuning knobs (tools/sgs_bench.py)
+        if (const char* e = getenv("SMM_B200_SGS_SLEEP_FIRST")) sleep_first = (unsigned int)atoi(e);
+        if (const char* e = getenv("SMM_B200_SGS_SLEEP_LATER")) sleep_later = (unsigned int)atoi(e);
+        sleeps_read = true;
+    }
+    SweepArgs F{p->order_fwd, nullptr, p->slice_ptr[0], p->ecol[0], p->eval[0], p->dval[0], p->threads_fwd, sleep_first, sleep_later};
+    SweepArgs Bk{p->order_bwd, p->ypos, p->slice_ptr[1], p->ecol[1], p->eval[1], p->dval[1], p->threads_bwd, sleep_first, sleep_later};
     if (p->kind == 1) {
-        sgs_sweep_kernel<true, true><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->y, x_dev, p->tickets, state);
-        sgs_sweep_kernel<false, true><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->y, x_dev, p->tickets, state);
+        sgs_sweep_kernel<true, true><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+        sgs_sweep_kernel<false, true><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
     } else {
-        sgs_sweep_kernel<true, false><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->y, x_dev, p->tickets, state);
-        sgs_sweep_kernel<false, false><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->y, x_dev, p->tickets, state);
+        sgs_sweep_kernel<true, false><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+        sgs_sweep_kernel<false, false><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
     }
     sgs_status_kernel<<<1, 1, 0, s>>>(p->tickets, state, rc_dev);
     SMM_COUNT_LAUNCH(4);
@@ -385,14 +450,23 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
         SMM_CUDA(cudaMalloc(&p->order_fwd, sizeof(int32_t) * of.size()));
         SMM_CUDA(cudaMalloc(&p->order_bwd, sizeof(int32_t) * ob.size()));
         SMM_CUDA(cudaMalloc(&p->diag_pos, sizeof(int32_t) * diag.size()));
-        SMM_CUDA(cudaMalloc(&p->y, sizeof(float) * (size_t)m->rows));
+        if (of.size() >= (size_t)INT32_MAX || ob.size() >= (size_t)INT32_MAX) { smm_set_error("preconditioner: too many rows"); return SMM_E_INVALID; }
+        // where every row sits in each sweep's order; operands are addressed by these positions so that a warp's
+        // polls and publishes touch whole lines instead of one sector per lane
+        std::vector<int32_t> wf((size_t)m->rows, 0), wb((size_t)m->rows, 0), yp(ob.size(), 0);
+        for (size_t t = 0; t < of.size(); ++t) if (of[t] >= 0) wf[(size_t)of[t]] = (int32_t)t;
+        for (size_t t = 0; t < ob.size(); ++t) if (ob[t] >= 0) { wb[(size_t)ob[t]] = (int32_t)t; yp[t] = wf[(size_t)ob[t]]; }
+        SMM_CUDA(cudaMalloc(&p->yperm, sizeof(float) * of.size()));
+        SMM_CUDA(cudaMalloc(&p->xperm, sizeof(float) * ob.size()));
+        SMM_CUDA(cudaMalloc(&p->ypos, sizeof(int32_t) * ob.size()));
+        SMM_CUDA(cudaMemcpy(p->ypos, yp.data(), sizeof(int32_t) * yp.size(), cudaMemcpyHostToDevice));
         SMM_CUDA(cudaMemcpy(p->order_fwd, of.data(), sizeof(int32_t) * of.size(), cudaMemcpyHostToDevice));
         SMM_CUDA(cudaMemcpy(p->order_bwd, ob.data(), sizeof(int32_t) * ob.size(), cudaMemcpyHostToDevice));
         SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
         for (int w = 0; w < 2; ++w) {
             std::vector<long long> sp;
             std::vector<int32_t> ec, ei;
-            build_sell(w == 0, w == 0 ? of : ob, start, pos, diag, &sp, &ec, &ei);
+            build_sell(w == 0, w == 0 ? of : ob, start, pos, diag, w == 0 ? wf : wb, &sp, &ec, &ei);
             const size_t n = ec.size() ? ec.size() : 1;
             const size_t nt = (w == 0 ? of : ob).size();
             p->esize[w] = (long long)ec.size();
@@ -470,7 +544,7 @@ int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backwar
 
 int smm_precond_destroy(smm_precond_t* p) {
     if (!p) return SMM_OK;
-    cudaFree(p->order_fwd); cudaFree(p->order_bwd); cudaFree(p->diag_pos); cudaFree(p->y); cudaFree(p->tickets); cudaFree(p->factor);
+    cudaFree(p->order_fwd); cudaFree(p->order_bwd); cudaFree(p->diag_pos); cudaFree(p->yperm); cudaFree(p->xperm); cudaFree(p->ypos); cudaFree(p->tickets); cudaFree(p->factor);
     for (int w = 0; w < 2; ++w) { cudaFree(p->slice_ptr[w]); cudaFree(p->ecol[w]); cudaFree(p->eidx[w]); cudaFree(p->eval[w]); cudaFree(p->dval[w]); }
     cudaFree(p->io[0]); cudaFree(p->io[1]);
     delete p;
