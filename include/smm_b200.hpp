@@ -775,9 +775,12 @@ enum class MatrixLoadStatus {
     PARSE_ERROR_MMX_FILE_UNSUPPORTED_STRUCTURE
 };
 
-// coordinate x {real, integer} x symmetric; off-diagonals mirrored; explicit zeros kept
+namespace b200 {
+// One parser behind both loaders.  extended == false: exactly the reference's loadMatrixMarketMatrix (H:2531-2609).
+// extended == true (not in the reference): also `general` and `skew-symmetric` structure and the
+// `pattern` field (every stored entry is 1).
 template <typename T>
-inline MatrixLoadStatus loadMatrixMarketMatrix(const char* filepath, TripletMatrix<T>& out) {
+inline MatrixLoadStatus loadMatrixMarketImpl(const char* filepath, TripletMatrix<T>& out, bool extended) {
     std::ifstream in(filepath);
     if (!in.is_open()) return MatrixLoadStatus::FAILED_TO_OPEN_FILE;
     auto lowered = [&in]() {
@@ -792,24 +795,37 @@ inline MatrixLoadStatus loadMatrixMarketMatrix(const char* filepath, TripletMatr
     if (lowered() != "matrix") return MatrixLoadStatus::PARSE_ERROR_MMX_FILE_UNSUPPORTED_TYPE;
     if (lowered() != "coordinate") return MatrixLoadStatus::PARSE_ERROR_MMX_FILE_UNSUPPORTED_FORMAT;
     const std::string elType = lowered();
-    if (elType != "real" && elType != "integer") return MatrixLoadStatus::PARSE_ERROR_MMX_FILE_UNSUPPORTED_EL_TYPE;
-    if (lowered() != "symmetric") return MatrixLoadStatus::PARSE_ERROR_MMX_FILE_UNSUPPORTED_STRUCTURE;
+    const bool pattern = extended && elType == "pattern";
+    if (elType != "real" && elType != "integer" && !pattern) return MatrixLoadStatus::PARSE_ERROR_MMX_FILE_UNSUPPORTED_EL_TYPE;
+    const std::string structure = lowered();
+    const bool general = extended && structure == "general";
+    const bool skew = extended && structure == "skew-symmetric";
+    if (structure != "symmetric" && !general && !skew) return MatrixLoadStatus::PARSE_ERROR_MMX_FILE_UNSUPPORTED_STRUCTURE;
     const auto skipLine = [&in]() { in.ignore(std::numeric_limits<std::streamsize>::max(), '\n'); };
     while (in.peek() == '%' || std::isspace(in.peek())) skipLine();
     int rows = 0, cols = 0, nnz = 0;
     in >> rows >> cols >> nnz;
     if (in.fail()) return MatrixLoadStatus::FAILED_TO_PARSE_FILE;
     out.init(rows, cols, nnz);
+    if (extended && nnz == 0) return MatrixLoadStatus::SUCCESS;   // the reference's loop body runs at least once (H:2588)
     while (!in.eof()) {
         int r = 0, c = 0;
-        T v{};
-        in >> r >> c >> v;
+        T v = T(1);
+        in >> r >> c;
+        if (!pattern) in >> v;
         if (in.fail()) return MatrixLoadStatus::FAILED_TO_PARSE_FILE;
         out.addEntry(r - 1, c - 1, v);
-        if (r != c) out.addEntry(c - 1, r - 1, v);
+        if (!general && r != c) out.addEntry(c - 1, r - 1, skew ? -v : v);
         while (std::isspace(in.peek())) skipLine();
     }
     return MatrixLoadStatus::SUCCESS;
+}
+}  // namespace b200
+
+// coordinate x {real, integer} x symmetric; off-diagonals mirrored; explicit zeros kept
+template <typename T>
+inline MatrixLoadStatus loadMatrixMarketMatrix(const char* filepath, TripletMatrix<T>& out) {
+    return b200::loadMatrixMarketImpl(filepath, out, false);
 }
 
 // "rows cols\n{{a,b,..},\n{..}}" as written by saveDenseText
@@ -854,5 +870,35 @@ inline MatrixLoadStatus loadMatrix(const char* filepath, CSRMatrix<T>& out) {
     out.init(triplet);
     return MatrixLoadStatus::SUCCESS;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// EXTENSION (not in the reference): Matrix Market files the reference rejects -- `general` and
+// `skew-symmetric` structure, `pattern` field -- so that non-symmetric SuiteSparse matrices can be fed to
+// CGS / BiCGStab.  The reference-named loaders above keep the reference's behaviour, including its rejections.
+// ---------------------------------------------------------------------------------------------------------------
+namespace ext {
+template <typename T>
+inline MatrixLoadStatus loadMatrixMarketMatrix(const char* filepath, TripletMatrix<T>& out) {
+    return b200::loadMatrixMarketImpl(filepath, out, true);
+}
+
+template <typename T>
+inline MatrixLoadStatus loadMatrix(const char* filepath, TripletMatrix<T>& out) {
+    const char* dot = std::strrchr(filepath, '.');
+    const std::string e = dot ? dot + 1 : "";
+    if (e == "mtx") return ext::loadMatrixMarketMatrix(filepath, out);
+    if (e == "smmdt") return loadSMMDTMatrix(filepath, out);
+    return MatrixLoadStatus::FAILED_TO_OPEN_FILE_UNKNOWN_FORMAT;
+}
+
+template <typename T>
+inline MatrixLoadStatus loadMatrix(const char* filepath, CSRMatrix<T>& out) {
+    TripletMatrix<T> triplet;
+    const MatrixLoadStatus status = ext::loadMatrix(filepath, triplet);
+    if (status != MatrixLoadStatus::SUCCESS) return status;
+    out.init(triplet);
+    return MatrixLoadStatus::SUCCESS;
+}
+}  // namespace ext
 
 }  // namespace SMM

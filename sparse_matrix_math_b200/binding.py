@@ -511,15 +511,16 @@ def dot(a, b, reduction_mode=REDUCE_FAST):
     return float(out.value)
 
 
-def loadMatrix(path, out):
-    """SMM::loadMatrix (H:2648-2669) for .mtx: host-side parse (H:2531-2609) -> TripletMatrix -> CSRMatrix."""
+def loadMatrix(path, out, extended=False):
+    """SMM::loadMatrix (H:2648-2669) for .mtx: host-side parse (H:2531-2609) -> TripletMatrix -> CSRMatrix.
+    extended=True is SMM::ext::loadMatrix (extension): general / skew-symmetric structure and pattern files too."""
     from .mmio import load_matrix_market
     dot_pos = path.rfind(".")
     ext = path[dot_pos + 1:] if dot_pos >= 0 else ""
     if ext != "mtx":
         return MatrixLoadStatus.FAILED_TO_OPEN_FILE_UNKNOWN_FORMAT
     t = out if isinstance(out, TripletMatrix) else TripletMatrix()
-    st = load_matrix_market(path, t)
+    st = load_matrix_market(path, t, extended)
     if st != MatrixLoadStatus.SUCCESS:
         return st
     if isinstance(out, CSRMatrix):

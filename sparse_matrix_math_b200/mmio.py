@@ -6,7 +6,9 @@ entries mirrored; explicit zeros kept; values parsed straight to float32 (correc
 import numpy as np
 
 
-def load_matrix_market(path, out):
+def load_matrix_market(path, out, extended=False):
+    """extended=False: the reference's loader.  extended=True (extension): also `general` /
+    `skew-symmetric` structure and the `pattern` field (every stored entry is 1)."""
     from .binding import MatrixLoadStatus as S
     try:
         f = open(path, "r")
@@ -34,9 +36,14 @@ def load_matrix_market(path, out):
         return S.PARSE_ERROR_MMX_FILE_UNSUPPORTED_TYPE
     if (token() or "").lower() != "coordinate":
         return S.PARSE_ERROR_MMX_FILE_UNSUPPORTED_FORMAT
-    if (token() or "").lower() not in ("real", "integer"):
+    el_type = (token() or "").lower()
+    pattern = extended and el_type == "pattern"
+    if el_type not in ("real", "integer") and not pattern:
         return S.PARSE_ERROR_MMX_FILE_UNSUPPORTED_EL_TYPE
-    if (token() or "").lower() != "symmetric":
+    structure = (token() or "").lower()
+    general = extended and structure == "general"
+    skew = extended and structure == "skew-symmetric"
+    if structure != "symmetric" and not general and not skew:
         return S.PARSE_ERROR_MMX_FILE_UNSUPPORTED_STRUCTURE
     # H:2576-2578: drop every line that starts with '%' or whitespace
     n = len(text)
@@ -48,17 +55,19 @@ def load_matrix_market(path, out):
     except (TypeError, ValueError):
         return S.FAILED_TO_PARSE_FILE
     out.init(rows, cols, _nnz)
+    if extended and _nnz == 0:
+        return S.SUCCESS
     while True:                                   # H:2588: the body runs at least once
         try:
             r, c = int(token()), int(token())
-            v = np.float32(token())
+            v = np.float32(1.0) if pattern else np.float32(token())
         except (TypeError, ValueError):
             return S.FAILED_TO_PARSE_FILE
         r -= 1
         c -= 1
         out.addEntry(r, c, v)
-        if r != c:
-            out.addEntry(c, r, v)
+        if not general and r != c:
+            out.addEntry(c, r, -v if skew else v)
         while pos < n and text[pos].isspace():    # H:2603-2605
             nl = text.find("\n", pos)
             pos = n if nl < 0 else nl + 1
