@@ -133,6 +133,14 @@ int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backwar
  * run on the GPU with the same level-scheduled sweeps as SGS. */
 int smm_precond_ic0_create(const smm_csr_t* m, int* rc, smm_precond_t** out);
 int smm_precond_ic0_factor(const smm_precond_t* p, float* factor_host);
+/* EXTENSION -- CSRMatrix::ILU0Preconditioner (H:1188-1212, 1715-1790).  The reference declares it but its factorize()
+ * cannot succeed and apply() is never defined (dead code), so there is nothing to be bit-identical to: this is the
+ * zero-fill LU that code describes (row-wise IKJ in A's pattern, unit lower factor, multipliers formed with the
+ * reciprocal pivot), factorised on the host at create time; apply = L y = rhs, U x = y on the GPU with the level-scheduled
+ * sweeps.  *rc: 0 ok, 1 structurally unusable, 2 pivot not > 1e-6 in magnitude.  smm_precond_ic0_factor returns the
+ * factor of either kind (strict L and U in A's pattern).  smm_solve_bicgstab accepts it as `precond`. */
+int smm_precond_ilu0_create(const smm_csr_t* m, int* rc, smm_precond_t** out);
+/* 0 Symmetric Gauss-Seidel, 1 IC(0), 2 ILU(0) */
 int smm_precond_kind(const smm_precond_t* p);
 int smm_precond_destroy(smm_precond_t* p);
 

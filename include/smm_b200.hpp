@@ -563,17 +563,36 @@ public:
         mutable unsigned long long stamp = 0;
     };
 
-    // ILU(0) is dead code in the reference (factorize() always returns 2, apply() is never defined, the factory
-    // returns void for it, ref H:1188-1212, 1715-1790); the type is kept so that code naming it still compiles.
+    // EXTENSION.  ILU(0) is dead code in the reference (factorize() can only fail, apply() is never defined, the
+    // factory returns void for it; ref H:1188-1212, 1715-1790).  Here the type works: validate() performs the
+    // zero-fill LU those lines describe on the host (0 ok, 1 unusable structure, 2 pivot not > 1e-6), apply() runs
+    // L y = rhs, U x = y on the GPU, and BiCGStab accepts the object like any other preconditioner.
     class ILU0Preconditioner {
     public:
         ILU0Preconditioner(const CSRMatrix& matrix) noexcept : m(matrix) {}
         ILU0Preconditioner(const ILU0Preconditioner&) = delete;
         ILU0Preconditioner& operator=(const ILU0Preconditioner&) = delete;
-        ILU0Preconditioner(ILU0Preconditioner&&) noexcept = default;
-        int validate() noexcept { return m.firstActiveStart != 0 ? 1 : 2; }
+        ILU0Preconditioner(ILU0Preconditioner&& o) noexcept : m(o.m), handle(o.handle), code(o.code) { o.handle = nullptr; }
+        ~ILU0Preconditioner() { if (handle) smm_precond_destroy(handle); }
+        int validate() noexcept {
+            b200::requireFloat<T>();
+            if (handle) { smm_precond_destroy(handle); handle = nullptr; }
+            b200::check(smm_precond_ilu0_create(m.device(), &code, &handle), "smm_precond_ilu0_create");
+            return code;
+        }
+        int apply(const T* rhs, T* x) const noexcept {
+            b200::requireFloat<T>();
+            if (!handle) return 1;
+            int rc = 0;
+            b200::check(smm_precond_apply(handle, rhs, x, &rc), "smm_precond_apply");
+            return rc;
+        }
+        const smm_precond_t* device() const { return handle; }
+        const CSRMatrix& matrix() const { return m; }
     private:
         const CSRMatrix& m;
+        smm_precond_t* handle = nullptr;
+        int code = 1;
     };
 
     // Zero-fill incomplete Cholesky (ref H:1214-1235): IC0Preconditioner M(m); M.init(); M.apply(rhs, x) and the
@@ -609,6 +628,11 @@ public:
     decltype(auto) getPreconditioner() const noexcept {
         if constexpr (precond == SolverPreconditioner::NONE) return IDPreconditioner();
         else if constexpr (precond == SolverPreconditioner::SYMMETRIC_GAUS_SEIDEL) return SGSPreconditioner(*this);
+        else {                                          // extension: the reference's factory has no ILU0 branch (returns void)
+            ILU0Preconditioner M(*this);
+            M.validate();
+            return M;
+        }
     }
 
     // ---- device mirror ----
@@ -722,12 +746,21 @@ inline SolverStatus BiCGStab(const CSRMatrix<T>& a, T* b, T* x, int maxIteration
     b200::requireFloat<T>();
     using Id = typename CSRMatrix<T>::IDPreconditioner;
     using Sgs = typename CSRMatrix<T>::SGSPreconditioner;
-    static_assert(std::is_same_v<Preconditioner, Id> || std::is_same_v<Preconditioner, Sgs>,
-                  "BiCGStab on the B200 path takes the preconditioners CSRMatrix::getPreconditioner() returns");
+    using Ic0 = typename CSRMatrix<T>::IC0Preconditioner;
+    using Ilu0 = typename CSRMatrix<T>::ILU0Preconditioner;
+    // the reference's template takes any object with apply(rhs, x) (H:2191-2199); on this path the object must be one
+    // whose apply lives on the GPU
+    static_assert(std::is_same_v<Preconditioner, Id> || std::is_same_v<Preconditioner, Sgs> || std::is_same_v<Preconditioner, Ic0> ||
+                      std::is_same_v<Preconditioner, Ilu0>,
+                  "BiCGStab on the B200 path takes the preconditioner classes of CSRMatrix (ID, SGS, IC0, ILU0)");
     const smm_precond_t* p = nullptr;
-    if constexpr (std::is_same_v<Preconditioner, Sgs>) {
+    if constexpr (!std::is_same_v<Preconditioner, Id>) {
         assert(&preconditioner.matrix() == &a);
         p = preconditioner.device();
+        if (!p) {
+            std::fprintf(stderr, "sparse_matrix_math (B200): BiCGStab: the preconditioner has not been initialised (init() / validate())\n");
+            std::abort();
+        }
     }
     smm_solve_info info;
     b200::check(smm_solve_bicgstab(a.device(), p, b, x, maxIterations, eps, &b200::options(), &info), "smm_solve_bicgstab");

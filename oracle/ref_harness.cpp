@@ -173,6 +173,11 @@ int smm_ref_cgs(void* h, float* b, float* x, int maxIterations, float eps) {
 
 int smm_ref_bicgstab(void* h, int precond, float* b, float* x, int maxIterations, float eps) {
     Csr* m = static_cast<Csr*>(h);
+    if (precond == 3) {                                        // the template over any object with apply(): IC0Preconditioner
+        Csr::IC0Preconditioner M(*m);
+        if (M.init()) return -1;
+        return int(SMM::BiCGStab<Csr::IC0Preconditioner, float>(*m, b, x, maxIterations, eps, M));
+    }
     if (precond) {
         using SGS = Csr::SGSPreconditioner;
         const SGS& M = m->getPreconditioner<SMM::SolverPreconditioner::SYMMETRIC_GAUS_SEIDEL>();

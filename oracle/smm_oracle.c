@@ -278,6 +278,63 @@ int smm_oracle_ic0_apply(int rows, const int *start, const int *positions, const
     return 0;
 }
 
+/* EXTENSION (parity UNPINNED by the reference): zero-fill incomplete LU as ILU0Preconditioner::factorize describes it
+ * (H:1723-1790): row-wise IKJ on A's pattern, unit L with the diagonal implied, U's diagonal stored, multiplier
+ * alphaIK = ilu0Val[kPos] * diagonalElementsInv[k] (H:1762), update ilu0Val[..] -= alphaIK * betaKJ (H:1766-1768).
+ * The reference's code cannot run to completion (inverted guards at H:1744 / H:1775, inner loop bound `col > 0`
+ * at H:1764 instead of `col > k`), and it has no apply(); this restates the algorithm those lines describe.
+ * Returns 0, 1 (first_active_start != 0 / empty row / missing diagonal), 2 (pivot not > 1e-6 in magnitude). */
+int smm_oracle_ilu0_factorize(int rows, const int *start, const int *positions, const float *values,
+                              int first_active_start, float *ilu0) {
+    if (rows == 0) return 0;
+    if (first_active_start != 0) return 1;                 /* H:1734-1737 */
+    const int nnz = start[rows];
+    memcpy(ilu0, values, sizeof(float) * (size_t)nnz);     /* H:1732 */
+    int *column_index = (int *)malloc(sizeof(int) * (size_t)rows);
+    float *dinv = (float *)malloc(sizeof(float) * (size_t)rows);
+    for (int i = 0; i < rows; ++i) column_index[i] = -1;
+    int rc = 0;
+    for (int row = 0; row < rows && rc == 0; ++row) {
+        const int rs = start[row], re = start[row + 1];
+        for (int i = rs; i < re; ++i) column_index[positions[i]] = i;
+        int kp = rs;
+        for (; kp < re && positions[kp] < row; ++kp) {
+            const int k = positions[kp];
+            const float alpha = ilu0[kp] * dinv[k];
+            ilu0[kp] = alpha;
+            for (int cp = start[k + 1] - 1; cp >= start[k] && positions[cp] > k; --cp) {
+                const int ci = column_index[positions[cp]];
+                if (ci != -1) ilu0[ci] -= alpha * ilu0[cp];
+            }
+        }
+        for (int i = rs; i < re; ++i) column_index[positions[i]] = -1;
+        if (kp >= re || positions[kp] != row) { rc = 1; break; }
+        if (!(fabsf(ilu0[kp]) > 1e-6f)) { rc = 2; break; }
+        dinv[row] = 1.0f / ilu0[kp];
+    }
+    free(column_index);
+    free(dinv);
+    return rc;
+}
+
+/* L y = rhs (unit diagonal, columns ascending), U x = y (columns descending, one division by u_ii): the same loop
+ * shape as IC0Preconditioner::apply (H:1802-1837), which is the only factor-based apply the reference defines. */
+int smm_oracle_ilu0_apply(int rows, const int *start, const int *positions, const float *ilu0,
+                          const float *rhs, float *x) {
+    for (int row = 0; row < rows; ++row) {
+        float sum = rhs[row];
+        for (int j = start[row]; j < start[row + 1] && positions[j] < row; ++j) sum -= ilu0[j] * x[positions[j]];
+        x[row] = sum;
+    }
+    for (int row = rows - 1; row >= 0; --row) {
+        float sum = x[row];
+        int j = start[row + 1] - 1;
+        for (; j >= start[row] && positions[j] > row; --j) sum -= ilu0[j] * x[positions[j]];
+        x[row] = sum / ilu0[j];
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Solvers
  * ---------------------------------------------------------------------------------------------- */
@@ -439,10 +496,26 @@ void smm_oracle_cgs(int rows, const int *start, const int *positions, const floa
 }
 
 /* BiCGStab, H:2191-2283 (+ wrapper H:2294-2303) */
+static int apply_precond(int kind, const float *factor, int rows, const int *start, const int *positions, const float *values,
+                         int first_active_start, const float *rhs, float *x) {
+    if (kind == 1) return smm_oracle_sgs_apply(rows, start, positions, values, first_active_start, rhs, x);
+    if (kind == 2) return smm_oracle_ilu0_apply(rows, start, positions, factor, rhs, x);
+    return smm_oracle_ic0_apply(rows, start, positions, factor, rhs, x);
+}
+
 void smm_oracle_bicgstab(int rows, const int *start, const int *positions, const float *values,
                          int first_active_start, int precond,
                          const float *b, float *x, int max_iterations, float eps, int mt,
                          smm_oracle_info *info, float *history, int history_cap) {
+    smm_oracle_bicgstab_pc(rows, start, positions, values, first_active_start, precond, NULL, b, x, max_iterations, eps, mt,
+                           info, history, history_cap);
+}
+
+/* the template instantiated with any preconditioner object (H:2191-2199): precond 2 = ILU(0), 3 = IC(0), factor = its values */
+void smm_oracle_bicgstab_pc(int rows, const int *start, const int *positions, const float *values,
+                            int first_active_start, int precond, const float *factor,
+                            const float *b, float *x, int max_iterations, float eps, int mt,
+                            smm_oracle_info *info, float *history, int history_cap) {
     const int dm = mt ? SMM_ORACLE_DOT_TBB8192 : SMM_ORACLE_DOT_SERIAL;
     max_iterations = clamp_max_iterations(max_iterations, rows);
     float *scratch = precond ? vec_alloc(rows) : NULL;     /* H:2208-2212 */
@@ -450,7 +523,7 @@ void smm_oracle_bicgstab(int rows, const int *start, const int *positions, const
     float *ap = vec_alloc(rows), *s = vec_alloc(rows), *as = vec_alloc(rows);
     int perr = 0;
     smm_oracle_spmv(rows, start, positions, values, 2, b, x, r);  /* H:2215 */
-    if (precond) perr |= smm_oracle_sgs_apply(rows, start, positions, values, first_active_start, r, scratch); /* H:2218 */
+    if (precond) perr |= apply_precond(precond, factor, rows, start, positions, values, first_active_start, r, scratch); /* H:2218 */
     for (int i = 0; i < rows; ++i) {                       /* H:2221-2227 */
         if (precond) r[i] = scratch[i];
         r0[i] = r[i];
@@ -462,7 +535,7 @@ void smm_oracle_bicgstab(int rows, const int *start, const int *positions, const
     do {
         if (precond) {                                     /* H:2233-2241 */
             smm_oracle_spmv(rows, start, positions, values, 0, NULL, p, scratch);
-            perr |= smm_oracle_sgs_apply(rows, start, positions, values, first_active_start, scratch, ap);
+            perr |= apply_precond(precond, factor, rows, start, positions, values, first_active_start, scratch, ap);
         } else {
             smm_oracle_spmv(rows, start, positions, values, 0, NULL, p, ap);
         }
@@ -471,7 +544,7 @@ void smm_oracle_bicgstab(int rows, const int *start, const int *positions, const
         for (int i = 0; i < rows; ++i) s[i] = smm_fma(-alpha, ap[i], r[i]);   /* H:2245-2247 */
         if (precond) {                                     /* H:2249-2257 */
             smm_oracle_spmv(rows, start, positions, values, 0, NULL, s, scratch);
-            perr |= smm_oracle_sgs_apply(rows, start, positions, values, first_active_start, scratch, as);
+            perr |= apply_precond(precond, factor, rows, start, positions, values, first_active_start, scratch, as);
         } else {
             smm_oracle_spmv(rows, start, positions, values, 0, NULL, s, as);
         }

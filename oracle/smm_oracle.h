@@ -86,6 +86,17 @@ void smm_oracle_bicgstab(int rows, const int *start, const int *positions, const
                          int first_active_start, int precond,
                          const float *b, float *x, int max_iterations, float eps, int mt,
                          smm_oracle_info *info, float *history, int history_cap);    /* H:2191-2283 */
+/* precond: 0 / 1 as above, 2 = ILU(0) (extension), 3 = IC(0); factor = that preconditioner's values (NULL for 0 / 1) */
+void smm_oracle_bicgstab_pc(int rows, const int *start, const int *positions, const float *values,
+                            int first_active_start, int precond, const float *factor,
+                            const float *b, float *x, int max_iterations, float eps, int mt,
+                            smm_oracle_info *info, float *history, int history_cap);
+/* EXTENSION, parity unpinned by the reference (its ILU0Preconditioner is dead code, H:1188-1212, 1715-1790): the
+ * zero-fill LU those lines describe, and the two triangular solves in the shape of IC0Preconditioner::apply. */
+int smm_oracle_ilu0_factorize(int rows, const int *start, const int *positions, const float *values,
+                              int first_active_start, float *ilu0);
+int smm_oracle_ilu0_apply(int rows, const int *start, const int *positions, const float *ilu0,
+                          const float *rhs, float *x);
 /* PCG with IC0 (H:2414-2505). */
 void smm_oracle_cg_ic0(int rows, const int *start, const int *positions, const float *values,
                        const float *ic0, const float *b, const float *x0, float *x,

@@ -17,6 +17,7 @@ from .binding import (  # noqa: F401
     CSRMatrix,
     DeviceVector,
     IC0Preconditioner,
+    ILU0Preconditioner,
     MatrixLoadStatus,
     SGSPreconditioner,
     SmmError,

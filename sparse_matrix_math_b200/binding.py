@@ -119,6 +119,7 @@ def lib():
         L.smm_precond_destroy.argtypes = [_vp]
         L.smm_precond_ic0_create.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_vp)]
         L.smm_precond_ic0_factor.argtypes = [_vp, _vp]
+        L.smm_precond_ilu0_create.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_vp)]
         L.smm_precond_kind.argtypes = [_vp]
         op, ip = C.POINTER(_Options), C.POINTER(_Info)
         L.smm_solve_cg.argtypes = [_vp, _vp, _vp, _vp, _i32, _f32, op, ip]
@@ -329,6 +330,19 @@ class IC0Preconditioner(SGSPreconditioner):
         return out[: self.matrix.nnz]
 
 
+class ILU0Preconditioner(IC0Preconditioner):
+    """EXTENSION: CSRMatrix<float>::ILU0Preconditioner (dead code in the reference, H:1188-1212, 1715-1790) made to
+    work: ILU0Preconditioner(m); validate() factorises (0 ok, 1 structure, 2 pivot); apply(rhs, x); BiCGStab takes it."""
+
+    def validate(self):
+        h, rc = _vp(), _i32()
+        _check(lib().smm_precond_ilu0_create(self.matrix.handle, C.byref(rc), C.byref(h)), "smm_precond_ilu0_create")
+        self.handle, self.init_code = h.value, rc.value
+        return rc.value
+
+    init = validate
+
+
 class CSRMatrix:
     """SMM::CSRMatrix<float> (H:1011-1302) with its arrays resident in HBM."""
 
@@ -439,7 +453,10 @@ class CSRMatrix:
             return None                         # IDPreconditioner
         if kind == SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL:
             return SGSPreconditioner(self)
-        raise SmmError("getPreconditioner<ILU0>() returns void in the reference (H:1645-1651)")
+        # the reference's factory returns void for ILU0 (H:1645-1651); here it hands out the working extension
+        M = ILU0Preconditioner(self)
+        M.validate()
+        return M
 
 
 def _options(reduction_mode, driver_mode, check_every, history_cap):

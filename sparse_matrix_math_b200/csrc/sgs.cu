@@ -35,8 +35,9 @@
 #include "smm_internal.cuh"
 
 struct smm_precond {
-    int kind = 0;                    // 0: Symmetric Gauss-Seidel on A's values; 1: IC(0) on its own factor values
+    int kind = 0;                    // 0: Symmetric Gauss-Seidel on A's values; 1: IC(0), 2: ILU(0) on their own factor values
     float* factor = nullptr;         // IC(0): [nnz] factor in A's pattern (L below and on the diagonal, L^T above), ref H:1233-1234
+                                     // ILU(0): strict L (unit diagonal implied) below, U on and above the diagonal, ref H:1203-1211
     const smm_csr* m = nullptr;
     int rows = 0;
     bool valid = true;               // structure admits the sweeps (else apply returns the reference's code 1)
@@ -107,10 +108,12 @@ struct SweepArgs {
 };
 
 __global__ void sgs_gather_values_kernel(const float* __restrict__ values, const int32_t* __restrict__ eidx, float* __restrict__ eval, long long n,
-                                         const int32_t* __restrict__ order, const int32_t* __restrict__ diag_pos, float* __restrict__ dval, long long nthreads) {
+                                         const int32_t* __restrict__ order, const int32_t* __restrict__ diag_pos, float* __restrict__ dval, long long nthreads,
+                                         const bool unit_diagonal) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const int k = eidx[i]; eval[i] = k >= 0 ? values[k] : 0.0f; }
-    if (i < nthreads) { const int r = order[i]; dval[i] = r >= 0 ? values[diag_pos[r]] : 1.0f; }
+    // unit_diagonal: the L factor of ILU(0) has an implied diagonal of ones (x / 1.0f == x exactly)
+    if (i < nthreads) { const int r = order[i]; dval[i] = (r >= 0 && !unit_diagonal) ? values[diag_pos[r]] : 1.0f; }
 }
 
 // IC0 = false: SGS sweeps (H:1658-1713).  IC0 = true: L y = rhs then L^T x = y (IC0Preconditioner::apply, H:1802-1837):
@@ -355,6 +358,42 @@ int ic0_factorize_host(int rows, const std::vector<int32_t>& start, const std::v
     return 0;
 }
 
+// Zero-fill incomplete LU in A's pattern: the factorisation ILU0Preconditioner::factorize (H:1723-1790) describes --
+// row-wise IKJ, unit lower factor with its diagonal implied, U's diagonal stored, multipliers formed with the
+// reciprocal of the pivot (`ilu0Val[kPos] * diagonalElementsInv[k]`, H:1762), updates `-= alphaIK * betaKJ` (H:1766-1768).
+// The reference's own loop never completes (its guards at H:1744 and H:1775 are inverted and the inner loop at H:1764
+// runs to column 0 instead of stopping above the diagonal), so this is an EXTENSION: parity is pinned by the oracle's
+// restatement of the same algorithm, not by the reference.  Returns 0, or 2 on a pivot that is not > 1e-6 in
+// magnitude (the condition H:1774 asserts).
+int ilu0_factorize_host(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag,
+                        const std::vector<float>& a, std::vector<float>* out) {
+    std::vector<float>& lu = *out;
+    lu = a;                                                    // H:1732
+    std::vector<int32_t> column_index((size_t)rows, -1);       // H:1749
+    std::vector<float> dinv((size_t)rows, 0.0f);               // H:1752
+    for (int row = 0; row < rows; ++row) {
+        const int rs = start[row], re = start[row + 1];
+        for (int i = rs; i < re; ++i) column_index[(size_t)pos[i]] = i;          // H:1760-1763
+        for (int kp = rs; kp < diag[row]; ++kp) {              // columns k < row, ascending
+            const int k = pos[kp];
+            const float alpha = lu[kp] * dinv[(size_t)k];
+            lu[kp] = alpha;
+            for (int cp = start[k + 1] - 1; cp > diag[k]; --cp) {                 // row k of U, strictly right of its diagonal
+                const int ci = column_index[(size_t)pos[cp]];
+                if (ci != -1) {
+                    const float prod = alpha * lu[cp];                            // two roundings, like the reference's default build
+                    lu[ci] -= prod;
+                }
+            }
+        }
+        for (int i = rs; i < re; ++i) column_index[(size_t)pos[i]] = -1;          // H:1781-1784
+        const float pivot = lu[diag[row]];
+        if (!(std::fabs(pivot) > 1e-6f)) return 2;
+        dinv[(size_t)row] = 1.0f / pivot;                      // H:1778
+    }
+    return 0;
+}
+
 }  // namespace
 
 int smm_sgs_kernels_per_apply(const smm_precond* p) { return p && p->valid ? 4 : 1; }
@@ -382,14 +421,15 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) { const char* e = getenv("SMM_B200_SGS_CTAS_PER_SM"); ctas_per_sm = e ? atoi(e) : 8; if (ctas_per_sm < 1) ctas_per_sm = 1; }
     // SGS reads A's current values; an IC(0) factor is frozen at init() like the reference's ic0Val
-    const unsigned long long want_version = p->kind == 1 ? 0ull : m->values_version;
+    const unsigned long long want_version = p->kind != 0 ? 0ull : m->values_version;
     if (p->values_version != want_version) {                   // matrix values changed since the packed copies were gathered
         smm_precond* pm = const_cast<smm_precond*>(p);
         for (int w = 0; w < 2; ++w) {
             const long long nt = w == 0 ? p->threads_fwd : p->threads_bwd;
             const long long n = std::max(p->esize[w], nt);
-            sgs_gather_values_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->kind == 1 ? p->factor : m->values, p->eidx[w], p->eval[w], p->esize[w],
-                                                                                 w == 0 ? p->order_fwd : p->order_bwd, p->diag_pos, p->dval[w], nt);
+            sgs_gather_values_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->kind != 0 ? p->factor : m->values, p->eidx[w], p->eval[w], p->esize[w],
+                                                                                 w == 0 ? p->order_fwd : p->order_bwd, p->diag_pos, p->dval[w], nt,
+                                                                                 p->kind == 2 && w == 0);
         }
         SMM_COUNT_LAUNCH(2);
         pm->values_version = want_version;
@@ -405,7 +445,7 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
     }
     SweepArgs F{p->order_fwd, nullptr, p->slice_ptr[0], p->ecol[0], p->eval[0], p->dval[0], p->threads_fwd, sleep_first, sleep_later};
     SweepArgs Bk{p->order_bwd, p->ypos, p->slice_ptr[1], p->ecol[1], p->eval[1], p->dval[1], p->threads_bwd, sleep_first, sleep_later};
-    if (p->kind == 1) {
+    if (p->kind != 0) {                                        // IC(0) and ILU(0) share the `sum -= f * x; x = sum / d` sweeps
         sgs_sweep_kernel<true, true><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
         sgs_sweep_kernel<false, true><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
     } else {
@@ -435,10 +475,15 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
     std::vector<int32_t> diag, of, ob;
     analyse(m->rows, start, pos, m->first_active_start, &p->valid, &diag, &of, &ob, &p->levels_fwd, &p->levels_bwd);
     if (rc_out) *rc_out = p->valid ? 0 : 1;
-    if (kind == 1 && p->valid && m->nnz > 0) {
+    if (kind != 0 && p->valid && m->nnz > 0) {
         std::vector<float> a((size_t)m->nnz), l;
         SMM_CUDA(cudaMemcpy(a.data(), m->values, sizeof(float) * a.size(), cudaMemcpyDeviceToHost));
-        ic0_factorize_host(m->rows, start, pos, diag, a, &l);
+        if (kind == 1) {
+            ic0_factorize_host(m->rows, start, pos, diag, a, &l);
+        } else if (ilu0_factorize_host(m->rows, start, pos, diag, a, &l) != 0) {
+            p->valid = false;                                  // no usable pivot: apply() reports an error instead of dividing by ~0
+            if (rc_out) *rc_out = 2;
+        }
         SMM_CUDA(cudaMalloc(&p->factor, sizeof(float) * l.size()));
         SMM_CUDA(cudaMemcpy(p->factor, l.data(), sizeof(float) * l.size(), cudaMemcpyHostToDevice));
     }
@@ -493,8 +538,12 @@ int smm_precond_sgs_create(const smm_csr_t* m, smm_precond_t** out) { return pre
 int smm_precond_ic0_create(const smm_csr_t* m, int* rc, smm_precond_t** out) { return precond_create(m, 1, rc, out); }
 
 // copy of the factor values (nnz floats, A's pattern) for parity checks
+// ILU0Preconditioner(m) + validate() (H:1188-1212, 1715-1790) as an extension: *rc receives 0, 1 (leading empty rows /
+// an empty row / a missing diagonal) or 2 (pivot not > 1e-6 in magnitude).
+int smm_precond_ilu0_create(const smm_csr_t* m, int* rc, smm_precond_t** out) { return precond_create(m, 2, rc, out); }
+
 int smm_precond_ic0_factor(const smm_precond_t* p, float* factor_host) {
-    if (!p || p->kind != 1 || !factor_host) return SMM_E_INVALID;
+    if (!p || p->kind == 0 || !factor_host) return SMM_E_INVALID;
     if (!p->factor) return SMM_E_STATE;
     SMM_CUDA(cudaMemcpy(factor_host, p->factor, sizeof(float) * (size_t)p->m->nnz, cudaMemcpyDeviceToHost));
     return SMM_OK;

@@ -464,7 +464,8 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
                 SMM_TRY(cgs_init(c)); iter = cgs_iter; budget = max_it > 1 ? max_it : 1;           // H:2131/2172
                 break;
             case S_BICGSTAB:
-                if (precond && smm_precond_kind(precond) != 0) { smm_set_error("BiCGStab takes the SGS preconditioner (getPreconditioner())"); return SMM_E_INVALID; }
+                // the reference's BiCGStab is a template over anything with apply(rhs, x) (H:2191-2199): SGS from
+                // getPreconditioner(), an IC0Preconditioner, or (extension) ILU(0) all go through the same sweeps
                 SMM_TRY(stab_init(c)); iter = stab_iter; budget = max_it > 1 ? max_it : 1;         // H:2232/2277
                 break;
         }

@@ -285,6 +285,38 @@ TEST_CASE("Preconditioned Conjugate Gradient method. IC0 Preconditioner") {
     }
 }
 
+// ---- BiCGStab over the factor-based preconditioners: IC0 (a legal instantiation of the reference's template) and the
+// ILU(0) extension (dead code in the reference; here getPreconditioner<ILU0>() hands out a working object) ----------
+TEST_CASE("Preconditioned BiCGStab. IC0 and ILU0 preconditioners") {
+    for (const auto& name : kMeshes) {
+        SMM::CSRMatrix<T> m;
+        REQUIRE_EQ(SMM::loadMatrix((std::string(ASSET_PATH) + name).c_str(), m), SMM::MatrixLoadStatus::SUCCESS);
+        SMM::Vector<T> rhs = sumColumsPerRow(m);
+        const int n = m.getDenseRowCount();
+        SMM::Vector<T> x0(n, 0);
+        REQUIRE_EQ(SMM::BiCGStab<T>(m, rhs, x0, -1, kL2Eps), SMM::SolverStatus::SUCCESS);
+        const int plain = SMM::b200::lastSolveInfo().iterations;
+        {
+            using IC0 = typename SMM::CSRMatrix<T>::IC0Preconditioner;
+            IC0 M(m);
+            REQUIRE_EQ(M.init(), 0);
+            SMM::Vector<T> x(n, 0);
+            REQUIRE_EQ((SMM::BiCGStab<IC0, T>(m, rhs, x, -1, kL2Eps, M)), SMM::SolverStatus::SUCCESS);
+            CHECK(SMM::b200::lastSolveInfo().iterations < plain);
+            for (const T ri : x) CHECK_APPROX(T(1), ri, kInfEps);
+        }
+        {
+            using ILU0 = typename SMM::CSRMatrix<T>::ILU0Preconditioner;
+            const ILU0& M = m.template getPreconditioner<SMM::SolverPreconditioner::ILU0>();
+            SMM::Vector<T> x(n, 0), y(n, 0);
+            CHECK_EQ(M.apply(rhs, y), 0);
+            REQUIRE_EQ((SMM::BiCGStab<ILU0, T>(m, rhs, x, -1, kL2Eps, M)), SMM::SolverStatus::SUCCESS);
+            CHECK(SMM::b200::lastSolveInfo().iterations < plain);
+            for (const T ri : x) CHECK_APPROX(T(1), ri, kInfEps);
+        }
+    }
+}
+
 // ---- iteration counts of the reference on its own assets, in the reference's summation order --
 TEST_CASE("Iteration counts equal the reference's (reference-order reductions)") {
     SMM::b200::options().reduction_mode = SMM_REDUCE_REFERENCE_TREE;

@@ -58,6 +58,12 @@ def oracle():
         lib.smm_oracle_cgs.argtypes = common + [_f32p, _f32p] + tail
         lib.smm_oracle_bicgstab.restype = None
         lib.smm_oracle_bicgstab.argtypes = common + [C.c_int, C.c_int, _f32p, _f32p] + tail
+        lib.smm_oracle_bicgstab_pc.restype = None
+        lib.smm_oracle_bicgstab_pc.argtypes = common + [C.c_int, C.c_int, C.c_void_p, _f32p, _f32p] + tail
+        lib.smm_oracle_ilu0_factorize.restype = C.c_int
+        lib.smm_oracle_ilu0_factorize.argtypes = [C.c_int, _i32p, _i32p, _f32p, C.c_int, _f32p]
+        lib.smm_oracle_ilu0_apply.restype = C.c_int
+        lib.smm_oracle_ilu0_apply.argtypes = [C.c_int, _i32p, _i32p, _f32p, _f32p, _f32p]
         lib.smm_oracle_cg_ic0.restype = None
         lib.smm_oracle_cg_ic0.argtypes = common + [_f32p, _f32p, _f32p, _f32p] + tail
         lib.smm_oracle_load_mtx.restype = C.c_int
@@ -145,6 +151,20 @@ def ic0_apply(m, ic0, rhs):
     return x
 
 
+def ilu0_factorize(m):
+    """EXTENSION (parity unpinned by the reference): returns (rc, factor)."""
+    lu = np.zeros(max(m.nnz, 1), np.float32)
+    pos, val = m._pad()
+    rc = oracle().smm_oracle_ilu0_factorize(m.rows, m.start, pos, val, m.first_active_start, lu)
+    return rc, lu
+
+
+def ilu0_apply(m, lu, rhs):
+    x = np.zeros(m.rows, np.float32)
+    oracle().smm_oracle_ilu0_apply(m.rows, m.start, m.positions, lu, np.ascontiguousarray(rhs, np.float32), x)
+    return x
+
+
 def _hist(cap):
     if not cap:
         return None, None
@@ -152,8 +172,9 @@ def _hist(cap):
     return h, h.ctypes.data_as(C.c_void_p)
 
 
-def solve(solver, m, b, x0, max_iterations, eps, mt, precond=0, ic0=None, history_cap=0):
-    """Run an oracle solver.  Returns dict(status, iterations, residual, precond_error, x, history)."""
+def solve(solver, m, b, x0, max_iterations, eps, mt, precond=0, ic0=None, history_cap=0, factor=None):
+    """Run an oracle solver.  Returns dict(status, iterations, residual, precond_error, x, history).
+    bicgstab: precond 0 none, 1 SGS, 2 ILU(0) (factor = ilu0_factorize), 3 IC(0) (factor = ic0_factorize)."""
     lib = oracle()
     info = Info()
     b = np.ascontiguousarray(b, np.float32).copy()
@@ -172,7 +193,8 @@ def solve(solver, m, b, x0, max_iterations, eps, mt, precond=0, ic0=None, histor
     elif solver == "cgs":
         lib.smm_oracle_cgs(*args, b, x, *tail)
     elif solver == "bicgstab":
-        lib.smm_oracle_bicgstab(*args, m.first_active_start, precond, b, x, *tail)
+        fp = None if factor is None else np.ascontiguousarray(factor, np.float32).ctypes.data_as(C.c_void_p)
+        lib.smm_oracle_bicgstab_pc(*args, m.first_active_start, precond, fp, b, x, *tail)
     else:
         raise ValueError(solver)
     return dict(status=info.status, iterations=info.iterations, residual=float(info.residual),

@@ -520,3 +520,58 @@ def test_pcg_ic0_larger_parity(smm):
     # a matrix without a usable diagonal: init() reports 1 as the reference's factorize does (H:1873-1876)
     bad = upload(smm, ol.triplets_to_csr(3, 3, [0, 1, 1, 2], [0, 0, 2, 2], [1, 1, 1, 1]))
     assert smm.IC0Preconditioner(bad).init() == 1
+
+
+# ---------------------------------------------------------------------------------------------
+# BiCGStab over the factor-based preconditioners.  IC0: a legal instantiation of the reference's template
+# (H:2191-2199), oracle pinned against oracle/_ref (tests/test_ilu0_oracle.py).  ILU(0): EXTENSION,
+# dead code in the reference -> parity unpinned by the reference, bit-exact against the oracle's restatement.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("gen", ["convdiff3d_14", "poisson2d_40x33", "powerlaw_3000", "mesh1em1"])
+def test_ilu0_factor_and_apply_bit_exact(smm, golden, gen):
+    g = {"convdiff3d_14": lambda: matgen.convdiff3d(14, 0.5), "poisson2d_40x33": lambda: matgen.poisson2d(40, 33),
+         "powerlaw_3000": lambda: matgen.powerlaw(3000), "mesh1em1": lambda: gold_csr(golden, "mesh1em1")}[gen]()
+    m = upload(smm, g)
+    M = smm.ILU0Preconditioner(m)
+    assert M.validate() == 0
+    rc, lu = ol.ilu0_factorize(g)
+    assert rc == 0 and M.factor().tobytes() == lu[: g.nnz].tobytes()
+    rhs = matgen.xstar(g.rows)
+    rc, x = M.apply(rhs)
+    assert rc == 0 and x.tobytes() == ol.ilu0_apply(g, lu, rhs).tobytes()
+
+
+def test_ilu0_error_codes(smm):
+    up = lambda *a: upload(smm, ol.triplets_to_csr(*a))
+    assert smm.ILU0Preconditioner(up(3, 3, [1, 2], [1, 2], [1, 1])).validate() == 1
+    assert smm.ILU0Preconditioner(up(3, 3, [0, 1, 1, 2], [0, 0, 2, 2], [1, 1, 1, 1])).validate() == 1
+    M = smm.ILU0Preconditioner(up(2, 2, [0, 0, 1, 1], [0, 1, 0, 1], [1, 1, 1, 1]))
+    assert M.validate() == 2
+    assert M.apply(np.ones(2, np.float32))[0] == 1          # unusable: apply reports an error, x is not produced
+
+
+@pytest.mark.parametrize("precond", ["ilu0", "ic0"])
+def test_bicgstab_factor_preconditioners_parity(smm, precond):
+    g = matgen.convdiff3d(18, 0.5) if precond == "ilu0" else matgen.poisson2d(50, 45)
+    m = upload(smm, g)
+    xs = matgen.xstar(g.rows)
+    b = ol.spmv(g, 0, None, xs)
+    if precond == "ilu0":
+        M = m.getPreconditioner(smm.SolverPreconditioner.ILU0)      # extension: the reference's factory returns void here
+        assert M.init_code == 0
+        kind, f = 2, ol.ilu0_factorize(g)[1]
+    else:
+        M = smm.IC0Preconditioner(m)
+        assert M.init() == 0
+        kind, f = 3, ol.ic0_factorize(g)[1]
+    plain = ol.solve("bicgstab", g, b, np.zeros(g.rows, np.float32), -1, 1e-5, 1)
+    for mt, mode in ((1, smm.REDUCE_REFERENCE_TREE), (0, smm.REDUCE_REFERENCE_SERIAL)):
+        o = ol.solve("bicgstab", g, b, np.zeros(g.rows, np.float32), -1, 1e-5, mt, precond=kind, factor=f)
+        x = np.zeros(g.rows, np.float32)
+        info = smm.BiCGStab(m, b, x, -1, 1e-5, preconditioner=M, reduction_mode=mode)
+        assert int(info.status) == o["status"] == 0 and info.iterations == o["iterations"] and x.tobytes() == o["x"].tobytes()
+        assert o["iterations"] < plain["iterations"]
+    x = np.zeros(g.rows, np.float32)
+    info = smm.BiCGStab(m, b, x, -1, 1e-5, preconditioner=M)
+    assert int(info.status) == 0 and info.residual <= 1e-5 and abs(info.iterations - o["iterations"]) <= max(2, round(0.05 * o["iterations"]))
+    assert np.max(np.abs(x - xs)) < 1e-3
