@@ -127,6 +127,10 @@ int smm_precond_sgs_create(const smm_csr_t* m, smm_precond_t** out);
 int smm_precond_apply(const smm_precond_t* p, const float* rhs, float* x, int* rc);
 int smm_precond_apply_dev(const smm_precond_t* p, const float* rhs_dev, float* x_dev, int* rc, void* stream);
 int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backward_levels);
+/* Levels of the TILE graph when the sweeps run tile by tile (matrices whose column offsets are those of a natural-order
+ * 2D / 3D grid stencil: rows are grouped into tiles of <= 64 that one warp solves in shared memory), 0 / 0 when the
+ * row-level schedule is in use.  Diagnostic; additive. */
+int smm_precond_tile_levels(const smm_precond_t* p, int* forward_levels, int* backward_levels);
 /* CSRMatrix::IC0Preconditioner (H:1214-1235): construction + init() (factorize, H:1839-1928; *rc = its return code) and
  * apply (H:1802-1837, through smm_precond_apply[_dev]).  The factorisation is set-up code and runs on the host, row by
  * row instead of the reference's O(rows^2) scan, with bit-identical values; the two triangular solves of every apply

@@ -116,6 +116,7 @@ def lib():
         L.smm_precond_apply.argtypes = [_vp, _vp, _vp, C.POINTER(_i32)]
         L.smm_precond_apply_dev.argtypes = [_vp, _vp, _vp, C.POINTER(_i32), _vp]
         L.smm_precond_levels.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_i32)]
+        L.smm_precond_tile_levels.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_i32)]
         L.smm_precond_destroy.argtypes = [_vp]
         L.smm_precond_ic0_create.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_vp)]
         L.smm_precond_ic0_factor.argtypes = [_vp, _vp]
@@ -299,6 +300,12 @@ class SGSPreconditioner:
     def levels(self):
         f, b = _i32(), _i32()
         _check(lib().smm_precond_levels(self.handle, C.byref(f), C.byref(b)), "smm_precond_levels")
+        return f.value, b.value
+
+    def tile_levels(self):
+        """(forward, backward) levels of the tile graph, (0, 0) when the sweeps run row by row."""
+        f, b = _i32(), _i32()
+        _check(lib().smm_precond_tile_levels(self.handle, C.byref(f), C.byref(b)), "smm_precond_tile_levels")
         return f.value, b.value
 
     def __del__(self):

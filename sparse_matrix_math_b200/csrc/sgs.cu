@@ -32,40 +32,9 @@
 #include <cmath>
 #include <vector>
 
-#include "smm_internal.cuh"
-
-struct smm_precond {
-    int kind = 0;                    // 0: Symmetric Gauss-Seidel on A's values; 1: IC(0), 2: ILU(0) on their own factor values
-    float* factor = nullptr;         // IC(0): [nnz] factor in A's pattern (L below and on the diagonal, L^T above), ref H:1233-1234
-                                     // ILU(0): strict L (unit diagonal implied) below, U on and above the diagonal, ref H:1203-1211
-    const smm_csr* m = nullptr;
-    int rows = 0;
-    bool valid = true;               // structure admits the sweeps (else apply returns the reference's code 1)
-    int levels_fwd = 0, levels_bwd = 0;
-    long long threads_fwd = 0, threads_bwd = 0;   // padded launch sizes
-    int32_t* order_fwd = nullptr;    // [threads_fwd] row index or -1 (padding)
-    int32_t* order_bwd = nullptr;    // [threads_bwd]
-    int32_t* diag_pos = nullptr;     // [rows] index of a_ii in positions/values
-    // sliced-ELL copies of the strict lower / upper triangles in sweep order (index 0: forward, 1: backward)
-    long long* slice_ptr[2] = {nullptr, nullptr};   // [threads/32 + 1]
-    int32_t* ecol[2] = {nullptr, nullptr};          // column or -1 (padding)
-    int32_t* eidx[2] = {nullptr, nullptr};          // index into the CSR values (to refresh eval after value updates)
-    float* eval[2] = {nullptr, nullptr};
-    float* dval[2] = {nullptr, nullptr};            // [threads] a_ii of the thread's row
-    long long esize[2] = {0, 0};
-    unsigned long long values_version = ~0ull;      // version of m->values the packed copies were gathered from
-    float* yperm = nullptr;          // [threads_fwd] forward result, stored in forward sweep order
-    float* xperm = nullptr;          // [threads_bwd] backward result in backward sweep order (x itself is also written in natural order)
-    int32_t* ypos = nullptr;         // [threads_bwd] where the backward thread's own row sits in yperm
-    unsigned int* tickets = nullptr; // [2] logical CTA counters, [2] = abort flag, [3] = error bits
-    float* io[2] = {nullptr, nullptr};   // staging for the host-pointer apply
-};
+#include "sgs_internal.cuh"
 
 namespace {
-
-constexpr unsigned int SENTINEL = 0x7FC0DEADu;   // quiet NaN with a payload; GPU arithmetic only produces 0x7FFFFFFF
-constexpr int SGS_THREADS = 128;
-constexpr unsigned int POLL_LIMIT = 1u << 22;
 
 __global__ void sgs_fill_kernel(float* __restrict__ yperm, long long nf, float* __restrict__ xperm, long long nb, unsigned int* tickets, const SolveState* st) {
     if (st != nullptr && st->done) return;
@@ -73,27 +42,6 @@ __global__ void sgs_fill_kernel(float* __restrict__ yperm, long long nf, float* 
     if (i < nf) yperm[i] = __uint_as_float(SENTINEL);
     if (i < nb) xperm[i] = __uint_as_float(SENTINEL);
     if (i == 0) { tickets[0] = 0u; tickets[1] = 0u; tickets[2] = 0u; tickets[3] = 0u; }
-}
-
-__device__ __forceinline__ unsigned int peek(const float* p) {
-    unsigned int bits;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bits) : "l"(p));
-    return bits;
-}
-
-// back off between polls: thousands of lanes may be waiting on L2.  Returns false when the wait must be abandoned.
-__device__ __forceinline__ bool poll_pause(unsigned int* polls, unsigned int* abort_flag, unsigned int sleep_first, unsigned int sleep_later) {
-    const unsigned int ns = *polls < 16u ? sleep_first : sleep_later;
-    if (ns) __nanosleep(ns);
-    if ((++*polls & 255u) == 0u) {
-        if (peek(reinterpret_cast<const float*>(abort_flag)) != 0u || *polls >= POLL_LIMIT) { atomicExch(abort_flag, 1u); return false; }
-    }
-    return true;
-}
-
-__device__ __forceinline__ void publish(float* p, float v) {
-    // a computed value can never equal the sentinel payload, so the store itself is the ready flag
-    asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
 struct SweepArgs {
@@ -415,7 +363,6 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
         smm_set_error("SGS preconditioner unusable for this matrix (leading empty rows, an empty row or a missing diagonal): apply() returns 1");
         return SMM_E_STATE;
     }
-    const long long n = p->rows;
     const long long nfill = std::max(p->threads_fwd, p->threads_bwd);
     sgs_fill_kernel<<<(unsigned)((nfill + 255) / 256), 256, 0, s>>>(p->yperm, p->threads_fwd, p->xperm, p->threads_bwd, p->tickets, state);
     static int ctas_per_sm = 0;
@@ -434,8 +381,6 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
         SMM_COUNT_LAUNCH(2);
         pm->values_version = want_version;
     }
-    const long long cap = (long long)m->sm_count * ctas_per_sm;
-    const long long bf = (p->threads_fwd + SGS_THREADS - 1) / SGS_THREADS, bb = (p->threads_bwd + SGS_THREADS - 1) / SGS_THREADS;
     static unsigned int sleep_first = 0u, sleep_later = 64u;
     static bool sleeps_read = false;
     if (!sleeps_read) {                                        // tuning knobs (tools/sgs_bench.py)
@@ -443,14 +388,20 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
         if (const char* e = getenv("SMM_B200_SGS_SLEEP_LATER")) sleep_later = (unsigned int)atoi(e);
         sleeps_read = true;
     }
-    SweepArgs F{p->order_fwd, nullptr, p->slice_ptr[0], p->ecol[0], p->eval[0], p->dval[0], p->threads_fwd, sleep_first, sleep_later};
-    SweepArgs Bk{p->order_bwd, p->ypos, p->slice_ptr[1], p->ecol[1], p->eval[1], p->dval[1], p->threads_bwd, sleep_first, sleep_later};
-    if (p->kind != 0) {                                        // IC(0) and ILU(0) share the `sum -= f * x; x = sum / d` sweeps
-        sgs_sweep_kernel<true, true><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
-        sgs_sweep_kernel<false, true><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+    if (p->tiled) {
+        SMM_TRY(smm_sgs_tiles_launch(p, rhs_dev, x_dev, state, ctas_per_sm, sleep_first, sleep_later, s));
     } else {
-        sgs_sweep_kernel<true, false><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
-        sgs_sweep_kernel<false, false><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+        const long long cap = (long long)m->sm_count * ctas_per_sm;
+        const long long bf = (p->threads_fwd + SGS_THREADS - 1) / SGS_THREADS, bb = (p->threads_bwd + SGS_THREADS - 1) / SGS_THREADS;
+        SweepArgs F{p->order_fwd, nullptr, p->slice_ptr[0], p->ecol[0], p->eval[0], p->dval[0], p->threads_fwd, sleep_first, sleep_later};
+        SweepArgs Bk{p->order_bwd, p->ypos, p->slice_ptr[1], p->ecol[1], p->eval[1], p->dval[1], p->threads_bwd, sleep_first, sleep_later};
+        if (p->kind != 0) {                                    // IC(0) and ILU(0) share the `sum -= f * x; x = sum / d` sweeps
+            sgs_sweep_kernel<true, true><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+            sgs_sweep_kernel<false, true><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+        } else {
+            sgs_sweep_kernel<true, false><<<(unsigned)(bf < cap ? bf : cap), SGS_THREADS, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+            sgs_sweep_kernel<false, false><<<(unsigned)(bb < cap ? bb : cap), SGS_THREADS, 0, s>>>(Bk, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+        }
     }
     sgs_status_kernel<<<1, 1, 0, s>>>(p->tickets, state, rc_dev);
     SMM_COUNT_LAUNCH(4);
@@ -490,11 +441,15 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
     SMM_CUDA(cudaMalloc(&p->tickets, 4 * sizeof(unsigned int)));
     SMM_CUDA(cudaMemset(p->tickets, 0, 4 * sizeof(unsigned int)));
     if (p->valid && m->rows > 0) {
+        SMM_CUDA(cudaMalloc(&p->diag_pos, sizeof(int32_t) * diag.size()));
+        SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
+    }
+    // tile-level schedule when the matrix admits one (sgs_tiles.cu), else the row-level schedule below
+    if (p->valid && m->rows > 0 && !smm_sgs_tiles_build(p, m->rows, start, pos, diag)) {
         p->threads_fwd = (long long)of.size();
         p->threads_bwd = (long long)ob.size();
         SMM_CUDA(cudaMalloc(&p->order_fwd, sizeof(int32_t) * of.size()));
         SMM_CUDA(cudaMalloc(&p->order_bwd, sizeof(int32_t) * ob.size()));
-        SMM_CUDA(cudaMalloc(&p->diag_pos, sizeof(int32_t) * diag.size()));
         if (of.size() >= (size_t)INT32_MAX || ob.size() >= (size_t)INT32_MAX) { smm_set_error("preconditioner: too many rows"); return SMM_E_INVALID; }
         // where every row sits in each sweep's order; operands are addressed by these positions so that a warp's
         // polls and publishes touch whole lines instead of one sector per lane
@@ -507,7 +462,6 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
         SMM_CUDA(cudaMemcpy(p->ypos, yp.data(), sizeof(int32_t) * yp.size(), cudaMemcpyHostToDevice));
         SMM_CUDA(cudaMemcpy(p->order_fwd, of.data(), sizeof(int32_t) * of.size(), cudaMemcpyHostToDevice));
         SMM_CUDA(cudaMemcpy(p->order_bwd, ob.data(), sizeof(int32_t) * ob.size(), cudaMemcpyHostToDevice));
-        SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
         for (int w = 0; w < 2; ++w) {
             std::vector<long long> sp;
             std::vector<int32_t> ec, ei;
@@ -591,8 +545,17 @@ int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backwar
     return SMM_OK;
 }
 
+// levels of the tile graph when the tile-level schedule is in use (sgs_tiles.cu), 0 / 0 otherwise
+int smm_precond_tile_levels(const smm_precond_t* p, int* forward_levels, int* backward_levels) {
+    if (!p) return SMM_E_INVALID;
+    if (forward_levels) *forward_levels = p->tiled ? p->tile_levels[0] : 0;
+    if (backward_levels) *backward_levels = p->tiled ? p->tile_levels[1] : 0;
+    return SMM_OK;
+}
+
 int smm_precond_destroy(smm_precond_t* p) {
     if (!p) return SMM_OK;
+    cudaFree(p->tile_steps[0]); cudaFree(p->tile_steps[1]); cudaFree(p->tile_push[0]); cudaFree(p->tile_push[1]);
     cudaFree(p->order_fwd); cudaFree(p->order_bwd); cudaFree(p->diag_pos); cudaFree(p->yperm); cudaFree(p->xperm); cudaFree(p->ypos); cudaFree(p->tickets); cudaFree(p->factor);
     for (int w = 0; w < 2; ++w) { cudaFree(p->slice_ptr[w]); cudaFree(p->ecol[w]); cudaFree(p->eidx[w]); cudaFree(p->eval[w]); cudaFree(p->dval[w]); }
     cudaFree(p->io[0]); cudaFree(p->io[1]);

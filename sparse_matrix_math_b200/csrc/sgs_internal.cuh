@@ -1,0 +1,75 @@
+// sgs_internal.cuh -- shared between sgs.cu (row-level schedule) and sgs_tiles.cu (tile-level schedule)
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+#include "smm_internal.cuh"
+
+struct smm_precond {
+    int kind = 0;                    // 0: Symmetric Gauss-Seidel on A's values; 1: IC(0), 2: ILU(0) on their own factor values
+    float* factor = nullptr;         // IC(0): [nnz] factor in A's pattern (L below and on the diagonal, L^T above), ref H:1233-1234
+                                     // ILU(0): strict L (unit diagonal implied) below, U on and above the diagonal, ref H:1203-1211
+    const smm_csr* m = nullptr;
+    int rows = 0;
+    bool valid = true;               // structure admits the sweeps (else apply returns the reference's code 1)
+    int levels_fwd = 0, levels_bwd = 0;
+    long long threads_fwd = 0, threads_bwd = 0;   // padded launch sizes
+    int32_t* order_fwd = nullptr;    // [threads_fwd] row index or -1 (padding)
+    int32_t* order_bwd = nullptr;    // [threads_bwd]
+    int32_t* diag_pos = nullptr;     // [rows] index of a_ii in positions/values
+    // sliced-ELL copies of the strict lower / upper triangles in sweep order (index 0: forward, 1: backward)
+    long long* slice_ptr[2] = {nullptr, nullptr};   // [threads/32 + 1]
+    int32_t* ecol[2] = {nullptr, nullptr};          // column or -1 (padding)
+    int32_t* eidx[2] = {nullptr, nullptr};          // index into the CSR values (to refresh eval after value updates)
+    float* eval[2] = {nullptr, nullptr};
+    float* dval[2] = {nullptr, nullptr};            // [threads] a_ii of the thread's row
+    long long esize[2] = {0, 0};
+    unsigned long long values_version = ~0ull;      // version of m->values the packed copies were gathered from
+    float* yperm = nullptr;          // [threads_fwd] forward result, stored in forward sweep order
+    float* xperm = nullptr;          // [threads_bwd] backward result in backward sweep order (x itself is also written in natural order)
+    int32_t* ypos = nullptr;         // [threads_bwd] where the backward thread's own row sits in yperm
+    unsigned int* tickets = nullptr; // [2] logical CTA counters, [2] = abort flag, [3] = error bits
+    float* io[2] = {nullptr, nullptr};   // staging for the host-pointer apply
+    // tile-level schedule (sgs_tiles.cu): rows grouped into tiles of up to 64, one warp per tile; when `tiled`, the
+    // position-ordered arrays above are laid out tile by tile (position = 64 * tile + index inside the tile)
+    bool tiled = false;
+    int tile_width = 0;              // entries kept per row and sweep (<= 4), same for every tile
+    uint8_t* tile_steps[2] = {nullptr, nullptr};   // [tiles * 64] step of every row, then [tiles] number of steps
+    uint32_t* tile_push[2] = {nullptr, nullptr};   // [tiles * 64] operand slots inside the tile that consume the row's result
+    int tile_levels[2] = {0, 0};
+};
+
+// sgs_tiles.cu
+bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag);
+int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, int ctas_per_sm, unsigned int sleep_first,
+                         unsigned int sleep_later, cudaStream_t s);
+
+namespace {
+
+constexpr unsigned int SENTINEL = 0x7FC0DEADu;   // quiet NaN with a payload; GPU arithmetic only produces 0x7FFFFFFF
+constexpr int SGS_THREADS = 128;
+constexpr unsigned int POLL_LIMIT = 1u << 22;
+
+__device__ __forceinline__ unsigned int peek(const float* p) {
+    unsigned int bits;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bits) : "l"(p));
+    return bits;
+}
+
+// back off between polls: thousands of lanes may be waiting on L2.  Returns false when the wait must be abandoned.
+__device__ __forceinline__ bool poll_pause(unsigned int* polls, unsigned int* abort_flag, unsigned int sleep_first, unsigned int sleep_later) {
+    const unsigned int ns = *polls < 16u ? sleep_first : sleep_later;
+    if (ns) __nanosleep(ns);
+    if ((++*polls & 255u) == 0u) {
+        if (peek(reinterpret_cast<const float*>(abort_flag)) != 0u || *polls >= POLL_LIMIT) { atomicExch(abort_flag, 1u); return false; }
+    }
+    return true;
+}
+
+__device__ __forceinline__ void publish(float* p, float v) {
+    // a computed value can never equal the sentinel payload, so the store itself is the ready flag
+    asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+}  // namespace

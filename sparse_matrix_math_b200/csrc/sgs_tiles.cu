@@ -1,0 +1,456 @@
+// sgs_tiles.cu -- tile-level schedule for the triangular sweeps of sgs.cu (SGS, IC(0), ILU(0) apply).
+//
+// The row-level schedule of sgs.cu pays one producer->L2->consumer hand-off (340-530 ns, tools/hop_latency.cu) per
+// dependency level, and a 7-point stencil on an N^3 grid has 3N-2 of them.  Here rows are grouped into TILES of up to
+// 64 rows that one warp solves in shared memory, so that only the hand-offs BETWEEN tiles go through L2: a 4x4x4 tile
+// has 10 internal levels (about 50 ns each) and the tile graph of the same grid has 3N/4-2 levels.
+//
+//   * Any grouping is legal as long as the tile graph stays acyclic; the per-row arithmetic (operand order, two
+//     roundings per term, one division) is that of the row-level kernel, so the result has the same bits for any
+//     grouping.  build() takes a PROPOSAL (geometric tiles when the column offsets of the matrix are those of a
+//     natural-order 2D / 3D grid stencil) and VERIFIES it generically: tiles of <= 64 rows, <= 4 stored operands
+//     per row and sweep, an acyclic tile graph (Kahn).  Anything else falls back to the
+//     row-level schedule.
+//   * Layout: tiles sorted by tile level; position = 64 * tile + index, rows inside a tile sorted by internal level.
+//     Intermediate vectors are stored by position (as in sgs.cu), entries as [tile][operand slot][64].
+//   * Kernel: one warp per tile, lane l holds rows l and l + 32 of the tile in registers (loaded, with the next
+//     tile's, ahead of time).  Step s solves the rows of internal level s: operands inside the tile come from shared
+//     memory, operands from other tiles are polled by position -- all of the tile's at once, up front, and again
+//     (by every lane, for everything it still misses) whenever a step finds one of its rows waiting.  Neighbouring
+//     tiles run the same steps slightly ahead, so a tile typically waits once, for its first step.
+//     Tiles are handed out in order by an atomic ticket (a block of TILE_WARPS tiles per CTA claim), so every
+//     awaited producer belongs to a tile that a running warp already owns: no deadlock.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "sgs_internal.cuh"
+
+namespace {
+
+constexpr int TILE = 64;
+constexpr int TILE_WARPS = 4;
+constexpr int TILE_MAX_W = 4;
+constexpr int MAX_STEPS = 64;
+constexpr int MAX_PREDS = 8;
+
+struct TileArgs {
+    const uint8_t* nsteps;      // [tiles]
+    const uint8_t* row_step;    // [tiles * 64] the step in which the row is solved (255: padding)
+    const uint32_t* push;       // [tiles * 64] four operand slots (64-row tile x 4) of rows of the SAME tile that consume this row
+    const int32_t* order;       // [tiles * 64] row or -1
+    const int32_t* ypos;        // backward: position of the row in yperm
+    const int32_t* ecol;        // [tiles][width][64] operand position or -1
+    const float* eval;
+    const float* dval;          // [tiles * 64]
+    long long ntiles;
+    int width;
+    unsigned int sleep_first, sleep_later;
+    unsigned long long* trace;  // debug (SMM_B200_SGS_TRACE): [tiles][4] globaltimer at claim / first step / solved, and the SM
+};
+
+struct TileHead { int row[2]; int yp[2]; };
+struct TileBody {
+    int nsteps, step[2];
+    unsigned int push[2];
+    float d[2], init[2];
+    int c[2][TILE_MAX_W];
+    float v[2][TILE_MAX_W];
+};
+
+__device__ __forceinline__ unsigned long long tile_clock() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <bool FORWARD, bool IC0>
+__global__ void __launch_bounds__(TILE_WARPS * 32) sgs_tile_kernel(const TileArgs A, const float* __restrict__ rhs, float* yperm, float* xperm,
+                                                                  float* __restrict__ x, unsigned int* tickets, const SolveState* st) {
+    if (st != nullptr && st->done) return;
+    // operand staging: slot 4 * r + e holds operand e of row r of the warp's current tile.  Operands from other tiles
+    // are put there by the row's own lane once they have been published; operands from the same tile are PUSHED
+    // there by the lane that solves them, so a row needs a single 128-bit shared-memory load when its step comes
+    __shared__ __align__(16) float stage[TILE_WARPS][TILE * TILE_MAX_W];
+    __shared__ unsigned int sh_bid[2];
+    unsigned int* abort_flag = tickets + 2;
+    unsigned int* ticket = tickets + (FORWARD ? 0 : 1);
+    const long long nblocks = (A.ntiles + TILE_WARPS - 1) / TILE_WARPS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* src = FORWARD ? yperm : xperm;
+    float* dst = FORWARD ? yperm : xperm;
+    float* mine = stage[warp];
+
+    auto load_head = [&](long long bid) {
+        TileHead h;
+        h.row[0] = h.row[1] = -1;
+        h.yp[0] = h.yp[1] = 0;
+        const long long tile = bid * TILE_WARPS + warp;
+        if (bid < nblocks && tile < A.ntiles) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                h.row[k] = A.order[tile * TILE + k * 32 + lane];
+                if (!FORWARD) h.yp[k] = A.ypos[tile * TILE + k * 32 + lane];
+            }
+        }
+        return h;
+    };
+    auto load_body = [&](long long bid, const TileHead& h) {
+        TileBody b;
+        const long long tile = bid * TILE_WARPS + warp;
+        const bool live = bid < nblocks && tile < A.ntiles;
+        b.nsteps = live ? A.nsteps[tile] : 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const long long at = tile * TILE + k * 32 + lane;
+            b.step[k] = live ? A.row_step[at] : 255;
+            b.push[k] = live ? A.push[at] : 0u;
+            b.d[k] = live ? A.dval[at] : 1.0f;
+#pragma unroll
+            for (int e = 0; e < TILE_MAX_W; ++e) {
+                const bool in = live && e < A.width;
+                b.c[k][e] = in ? A.ecol[(tile * A.width + e) * TILE + k * 32 + lane] : -1;
+                b.v[k][e] = in ? A.eval[(tile * A.width + e) * TILE + k * 32 + lane] : 0.0f;
+            }
+            // forward: the right-hand side (H:1683 / H:1807); backward: the row's own forward result (previous launch)
+            b.init[k] = h.row[k] >= 0 ? (FORWARD ? rhs[h.row[k]] : yperm[h.yp[k]]) : 0.0f;
+        }
+        return b;
+    };
+    auto solve_tile = [&](long long bid, const TileHead& h, const TileBody& b) {
+        const int tile = (int)(bid * TILE_WARPS + warp);
+        if (A.trace && lane == 0) A.trace[4ll * tile] = tile_clock();
+        // Operands from other tiles (both rows of this lane) are requested up front; whatever has not been published
+        // yet is requested again -- by every lane, for everything it still misses -- each time a step finds one of
+        // ITS rows waiting.  Neighbouring tiles run the same steps slightly ahead, so a tile typically waits once.
+        unsigned int pend = 0u;                                // bit 4 k + e: operand e of row k is still awaited
+        unsigned int first[2 * TILE_MAX_W];
+#pragma unroll
+        for (int q = 0; q < 2 * TILE_MAX_W; ++q) {                                // all requests first
+            const int c = b.c[q / TILE_MAX_W][q % TILE_MAX_W];
+            first[q] = (c >= 0 && (c >> 6) != tile) ? peek(src + c) : 0u;         // no operand: 0 * 0 leaves the sum unchanged
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+#pragma unroll
+            for (int e = 0; e < TILE_MAX_W; ++e) if (first[4 * k + e] == SENTINEL) pend |= 1u << (4 * k + e);
+            // own-tile slots are overwritten by their producer before the row's step
+            *reinterpret_cast<float4*>(mine + 4 * (k * 32 + lane)) = make_float4(__uint_as_float(first[4 * k]), __uint_as_float(first[4 * k + 1]),
+                                                                                   __uint_as_float(first[4 * k + 2]), __uint_as_float(first[4 * k + 3]));
+            if (FORWARD && !IC0 && h.row[k] >= 0 && fabsf(b.d[k]) < 1e-5) atomicOr(tickets + 3, 1u);   // H:1691-1693 (reported, not fatal here)
+        }
+        __syncwarp();
+        bool any_pending = __any_sync(0xFFFFFFFFu, pend != 0u);
+        float* const out = dst + ((long long)tile * TILE + lane);
+        unsigned int polls = 0;
+        for (int s = 0; s < b.nsteps; ++s) {
+            const bool a0 = s == b.step[0], a1 = s == b.step[1];
+            if (any_pending) {
+                while (__any_sync(0xFFFFFFFFu, (a0 && (pend & 0xFu)) || (a1 && (pend & 0xF0u)))) {
+                    if (!poll_pause(&polls, abort_flag, A.sleep_first, A.sleep_later)) pend = 0u;
+                    unsigned int bits[2 * TILE_MAX_W];
+#pragma unroll
+                    for (int q = 0; q < 2 * TILE_MAX_W; ++q)                      // all requests first: one L2 round trip per round
+                        bits[q] = (pend >> q) & 1u ? peek(src + b.c[q / TILE_MAX_W][q % TILE_MAX_W]) : SENTINEL;
+#pragma unroll
+                    for (int q = 0; q < 2 * TILE_MAX_W; ++q) {
+                        if (bits[q] != SENTINEL) { pend &= ~(1u << q); mine[4 * ((q / TILE_MAX_W) * 32 + lane) + (q % TILE_MAX_W)] = __uint_as_float(bits[q]); }
+                    }
+                }
+                any_pending = __any_sync(0xFFFFFFFFu, pend != 0u);
+                __syncwarp();
+            }
+            if (A.trace && s == 0 && lane == 0) A.trace[4ll * tile + 1] = tile_clock();
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k == 0 ? a0 : a1) {
+                    const float4 xo = *reinterpret_cast<const float4*>(mine + 4 * (k * 32 + lane));
+                    // same operand order and roundings as the row-level kernel (H:1685, H:1704, H:1813, H:1829); only the
+                    // additions and the division are on the step's dependent chain
+                    const float p0 = __fmul_rn(b.v[k][0], xo.x), p1 = __fmul_rn(b.v[k][1], xo.y), p2 = __fmul_rn(b.v[k][2], xo.z), p3 = __fmul_rn(b.v[k][3], xo.w);
+                    float acc = (FORWARD || IC0) ? b.init[k] : 0.0f;              // H:1683 / T sum = x[row], H:1823 / H:1702
+                    if (FORWARD || IC0) { acc = __fsub_rn(acc, p0); acc = __fsub_rn(acc, p1); acc = __fsub_rn(acc, p2); acc = __fsub_rn(acc, p3); }
+                    else { acc = __fadd_rn(p0, acc); acc = __fadd_rn(p1, acc); acc = __fadd_rn(p2, acc); acc = __fadd_rn(p3, acc); }
+                    const float res = (FORWARD || IC0) ? __fdiv_rn(acc, b.d[k])   // H:1694 / H:1818, H:1834
+                                                       : __fsub_rn(b.init[k], __fdiv_rn(acc, b.d[k]));   // H:1710
+                    const unsigned int pu = b.push[k];                            // hand the result to the rows of this tile that use it
+                    mine[pu & 255u] = res; mine[(pu >> 8) & 255u] = res; mine[(pu >> 16) & 255u] = res; mine[pu >> 24] = res;
+                    publish(out + k * 32, res);
+                    if (!FORWARD) x[h.row[k]] = res;
+                }
+            }
+            __syncwarp();
+        }
+        if (A.trace && lane == 0) {
+            unsigned int sm;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+            A.trace[4ll * tile + 2] = tile_clock(); A.trace[4ll * tile + 3] = sm;
+        }
+    };
+
+    unsigned int pending = 0u;
+    if (threadIdx.x == 0) {
+        sh_bid[0] = atomicAdd(ticket, 1u);
+        sh_bid[1] = atomicAdd(ticket, 1u);
+        pending = atomicAdd(ticket, 1u);
+    }
+    __syncthreads();
+    long long b0 = sh_bid[0], b1 = sh_bid[1];
+    __syncthreads();
+    TileHead h0 = load_head(b0), h1 = load_head(b1);
+    TileBody r0 = load_body(b0, h0);
+    for (unsigned int it = 0; b0 < nblocks; ++it) {
+        if (threadIdx.x == 0) sh_bid[it & 1u] = pending;
+        __syncthreads();
+        const long long b2 = sh_bid[it & 1u];
+        if (threadIdx.x == 0) pending = atomicAdd(ticket, 1u);
+        const TileHead h2 = load_head(b2);
+        const TileBody r1 = load_body(b1, h1);
+        solve_tile(b0, h0, r0);
+        b0 = b1; b1 = b2; h0 = h1; h1 = h2; r0 = r1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: proposal + generic verification + layout
+// ---------------------------------------------------------------------------------------------------------------
+struct SweepLayout {
+    std::vector<int32_t> order, ecol, eidx, where;   // where[row] = position
+    std::vector<uint8_t> steps;
+    std::vector<uint32_t> push;
+    int levels = 0;
+};
+
+// cluster ids for a natural-order grid stencil, or empty when the column offsets are not of that kind
+std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int* nclusters) {
+    std::vector<long long> offs;                               // distinct |col - row| > 0
+    for (int r = 0; r < rows; ++r) {
+        for (int k = start[r]; k < start[r + 1]; ++k) {
+            long long d = (long long)pos[k] - r;
+            if (d < 0) d = -d;
+            if (d == 0) continue;
+            if (std::find(offs.begin(), offs.end(), d) == offs.end()) {
+                if (offs.size() == 3) return {};
+                offs.push_back(d);
+            }
+        }
+    }
+    std::sort(offs.begin(), offs.end());
+    if (offs.size() < 2 || offs[0] != 1) return {};
+    long long nx = offs[1], ny = 0, nz = 1;
+    if (offs.size() == 2) {
+        if (rows % nx) return {};
+        ny = rows / nx;
+    } else {
+        if (offs[2] % nx || rows % offs[2]) return {};
+        ny = offs[2] / nx;
+        nz = rows / offs[2];
+    }
+    const int ti = nz > 1 ? 4 : 8, tj = nz > 1 ? 4 : 8, tk = nz > 1 ? 4 : 1;
+    const long long TI = (nx + ti - 1) / ti, TJ = (ny + tj - 1) / tj, TK = (nz + tk - 1) / tk;
+    if (TI * TJ * TK >= (1ll << 25)) return {};                // positions are int32: 64 * tiles < 2^31
+    std::vector<int32_t> cl((size_t)rows);
+    for (int r = 0; r < rows; ++r) {
+        const long long i = r % nx, j = (r / nx) % ny, k = r / (nx * ny);
+        cl[(size_t)r] = (int32_t)(((k / tk) * TJ + j / tj) * TI + i / ti);
+    }
+    *nclusters = (int)(TI * TJ * TK);
+    return cl;
+}
+
+// Lay one sweep out by tiles.  Returns false when the proposal does not verify.
+bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag,
+                  const std::vector<int32_t>& cl, int ncl, int width, SweepLayout* out) {
+    auto dep_begin = [&](int r) { return forward ? start[r] : diag[r] + 1; };
+    auto dep_end = [&](int r) { return forward ? diag[r] : start[r + 1]; };
+    // rows of every cluster, ascending
+    std::vector<int32_t> cptr((size_t)ncl + 1, 0);
+    for (int r = 0; r < rows; ++r) cptr[(size_t)cl[r] + 1]++;
+    for (int a = 0; a < ncl; ++a) {
+        if (cptr[(size_t)a + 1] > TILE) return false;
+        cptr[(size_t)a + 1] += cptr[a];
+    }
+    std::vector<int32_t> crow((size_t)rows);
+    {
+        std::vector<int32_t> cur(cptr.begin(), cptr.end() - 1);
+        for (int r = 0; r < rows; ++r) crow[(size_t)cur[cl[r]]++] = r;
+    }
+    // distinct predecessor tiles
+    std::vector<int32_t> pred((size_t)ncl * MAX_PREDS, -1);
+    std::vector<uint8_t> npred((size_t)ncl, 0);
+    for (int r = 0; r < rows; ++r) {
+        const int a = cl[r];
+        for (int k = dep_begin(r); k < dep_end(r); ++k) {
+            const int b = cl[pos[k]];
+            if (b == a) continue;
+            int32_t* pa = &pred[(size_t)a * MAX_PREDS];
+            int n = npred[a], i = 0;
+            while (i < n && pa[i] != b) ++i;
+            if (i == n) {
+                if (n == MAX_PREDS) return false;
+                pa[n] = b;
+                npred[a] = (uint8_t)(n + 1);
+            }
+        }
+    }
+    // Kahn: tile levels, cycle check
+    std::vector<int32_t> sptr((size_t)ncl + 1, 0);
+    for (int a = 0; a < ncl; ++a) for (int i = 0; i < npred[a]; ++i) sptr[(size_t)pred[(size_t)a * MAX_PREDS + i] + 1]++;
+    for (int a = 0; a < ncl; ++a) sptr[(size_t)a + 1] += sptr[a];
+    std::vector<int32_t> succ((size_t)sptr[ncl]);
+    {
+        std::vector<int32_t> cur(sptr.begin(), sptr.end() - 1);
+        for (int a = 0; a < ncl; ++a) for (int i = 0; i < npred[a]; ++i) succ[(size_t)cur[pred[(size_t)a * MAX_PREDS + i]]++] = a;
+    }
+    std::vector<int32_t> level((size_t)ncl, 0), indeg((size_t)ncl), queue;
+    queue.reserve((size_t)ncl);
+    for (int a = 0; a < ncl; ++a) { indeg[a] = npred[a]; if (!indeg[a]) queue.push_back(a); }
+    int maxl = -1;
+    for (size_t q = 0; q < queue.size(); ++q) {
+        const int a = queue[q];
+        maxl = std::max(maxl, level[a]);
+        for (int i = sptr[a]; i < sptr[a + 1]; ++i) {
+            const int b = succ[i];
+            level[b] = std::max(level[b], level[a] + 1);
+            if (--indeg[b] == 0) queue.push_back(b);
+        }
+    }
+    if ((int)queue.size() != ncl) return false;                // the tile graph has a cycle
+    out->levels = maxl + 1;
+    // tiles in level order (stable in the cluster id; the backward sweep runs the ids downwards for locality)
+    std::vector<int32_t> lptr((size_t)out->levels + 1, 0), tile_of((size_t)ncl);
+    for (int a = 0; a < ncl; ++a) lptr[(size_t)level[a] + 1]++;
+    for (int l = 0; l < out->levels; ++l) lptr[(size_t)l + 1] += lptr[l];
+    {
+        std::vector<int32_t> cur(lptr.begin(), lptr.end() - 1);
+        if (forward) { for (int a = 0; a < ncl; ++a) tile_of[a] = cur[level[a]]++; }
+        else { for (int a = ncl - 1; a >= 0; --a) tile_of[a] = cur[level[a]]++; }
+    }
+    out->order.assign((size_t)ncl * TILE, -1);
+    out->where.assign((size_t)rows, 0);
+    out->steps.assign((size_t)ncl * TILE + (size_t)ncl, 255);    // [tiles * 64] step of every row, then [tiles] number of steps
+    std::vector<int8_t> ilev((size_t)rows, 0);
+    std::vector<int32_t> tmp;
+    for (int a = 0; a < ncl; ++a) {
+        const int n = cptr[a + 1] - cptr[a];
+        const int32_t* R = &crow[(size_t)cptr[a]];
+        int nl = 0;
+        for (int q = 0; q < n; ++q) {                          // internal levels, in dependency order
+            const int r = forward ? R[q] : R[n - 1 - q];
+            int l = 0;
+            for (int k = dep_begin(r); k < dep_end(r); ++k) if (cl[pos[k]] == a) l = std::max(l, ilev[pos[k]] + 1);
+            if (l >= MAX_STEPS) return false;
+            ilev[r] = (int8_t)l;
+            nl = std::max(nl, l + 1);
+        }
+        tmp.assign(R, R + n);
+        if (!forward) std::reverse(tmp.begin(), tmp.end());
+        std::stable_sort(tmp.begin(), tmp.end(), [&](int32_t p, int32_t q) { return ilev[p] < ilev[q]; });
+        const int t = tile_of[a];
+        out->steps[(size_t)ncl * TILE + t] = (uint8_t)nl;       // a step = an internal level (lane l solves rows l and l + 32)
+        for (int i = 0; i < n; ++i) out->steps[(size_t)t * TILE + i] = (uint8_t)ilev[tmp[i]];
+        for (int i = 0; i < n; ++i) {
+            out->order[(size_t)t * TILE + i] = tmp[i];
+            out->where[(size_t)tmp[i]] = t * TILE + i;
+        }
+    }
+    // entries: [tile][slot][64], operand order = the reference's (ascending columns forward, descending backward);
+    // push lists: where inside the tile's operand staging a row's result has to go (unused entries point at the row's
+    // own first slot, which nobody reads once the row is solved)
+    out->ecol.assign((size_t)ncl * width * TILE, -1);
+    out->eidx.assign((size_t)ncl * width * TILE, -1);
+    out->push.assign((size_t)ncl * TILE, 0u);
+    std::vector<uint8_t> npush((size_t)ncl * TILE, 0);
+    for (size_t p = 0; p < out->push.size(); ++p) { const uint32_t own = (uint32_t)((p & (TILE - 1)) * TILE_MAX_W); out->push[p] = own * 0x01010101u; }
+    for (int r = 0; r < rows; ++r) {
+        const int p = out->where[r], t = p >> 6, i = p & (TILE - 1);
+        const int cnt = dep_end(r) - dep_begin(r);
+        for (int e = 0; e < cnt; ++e) {
+            const int srci = forward ? start[r] + e : start[r + 1] - 1 - e;
+            const size_t at = ((size_t)t * width + e) * TILE + i;
+            const int q = out->where[pos[srci]];
+            out->ecol[at] = q;
+            out->eidx[at] = srci;
+            if ((q >> 6) == t) {                               // produced inside the tile: the producer pushes it
+                if (npush[q] == 4) return false;
+                const int sh = 8 * npush[q]++;
+                out->push[q] = (out->push[q] & ~(0xFFu << sh)) | ((uint32_t)(i * TILE_MAX_W + e) << sh);
+            }
+        }
+    }
+    return true;
+}
+
+template <class V>
+int upload(const std::vector<V>& h, V** d) {
+    SMM_CUDA(cudaMalloc(d, sizeof(V) * (h.empty() ? 1 : h.size())));
+    if (!h.empty()) SMM_CUDA(cudaMemcpy(*d, h.data(), sizeof(V) * h.size(), cudaMemcpyHostToDevice));
+    return SMM_OK;
+}
+
+}  // namespace
+
+bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag) {
+    if (const char* e = getenv("SMM_B200_SGS_TILES")) { if (atoi(e) == 0) return false; }
+    if (rows < 2 * TILE) return false;
+    int width = 0;
+    for (int r = 0; r < rows; ++r) width = std::max(width, std::max(diag[r] - start[r], start[r + 1] - 1 - diag[r]));
+    if (width > TILE_MAX_W) return false;
+    if (width == 0) width = 1;
+    int ncl = 0;
+    const std::vector<int32_t> cl = propose_grid_tiles(rows, start, pos, &ncl);
+    if (cl.empty()) return false;
+    SweepLayout L[2];
+    if (!layout_sweep(true, rows, start, pos, diag, cl, ncl, width, &L[0])) return false;
+    if (!layout_sweep(false, rows, start, pos, diag, cl, ncl, width, &L[1])) return false;
+    std::vector<int32_t> yp(L[1].order.size(), 0);
+    for (size_t t = 0; t < yp.size(); ++t) if (L[1].order[t] >= 0) yp[t] = L[0].where[(size_t)L[1].order[t]];
+    const size_t npos = (size_t)ncl * TILE;
+    p->threads_fwd = p->threads_bwd = (long long)npos;
+    p->tile_width = width;
+    p->tile_levels[0] = L[0].levels;
+    p->tile_levels[1] = L[1].levels;
+    if (upload(L[0].order, &p->order_fwd) != SMM_OK || upload(L[1].order, &p->order_bwd) != SMM_OK || upload(yp, &p->ypos) != SMM_OK) return false;
+    if (cudaMalloc(&p->yperm, sizeof(float) * npos) != cudaSuccess || cudaMalloc(&p->xperm, sizeof(float) * npos) != cudaSuccess) return false;
+    for (int w = 0; w < 2; ++w) {
+        p->esize[w] = (long long)L[w].ecol.size();
+        if (upload(L[w].ecol, &p->ecol[w]) != SMM_OK || upload(L[w].eidx, &p->eidx[w]) != SMM_OK || upload(L[w].steps, &p->tile_steps[w]) != SMM_OK ||
+            upload(L[w].push, &p->tile_push[w]) != SMM_OK) return false;
+        if (cudaMalloc(&p->eval[w], sizeof(float) * L[w].ecol.size()) != cudaSuccess || cudaMalloc(&p->dval[w], sizeof(float) * npos) != cudaSuccess) return false;
+    }
+    p->tiled = true;
+    return true;
+}
+
+int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, int ctas_per_sm, unsigned int sleep_first,
+                         unsigned int sleep_later, cudaStream_t s) {
+    const long long ntiles = p->threads_fwd / TILE;
+    const long long nblocks = (ntiles + TILE_WARPS - 1) / TILE_WARPS;
+    const long long cap = (long long)p->m->sm_count * ctas_per_sm;
+    const unsigned grid = (unsigned)(nblocks < cap ? nblocks : cap);
+    // debug: SMM_B200_SGS_TRACE=<file> records per-tile timestamps of the forward sweep of every apply (last one kept)
+    static const char* trace_path = getenv("SMM_B200_SGS_TRACE");
+    static unsigned long long* trace = nullptr;
+    if (trace_path && !trace) SMM_CUDA(cudaMalloc(&trace, sizeof(unsigned long long) * 4 * (size_t)ntiles));
+    const uint8_t* nsf = p->tile_steps[0] + ntiles * TILE;
+    const uint8_t* nsb = p->tile_steps[1] + ntiles * TILE;
+    TileArgs F{nsf, p->tile_steps[0], p->tile_push[0], p->order_fwd, nullptr, p->ecol[0], p->eval[0], p->dval[0], ntiles, p->tile_width, sleep_first, sleep_later, trace};
+    TileArgs B{nsb, p->tile_steps[1], p->tile_push[1], p->order_bwd, p->ypos, p->ecol[1], p->eval[1], p->dval[1], ntiles, p->tile_width, sleep_first, sleep_later, nullptr};
+    if (p->kind != 0) {
+        sgs_tile_kernel<true, true><<<grid, TILE_WARPS * 32, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+        sgs_tile_kernel<false, true><<<grid, TILE_WARPS * 32, 0, s>>>(B, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+    } else {
+        sgs_tile_kernel<true, false><<<grid, TILE_WARPS * 32, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+        sgs_tile_kernel<false, false><<<grid, TILE_WARPS * 32, 0, s>>>(B, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+    }
+    SMM_CUDA(cudaGetLastError());
+    if (trace) {
+        std::vector<unsigned long long> h(4 * (size_t)ntiles);
+        SMM_CUDA(cudaStreamSynchronize(s));
+        SMM_CUDA(cudaMemcpy(h.data(), trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
+    }
+    return SMM_OK;
+}

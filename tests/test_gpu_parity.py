@@ -575,3 +575,49 @@ def test_bicgstab_factor_preconditioners_parity(smm, precond):
     info = smm.BiCGStab(m, b, x, -1, 1e-5, preconditioner=M)
     assert int(info.status) == 0 and info.residual <= 1e-5 and abs(info.iterations - o["iterations"]) <= max(2, round(0.05 * o["iterations"]))
     assert np.max(np.abs(x - xs)) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# schedule selection of the triangular sweeps: tile-level for grid stencils, row-level otherwise -- same bits either way
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["convdiff3d_23", "poisson2d_50x37", "poisson3d_8x12x20", "powerlaw", "periodic_ring", "wide_offsets"])
+def test_sweep_schedules_bit_exact(smm, case):
+    if case == "convdiff3d_23":
+        g, tiled = matgen.convdiff3d(23, 0.5), True                  # grid sizes that are not multiples of the tile edge
+    elif case == "poisson2d_50x37":
+        g, tiled = matgen.poisson2d(50, 37), True
+    elif case == "poisson3d_8x12x20":
+        g, tiled = matgen.convdiff3d(8, 0.0, ny=12, nz=20), True
+    elif case == "powerlaw":
+        g, tiled = matgen.powerlaw(4000), False                      # no grid structure: row-level schedule
+    elif case == "periodic_ring":
+        # offsets {1, 16} like a 16 x 16 grid, but the +-1 couplings run across the grid lines: the tile graph has cycles,
+        # the proposal must be rejected by the verification
+        n = 256
+        r = np.arange(n)
+        trow = np.concatenate([r, r, r, r, r]); tcol = np.concatenate([r, (r + 1) % n, (r - 1) % n, (r + 16) % n, (r - 16) % n])
+        keep = np.abs(trow - tcol) <= 16
+        tval = np.where(trow == tcol, 4.5, -1.0).astype(np.float32)
+        g, tiled = ol.triplets_to_csr(n, n, trow[keep], tcol[keep], tval[keep]), False
+    else:
+        # three distinct offsets that do not describe a grid (rows not divisible): proposal refused
+        n = 1000
+        r = np.arange(n)
+        trow = np.concatenate([r, r[1:], r[:-1], r[7:], r[:-7], r[131:], r[:-131]])
+        tcol = np.concatenate([r, r[1:] - 1, r[:-1] + 1, r[7:] - 7, r[:-7] + 7, r[131:] - 131, r[:-131] + 131])
+        tval = np.where(trow == tcol, 7.0, -1.0).astype(np.float32)
+        g, tiled = ol.triplets_to_csr(n, n, trow, tcol, tval), False
+    m = upload(smm, g)
+    M = m.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
+    assert (M.tile_levels() != (0, 0)) == tiled, M.tile_levels()
+    if tiled:
+        assert M.tile_levels()[0] < M.levels()[0]
+    rhs = matgen.xstar(g.rows)
+    rc, x = M.apply(rhs)
+    orc, ox = ol.sgs_apply(g, rhs)
+    assert rc == orc == 0 and x.tobytes() == ox.tobytes()
+    # the factor-based sweeps share the schedule
+    I = smm.ILU0Preconditioner(m)
+    assert I.validate() == 0
+    lu = ol.ilu0_factorize(g)[1]
+    assert I.apply(rhs)[1].tobytes() == ol.ilu0_apply(g, lu, rhs).tobytes()
