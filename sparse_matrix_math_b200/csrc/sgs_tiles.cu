@@ -31,7 +31,6 @@
 namespace {
 
 constexpr int TILE = 64;
-constexpr int TILE_WARPS = 4;
 constexpr int TILE_MAX_W = 4;
 constexpr int MAX_STEPS = 64;
 constexpr int MAX_PREDS = 8;
@@ -66,7 +65,7 @@ __device__ __forceinline__ unsigned long long tile_clock() {
     return t;
 }
 
-template <bool FORWARD, bool IC0>
+template <bool FORWARD, bool IC0, int TILE_WARPS>
 __global__ void __launch_bounds__(TILE_WARPS * 32) sgs_tile_kernel(const TileArgs A, const float* __restrict__ rhs, float* yperm, float* xperm,
                                                                   float* __restrict__ x, unsigned int* tickets, const SolveState* st) {
     if (st != nullptr && st->done) return;
@@ -424,12 +423,28 @@ bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& s
     return true;
 }
 
+namespace {
+template <int TILE_WARPS>
+void launch_tiles(const smm_precond* p, const TileArgs& F, const TileArgs& B, const float* rhs_dev, float* x_dev, SolveState* state, long long cap,
+                  cudaStream_t s) {
+    const long long nblocks = (F.ntiles + TILE_WARPS - 1) / TILE_WARPS;
+    const unsigned grid = (unsigned)(nblocks < cap ? nblocks : cap);
+    if (p->kind != 0) {
+        sgs_tile_kernel<true, true, TILE_WARPS><<<grid, TILE_WARPS * 32, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+        sgs_tile_kernel<false, true, TILE_WARPS><<<grid, TILE_WARPS * 32, 0, s>>>(B, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+    } else {
+        sgs_tile_kernel<true, false, TILE_WARPS><<<grid, TILE_WARPS * 32, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+        sgs_tile_kernel<false, false, TILE_WARPS><<<grid, TILE_WARPS * 32, 0, s>>>(B, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+    }
+}
+}  // namespace
+
 int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, int ctas_per_sm, unsigned int sleep_first,
                          unsigned int sleep_later, cudaStream_t s) {
     const long long ntiles = p->threads_fwd / TILE;
-    const long long nblocks = (ntiles + TILE_WARPS - 1) / TILE_WARPS;
-    const long long cap = (long long)p->m->sm_count * ctas_per_sm;
-    const unsigned grid = (unsigned)(nblocks < cap ? nblocks : cap);
+    static int warps = 0;                                       // tiles per CTA claim (tuning knob)
+    if (!warps) { const char* e = getenv("SMM_B200_SGS_TILE_WARPS"); warps = e ? atoi(e) : 4; }
+    const long long cap = (long long)p->m->sm_count * ctas_per_sm * 4 / warps;
     // debug: SMM_B200_SGS_TRACE=<file> records per-tile timestamps of the forward sweep of every apply (last one kept)
     static const char* trace_path = getenv("SMM_B200_SGS_TRACE");
     static unsigned long long* trace = nullptr;
@@ -438,13 +453,10 @@ int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_de
     const uint8_t* nsb = p->tile_steps[1] + ntiles * TILE;
     TileArgs F{nsf, p->tile_steps[0], p->tile_push[0], p->order_fwd, nullptr, p->ecol[0], p->eval[0], p->dval[0], ntiles, p->tile_width, sleep_first, sleep_later, trace};
     TileArgs B{nsb, p->tile_steps[1], p->tile_push[1], p->order_bwd, p->ypos, p->ecol[1], p->eval[1], p->dval[1], ntiles, p->tile_width, sleep_first, sleep_later, nullptr};
-    if (p->kind != 0) {
-        sgs_tile_kernel<true, true><<<grid, TILE_WARPS * 32, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
-        sgs_tile_kernel<false, true><<<grid, TILE_WARPS * 32, 0, s>>>(B, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
-    } else {
-        sgs_tile_kernel<true, false><<<grid, TILE_WARPS * 32, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
-        sgs_tile_kernel<false, false><<<grid, TILE_WARPS * 32, 0, s>>>(B, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
-    }
+    if (warps == 2) launch_tiles<2>(p, F, B, rhs_dev, x_dev, state, cap, s);
+    else if (warps == 8) launch_tiles<8>(p, F, B, rhs_dev, x_dev, state, cap, s);
+    else if (warps == 1) launch_tiles<1>(p, F, B, rhs_dev, x_dev, state, cap, s);
+    else launch_tiles<4>(p, F, B, rhs_dev, x_dev, state, cap, s);
     SMM_CUDA(cudaGetLastError());
     if (trace) {
         std::vector<unsigned long long> h(4 * (size_t)ntiles);

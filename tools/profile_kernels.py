@@ -3,7 +3,7 @@
 the irregular-row SpMV on the power-law matrix (config 4), the SGS sweeps on convection-diffusion 256^3 (config 3),
 the fused vector kernels of a BiCGStab iteration and the reference-order dot product.
 
-    ncu --set full --clock-control none --import-source on -k regex:'spmv_kernel|sgs_sweep|dot_tree|vec_kernel' \
+    ncu --set full --clock-control none --import-source on -k regex:'spmv_kernel|sgs_sweep|sgs_tile|dot_tree|vec_kernel' \
         -c 14 -o gpurun_out/r01e_kernels python tools/profile_kernels.py
 """
 import ctypes as C
