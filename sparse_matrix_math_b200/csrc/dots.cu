@@ -131,6 +131,7 @@ struct SerialParams {
     int ndots;
     const float* a[2];
     const float* b[2];
+    const float* pre[2];   // total already computed by sum_squares_serial_kernel (a == b), or null
     SolveState* state;
     int finish;
     float* out_dev;
@@ -141,9 +142,10 @@ constexpr int SER_CHUNK = 4096;
 
 __global__ void __launch_bounds__(SER_THREADS) dot_serial_kernel(const SerialParams P) {
     if (P.state != nullptr && P.state->done) return;
-    __shared__ float buf[2][SER_CHUNK];
+    __shared__ __align__(16) float buf[2][SER_CHUNK];
     float totals[2] = {0.f, 0.f};
     for (int d = 0; d < P.ndots; ++d) {
+        if (P.pre[d] != nullptr) { totals[d] = *P.pre[d]; continue; }   // uniform across the CTA
         const float* a = P.a[d];
         const float* b = P.b[d];
         float cur = 0.0f;
@@ -166,7 +168,12 @@ __global__ void __launch_bounds__(SER_THREADS) dot_serial_kernel(const SerialPar
             } else if (threadIdx.x == 0) {                    // one thread adds left to right, H:322-326
                 const long long left = P.n - c * SER_CHUNK;
                 const int m = left < SER_CHUNK ? (int)left : SER_CHUNK;
-                for (int t = 0; t < m; ++t) cur = __fadd_rn(cur, buf[pb][t]);
+                int t = 0;
+                for (; t + 4 <= m; t += 4) {                  // one 128-bit load per four additions: the FADD chain is the only cost
+                    const float4 q = *reinterpret_cast<const float4*>(&buf[pb][t]);
+                    cur = __fadd_rn(cur, q.x); cur = __fadd_rn(cur, q.y); cur = __fadd_rn(cur, q.z); cur = __fadd_rn(cur, q.w);
+                }
+                for (; t < m; ++t) cur = __fadd_rn(cur, buf[pb][t]);
             }
             __syncthreads();
         }
@@ -178,11 +185,183 @@ __global__ void __launch_bounds__(SER_THREADS) dot_serial_kernel(const SerialPar
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Left-to-right float sum of SQUARES, exactly, in parallel.
+//
+// The reference adds ||r||^2 serially in both of its builds (BiCGStab, H:2262-2267), and its serial build adds every
+// dot product that way; one thread doing the same costs 4 cycles per element (the FADD chain).  When every term is a
+// square the running sum s only grows, and while it stays inside one binade [2^e, 2^(e+1)) adding a term is integer
+// arithmetic on its significand m (s = m ulp): with p = (k + f) ulp, RN(s + p) = (m + k) ulp rounded up when f > 1/2,
+// or when f = 1/2 and m + k is odd (ties to even).  So a term is a map m -> m + inc[parity of m], and such maps
+// compose associatively: a thread folds its 32 terms into one map, the block scans the maps, and the first thread
+// at which m would reach 2^24 (the sum leaves the binade; also any infinity / NaN term) replays its own 32 terms with
+// real float additions, which hands the next round its binade.  Everything before that thread is exact by
+// construction, so the result has the reference's bits for any input.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SQ_THREADS = 1024;
+constexpr int SQ_EPT = 32;                                   // terms per thread and window
+constexpr int SQ_WINDOW = SQ_THREADS * SQ_EPT;
+constexpr int SQ_SMEM_BYTES = SQ_THREADS * (SQ_EPT + 1) * (int)sizeof(unsigned int);
+constexpr unsigned int SQ_CAP = 1u << 26;                    // "leaves the binade" (saturating; parities beyond it are meaningless)
+
+struct Inc2 { unsigned int e, o; };                          // increment of the significand when it is even / odd
+
+__device__ __forceinline__ Inc2 inc_then(const Inc2 a, const Inc2 b) {      // first a, then b
+    Inc2 c;
+    c.e = min(a.e + ((a.e & 1u) ? b.o : b.e), SQ_CAP);
+    c.o = min(a.o + ((a.o & 1u) ? b.e : b.o), SQ_CAP);
+    return c;
+}
+
+// p >= 0 given by its bits; e_eff = max(biased exponent of the running sum, 1).  Branch-free: with p = P 2^-sh ulp,
+// k = P >> sh, and the discarded bits decide the rounding; sh >= 25 gives k = 0 and less than half an ulp by itself.
+__device__ __forceinline__ Inc2 term_inc(const unsigned int pbits, const int e_eff) {
+    const unsigned int ep = (pbits >> 23) & 0xFFu, mant = pbits & 0x7FFFFFu;
+    const unsigned int P = ep ? (mant | 0x800000u) : mant;
+    const int sh_raw = e_eff - (int)(ep ? ep : 1u);
+    const unsigned int sh = (unsigned int)min(max(sh_raw, 0), 31);
+    const unsigned int k = P >> sh, rem = P & ((1u << sh) - 1u), half = (1u << sh) >> 1;
+    const unsigned int up = rem > half ? 1u : 0u;
+    const unsigned int tie = (rem == half && sh != 0u) ? 1u : 0u;          // ties go to the even significand
+    Inc2 r;
+    r.e = k + up + (tie & k);
+    r.o = k + up + (tie & ~k);
+    // infinity / NaN terms and terms that alone exceed the binade are left to real arithmetic
+    if (ep == 255u || (sh_raw < 0 && P != 0u)) r.e = r.o = SQ_CAP;
+    return r;
+}
+
+struct SquaresParams {
+    long long n;
+    const float* r;
+    float* out_dev;        // optional: the total
+    SolveState* state;     // optional: smm_finish(finish, state, total, 0)
+    int finish;
+};
+
+__global__ void __launch_bounds__(SQ_THREADS, 1) sum_squares_serial_kernel(const SquaresParams P) {
+    if (P.state != nullptr && P.state->done) return;
+    extern __shared__ unsigned int sq_terms[];               // [SQ_THREADS][SQ_EPT + 1] products (bits)
+    __shared__ Inc2 sh_warp[32];
+    __shared__ unsigned int sh_first, sh_bits, sh_flag;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned int sbits = 0u;                                 // the running sum (H:2262: res = 0)
+    long long base = 0;
+    bool open_ended = false;                                 // the sum has become infinite or NaN
+    // values of the window, coalesced, all 32 loads of a thread in flight; the NEXT window is requested as soon as this
+    // one has been parked in shared memory, so its latency hides behind the scan
+    float v[SQ_EPT];
+    auto fetch = [&](long long from) {
+#pragma unroll
+        for (int it = 0; it < SQ_EPT; ++it) {
+            const long long j = from + it * SQ_THREADS + tid;
+            v[it] = j < P.n ? __ldg(P.r + j) : 0.0f;
+        }
+    };
+    fetch(0);
+    while (base < P.n && !open_ended) {
+        // products parked so that thread t finds its 32 terms in consecutive banks
+#pragma unroll
+        for (int it = 0; it < SQ_EPT; ++it) {
+            const int w = it * SQ_THREADS + tid;
+            sq_terms[(w >> 5) * (SQ_EPT + 1) + (w & 31)] = __float_as_uint(__fmul_rn(v[it], v[it]));
+        }
+        __syncthreads();
+        if (base + SQ_WINDOW < P.n) fetch(base + SQ_WINDOW);
+        int done = 0;                                        // threads [0, done) of this window are already in the sum
+        while (done < SQ_THREADS) {
+            const unsigned int se = (sbits >> 23) & 0xFFu;
+            if (se == 255u) { open_ended = true; break; }    // infinity or NaN: see below
+            const int e_eff = se ? (int)se : 1;
+            const unsigned int m = se ? ((sbits & 0x7FFFFFu) | 0x800000u) : sbits;
+            if (tid == 0) sh_first = SQ_THREADS;
+            Inc2 mine = {0u, 0u};
+            if (tid >= done) {
+#pragma unroll 8
+                for (int j = 0; j < SQ_EPT; ++j) mine = inc_then(mine, term_inc(sq_terms[tid * (SQ_EPT + 1) + j], e_eff));
+            }
+            // exclusive scan of the maps in thread order
+            Inc2 incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                Inc2 prev;
+                prev.e = __shfl_up_sync(0xFFFFFFFFu, incl.e, off);
+                prev.o = __shfl_up_sync(0xFFFFFFFFu, incl.o, off);
+                if (lane >= off) incl = inc_then(prev, incl);
+            }
+            if (lane == 31) sh_warp[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                Inc2 w = sh_warp[lane];
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    Inc2 prev;
+                    prev.e = __shfl_up_sync(0xFFFFFFFFu, w.e, off);
+                    prev.o = __shfl_up_sync(0xFFFFFFFFu, w.o, off);
+                    if (lane >= off) w = inc_then(prev, w);
+                }
+                sh_warp[lane] = w;                           // inclusive over warps
+            }
+            __syncthreads();
+            Inc2 before = {0u, 0u};                          // everything ahead of this thread
+            if (warp > 0) before = sh_warp[warp - 1];
+            {
+                Inc2 prev;
+                prev.e = __shfl_up_sync(0xFFFFFFFFu, incl.e, 1);
+                prev.o = __shfl_up_sync(0xFFFFFFFFu, incl.o, 1);
+                if (lane > 0) before = inc_then(before, prev);
+            }
+            const unsigned int excl = (m & 1u) ? before.o : before.e;
+            const unsigned int own = ((m + excl) & 1u) ? mine.o : mine.e;
+            const bool leaves = excl >= SQ_CAP || own >= SQ_CAP || m + excl + own >= (1u << 24);
+            if (leaves) atomicMin(&sh_first, (unsigned int)tid);
+            __syncthreads();
+            const unsigned int first = sh_first;
+            if (first == SQ_THREADS) {                       // the rest of the window stays inside the binade
+                if (tid == SQ_THREADS - 1) {
+                    const unsigned int m2 = m + excl + own;  // < 2^24
+                    sh_bits = m2 >= 0x800000u ? (((unsigned int)e_eff << 23) | (m2 & 0x7FFFFFu)) : m2;
+                }
+                done = SQ_THREADS;
+            } else {
+                if (tid == (int)first) {                     // real additions from the exact sum ahead of this thread
+                    const unsigned int m2 = m + excl;        // < 2^24
+                    float cur = __uint_as_float(m2 >= 0x800000u ? (((unsigned int)e_eff << 23) | (m2 & 0x7FFFFFu)) : m2);
+                    for (int j = 0; j < SQ_EPT; ++j) cur = __fadd_rn(cur, __uint_as_float(sq_terms[tid * (SQ_EPT + 1) + j]));   // H:2266 (absent terms are +0)
+                    sh_bits = __float_as_uint(cur);
+                }
+                done = (int)first + 1;
+            }
+            __syncthreads();
+            sbits = sh_bits;
+        }
+        if (!open_ended) base += SQ_WINDOW;
+        else base += (long long)done * SQ_EPT;
+        __syncthreads();                                     // sq_terms is refilled
+    }
+    // +infinity stays +infinity unless a NaN term follows (NaN stays NaN): r*r is NaN only for a NaN r
+    if (((sbits >> 23) & 0xFFu) == 255u && (sbits & 0x7FFFFFu) == 0u && base < P.n) {
+        if (tid == 0) sh_flag = 0u;
+        __syncthreads();
+        bool nan = false;
+        for (long long j = base + tid; j < P.n; j += SQ_THREADS) { const float v = __ldg(P.r + j); nan |= v != v; }
+        if (nan) sh_flag = 1u;
+        __syncthreads();
+        if (sh_flag) sbits = 0x7FFFFFFFu;
+    }
+    if (tid == 0) {
+        const float total = __uint_as_float(sbits);
+        if (P.out_dev) P.out_dev[0] = total;
+        if (P.state) smm_finish(P.finish, P.state, total, 0.0f);
+    }
+}
+
 struct DotScratch {
     float* nodes = nullptr;
     size_t nodes_cap = 0;
     unsigned int* ticket = nullptr;
     float* out = nullptr;        // 2 floats
+    float* sq = nullptr;         // 2 floats: totals of sum_squares_serial_kernel on their way to dot_serial_kernel
 };
 DotScratch g_scratch[64];
 }  // namespace
@@ -197,6 +376,8 @@ int scratch_for(long long nn, DotScratch** out) {
         SMM_CUDA(cudaMalloc(&sc.ticket, sizeof(unsigned int)));
         SMM_CUDA(cudaMemset(sc.ticket, 0, sizeof(unsigned int)));
         SMM_CUDA(cudaMalloc(&sc.out, 2 * sizeof(float)));
+        SMM_CUDA(cudaMalloc(&sc.sq, 2 * sizeof(float)));
+        SMM_CUDA(cudaFuncSetAttribute(sum_squares_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_SMEM_BYTES));
     }
     const size_t need = (size_t)nn * 4;
     if (sc.nodes_cap < need) {
@@ -236,11 +417,29 @@ int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const 
         const long long jobs = (1ll << P.depth) * ndots;       // one warp per (dot, depth-D' node)
         dot_tree_kernel<<<(unsigned)((jobs + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, 0, s>>>(P);
     } else {
-        SerialParams P;
-        P.n = n; P.ndots = ndots;
-        P.a[0] = a0; P.b[0] = b0; P.a[1] = a1; P.b[1] = b1;
-        P.state = state; P.finish = finish; P.out_dev = out_dev;
-        dot_serial_kernel<<<1, SER_THREADS, 0, s>>>(P);
+        // left to right.  Dots of a vector with itself are sums of squares: exact in parallel (sum_squares_serial_kernel)
+        DotScratch* sc = nullptr;
+        SMM_TRY(scratch_for(1, &sc));
+        const float* aa[2] = {a0, a1};
+        const float* bb[2] = {b0, b1};
+        if (ndots == 1 && a0 == b0) {
+            SquaresParams Q{n, a0, out_dev, state, finish};
+            sum_squares_serial_kernel<<<1, SQ_THREADS, SQ_SMEM_BYTES, s>>>(Q);
+        } else {
+            SerialParams P;
+            P.n = n; P.ndots = ndots;
+            for (int d = 0; d < 2; ++d) {
+                P.a[d] = aa[d]; P.b[d] = bb[d]; P.pre[d] = nullptr;
+                if (d < ndots && aa[d] == bb[d]) {
+                    SquaresParams Q{n, aa[d], sc->sq + d, nullptr, FIN_NONE};
+                    sum_squares_serial_kernel<<<1, SQ_THREADS, SQ_SMEM_BYTES, s>>>(Q);
+                    SMM_COUNT_LAUNCH(1);
+                    P.pre[d] = sc->sq + d;
+                }
+            }
+            P.state = state; P.finish = finish; P.out_dev = out_dev;
+            dot_serial_kernel<<<1, SER_THREADS, 0, s>>>(P);
+        }
     }
     SMM_COUNT_LAUNCH(1);
     SMM_CUDA(cudaGetLastError());
@@ -303,12 +502,13 @@ int smm_dot(int64_t n, const float* a, const float* b, int reduction_mode, float
     if (n < 0 || !out || (n && (!a || !b))) { smm_set_error("smm_dot: bad arguments"); return SMM_E_INVALID; }
     float *da = nullptr, *db = nullptr;
     const size_t bytes = sizeof(float) * (size_t)(n ? n : 1);
+    const bool same = a == b;                                  // a vector with itself: one device copy (and the sum-of-squares path)
     SMM_CUDA(cudaMalloc(&da, bytes));
-    if (cudaMalloc(&db, bytes) != cudaSuccess) { cudaFree(da); return smm_cuda_fail(cudaGetLastError(), "cudaMalloc", __FILE__, __LINE__); }
+    if (!same && cudaMalloc(&db, bytes) != cudaSuccess) { cudaFree(da); return smm_cuda_fail(cudaGetLastError(), "cudaMalloc", __FILE__, __LINE__); }
     int rc = SMM_OK;
-    if (n && (cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice) != cudaSuccess))
+    if (n && (cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice) != cudaSuccess || (!same && cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice) != cudaSuccess)))
         rc = smm_cuda_fail(cudaGetLastError(), "memcpy", __FILE__, __LINE__);
-    if (rc == SMM_OK) rc = smm_dot_dev(n, da, db, reduction_mode, out, nullptr);
+    if (rc == SMM_OK) rc = smm_dot_dev(n, da, same ? da : db, reduction_mode, out, nullptr);
     cudaFree(da);
     cudaFree(db);
     return rc;

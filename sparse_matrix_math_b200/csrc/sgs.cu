@@ -411,11 +411,17 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
 
 extern "C" {
 
+int smm_precond_destroy(smm_precond_t* p);
+
 static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond_t** out) {
     if (!m || !out) return SMM_E_INVALID;
     if (m->rows != m->cols) { smm_set_error("preconditioner: matrix must be square"); return SMM_E_INVALID; }
     SMM_CUDA(cudaSetDevice(m->device));
-    smm_precond* p = new smm_precond();
+    struct Guard {                                             // every early return below releases what has been allocated
+        smm_precond* p;
+        ~Guard() { if (p) smm_precond_destroy(p); }
+    } guard{new smm_precond()};
+    smm_precond* p = guard.p;
     p->m = m;
     p->kind = kind;
     p->rows = m->rows;
@@ -482,6 +488,7 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
         }
     }
     *out = p;
+    guard.p = nullptr;
     return SMM_OK;
 }
 

@@ -411,13 +411,26 @@ bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& s
     p->tile_width = width;
     p->tile_levels[0] = L[0].levels;
     p->tile_levels[1] = L[1].levels;
-    if (upload(L[0].order, &p->order_fwd) != SMM_OK || upload(L[1].order, &p->order_bwd) != SMM_OK || upload(yp, &p->ypos) != SMM_OK) return false;
-    if (cudaMalloc(&p->yperm, sizeof(float) * npos) != cudaSuccess || cudaMalloc(&p->xperm, sizeof(float) * npos) != cudaSuccess) return false;
-    for (int w = 0; w < 2; ++w) {
+    bool ok = upload(L[0].order, &p->order_fwd) == SMM_OK && upload(L[1].order, &p->order_bwd) == SMM_OK && upload(yp, &p->ypos) == SMM_OK &&
+              cudaMalloc(&p->yperm, sizeof(float) * npos) == cudaSuccess && cudaMalloc(&p->xperm, sizeof(float) * npos) == cudaSuccess;
+    for (int w = 0; w < 2 && ok; ++w) {
         p->esize[w] = (long long)L[w].ecol.size();
-        if (upload(L[w].ecol, &p->ecol[w]) != SMM_OK || upload(L[w].eidx, &p->eidx[w]) != SMM_OK || upload(L[w].steps, &p->tile_steps[w]) != SMM_OK ||
-            upload(L[w].push, &p->tile_push[w]) != SMM_OK) return false;
-        if (cudaMalloc(&p->eval[w], sizeof(float) * L[w].ecol.size()) != cudaSuccess || cudaMalloc(&p->dval[w], sizeof(float) * npos) != cudaSuccess) return false;
+        ok = upload(L[w].ecol, &p->ecol[w]) == SMM_OK && upload(L[w].eidx, &p->eidx[w]) == SMM_OK && upload(L[w].steps, &p->tile_steps[w]) == SMM_OK &&
+             upload(L[w].push, &p->tile_push[w]) == SMM_OK && cudaMalloc(&p->eval[w], sizeof(float) * L[w].ecol.size()) == cudaSuccess &&
+             cudaMalloc(&p->dval[w], sizeof(float) * npos) == cudaSuccess;
+    }
+    if (!ok) {                                                  // out of memory: leave the handle as it was, the row-level schedule needs less
+        cudaGetLastError();
+        cudaFree(p->order_fwd); cudaFree(p->order_bwd); cudaFree(p->ypos); cudaFree(p->yperm); cudaFree(p->xperm);
+        p->order_fwd = p->order_bwd = p->ypos = nullptr;
+        p->yperm = p->xperm = nullptr;
+        for (int w = 0; w < 2; ++w) {
+            cudaFree(p->ecol[w]); cudaFree(p->eidx[w]); cudaFree(p->tile_steps[w]); cudaFree(p->tile_push[w]); cudaFree(p->eval[w]); cudaFree(p->dval[w]);
+            p->ecol[w] = p->eidx[w] = nullptr; p->tile_steps[w] = nullptr; p->tile_push[w] = nullptr; p->eval[w] = p->dval[w] = nullptr;
+            p->esize[w] = 0;
+        }
+        p->threads_fwd = p->threads_bwd = 0;
+        return false;
     }
     p->tiled = true;
     return true;

@@ -621,3 +621,41 @@ def test_sweep_schedules_bit_exact(smm, case):
     assert I.validate() == 0
     lu = ol.ilu0_factorize(g)[1]
     assert I.apply(rhs)[1].tobytes() == ol.ilu0_apply(g, lu, rhs).tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's serial sums of squares (BiCGStab's ||r||^2 in both builds, every r.r of the serial build), reproduced
+# exactly by a parallel kernel (dots.cu: sum_squares_serial_kernel) -- adversarial inputs for the rounding model
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["normal", "wide_range", "ties", "denormal", "overflow", "nan_inf", "zeros"])
+@pytest.mark.parametrize("n", [1, 31, 33, 1000, 32767, 32768, 32769, 100003, 1 << 21])
+def test_serial_sum_of_squares_bit_exact(smm, kind, n):
+    rng = np.random.default_rng(n * 7 + len(kind))
+    with np.errstate(all="ignore"):
+        if kind == "normal":
+            r = rng.standard_normal(n).astype(np.float32)
+        elif kind == "wide_range":
+            r = (rng.standard_normal(n) * np.exp2(rng.integers(-70, 60, n))).astype(np.float32)
+        elif kind == "ties":                                 # squares are powers of two: many exact half-ulp cases
+            r = np.exp2(rng.integers(-24, 6, n) / 2.0).astype(np.float32)
+            r[rng.random(n) < 0.5] = np.float32(2.0) ** int(rng.integers(-12, 3))
+        elif kind == "denormal":
+            r = (rng.standard_normal(n) * 1e-20).astype(np.float32)
+            r[rng.random(n) < 0.2] = 0
+        elif kind == "overflow":
+            r = (rng.standard_normal(n) * 3e18).astype(np.float32)
+        elif kind == "nan_inf":
+            r = rng.standard_normal(n).astype(np.float32)
+            r[rng.integers(0, n)] = np.inf
+            if n > 2:
+                r[rng.integers(n // 2, n)] = np.nan
+        else:
+            r = np.zeros(n, np.float32)
+            r[rng.random(n) < 0.01] = 1.0
+    got = np.float32(smm.dot(r, r, smm.REDUCE_REFERENCE_SERIAL))
+    want = np.float32(ol.dot(r, r, False))
+    assert (np.isnan(got) and np.isnan(want)) or got.tobytes() == want.tobytes(), (got, want)
+    # two different vectors still take the one-thread kernel
+    q = r.copy()
+    got2 = np.float32(smm.dot(r, q, smm.REDUCE_REFERENCE_SERIAL))
+    assert (np.isnan(got2) and np.isnan(want)) or got2.tobytes() == want.tobytes()
