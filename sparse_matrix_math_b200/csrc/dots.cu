@@ -11,6 +11,8 @@
 //   SMM_REDUCE_REFERENCE_SERIAL the serial build (H:322-326): left to right.  One thread adds, the rest of its CTA
 //       streams products into shared memory ahead of it.
 //   SMM_REDUCE_FAST             vecops.cu's fused two-stage reduction (VEC_DOT2).
+#include <cooperative_groups.h>
+
 #include "epilogue.cuh"
 #include "smm_internal.cuh"
 
@@ -193,16 +195,19 @@ __global__ void __launch_bounds__(SER_THREADS) dot_serial_kernel(const SerialPar
 // square the running sum s only grows, and while it stays inside one binade [2^e, 2^(e+1)) adding a term is integer
 // arithmetic on its significand m (s = m ulp): with p = (k + f) ulp, RN(s + p) = (m + k) ulp rounded up when f > 1/2,
 // or when f = 1/2 and m + k is odd (ties to even).  So a term is a map m -> m + inc[parity of m], and such maps
-// compose associatively: a thread folds its 32 terms into one map, the block scans the maps, and the first thread
-// at which m would reach 2^24 (the sum leaves the binade; also any infinity / NaN term) replays its own 32 terms with
-// real float additions, which hands the next round its binade.  Everything before that thread is exact by
+// compose associatively: a thread folds its 8 terms into one map, a cluster of 8 CTAs scans the maps (warp shuffles,
+// shared memory, then DSMEM between the CTAs), and the first thread at which m would reach 2^24 (the sum leaves the
+// binade; also any infinity / NaN term) replays its own terms with real float additions, which hands the next
+// round its binade; the 64 K-term window is then re-scanned in place.  Everything before that thread is exact by
 // construction, so the result has the reference's bits for any input.
 // ---------------------------------------------------------------------------------------------------
 constexpr int SQ_THREADS = 1024;
-constexpr int SQ_EPT = 32;                                   // terms per thread and window
-constexpr int SQ_WINDOW = SQ_THREADS * SQ_EPT;
+constexpr int SQ_CTAS = 8;                                   // one thread-block cluster: the CTAs trade their maps over DSMEM
+constexpr int SQ_EPT = 8;                                    // terms per thread and window
+constexpr int SQ_WINDOW = SQ_CTAS * SQ_THREADS * SQ_EPT;
 constexpr int SQ_SMEM_BYTES = SQ_THREADS * (SQ_EPT + 1) * (int)sizeof(unsigned int);
 constexpr unsigned int SQ_CAP = 1u << 26;                    // "leaves the binade" (saturating; parities beyond it are meaningless)
+constexpr unsigned int SQ_NONE = 0xFFFFFFFFu;
 
 struct Inc2 { unsigned int e, o; };                          // increment of the significand when it is even / odd
 
@@ -239,48 +244,55 @@ struct SquaresParams {
     int finish;
 };
 
-__global__ void __launch_bounds__(SQ_THREADS, 1) sum_squares_serial_kernel(const SquaresParams P) {
+__global__ void __cluster_dims__(SQ_CTAS, 1, 1) __launch_bounds__(SQ_THREADS, 1) sum_squares_serial_kernel(const SquaresParams P) {
+    // (every CTA of the cluster takes the same branch: the cluster barriers below stay matched)
     if (P.state != nullptr && P.state->done) return;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ unsigned int sq_terms[];               // [SQ_THREADS][SQ_EPT + 1] products (bits)
     __shared__ Inc2 sh_warp[32];
-    __shared__ unsigned int sh_first, sh_bits, sh_flag;
+    __shared__ Inc2 sh_cta[SQ_CTAS];                         // every CTA's map, written into every CTA (DSMEM)
+    __shared__ unsigned int sh_first[SQ_CTAS];               // every CTA's first thread that leaves the binade
+    __shared__ unsigned int sh_local_first, sh_bits, sh_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cluster.block_rank();
+    const unsigned int g = (unsigned int)rank * SQ_THREADS + tid;              // thread index inside the window
     unsigned int sbits = 0u;                                 // the running sum (H:2262: res = 0)
     long long base = 0;
     bool open_ended = false;                                 // the sum has become infinite or NaN
-    // values of the window, coalesced, all 32 loads of a thread in flight; the NEXT window is requested as soon as this
-    // one has been parked in shared memory, so its latency hides behind the scan
+    // values of this CTA's part of the window, coalesced, all loads of a thread in flight; the NEXT window is requested
+    // as soon as this one has been parked in shared memory
     float v[SQ_EPT];
     auto fetch = [&](long long from) {
 #pragma unroll
         for (int it = 0; it < SQ_EPT; ++it) {
-            const long long j = from + it * SQ_THREADS + tid;
+            const long long j = from + (long long)rank * (SQ_THREADS * SQ_EPT) + it * SQ_THREADS + tid;
             v[it] = j < P.n ? __ldg(P.r + j) : 0.0f;
         }
     };
     fetch(0);
     while (base < P.n && !open_ended) {
-        // products parked so that thread t finds its 32 terms in consecutive banks
+        // products parked so that thread t finds its terms in consecutive banks
 #pragma unroll
         for (int it = 0; it < SQ_EPT; ++it) {
             const int w = it * SQ_THREADS + tid;
-            sq_terms[(w >> 5) * (SQ_EPT + 1) + (w & 31)] = __float_as_uint(__fmul_rn(v[it], v[it]));
+            sq_terms[(w / SQ_EPT) * (SQ_EPT + 1) + (w % SQ_EPT)] = __float_as_uint(__fmul_rn(v[it], v[it]));
         }
         __syncthreads();
         if (base + SQ_WINDOW < P.n) fetch(base + SQ_WINDOW);
-        int done = 0;                                        // threads [0, done) of this window are already in the sum
-        while (done < SQ_THREADS) {
+        unsigned int done = 0;                               // threads [0, done) of this window are already in the sum
+        while (done < (unsigned int)(SQ_CTAS * SQ_THREADS)) {
             const unsigned int se = (sbits >> 23) & 0xFFu;
             if (se == 255u) { open_ended = true; break; }    // infinity or NaN: see below
             const int e_eff = se ? (int)se : 1;
             const unsigned int m = se ? ((sbits & 0x7FFFFFu) | 0x800000u) : sbits;
-            if (tid == 0) sh_first = SQ_THREADS;
+            if (tid == 0) sh_local_first = SQ_NONE;
             Inc2 mine = {0u, 0u};
-            if (tid >= done) {
-#pragma unroll 8
+            if (g >= done) {
+#pragma unroll
                 for (int j = 0; j < SQ_EPT; ++j) mine = inc_then(mine, term_inc(sq_terms[tid * (SQ_EPT + 1) + j], e_eff));
             }
-            // exclusive scan of the maps in thread order
+            // scan of the maps in thread order: warp, CTA, cluster
             Inc2 incl = mine;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
@@ -301,10 +313,15 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sum_squares_serial_kernel(const
                     if (lane >= off) w = inc_then(prev, w);
                 }
                 sh_warp[lane] = w;                           // inclusive over warps
+                Inc2 total;                                  // this CTA's map, handed to every CTA of the cluster
+                total.e = __shfl_sync(0xFFFFFFFFu, w.e, 31);
+                total.o = __shfl_sync(0xFFFFFFFFu, w.o, 31);
+                if (lane < SQ_CTAS) *cluster.map_shared_rank(&sh_cta[rank], lane) = total;
             }
-            __syncthreads();
-            Inc2 before = {0u, 0u};                          // everything ahead of this thread
-            if (warp > 0) before = sh_warp[warp - 1];
+            cluster.sync();
+            Inc2 before = {0u, 0u};                          // everything ahead of this thread: CTAs, warps, lanes
+            for (int c = 0; c < rank; ++c) before = inc_then(before, sh_cta[c]);
+            if (warp > 0) before = inc_then(before, sh_warp[warp - 1]);
             {
                 Inc2 prev;
                 prev.e = __shfl_up_sync(0xFFFFFFFFu, incl.e, 1);
@@ -314,37 +331,51 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sum_squares_serial_kernel(const
             const unsigned int excl = (m & 1u) ? before.o : before.e;
             const unsigned int own = ((m + excl) & 1u) ? mine.o : mine.e;
             const bool leaves = excl >= SQ_CAP || own >= SQ_CAP || m + excl + own >= (1u << 24);
-            if (leaves) atomicMin(&sh_first, (unsigned int)tid);
+            if (leaves) atomicMin(&sh_local_first, g);
             __syncthreads();
-            const unsigned int first = sh_first;
-            if (first == SQ_THREADS) {                       // the rest of the window stays inside the binade
-                if (tid == SQ_THREADS - 1) {
+            if (tid < SQ_CTAS) *cluster.map_shared_rank(&sh_first[rank], tid) = sh_local_first;
+            cluster.sync();
+            unsigned int first = SQ_NONE;
+#pragma unroll
+            for (int c = 0; c < SQ_CTAS; ++c) first = min(first, sh_first[c]);
+            unsigned int result = 0u;
+            bool writer = false;
+            if (first == SQ_NONE) {                          // the rest of the window stays inside the binade
+                if (g == (unsigned int)(SQ_CTAS * SQ_THREADS - 1)) {
                     const unsigned int m2 = m + excl + own;  // < 2^24
-                    sh_bits = m2 >= 0x800000u ? (((unsigned int)e_eff << 23) | (m2 & 0x7FFFFFu)) : m2;
+                    result = m2 >= 0x800000u ? (((unsigned int)e_eff << 23) | (m2 & 0x7FFFFFu)) : m2;
+                    writer = true;
                 }
-                done = SQ_THREADS;
+                done = SQ_CTAS * SQ_THREADS;
             } else {
-                if (tid == (int)first) {                     // real additions from the exact sum ahead of this thread
+                if (g == first) {                            // real additions from the exact sum ahead of this thread
                     const unsigned int m2 = m + excl;        // < 2^24
                     float cur = __uint_as_float(m2 >= 0x800000u ? (((unsigned int)e_eff << 23) | (m2 & 0x7FFFFFu)) : m2);
                     for (int j = 0; j < SQ_EPT; ++j) cur = __fadd_rn(cur, __uint_as_float(sq_terms[tid * (SQ_EPT + 1) + j]));   // H:2266 (absent terms are +0)
-                    sh_bits = __float_as_uint(cur);
+                    result = __float_as_uint(cur);
+                    writer = true;
                 }
-                done = (int)first + 1;
+                done = first + 1u;
             }
-            __syncthreads();
+            if (writer) {
+#pragma unroll
+                for (int c = 0; c < SQ_CTAS; ++c) *cluster.map_shared_rank(&sh_bits, c) = result;
+            }
+            cluster.sync();
             sbits = sh_bits;
         }
         if (!open_ended) base += SQ_WINDOW;
         else base += (long long)done * SQ_EPT;
         __syncthreads();                                     // sq_terms is refilled
     }
+    cluster.sync();                                          // nobody leaves while a peer may still write into it
+    if (rank != 0) return;
     // +infinity stays +infinity unless a NaN term follows (NaN stays NaN): r*r is NaN only for a NaN r
     if (((sbits >> 23) & 0xFFu) == 255u && (sbits & 0x7FFFFFu) == 0u && base < P.n) {
         if (tid == 0) sh_flag = 0u;
         __syncthreads();
         bool nan = false;
-        for (long long j = base + tid; j < P.n; j += SQ_THREADS) { const float v = __ldg(P.r + j); nan |= v != v; }
+        for (long long j = base + tid; j < P.n; j += SQ_THREADS) { const float x = __ldg(P.r + j); nan |= x != x; }
         if (nan) sh_flag = 1u;
         __syncthreads();
         if (sh_flag) sbits = 0x7FFFFFFFu;
@@ -424,7 +455,7 @@ int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const 
         const float* bb[2] = {b0, b1};
         if (ndots == 1 && a0 == b0) {
             SquaresParams Q{n, a0, out_dev, state, finish};
-            sum_squares_serial_kernel<<<1, SQ_THREADS, SQ_SMEM_BYTES, s>>>(Q);
+            sum_squares_serial_kernel<<<SQ_CTAS, SQ_THREADS, SQ_SMEM_BYTES, s>>>(Q);
         } else {
             SerialParams P;
             P.n = n; P.ndots = ndots;
@@ -432,7 +463,7 @@ int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const 
                 P.a[d] = aa[d]; P.b[d] = bb[d]; P.pre[d] = nullptr;
                 if (d < ndots && aa[d] == bb[d]) {
                     SquaresParams Q{n, aa[d], sc->sq + d, nullptr, FIN_NONE};
-                    sum_squares_serial_kernel<<<1, SQ_THREADS, SQ_SMEM_BYTES, s>>>(Q);
+                    sum_squares_serial_kernel<<<SQ_CTAS, SQ_THREADS, SQ_SMEM_BYTES, s>>>(Q);
                     SMM_COUNT_LAUNCH(1);
                     P.pre[d] = sc->sq + d;
                 }
