@@ -30,6 +30,9 @@
 
 namespace {
 
+#ifndef SMM_TILE_MIN_CTAS
+#define SMM_TILE_MIN_CTAS 4      // resident 4-warp CTAs per SM the register allocation must allow
+#endif
 constexpr int TILE = 64;
 constexpr int TILE_MAX_W = 4;
 constexpr int MAX_STEPS = 64;
@@ -66,7 +69,7 @@ __device__ __forceinline__ unsigned long long tile_clock() {
 }
 
 template <bool FORWARD, bool IC0, int TILE_WARPS>
-__global__ void __launch_bounds__(TILE_WARPS * 32) sgs_tile_kernel(const TileArgs A, const float* __restrict__ rhs, float* yperm, float* xperm,
+__global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_WARPS) sgs_tile_kernel(const TileArgs A, const float* __restrict__ rhs, float* yperm, float* xperm,
                                                                   float* __restrict__ x, unsigned int* tickets, const SolveState* st) {
     if (st != nullptr && st->done) return;
     // operand staging: slot 4 * r + e holds operand e of row r of the warp's current tile.  Operands from other tiles
