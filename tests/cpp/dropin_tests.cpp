@@ -317,6 +317,53 @@ TEST_CASE("Preconditioned BiCGStab. IC0 and ILU0 preconditioners") {
     }
 }
 
+// ---- extension: a NON-symmetric Matrix Market file (the reference's loader rejects `general`) -> BiCGStab / CGS ----
+TEST_CASE("General Matrix Market file through SMM::ext::loadMatrix, solved with BiCGStab + ILU0") {
+    const int n = 7;                                       // 7^3 convection-diffusion stencil, written as a general .mtx
+    const char* path = "/tmp/smm_b200_convdiff_general.mtx";
+    {
+        std::FILE* f = std::fopen(path, "w");
+        REQUIRE_EQ(f != nullptr, true);
+        long entries = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) std::fprintf(f, "%%%%MatrixMarket matrix coordinate real general\n%% generated by dropin_tests\n%d %d %ld\n", n * n * n, n * n * n, entries);
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                const int r = (k * n + j) * n + i;
+                const int off[7] = {-n * n, -n, -1, 0, 1, n, n * n};
+                const bool ok[7] = {k > 0, j > 0, i > 0, true, i < n - 1, j < n - 1, k < n - 1};
+                const double val[7] = {-1.5, -1.5, -1.5, 6.0, -0.5, -0.5, -0.5};
+                for (int e = 0; e < 7; ++e) {
+                    if (!ok[e]) continue;
+                    if (pass == 0) ++entries; else std::fprintf(f, "%d %d %.17g\n", r + 1, r + off[e] + 1, val[e]);
+                }
+            }
+        }
+        std::fclose(f);
+    }
+    SMM::CSRMatrix<T> strict;
+    CHECK(SMM::loadMatrix(path, strict) == SMM::MatrixLoadStatus::PARSE_ERROR_MMX_FILE_UNSUPPORTED_STRUCTURE);   // H:2572-2574
+    SMM::CSRMatrix<T> m;
+    REQUIRE_EQ(SMM::ext::loadMatrix(path, m), SMM::MatrixLoadStatus::SUCCESS);
+    CHECK_EQ(m.getDenseRowCount(), n * n * n);
+    CHECK_EQ(m.getNonZeroCount(), 7 * n * n * n - 6 * n * n);
+    CHECK_EQ(m.getValue(1, 0), -1.5f);
+    CHECK_EQ(m.getValue(0, 1), -0.5f);
+    SMM::Vector<T> rhs = sumColumsPerRow(m);
+    {
+        using ILU0 = typename SMM::CSRMatrix<T>::ILU0Preconditioner;
+        const ILU0& M = m.template getPreconditioner<SMM::SolverPreconditioner::ILU0>();
+        SMM::Vector<T> x(m.getDenseRowCount(), 0);
+        REQUIRE_EQ((SMM::BiCGStab<ILU0, T>(m, rhs, x, -1, kL2Eps, M)), SMM::SolverStatus::SUCCESS);
+        for (const T ri : x) CHECK_APPROX(T(1), ri, kInfEps);
+    }
+    {
+        SMM::Vector<T> x(m.getDenseRowCount(), 0);
+        REQUIRE_EQ(SMM::ConjugateGradientSquared<T>(m, rhs, x, -1, kL2Eps), SMM::SolverStatus::SUCCESS);
+        for (const T ri : x) CHECK_APPROX(T(1), ri, kInfEps);
+    }
+    std::remove(path);
+}
+
 // ---- iteration counts of the reference on its own assets, in the reference's summation order --
 TEST_CASE("Iteration counts equal the reference's (reference-order reductions)") {
     SMM::b200::options().reduction_mode = SMM_REDUCE_REFERENCE_TREE;
