@@ -15,9 +15,9 @@
 //     Intermediate vectors are stored by position (as in sgs.cu), entries as [tile][operand slot][64].
 //   * Kernel: one warp per tile, lane l holds rows l and l + 32 of the tile in registers (loaded, with the next
 //     tile's, ahead of time).  Step s solves the rows of internal level s: operands inside the tile come from shared
-//     memory, operands from other tiles are polled by position -- all of the tile's at once, up front, and again
-//     (by every lane, for everything it still misses) whenever a step finds one of its rows waiting.  Neighbouring
-//     tiles run the same steps slightly ahead, so a tile typically waits once, for its first step.
+//     memory (pushed there by their producer), operands from other tiles are polled by position -- all of the tile's
+//     at once, up front, and again (by every lane, for everything it still misses) whenever a step finds one of its
+//     rows waiting.  A tile publishes its 64 results together after its last step, so a successor waits once.
 //     Tiles are handed out in order by an atomic ticket (a block of TILE_WARPS tiles per CTA claim), so every
 //     awaited producer belongs to a tile that a running warp already owns: no deadlock.
 #include <stdio.h>
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
         bool any_pending = __any_sync(0xFFFFFFFFu, pend != 0u);
         float* const out = dst + ((long long)tile * TILE + lane);
         unsigned int polls = 0;
+        float solved[2] = {0.0f, 0.0f};
         for (int s = 0; s < b.nsteps; ++s) {
             const bool a0 = s == b.step[0], a1 = s == b.step[1];
             if (any_pending) {
@@ -165,6 +166,10 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
                 __syncwarp();
             }
             if (A.trace && s == 0 && lane == 0) A.trace[4ll * tile + 1] = tile_clock();
+            // Both rows of the lane go through the arithmetic in EVERY step, without a branch; only the row whose step
+            // this is keeps its result and hands it on (predicated stores).  The two chains are independent, so they
+            // overlap, and the warp never diverges inside the step.  A row that is not due yet works on stale staging
+            // values: its sum is replaced by 1 before the division so that it stays on the division's fast path.
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (k == 0 ? a0 : a1) {
@@ -179,11 +184,19 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
                                                        : __fsub_rn(b.init[k], __fdiv_rn(acc, b.d[k]));   // H:1710
                     const unsigned int pu = b.push[k];                            // hand the result to the rows of this tile that use it
                     mine[pu & 255u] = res; mine[(pu >> 8) & 255u] = res; mine[(pu >> 16) & 255u] = res; mine[pu >> 24] = res;
-                    publish(out + k * 32, res);
-                    if (!FORWARD) x[h.row[k]] = res;
+                    solved[k] = res;
                 }
             }
             __syncwarp();
+        }
+        // the tile's rows are published together, after its last step: the stores stay off the step chain, and a
+        // successor that waits for this tile finds all of it in one poll
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (h.row[k] >= 0) {
+                publish(out + k * 32, solved[k]);
+                if (!FORWARD) x[h.row[k]] = solved[k];
+            }
         }
         if (A.trace && lane == 0) {
             unsigned int sm;
