@@ -7,6 +7,8 @@
 // (deterministic results run to run).
 //
 // `_smm_fma(a,x,b)` of the reference is a*x+b with two roundings (H:27-37): smm_fma2 keeps that rounding.
+#include <stdlib.h>
+
 #include "epilogue.cuh"
 #include "smm_internal.cuh"
 
@@ -197,7 +199,13 @@ int launch(const VecArgs& a, cudaStream_t s) {
     smm_workspace* ws = a.ws;
     long long work = aligned ? ((a.n + 3) >> 2) : a.n;
     long long want = (work + VEC_THREADS - 1) / VEC_THREADS;
-    int grid = (int)(want < 1 ? 1 : (want > (long long)ws->sm_count * VEC_CTAS_PER_SM ? (long long)ws->sm_count * VEC_CTAS_PER_SM : want));
+    static int per_sm_env = -1;                                // tuning knob; the workspace is sized for VEC_CTAS_PER_SM
+    if (per_sm_env < 0) { const char* e = getenv("SMM_B200_VEC_CTAS_PER_SM"); per_sm_env = e ? atoi(e) : 0; if (per_sm_env > VEC_CTAS_PER_SM) per_sm_env = VEC_CTAS_PER_SM; }
+    // vectors of up to two waves (L2-resident sizes) are latency-bound: half as many CTAs doing two rounds each leave
+    // the last CTA half as many partial sums to fold (2 M rows: 12.3 -> 10.3 us); long vectors want every slot filled
+    const int per_sm = per_sm_env > 0 ? per_sm_env : (want <= 2ll * ws->sm_count * VEC_CTAS_PER_SM ? VEC_CTAS_PER_SM / 2 : VEC_CTAS_PER_SM);
+    const long long cap = (long long)ws->sm_count * per_sm;
+    int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     if (F::NRED > 0) {
         if (ws->partials_cap < (size_t)grid) { smm_set_error("vecops: reduction workspace too small"); return SMM_E_STATE; }
         P.partials = ws->partials + (size_t)a.slot * 2 * ws->partials_cap;
