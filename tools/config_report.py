@@ -90,7 +90,17 @@ def run(name, fn, A, pre, rhs_kind, eps, modes, bytes_per_it, ref_iters=None, ma
     return out
 
 
+def reference_iterations():
+    """Iteration counts of the reference's multithreaded build at full size (recorded by tests/golden/make_fullsize_golden.py)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "tests", "golden", "fullsize_reference.json")))
+        return {k: v["iterations"] for k, v in d.items()}
+    except Exception:
+        return {}
+
+
 def main():
+    REF = reference_iterations()
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,2,3,4,5")
     ap.add_argument("--modes", default="fast,tree")
@@ -102,15 +112,15 @@ def main():
     if 1 in todo:
         A = smm.CSRMatrix.generate(B.GEN_POISSON2D, 1024, 1024)
         report["configs"].append(run("1: CG, 2D 5-point Poisson 1024^2, eps 1e-6, b=A*1", "cg", A, None, "ones", 1e-6, modes,
-                                     8 * A.nnz + 48 * A.rows, ref_iters=2265))
+                                     8 * A.nnz + 48 * A.rows, ref_iters=REF.get("1")))
         del A
     if 2 in todo:
         A = smm.CSRMatrix.generate(B.GEN_CONVDIFF3D, 128, 128, 128, 0.5)
         report["configs"].append(run("2: BiCGStab, 3D convection-diffusion 128^3, eps 1e-6, b=A*x*", "bicgstab", A, None, "xstar", 1e-6, modes,
-                                     16 * A.nnz + 84 * A.rows, ref_iters=365))
+                                     16 * A.nnz + 84 * A.rows, ref_iters=REF.get("2")))
         M = A.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
         report["configs"].append(run("2': BiCGStab+SGS, 128^3, eps 1e-6", "bicgstab", A, M, "xstar", 1e-6, modes,
-                                     2 * (16 * A.nnz + 64 * A.rows) + 16 * A.nnz + 84 * A.rows, ref_iters=64))
+                                     2 * (16 * A.nnz + 64 * A.rows) + 16 * A.nnz + 84 * A.rows, ref_iters=REF.get("2s")))
         del M, A
     if 3 in todo:
         A = smm.CSRMatrix.generate(B.GEN_CONVDIFF3D, 256, 256, 256, 0.5)
@@ -118,7 +128,7 @@ def main():
         M = A.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
         print(json.dumps({"sgs_analysis_s": time.perf_counter() - t, "levels": M.levels()}), flush=True)
         report["configs"].append(run("3: BiCGStab+SGS, 3D convection-diffusion 256^3, eps 1e-6, b=A*x*", "bicgstab", A, M, "xstar", 1e-6, modes,
-                                     2 * (16 * A.nnz + 64 * A.rows) + 16 * A.nnz + 84 * A.rows, ref_iters=122))
+                                     2 * (16 * A.nnz + 64 * A.rows) + 16 * A.nnz + 84 * A.rows, ref_iters=REF.get("3")))
         del M, A
     if 4 in todo:
         A = smm.CSRMatrix.generate(B.GEN_POWERLAW, 8388608)
@@ -128,7 +138,7 @@ def main():
     if 5 in todo:
         A = smm.CSRMatrix.generate(B.GEN_CONVDIFF3D, 512, 512, 512, 0.0)
         report["configs"].append(run("5: CG, 3D 7-point Poisson 512^3, eps 1e-6, b=A*1", "cg", A, None, "ones", 1e-6, modes,
-                                     8 * A.nnz + 48 * A.rows, ref_iters=1570))
+                                     8 * A.nnz + 48 * A.rows, ref_iters=REF.get("5")))
         del A
     json.dump(report, open(args.out, "w"), indent=1)
     print("wrote", args.out)
