@@ -457,6 +457,14 @@ template <int TILE_WARPS>
 void launch_tiles(const smm_precond* p, const TileArgs& F, const TileArgs& B, const float* rhs_dev, float* x_dev, SolveState* state, long long cap,
                   cudaStream_t s) {
     const long long nblocks = (F.ntiles + TILE_WARPS - 1) / TILE_WARPS;
+    // persistent grid: no more CTAs than can be resident (the rest would only find the tickets used up)
+    static int resident = 0;
+    if (!resident) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgs_tile_kernel<false, false, TILE_WARPS>, TILE_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        resident = per_sm * p->m->sm_count;
+    }
+    if (cap > resident) cap = resident;
     const unsigned grid = (unsigned)(nblocks < cap ? nblocks : cap);
     if (p->kind != 0) {
         sgs_tile_kernel<true, true, TILE_WARPS><<<grid, TILE_WARPS * 32, 0, s>>>(F, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
