@@ -144,7 +144,11 @@ int smm_precond_ic0_factor(const smm_precond_t* p, float* factor_host);
  * sweeps.  *rc: 0 ok, 1 structurally unusable, 2 pivot not > 1e-6 in magnitude.  smm_precond_ic0_factor returns the
  * factor of either kind (strict L and U in A's pattern).  smm_solve_bicgstab accepts it as `precond`. */
 int smm_precond_ilu0_create(const smm_csr_t* m, int* rc, smm_precond_t** out);
-/* 0 Symmetric Gauss-Seidel, 1 IC(0), 2 ILU(0) */
+/* EXTENSION -- diagonal (Jacobi) preconditioner, not in the reference: apply is the element-wise x_i = rhs_i / a_ii on the
+ * matrix's current values (*rc = 1 when |a_ii| < 1e-5 for some row, the guard of the SGS sweeps).  smm_solve_bicgstab
+ * accepts it as `precond`. */
+int smm_precond_jacobi_create(const smm_csr_t* m, smm_precond_t** out);
+/* 0 Symmetric Gauss-Seidel, 1 IC(0), 2 ILU(0), 3 Jacobi */
 int smm_precond_kind(const smm_precond_t* p);
 int smm_precond_destroy(smm_precond_t* p);
 

@@ -386,6 +386,7 @@ enum class SolverPreconditioner {
     NONE,
     SYMMETRIC_GAUS_SEIDEL,
     ILU0,
+    JACOBI,                                          // extension (not in the reference): diagonal preconditioner
     SYMMETRIC_GAUSS_SEIDEL = SYMMETRIC_GAUS_SEIDEL   // README spelling
 };
 
@@ -563,6 +564,39 @@ public:
         mutable unsigned long long stamp = 0;
     };
 
+    // EXTENSION (not in the reference): diagonal preconditioner, apply(rhs, x) is x_i = rhs_i / a_ii on the GPU, on the
+    // matrix's current values.  getPreconditioner<SolverPreconditioner::JACOBI>() hands it out; BiCGStab accepts it.
+    class JacobiPreconditioner {
+    public:
+        JacobiPreconditioner(const CSRMatrix& matrix) noexcept : m(matrix) {}
+        JacobiPreconditioner(const JacobiPreconditioner&) = delete;
+        JacobiPreconditioner& operator=(const JacobiPreconditioner&) = delete;
+        JacobiPreconditioner(JacobiPreconditioner&& o) noexcept : m(o.m), handle(o.handle), stamp(o.stamp) { o.handle = nullptr; }
+        ~JacobiPreconditioner() { if (handle) smm_precond_destroy(handle); }
+        int apply(const T* rhs, T* x) const noexcept {
+            b200::requireFloat<T>();
+            assert(rhs != x);
+            int rc = 0;
+            b200::check(smm_precond_apply(device(), rhs, x, &rc), "smm_precond_apply");
+            return rc;
+        }
+        smm_precond_t* device() const {
+            const smm_csr_t* a = m.device();
+            if (!handle || stamp != m.structureStamp) {
+                if (handle) smm_precond_destroy(handle);
+                handle = nullptr;
+                b200::check(smm_precond_jacobi_create(a, &handle), "smm_precond_jacobi_create");
+                stamp = m.structureStamp;
+            }
+            return handle;
+        }
+        const CSRMatrix& matrix() const { return m; }
+    private:
+        const CSRMatrix& m;
+        mutable smm_precond_t* handle = nullptr;
+        mutable unsigned long long stamp = 0;
+    };
+
     // EXTENSION.  ILU(0) is dead code in the reference (factorize() can only fail, apply() is never defined, the
     // factory returns void for it; ref H:1188-1212, 1715-1790).  Here the type works: validate() performs the
     // zero-fill LU those lines describe on the host (0 ok, 1 unusable structure, 2 pivot not > 1e-6), apply() runs
@@ -628,6 +662,7 @@ public:
     decltype(auto) getPreconditioner() const noexcept {
         if constexpr (precond == SolverPreconditioner::NONE) return IDPreconditioner();
         else if constexpr (precond == SolverPreconditioner::SYMMETRIC_GAUS_SEIDEL) return SGSPreconditioner(*this);
+        else if constexpr (precond == SolverPreconditioner::JACOBI) return JacobiPreconditioner(*this);
         else {                                          // extension: the reference's factory has no ILU0 branch (returns void)
             ILU0Preconditioner M(*this);
             M.validate();
@@ -748,11 +783,12 @@ inline SolverStatus BiCGStab(const CSRMatrix<T>& a, T* b, T* x, int maxIteration
     using Sgs = typename CSRMatrix<T>::SGSPreconditioner;
     using Ic0 = typename CSRMatrix<T>::IC0Preconditioner;
     using Ilu0 = typename CSRMatrix<T>::ILU0Preconditioner;
+    using Jac = typename CSRMatrix<T>::JacobiPreconditioner;
     // the reference's template takes any object with apply(rhs, x) (H:2191-2199); on this path the object must be one
     // whose apply lives on the GPU
     static_assert(std::is_same_v<Preconditioner, Id> || std::is_same_v<Preconditioner, Sgs> || std::is_same_v<Preconditioner, Ic0> ||
-                      std::is_same_v<Preconditioner, Ilu0>,
-                  "BiCGStab on the B200 path takes the preconditioner classes of CSRMatrix (ID, SGS, IC0, ILU0)");
+                      std::is_same_v<Preconditioner, Ilu0> || std::is_same_v<Preconditioner, Jac>,
+                  "BiCGStab on the B200 path takes the preconditioner classes of CSRMatrix (ID, SGS, IC0, ILU0, Jacobi)");
     const smm_precond_t* p = nullptr;
     if constexpr (!std::is_same_v<Preconditioner, Id>) {
         assert(&preconditioner.matrix() == &a);

@@ -496,10 +496,23 @@ void smm_oracle_cgs(int rows, const int *start, const int *positions, const floa
 }
 
 /* BiCGStab, H:2191-2283 (+ wrapper H:2294-2303) */
+/* EXTENSION (not in the reference): diagonal preconditioner, x_i = rhs_i / a_ii; 1 when a row has no diagonal entry */
+int smm_oracle_jacobi_apply(int rows, const int *start, const int *positions, const float *values,
+                            const float *rhs, float *x) {
+    for (int row = 0; row < rows; ++row) {
+        int j = start[row];
+        while (j < start[row + 1] && positions[j] < row) ++j;
+        if (j >= start[row + 1] || positions[j] != row) return 1;
+        x[row] = rhs[row] / values[j];
+    }
+    return 0;
+}
+
 static int apply_precond(int kind, const float *factor, int rows, const int *start, const int *positions, const float *values,
                          int first_active_start, const float *rhs, float *x) {
     if (kind == 1) return smm_oracle_sgs_apply(rows, start, positions, values, first_active_start, rhs, x);
     if (kind == 2) return smm_oracle_ilu0_apply(rows, start, positions, factor, rhs, x);
+    if (kind == 4) return smm_oracle_jacobi_apply(rows, start, positions, values, rhs, x);
     return smm_oracle_ic0_apply(rows, start, positions, factor, rhs, x);
 }
 

@@ -86,7 +86,7 @@ void smm_oracle_bicgstab(int rows, const int *start, const int *positions, const
                          int first_active_start, int precond,
                          const float *b, float *x, int max_iterations, float eps, int mt,
                          smm_oracle_info *info, float *history, int history_cap);    /* H:2191-2283 */
-/* precond: 0 / 1 as above, 2 = ILU(0) (extension), 3 = IC(0); factor = that preconditioner's values (NULL for 0 / 1) */
+/* precond: 0 / 1 as above, 2 = ILU(0) (extension), 3 = IC(0), 4 = Jacobi (extension); factor = the values of 2 / 3 (else NULL) */
 void smm_oracle_bicgstab_pc(int rows, const int *start, const int *positions, const float *values,
                             int first_active_start, int precond, const float *factor,
                             const float *b, float *x, int max_iterations, float eps, int mt,
@@ -97,6 +97,8 @@ int smm_oracle_ilu0_factorize(int rows, const int *start, const int *positions, 
                               int first_active_start, float *ilu0);
 int smm_oracle_ilu0_apply(int rows, const int *start, const int *positions, const float *ilu0,
                           const float *rhs, float *x);
+int smm_oracle_jacobi_apply(int rows, const int *start, const int *positions, const float *values,
+                            const float *rhs, float *x);
 /* PCG with IC0 (H:2414-2505). */
 void smm_oracle_cg_ic0(int rows, const int *start, const int *positions, const float *values,
                        const float *ic0, const float *b, const float *x0, float *x,

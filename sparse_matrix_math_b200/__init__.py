@@ -18,6 +18,7 @@ from .binding import (  # noqa: F401
     DeviceVector,
     IC0Preconditioner,
     ILU0Preconditioner,
+    JacobiPreconditioner,
     MatrixLoadStatus,
     SGSPreconditioner,
     SmmError,

@@ -30,6 +30,7 @@ class SolverPreconditioner(enum.IntEnum):  # H:1002-1006 (+ README spelling)
     SYMMETRIC_GAUS_SEIDEL = 1
     SYMMETRIC_GAUSS_SEIDEL = 1
     ILU0 = 2
+    JACOBI = 3                      # extension, not in the reference
 
 
 class MatrixLoadStatus(enum.IntEnum):      # H:2507-2522
@@ -121,6 +122,7 @@ def lib():
         L.smm_precond_ic0_create.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_vp)]
         L.smm_precond_ic0_factor.argtypes = [_vp, _vp]
         L.smm_precond_ilu0_create.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_vp)]
+        L.smm_precond_jacobi_create.argtypes = [_vp, C.POINTER(_vp)]
         L.smm_precond_kind.argtypes = [_vp]
         op, ip = C.POINTER(_Options), C.POINTER(_Info)
         L.smm_solve_cg.argtypes = [_vp, _vp, _vp, _vp, _i32, _f32, op, ip]
@@ -337,6 +339,16 @@ class IC0Preconditioner(SGSPreconditioner):
         return out[: self.matrix.nnz]
 
 
+class JacobiPreconditioner(SGSPreconditioner):
+    """EXTENSION (not in the reference): diagonal preconditioner, apply is x = rhs / diag(A) element-wise."""
+
+    def __init__(self, matrix):
+        self.matrix = matrix
+        h = _vp()
+        _check(lib().smm_precond_jacobi_create(matrix.handle, C.byref(h)), "smm_precond_jacobi_create")
+        self.handle = h.value
+
+
 class ILU0Preconditioner(IC0Preconditioner):
     """EXTENSION: CSRMatrix<float>::ILU0Preconditioner (dead code in the reference, H:1188-1212, 1715-1790) made to
     work: ILU0Preconditioner(m); validate() factorises (0 ok, 1 structure, 2 pivot); apply(rhs, x); BiCGStab takes it."""
@@ -460,6 +472,8 @@ class CSRMatrix:
             return None                         # IDPreconditioner
         if kind == SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL:
             return SGSPreconditioner(self)
+        if kind == SolverPreconditioner.JACOBI:
+            return JacobiPreconditioner(self)
         # the reference's factory returns void for ILU0 (H:1645-1651); here it hands out the working extension
         M = ILU0Preconditioner(self)
         M.validate()

@@ -178,6 +178,17 @@ __global__ void __launch_bounds__(SGS_THREADS) sgs_sweep_kernel(const SweepArgs 
     }
 }
 
+// EXTENSION: diagonal (Jacobi) preconditioner, x_i = rhs_i / a_ii on A's current values -- the "elementwise" kind of apply
+__global__ void jacobi_apply_kernel(const float* __restrict__ values, const int32_t* __restrict__ diag_pos, const float* __restrict__ rhs,
+                                    float* __restrict__ x, int n, unsigned int* tickets, const SolveState* st) {
+    if (st != nullptr && st->done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float d = values[diag_pos[i]];
+    if (fabsf(d) < 1e-5) atomicOr(tickets + 3, 1u);          // the same guard as the SGS sweeps (H:1691-1693)
+    x[i] = __fdiv_rn(rhs[i], d);
+}
+
 __global__ void sgs_status_kernel(const unsigned int* tickets, SolveState* st, int* rc_out) {
     // fold the apply's status into the solve (the reference only asserts on it, H:2235-2238) / report it to the caller
     const unsigned int aborted = tickets[2], bad_diag = tickets[3];
@@ -344,7 +355,7 @@ int ilu0_factorize_host(int rows, const std::vector<int32_t>& start, const std::
 
 }  // namespace
 
-int smm_sgs_kernels_per_apply(const smm_precond* p) { return p && p->valid ? 4 : 1; }
+int smm_sgs_kernels_per_apply(const smm_precond* p) { return p && p->valid ? (p->kind == 3 ? 3 : 4) : 1; }
 
 
 // rhs_dev -> x_dev on stream s.  With `state` (inside a solve) the kernels no-op once state->done is set.
@@ -362,6 +373,14 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
         // continuing on an unspecified vector; this build refuses instead of iterating on garbage
         smm_set_error("SGS preconditioner unusable for this matrix (leading empty rows, an empty row or a missing diagonal): apply() returns 1");
         return SMM_E_STATE;
+    }
+    if (p->kind == 3) {                                        // diagonal: one element-wise pass
+        sgs_fill_kernel<<<1, 32, 0, s>>>(nullptr, 0, nullptr, 0, p->tickets, state);          // resets the status words
+        jacobi_apply_kernel<<<(unsigned)((p->rows + 255) / 256), 256, 0, s>>>(m->values, p->diag_pos, rhs_dev, x_dev, p->rows, p->tickets, state);
+        sgs_status_kernel<<<1, 1, 0, s>>>(p->tickets, state, rc_dev);
+        SMM_COUNT_LAUNCH(3);
+        SMM_CUDA(cudaGetLastError());
+        return SMM_OK;
     }
     const long long nfill = std::max(p->threads_fwd, p->threads_bwd);
     sgs_fill_kernel<<<(unsigned)((nfill + 255) / 256), 256, 0, s>>>(p->yperm, p->threads_fwd, p->xperm, p->threads_bwd, p->tickets, state);
@@ -432,7 +451,7 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
     std::vector<int32_t> diag, of, ob;
     analyse(m->rows, start, pos, m->first_active_start, &p->valid, &diag, &of, &ob, &p->levels_fwd, &p->levels_bwd);
     if (rc_out) *rc_out = p->valid ? 0 : 1;
-    if (kind != 0 && p->valid && m->nnz > 0) {
+    if (kind != 0 && kind != 3 && p->valid && m->nnz > 0) {
         std::vector<float> a((size_t)m->nnz), l;
         SMM_CUDA(cudaMemcpy(a.data(), m->values, sizeof(float) * a.size(), cudaMemcpyDeviceToHost));
         if (kind == 1) {
@@ -451,7 +470,7 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
         SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
     }
     // tile-level schedule when the matrix admits one (sgs_tiles.cu), else the row-level schedule below
-    if (p->valid && m->rows > 0 && !smm_sgs_tiles_build(p, m->rows, start, pos, diag)) {
+    if (kind != 3 && p->valid && m->rows > 0 && !smm_sgs_tiles_build(p, m->rows, start, pos, diag)) {
         p->threads_fwd = (long long)of.size();
         p->threads_bwd = (long long)ob.size();
         SMM_CUDA(cudaMalloc(&p->order_fwd, sizeof(int32_t) * of.size()));
@@ -503,8 +522,11 @@ int smm_precond_ic0_create(const smm_csr_t* m, int* rc, smm_precond_t** out) { r
 // an empty row / a missing diagonal) or 2 (pivot not > 1e-6 in magnitude).
 int smm_precond_ilu0_create(const smm_csr_t* m, int* rc, smm_precond_t** out) { return precond_create(m, 2, rc, out); }
 
+// EXTENSION: the diagonal (Jacobi) preconditioner, x = D^-1 rhs on A's current values
+int smm_precond_jacobi_create(const smm_csr_t* m, smm_precond_t** out) { return precond_create(m, 3, nullptr, out); }
+
 int smm_precond_ic0_factor(const smm_precond_t* p, float* factor_host) {
-    if (!p || p->kind == 0 || !factor_host) return SMM_E_INVALID;
+    if (!p || p->kind == 0 || p->kind == 3 || !factor_host) return SMM_E_INVALID;
     if (!p->factor) return SMM_E_STATE;
     SMM_CUDA(cudaMemcpy(factor_host, p->factor, sizeof(float) * (size_t)p->m->nnz, cudaMemcpyDeviceToHost));
     return SMM_OK;

@@ -7,7 +7,7 @@
 #include "smm_internal.cuh"
 
 struct smm_precond {
-    int kind = 0;                    // 0: Symmetric Gauss-Seidel on A's values; 1: IC(0), 2: ILU(0) on their own factor values
+    int kind = 0;                    // 0: Symmetric Gauss-Seidel on A's values; 1: IC(0), 2: ILU(0) on their own factor values; 3: Jacobi (diagonal of A)
     float* factor = nullptr;         // IC(0): [nnz] factor in A's pattern (L below and on the diagonal, L^T above), ref H:1233-1234
                                      // ILU(0): strict L (unit diagonal implied) below, U on and above the diagonal, ref H:1203-1211
     const smm_csr* m = nullptr;

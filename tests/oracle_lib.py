@@ -64,6 +64,8 @@ def oracle():
         lib.smm_oracle_ilu0_factorize.argtypes = [C.c_int, _i32p, _i32p, _f32p, C.c_int, _f32p]
         lib.smm_oracle_ilu0_apply.restype = C.c_int
         lib.smm_oracle_ilu0_apply.argtypes = [C.c_int, _i32p, _i32p, _f32p, _f32p, _f32p]
+        lib.smm_oracle_jacobi_apply.restype = C.c_int
+        lib.smm_oracle_jacobi_apply.argtypes = [C.c_int, _i32p, _i32p, _f32p, _f32p, _f32p]
         lib.smm_oracle_cg_ic0.restype = None
         lib.smm_oracle_cg_ic0.argtypes = common + [_f32p, _f32p, _f32p, _f32p] + tail
         lib.smm_oracle_load_mtx.restype = C.c_int
@@ -165,6 +167,14 @@ def ilu0_apply(m, lu, rhs):
     return x
 
 
+def jacobi_apply(m, rhs):
+    """EXTENSION: x = D^-1 rhs.  Returns (rc, x)."""
+    x = np.zeros(m.rows, np.float32)
+    pos, val = m._pad()
+    rc = oracle().smm_oracle_jacobi_apply(m.rows, m.start, pos, val, np.ascontiguousarray(rhs, np.float32), x)
+    return rc, x
+
+
 def _hist(cap):
     if not cap:
         return None, None
@@ -174,7 +184,7 @@ def _hist(cap):
 
 def solve(solver, m, b, x0, max_iterations, eps, mt, precond=0, ic0=None, history_cap=0, factor=None):
     """Run an oracle solver.  Returns dict(status, iterations, residual, precond_error, x, history).
-    bicgstab: precond 0 none, 1 SGS, 2 ILU(0) (factor = ilu0_factorize), 3 IC(0) (factor = ic0_factorize)."""
+    bicgstab: precond 0 none, 1 SGS, 2 ILU(0) (factor = ilu0_factorize), 3 IC(0) (factor = ic0_factorize), 4 Jacobi."""
     lib = oracle()
     info = Info()
     b = np.ascontiguousarray(b, np.float32).copy()

@@ -550,9 +550,11 @@ def test_ilu0_error_codes(smm):
     assert M.apply(np.ones(2, np.float32))[0] == 1          # unusable: apply reports an error, x is not produced
 
 
-@pytest.mark.parametrize("precond", ["ilu0", "ic0"])
+@pytest.mark.parametrize("precond", ["ilu0", "ic0", "jacobi"])
 def test_bicgstab_factor_preconditioners_parity(smm, precond):
-    g = matgen.convdiff3d(18, 0.5) if precond == "ilu0" else matgen.poisson2d(50, 45)
+    g = matgen.poisson2d(50, 45) if precond == "ic0" else matgen.convdiff3d(18, 0.5)
+    if precond == "jacobi":                                  # make the diagonal matter
+        g.values[g.positions == np.repeat(np.arange(g.rows), np.diff(g.start))] *= (1.0 + (np.arange(g.rows) % 7)).astype(np.float32)
     m = upload(smm, g)
     xs = matgen.xstar(g.rows)
     b = ol.spmv(g, 0, None, xs)
@@ -560,6 +562,11 @@ def test_bicgstab_factor_preconditioners_parity(smm, precond):
         M = m.getPreconditioner(smm.SolverPreconditioner.ILU0)      # extension: the reference's factory returns void here
         assert M.init_code == 0
         kind, f = 2, ol.ilu0_factorize(g)[1]
+    elif precond == "jacobi":
+        M = m.getPreconditioner(smm.SolverPreconditioner.JACOBI)    # extension: element-wise x = rhs / diag(A)
+        rc, y = M.apply(b)
+        assert rc == 0 and y.tobytes() == ol.jacobi_apply(g, b)[1].tobytes()
+        kind, f = 4, None
     else:
         M = smm.IC0Preconditioner(m)
         assert M.init() == 0
