@@ -43,8 +43,10 @@ def measured_peak_gbs():
 
 def ncu_traffic_bytes(kernel_prefix, grid):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
-    same command (profiles/r01d_spmv_rows_kernel_full.txt, 512^3); None for any other problem size."""
-    p = os.path.join(ROOT, "profiles", "r01d_spmv_rows_kernel_full.txt")
+    same command (profiles/r01h_spmv_rows_kernel_full.txt, 512^3); None for any other problem size."""
+    p = os.path.join(ROOT, "profiles", "r01h_spmv_rows_kernel_full.txt")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01d_spmv_rows_kernel_full.txt")
     if grid != 512 or not os.path.exists(p):
         return None
     rd = wr = None
