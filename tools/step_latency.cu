@@ -5,7 +5,7 @@
 constexpr int N = 20000;
 template <int MODE>
 __global__ void steps(float* out, long long* cycles, float d, int clones) {
-    __shared__ __align__(16) float stage[8][256];
+    __shared__ __align__(16) float stage[32][256];
     float* mine = stage[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     for (int i = lane; i < 256; i += 32) mine[i] = 1.0f + i * 1e-3f;
@@ -33,7 +33,7 @@ int main() {
     float* out; long long* cyc;
     cudaMalloc(&out, 1 << 20); cudaMallocManaged(&cyc, 8);
     const char* names[5] = {"full step", "multiply instead of divide", "no __syncwarp", "no pushes", "all lanes store"};
-    for (int warps : {1, 4}) for (int m = 0; m < 5; ++m) {
+    for (int warps : {1, 4, 8, 16, 32}) for (int m = 0; m < 5; ++m) {
         *cyc = 0;
         if (m == 0) steps<0><<<1, 32 * warps>>>(out, cyc, 6.0f, 0);
         if (m == 1) steps<1><<<1, 32 * warps>>>(out, cyc, 6.0f, 0);
