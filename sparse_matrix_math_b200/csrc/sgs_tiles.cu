@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
         float* const out = dst + ((long long)tile * TILE + lane);
         unsigned int polls = 0;
         float solved[2] = {0.0f, 0.0f};
+        if (A.trace && !any_pending && lane == 0) A.trace[4ll * tile + 1] = tile_clock();   // nothing to wait for
         for (int s = 0; s < b.nsteps; ++s) {
             const bool a0 = s == b.step[0], a1 = s == b.step[1];
             if (any_pending) {
@@ -164,8 +165,8 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
                 }
                 any_pending = __any_sync(0xFFFFFFFFu, pend != 0u);
                 __syncwarp();
+                if (A.trace && s == 0 && lane == 0) A.trace[4ll * tile + 1] = tile_clock();   // first step released
             }
-            if (A.trace && s == 0 && lane == 0) A.trace[4ll * tile + 1] = tile_clock();
             // Both rows of the lane go through the arithmetic in EVERY step, without a branch; only the row whose step
             // this is keeps its result and hands it on (predicated stores).  The two chains are independent, so they
             // overlap, and the warp never diverges inside the step.  A row that is not due yet works on stale staging
