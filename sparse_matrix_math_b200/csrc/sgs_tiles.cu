@@ -14,10 +14,11 @@
 //   * Layout: tiles sorted by tile level; position = 64 * tile + index, rows inside a tile sorted by internal level.
 //     Intermediate vectors are stored by position (as in sgs.cu), entries as [tile][operand slot][64].
 //   * Kernel: one warp per tile, lane l holds rows l and l + 32 of the tile in registers (loaded, with the next
-//     tile's, ahead of time).  Step s solves the rows of internal level s: operands inside the tile come from shared
-//     memory (pushed there by their producer), operands from other tiles are polled by position -- all of the tile's
-//     at once, up front, and again (by every lane, for everything it still misses) whenever a step finds one of its
-//     rows waiting.  A tile publishes its 64 results together after its last step, so a successor waits once.
+//     tile's, ahead of time).  Operands from other tiles are polled by position -- all of the tile's at once, and again
+//     (every lane, everything it still misses) until all have been published; then step s solves the rows of internal
+//     level s, operands inside the tile coming from shared memory (pushed there by their producer).  A tile publishes
+//     its 64 results together after its last step.  The step loop is kept to about 30 instructions: the warps of an SM
+//     solve at the same time and share its issue slots.
 //     Tiles are handed out in order by an atomic ticket (a block of TILE_WARPS tiles per CTA claim), so every
 //     awaited producer belongs to a tile that a running warp already owns: no deadlock.
 #include <stdio.h>
@@ -41,7 +42,7 @@ constexpr int MAX_PREDS = 8;
 struct TileArgs {
     const uint8_t* nsteps;      // [tiles]
     const uint8_t* row_step;    // [tiles * 64] the step in which the row is solved (255: padding)
-    const uint32_t* push;       // [tiles * 64] four operand slots (64-row tile x 4) of rows of the SAME tile that consume this row
+    const uint32_t* push;       // [tiles * 64] up to three operand slots (row x 4 + operand) of rows of the SAME tile that consume this row
     const int32_t* order;       // [tiles * 64] row or -1
     const int32_t* ypos;        // backward: position of the row in yperm
     const int32_t* ecol;        // [tiles][width][64] operand position or -1
@@ -124,9 +125,10 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
     auto solve_tile = [&](long long bid, const TileHead& h, const TileBody& b) {
         const int tile = (int)(bid * TILE_WARPS + warp);
         if (A.trace && lane == 0) A.trace[4ll * tile] = tile_clock();
-        // Operands from other tiles (both rows of this lane) are requested up front; whatever has not been published
-        // yet is requested again -- by every lane, for everything it still misses -- each time a step finds one of
-        // ITS rows waiting.  Neighbouring tiles run the same steps slightly ahead, so a tile typically waits once.
+        // Operands from other tiles (both rows of this lane) are requested up front, all at once, and whatever has not
+        // been published yet is requested again until everything is there: predecessors publish their rows together
+        // after their last step, so there is nothing to gain from starting early, and the step loop below stays free of
+        // any waiting logic (every instruction in it is paid ten times per tile by warps that share an SM's issue slots)
         unsigned int pend = 0u;                                // bit 4 k + e: operand e of row k is still awaited
         unsigned int first[2 * TILE_MAX_W];
 #pragma unroll
@@ -143,51 +145,54 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
                                                                                    __uint_as_float(first[4 * k + 2]), __uint_as_float(first[4 * k + 3]));
             if (FORWARD && !IC0 && h.row[k] >= 0 && fabsf(b.d[k]) < 1e-5) atomicOr(tickets + 3, 1u);   // H:1691-1693 (reported, not fatal here)
         }
-        __syncwarp();
-        bool any_pending = __any_sync(0xFFFFFFFFu, pend != 0u);
-        float* const out = dst + ((long long)tile * TILE + lane);
         unsigned int polls = 0;
+        while (__any_sync(0xFFFFFFFFu, pend != 0u)) {
+            if (!poll_pause(&polls, abort_flag, A.sleep_first, A.sleep_later)) pend = 0u;
+            unsigned int bits[2 * TILE_MAX_W];
+#pragma unroll
+            for (int q = 0; q < 2 * TILE_MAX_W; ++q)                              // all requests first: one L2 round trip per round
+                bits[q] = (pend >> q) & 1u ? peek(src + b.c[q / TILE_MAX_W][q % TILE_MAX_W]) : SENTINEL;
+#pragma unroll
+            for (int q = 0; q < 2 * TILE_MAX_W; ++q) {
+                if (bits[q] != SENTINEL) { pend &= ~(1u << q); mine[4 * ((q / TILE_MAX_W) * 32 + lane) + (q % TILE_MAX_W)] = __uint_as_float(bits[q]); }
+            }
+        }
+        __syncwarp();
+        if (A.trace && lane == 0) A.trace[4ll * tile + 1] = tile_clock();         // operands complete
+        float* const out = dst + ((long long)tile * TILE + lane);
         float solved[2] = {0.0f, 0.0f};
-        if (A.trace && !any_pending && lane == 0) A.trace[4ll * tile + 1] = tile_clock();   // nothing to wait for
-        for (int s = 0; s < b.nsteps; ++s) {
-            const bool a0 = s == b.step[0], a1 = s == b.step[1];
-            if (any_pending) {
-                while (__any_sync(0xFFFFFFFFu, (a0 && (pend & 0xFu)) || (a1 && (pend & 0xF0u)))) {
-                    if (!poll_pause(&polls, abort_flag, A.sleep_first, A.sleep_later)) pend = 0u;
-                    unsigned int bits[2 * TILE_MAX_W];
-#pragma unroll
-                    for (int q = 0; q < 2 * TILE_MAX_W; ++q)                      // all requests first: one L2 round trip per round
-                        bits[q] = (pend >> q) & 1u ? peek(src + b.c[q / TILE_MAX_W][q % TILE_MAX_W]) : SENTINEL;
-#pragma unroll
-                    for (int q = 0; q < 2 * TILE_MAX_W; ++q) {
-                        if (bits[q] != SENTINEL) { pend &= ~(1u << q); mine[4 * ((q / TILE_MAX_W) * 32 + lane) + (q % TILE_MAX_W)] = __uint_as_float(bits[q]); }
-                    }
-                }
-                any_pending = __any_sync(0xFFFFFFFFu, pend != 0u);
-                __syncwarp();
-                if (A.trace && s == 0 && lane == 0) A.trace[4ll * tile + 1] = tile_clock();   // first step released
-            }
-            // Both rows of the lane go through the arithmetic in EVERY step, without a branch; only the row whose step
-            // this is keeps its result and hands it on (predicated stores).  The two chains are independent, so they
-            // overlap, and the warp never diverges inside the step.  A row that is not due yet works on stale staging
-            // values: its sum is replaced by 1 before the division so that it stays on the division's fast path.
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (k == 0 ? a0 : a1) {
-                    const float4 xo = *reinterpret_cast<const float4*>(mine + 4 * (k * 32 + lane));
-                    // same operand order and roundings as the row-level kernel (H:1685, H:1704, H:1813, H:1829); only the
-                    // additions and the division are on the step's dependent chain
-                    const float p0 = __fmul_rn(b.v[k][0], xo.x), p1 = __fmul_rn(b.v[k][1], xo.y), p2 = __fmul_rn(b.v[k][2], xo.z), p3 = __fmul_rn(b.v[k][3], xo.w);
-                    float acc = (FORWARD || IC0) ? b.init[k] : 0.0f;              // H:1683 / T sum = x[row], H:1823 / H:1702
-                    if (FORWARD || IC0) { acc = __fsub_rn(acc, p0); acc = __fsub_rn(acc, p1); acc = __fsub_rn(acc, p2); acc = __fsub_rn(acc, p3); }
-                    else { acc = __fadd_rn(p0, acc); acc = __fadd_rn(p1, acc); acc = __fadd_rn(p2, acc); acc = __fadd_rn(p3, acc); }
-                    const float res = (FORWARD || IC0) ? __fdiv_rn(acc, b.d[k])   // H:1694 / H:1818, H:1834
-                                                       : __fsub_rn(b.init[k], __fdiv_rn(acc, b.d[k]));   // H:1710
-                    const unsigned int pu = b.push[k];                            // hand the result to the rows of this tile that use it
-                    mine[pu & 255u] = res; mine[(pu >> 8) & 255u] = res; mine[(pu >> 16) & 255u] = res; mine[pu >> 24] = res;
-                    solved[k] = res;
-                }
-            }
+        // one row of the lane in one step: operands out of the staging slots, the sum in operand order, the division, and
+        // the result handed to the (up to three) rows of this tile that use it
+        auto solve_row = [&](const int k) {
+            const float4 xo = *reinterpret_cast<const float4*>(mine + 4 * (k * 32 + lane));
+            // same operand order and roundings as the row-level kernel (H:1685, H:1704, H:1813, H:1829); only the
+            // additions and the division are on the step's dependent chain
+            const float p0 = __fmul_rn(b.v[k][0], xo.x), p1 = __fmul_rn(b.v[k][1], xo.y), p2 = __fmul_rn(b.v[k][2], xo.z), p3 = __fmul_rn(b.v[k][3], xo.w);
+            float acc = (FORWARD || IC0) ? b.init[k] : 0.0f;                      // H:1683 / T sum = x[row], H:1823 / H:1702
+            if (FORWARD || IC0) { acc = __fsub_rn(acc, p0); acc = __fsub_rn(acc, p1); acc = __fsub_rn(acc, p2); acc = __fsub_rn(acc, p3); }
+            else { acc = __fadd_rn(p0, acc); acc = __fadd_rn(p1, acc); acc = __fadd_rn(p2, acc); acc = __fadd_rn(p3, acc); }
+            const float res = (FORWARD || IC0) ? __fdiv_rn(acc, b.d[k])           // H:1694 / H:1818, H:1834
+                                               : __fsub_rn(b.init[k], __fdiv_rn(acc, b.d[k]));   // H:1710
+            const unsigned int pu = b.push[k];
+            mine[pu & 255u] = res; mine[(pu >> 8) & 255u] = res; mine[(pu >> 16) & 255u] = res;
+            solved[k] = res;
+        };
+        // rows l (k = 0) belong to the early steps and rows l + 32 (k = 1) to the late ones (a tile's rows are sorted by
+        // step): three loops, so that a step only tests the rows that can be due
+        const int first1 = __reduce_min_sync(0xFFFFFFFFu, b.step[1]);              // 255 when the tile has no such row
+        const int last0 = __reduce_max_sync(0xFFFFFFFFu, b.step[0] == 255 ? -1 : b.step[0]);
+        int s = 0;
+        for (; s < b.nsteps && s < first1; ++s) {
+            if (s == b.step[0]) solve_row(0);
+            __syncwarp();
+        }
+        for (; s < b.nsteps && s <= last0; ++s) {
+            if (s == b.step[0]) solve_row(0);
+            if (s == b.step[1]) solve_row(1);
+            __syncwarp();
+        }
+        for (; s < b.nsteps; ++s) {
+            if (s == b.step[1]) solve_row(1);
             __syncwarp();
         }
         // the tile's rows are published together, after its last step: the stores stay off the step chain, and a
@@ -390,7 +395,7 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
             out->ecol[at] = q;
             out->eidx[at] = srci;
             if ((q >> 6) == t) {                               // produced inside the tile: the producer pushes it
-                if (npush[q] == 4) return false;
+                if (npush[q] == 3) return false;                   // a row with more than three consumers inside its tile
                 const int sh = 8 * npush[q]++;
                 out->push[q] = (out->push[q] & ~(0xFFu << sh)) | ((uint32_t)(i * TILE_MAX_W + e) << sh);
             }
