@@ -26,10 +26,13 @@
 // result is bit-identical to SGSPreconditioner::apply for any schedule.
 // Algorithmic bytes per apply: each stored entry once over the two sweeps (8 nnz) + start/diag index/order
 // (about 24 n) + rhs, y, x traffic (about 20 n).
+#include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cmath>
+#include <future>
 #include <vector>
 
 #include "sgs_internal.cuh"
@@ -233,24 +236,32 @@ void build_sell(bool forward, const std::vector<int32_t>& order, const std::vect
     }
 }
 
-void analyse(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int first_active_start, bool* valid,
-             std::vector<int32_t>* diag, std::vector<int32_t>* order_f, std::vector<int32_t>* order_b, int* lf, int* lb) {
-    *valid = first_active_start == 0 || rows == 0;                            // H:1668-1670
+// structure check of SGSPreconditioner::apply (H:1668-1670, 1678-1680, 1691) and the position of every diagonal entry
+bool find_diagonals(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int first_active_start, std::vector<int32_t>* diag) {
     diag->assign((size_t)rows, 0);
-    std::vector<int32_t> lev((size_t)rows, 0);
-    int maxl = -1;
-    for (int r = 0; r < rows && *valid; ++r) {
+    if (!(first_active_start == 0 || rows == 0)) return false;                // H:1668-1670
+    for (int r = 0; r < rows; ++r) {
         int k = start[r];
         const int e = start[r + 1];
-        if (e == k) { *valid = false; break; }                               // H:1678-1680
-        int l = 0;
-        while (k < e && pos[k] < r) { l = std::max(l, lev[pos[k]] + 1); ++k; }
-        if (k >= e || pos[k] != r) { *valid = false; break; }                 // H:1691 (col != row)
+        if (e == k) return false;                                            // H:1678-1680
+        while (k < e && pos[k] < r) ++k;
+        if (k >= e || pos[k] != r) return false;                             // H:1691 (col != row)
         (*diag)[r] = k;
+    }
+    return true;
+}
+
+// dependency levels of the two triangles and the level-ordered row lists of the row-level schedule
+void level_orders(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag,
+                  std::vector<int32_t>* order_f, std::vector<int32_t>* order_b, int* lf, int* lb) {
+    std::vector<int32_t> lev((size_t)rows, 0);
+    int maxl = -1;
+    for (int r = 0; r < rows; ++r) {
+        int l = 0;
+        for (int k = start[r]; k < diag[r]; ++k) l = std::max(l, lev[pos[k]] + 1);
         lev[r] = l;
         maxl = std::max(maxl, l);
     }
-    if (!*valid) { *lf = *lb = 0; order_f->clear(); order_b->clear(); return; }
     auto build_order = [&](const std::vector<int32_t>& level, int nlev, bool descending, std::vector<int32_t>* out) {
         std::vector<long long> count((size_t)nlev + 1, 0);
         for (int r = 0; r < rows; ++r) count[(size_t)level[r] + 1]++;
@@ -266,7 +277,7 @@ void analyse(int rows, const std::vector<int32_t>& start, const std::vector<int3
     maxl = -1;
     for (int r = rows - 1; r >= 0; --r) {
         int l = 0;
-        for (int k = start[r + 1] - 1; k > (*diag)[r]; --k) l = std::max(l, lev[pos[k]] + 1);   // lev[] of rows > r already hold backward levels
+        for (int k = start[r + 1] - 1; k > diag[r]; --k) l = std::max(l, lev[pos[k]] + 1);   // lev[] of rows > r already hold backward levels
         lev[r] = l;
         maxl = std::max(maxl, l);
     }
@@ -449,7 +460,13 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
     SMM_CUDA(cudaMemcpy(start.data(), m->start, sizeof(int32_t) * start.size(), cudaMemcpyDeviceToHost));
     if (m->nnz) SMM_CUDA(cudaMemcpy(pos.data(), m->positions, sizeof(int32_t) * pos.size(), cudaMemcpyDeviceToHost));
     std::vector<int32_t> diag, of, ob;
-    analyse(m->rows, start, pos, m->first_active_start, &p->valid, &diag, &of, &ob, &p->levels_fwd, &p->levels_bwd);
+    p->valid = find_diagonals(m->rows, start, pos, m->first_active_start, &diag);
+    // the level analysis (row-level schedule, and the level counts smm_precond_levels reports) runs beside the factorisation
+    // and the tile layout below: all of it is set-up time
+    std::future<void> levels;
+    if (p->valid && m->rows > 0 && kind != 3)
+        levels = std::async(std::launch::async, [&] { level_orders(m->rows, start, pos, diag, &of, &ob, &p->levels_fwd, &p->levels_bwd); });
+    struct Join { std::future<void>& f; ~Join() { if (f.valid()) f.wait(); } } join{levels};   // never leave with the task running
     if (rc_out) *rc_out = p->valid ? 0 : 1;
     if (kind != 0 && kind != 3 && p->valid && m->nnz > 0) {
         std::vector<float> a((size_t)m->nnz), l;
@@ -470,7 +487,9 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
         SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
     }
     // tile-level schedule when the matrix admits one (sgs_tiles.cu), else the row-level schedule below
-    if (kind != 3 && p->valid && m->rows > 0 && !smm_sgs_tiles_build(p, m->rows, start, pos, diag)) {
+    const bool tiles = kind != 3 && p->valid && m->rows > 0 && smm_sgs_tiles_build(p, m->rows, start, pos, diag);
+    if (levels.valid()) levels.get();
+    if (kind != 3 && p->valid && m->rows > 0 && !tiles) {
         p->threads_fwd = (long long)of.size();
         p->threads_bwd = (long long)ob.size();
         SMM_CUDA(cudaMalloc(&p->order_fwd, sizeof(int32_t) * of.size()));

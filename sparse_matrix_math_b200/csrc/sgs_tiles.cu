@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <future>
 #include <vector>
 
 #include "sgs_internal.cuh"
@@ -246,8 +247,12 @@ struct SweepLayout {
 
 // cluster ids for a natural-order grid stencil, or empty when the column offsets are not of that kind
 std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int* nclusters) {
-    std::vector<long long> offs;                               // distinct |col - row| > 0
+    // distinct |col - row| > 0 over a sample of the rows (head, middle, tail): this is only a proposal, what it leads to
+    // is verified on every row by layout_sweep
+    std::vector<long long> offs;
+    const int sample = 1 << 16;
     for (int r = 0; r < rows; ++r) {
+        if (r >= sample && r < rows - sample && !(r >= rows / 2 && r < rows / 2 + sample)) { r = (r < rows / 2 ? rows / 2 : rows - sample) - 1; continue; }
         for (int k = start[r]; k < start[r + 1]; ++k) {
             long long d = (long long)pos[k] - r;
             if (d < 0) d = -d;
@@ -423,9 +428,10 @@ bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& s
     int ncl = 0;
     const std::vector<int32_t> cl = propose_grid_tiles(rows, start, pos, &ncl);
     if (cl.empty()) return false;
-    SweepLayout L[2];
-    if (!layout_sweep(true, rows, start, pos, diag, cl, ncl, width, &L[0])) return false;
-    if (!layout_sweep(false, rows, start, pos, diag, cl, ncl, width, &L[1])) return false;
+    SweepLayout L[2];                                          // the two sweeps are laid out side by side (set-up time)
+    std::future<bool> bwd = std::async(std::launch::async, [&] { return layout_sweep(false, rows, start, pos, diag, cl, ncl, width, &L[1]); });
+    const bool fwd_ok = layout_sweep(true, rows, start, pos, diag, cl, ncl, width, &L[0]);
+    if (!bwd.get() || !fwd_ok) return false;
     std::vector<int32_t> yp(L[1].order.size(), 0);
     for (size_t t = 0; t < yp.size(); ++t) if (L[1].order[t] >= 0) yp[t] = L[0].where[(size_t)L[1].order[t]];
     const size_t npos = (size_t)ncl * TILE;
