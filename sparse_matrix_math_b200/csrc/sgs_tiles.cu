@@ -491,9 +491,7 @@ void launch_tiles(const smm_precond* p, const TileArgs& F, const TileArgs& B, co
 int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, int ctas_per_sm, unsigned int sleep_first,
                          unsigned int sleep_later, cudaStream_t s) {
     const long long ntiles = p->threads_fwd / TILE;
-    static int warps = 0;                                       // tiles per CTA claim (tuning knob)
-    if (!warps) { const char* e = getenv("SMM_B200_SGS_TILE_WARPS"); warps = e ? atoi(e) : 4; }
-    const long long cap = (long long)p->m->sm_count * ctas_per_sm * 4 / warps;
+    const long long cap = (long long)p->m->sm_count * ctas_per_sm;
     // debug: SMM_B200_SGS_TRACE=<file> records per-tile timestamps of the forward sweep of every apply (last one kept)
     static const char* trace_path = getenv("SMM_B200_SGS_TRACE");
     static unsigned long long* trace = nullptr;
@@ -502,10 +500,7 @@ int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_de
     const uint8_t* nsb = p->tile_steps[1] + ntiles * TILE;
     TileArgs F{nsf, p->tile_steps[0], p->tile_push[0], p->order_fwd, nullptr, p->ecol[0], p->eval[0], p->dval[0], ntiles, p->tile_width, sleep_first, sleep_later, trace};
     TileArgs B{nsb, p->tile_steps[1], p->tile_push[1], p->order_bwd, p->ypos, p->ecol[1], p->eval[1], p->dval[1], ntiles, p->tile_width, sleep_first, sleep_later, nullptr};
-    if (warps == 2) launch_tiles<2>(p, F, B, rhs_dev, x_dev, state, cap, s);
-    else if (warps == 8) launch_tiles<8>(p, F, B, rhs_dev, x_dev, state, cap, s);
-    else if (warps == 1) launch_tiles<1>(p, F, B, rhs_dev, x_dev, state, cap, s);
-    else launch_tiles<4>(p, F, B, rhs_dev, x_dev, state, cap, s);
+    launch_tiles<4>(p, F, B, rhs_dev, x_dev, state, cap, s);   // 1, 2 and 8 tiles per CTA claim measured the same
     SMM_CUDA(cudaGetLastError());
     if (trace) {
         std::vector<unsigned long long> h(4 * (size_t)ntiles);
