@@ -495,7 +495,13 @@ int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_de
     // debug: SMM_B200_SGS_TRACE=<file> records per-tile timestamps of the forward sweep of every apply (last one kept)
     static const char* trace_path = getenv("SMM_B200_SGS_TRACE");
     static unsigned long long* trace = nullptr;
-    if (trace_path && !trace) SMM_CUDA(cudaMalloc(&trace, sizeof(unsigned long long) * 4 * (size_t)ntiles));
+    static long long trace_cap = 0;
+    if (trace_path && trace_cap < ntiles) {
+        cudaFree(trace);
+        trace = nullptr;
+        SMM_CUDA(cudaMalloc(&trace, sizeof(unsigned long long) * 4 * (size_t)ntiles));
+        trace_cap = ntiles;
+    }
     const uint8_t* nsf = p->tile_steps[0] + ntiles * TILE;
     const uint8_t* nsb = p->tile_steps[1] + ntiles * TILE;
     TileArgs F{nsf, p->tile_steps[0], p->tile_push[0], p->order_fwd, nullptr, p->ecol[0], p->eval[0], p->dval[0], ntiles, p->tile_width, sleep_first, sleep_later, trace};
