@@ -22,7 +22,7 @@ struct DistComm {
     unsigned int red_seq;                       // reductions completed (same on every rank)
     unsigned int push_seq;                      // halo exchanges completed
     int error;                                  // 1: a bounded wait expired
-    int pad;
+    int tree_order;                             // 1: combine the ranks' values pairwise (reference-tree mode), 0: in rank order
     unsigned long long* mail[SMM_MAX_RANKS];    // mail[d]: rank d's mailbox [4 sets][nranks][2] (mail[rank] is local)
     unsigned int* flags[SMM_MAX_RANKS];         // flags[d]: rank d's flag array [nranks]; this rank writes flags[d][rank]
 };
@@ -45,7 +45,7 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p
     return v;
 }
 
-// Called by ONE thread per rank.  Sums t0 and t1 over all ranks, in rank order.
+// Called by ONE thread per rank.  Sums t0 and t1 over all ranks: in rank order, or pairwise in reference-tree mode.
 __device__ __forceinline__ void dist_allreduce2(DistComm* c, float& t0, float& t1) {
     const unsigned int seq = c->red_seq + 1u;
     const int P = c->nranks, me = c->rank;
@@ -57,7 +57,7 @@ __device__ __forceinline__ void dist_allreduce2(DistComm* c, float& t0, float& t
         st_sys_u64(c->mail[d] + set + 2 * me, w0);
         st_sys_u64(c->mail[d] + set + 2 * me + 1, w1);
     }
-    float s0 = 0.0f, s1 = 0.0f;
+    float v0[SMM_MAX_RANKS], v1[SMM_MAX_RANKS];
     const unsigned long long* mine = c->mail[me] + set;
     for (int s = 0; s < P; ++s) {
         unsigned long long a = 0, b = 0;
@@ -68,8 +68,19 @@ __device__ __forceinline__ void dist_allreduce2(DistComm* c, float& t0, float& t
             if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) break;
             if (++polls >= SMM_DIST_POLL_LIMIT) { c->error = 1; break; }
         }
-        s0 += __uint_as_float((unsigned int)a);
-        s1 += __uint_as_float((unsigned int)b);
+        v0[s] = __uint_as_float((unsigned int)a);
+        v1[s] = __uint_as_float((unsigned int)b);
+    }
+    float s0 = 0.0f, s1 = 0.0f;
+    if (c->tree_order) {
+        // the ranks own the depth-log2(P) nodes of the reference's reduction tree (tbb::parallel_deterministic_reduce over
+        // the whole vector, H:308-320): their values are joined pairwise, left + right, like the levels above them
+        for (int w = P >> 1; w >= 1; w >>= 1)
+            for (int k = 0; k < w; ++k) { v0[k] = __fadd_rn(v0[2 * k], v0[2 * k + 1]); v1[k] = __fadd_rn(v1[2 * k], v1[2 * k + 1]); }
+        s0 = v0[0];
+        s1 = v1[0];
+    } else {
+        for (int s = 0; s < P; ++s) { s0 += v0[s]; s1 += v1[s]; }
     }
     t0 = s0;
     t1 = s1;

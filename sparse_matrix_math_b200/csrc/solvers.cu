@@ -94,12 +94,26 @@ int cg_init_dist(Ctx& c, const float* x0) {
     smm_dist* d = c.dist;
     SMM_CUDA(cudaMemcpyAsync(d->ext + d->own_off, x0, sizeof(float) * (size_t)c.n, cudaMemcpyDeviceToDevice, c.s));
     SMM_TRY(smm_dist_exchange_async(d, c.st, c.s));
+    if (c.exact) {                                             // reference-tree mode: local tree, ranks joined pairwise
+        SMM_TRY(spmv(c, SMM_OP_SUB, c.b, d->ext, c.r, RED_NONE, FIN_NONE, nullptr));
+        SMM_TRY(dots(c, FIN_CG_INIT, c.r, c.r));
+    } else
     SMM_TRY(spmv(c, SMM_OP_SUB, c.b, d->ext, c.r, RED_OUT_OUT, FIN_CG_INIT, nullptr));
     SMM_TRY(vec(c, VEC_COPY3, FIN_NONE, {c.r}, {c.p, c.p, c.p}));
     return smm_dist_exchange_async(d, c.st, c.s);
 }
 int cg_iter_dist(Ctx& c) {
     smm_dist* d = c.dist;
+    if (c.exact) {
+        SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, d->ext, c.ap, RED_NONE, FIN_NONE, nullptr));
+        SMM_TRY(dots(c, FIN_CG_ALPHA, c.ap, c.p));
+        SMM_TRY(vec(c, VEC_CG_XR, FIN_NONE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
+        SMM_TRY(dots(c, FIN_CG_UPDATE, c.r, c.r));
+        SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}));
+        SMM_TRY(smm_dist_exchange_async(d, c.st, c.s));
+        c.kernels_per_iteration = 7;
+        return SMM_OK;
+    }
     SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, d->ext, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));
     SMM_TRY(vec(c, VEC_CG_XR, FIN_CG_UPDATE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
     SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}));
@@ -399,7 +413,29 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
     c.a = a; c.precond = precond; c.ws = ws; c.s = s; c.st = ws->state; c.n = a->rows; c.dist = dist;
     c.mode = opts ? opts->reduction_mode : SMM_REDUCE_FAST;
     if (c.mode < 0 || c.mode > 2) { smm_set_error("solve: unknown reduction mode"); return SMM_E_INVALID; }
-    if (dist && c.mode != SMM_REDUCE_FAST) { smm_set_error("multi-GPU solve: only the FAST reduction mode is distributed"); return SMM_E_INVALID; }
+    if (dist && c.mode != SMM_REDUCE_FAST) {
+        // The reference-tree mode distributes when every rank owns one node of the reference's reduction tree (the range
+        // [0, n) halved log2(P) times at lo + (hi - lo) / 2, H:308-320): local trees, then the ranks joined pairwise.
+        bool aligned = solver == S_CG && c.mode == SMM_REDUCE_REFERENCE_TREE && (dist->nranks & (dist->nranks - 1)) == 0;
+        if (aligned) {
+            long long lo = 0, hi = dist->global_rows;
+            for (int bit = dist->nranks >> 1; bit >= 1; bit >>= 1) {
+                const long long mid = lo + (hi - lo) / 2;
+                if (dist->rank & bit) lo = mid; else hi = mid;
+            }
+            aligned = lo == dist->row_begin && hi == dist->row_end && hi - lo > 8192;
+        }
+        if (!aligned) {
+            smm_set_error("multi-GPU solve: the reference-order modes need ConjugateGradient, REFERENCE_TREE, a power-of-two number of ranks and "
+                          "row blocks that are the nodes of the reference's reduction tree (dist.tbb_partition)");
+            return SMM_E_INVALID;
+        }
+    }
+    if (dist) {
+        const int tree_order = c.mode == SMM_REDUCE_REFERENCE_TREE ? 1 : 0;
+        SMM_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(dist->comm_dev) + offsetof(DistComm, tree_order), &tree_order, sizeof(int), cudaMemcpyHostToDevice, s));
+        SMM_CUDA(cudaStreamSynchronize(s));                    // the source is a stack variable
+    }
     c.exact = c.mode != SMM_REDUCE_FAST;
     if (c.exact) SMM_TRY(smm_dot_ref_prepare(a->rows));        // scratch must exist before the iteration graph is captured
     c.b = b_dev; c.x = x_dev;

@@ -27,6 +27,17 @@ def row_partition(global_rows, nranks, align=1):
     return [(cuts[r], cuts[r + 1]) for r in range(nranks)]
 
 
+def tbb_partition(global_rows, nranks):
+    """Row blocks that are the depth-log2(nranks) nodes of the reference's reduction tree over [0, global_rows)
+    (tbb::parallel_deterministic_reduce halves a range at lo + (hi - lo) / 2, H:308-320).  With this partition the
+    REFERENCE_TREE mode distributes bit-exactly: every rank sums its own subtree, the ranks are joined pairwise."""
+    assert nranks & (nranks - 1) == 0, "power-of-two number of ranks"
+    parts = [(0, global_rows)]
+    while len(parts) < nranks:
+        parts = [half for lo, hi in parts for half in ((lo, lo + (hi - lo) // 2), (lo + (hi - lo) // 2, hi))]
+    return parts
+
+
 def nnz_partition(start, nranks):
     """Contiguous blocks of rows with (nearly) equal numbers of stored entries; start = global CSR row pointer."""
     start = np.asarray(start, np.int64)
@@ -125,9 +136,12 @@ class DistMatrix:
     def spmv_dev(self, x_ptr, y_ptr, stream=None):
         B._check(self.L.smm_dist_spmv_dev(self.handle, x_ptr, y_ptr, stream), "smm_dist_spmv_dev")
 
-    def solve_cg_dev(self, b_ptr, x0_ptr, x_ptr, max_iterations, eps, stream=None, driver_mode=B.DRIVER_AUTO, check_every=0):
+    def solve_cg_dev(self, b_ptr, x0_ptr, x_ptr, max_iterations, eps, stream=None, driver_mode=B.DRIVER_AUTO, check_every=0,
+                     reduction_mode=B.REDUCE_FAST):
+        """reduction_mode REDUCE_REFERENCE_TREE needs the row blocks of tbb_partition (bit-identical to the reference's
+        multithreaded build on any power-of-two number of GPUs)."""
         o = B._Options()
-        o.reduction_mode, o.driver_mode, o.check_every = B.REDUCE_FAST, driver_mode, check_every
+        o.reduction_mode, o.driver_mode, o.check_every = reduction_mode, driver_mode, check_every
         info = B._Info()
         B._check(self.L.smm_dist_solve_cg(self.handle, b_ptr, x0_ptr, x_ptr, int(max_iterations), float(eps), C.byref(o), C.byref(info), stream),
                  "smm_dist_solve_cg")

@@ -88,6 +88,29 @@ def main():
             print(f"{name}: ok={not fails} (CG {info.iterations} capped; converged run vs reference {o['iterations']} iterations)", flush=True)
         dist.barrier()
         D.close()
+    # reference-tree mode, distributed: row blocks = nodes of the reference's reduction tree -> the SAME bits and the same
+    # iteration count as the reference's multithreaded build (oracle, mt) on the global problem
+    if world & (world - 1) == 0:
+        for name, g in [("poisson3d 40x40x48 (tree)", matgen.poisson3d(40, 40, 48)), ("poisson2d 301x299 (tree)", matgen.poisson2d(301, 299))]:
+            rb, re = smd.tbb_partition(g.rows, world)[rank]
+            start, pos, val = smd.slice_rows(g.start, g.positions, g.values, rb, re)
+            A = smm.CSRMatrix.from_arrays(re - rb, g.cols, start, pos, val)
+            D = smd.DistMatrix(A, g.rows, rb, re, rank, world, smd.all_gather_object)
+            xs = matgen.xstar(g.rows)
+            b_glob = ol.spmv(g, 0, None, xs)
+            o = ol.solve("cg", g, b_glob, np.zeros(g.rows, np.float32), -1, 1e-5, 1)
+            db, dxx = smm.DeviceVector(re - rb, b_glob[rb:re]), smm.DeviceVector(re - rb, np.zeros(re - rb, np.float32))
+            dist.barrier()
+            info = D.solve_cg_dev(db.ptr, dxx.ptr, dxx.ptr, -1, 1e-5, reduction_mode=B.REDUCE_REFERENCE_TREE)
+            x = dxx.download()
+            check(int(info.status) == o["status"] == 0 and info.iterations == o["iterations"],
+                  f"{name}: iterations {info.iterations} vs reference {o['iterations']}")
+            check(x.tobytes() == o["x"][rb:re].tobytes(), f"{name}: x differs from the reference's bits")
+            check(D.error() == 0, f"{name}: communication error flag")
+            if rank == 0:
+                print(f"{name}: ok={not fails} ({info.iterations} iterations, reference {o['iterations']})", flush=True)
+            dist.barrier()
+            D.close()
     total = [None] * world
     dist.all_gather_object(total, len(fails))
     dist.barrier()

@@ -108,3 +108,26 @@ def test_two_rank_halo_exchange_reproduces_global_spmv():
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def test_tbb_partition_reproduces_the_reference_tree():
+    """dist.tbb_partition: the blocks are nodes of tbb::parallel_deterministic_reduce's split tree (H:308-320), so the
+    per-block reference dots joined pairwise are the reference dot of the whole vector, bit for bit."""
+    import numpy as np
+
+    import oracle_lib as ol
+    from sparse_matrix_math_b200 import dist as smd
+    rng = np.random.default_rng(5)
+    for n in (65536, 89999, 100003, 1 << 18):
+        a = rng.standard_normal(n).astype(np.float32)
+        b = rng.standard_normal(n).astype(np.float32)
+        want = np.float32(ol.dot(a, b, True))
+        for P in (1, 2, 4, 8):
+            parts = smd.tbb_partition(n, P)
+            assert parts[0][0] == 0 and parts[-1][1] == n and all(parts[i][1] == parts[i + 1][0] for i in range(P - 1))
+            if min(hi - lo for lo, hi in parts) <= 8192:
+                continue                                     # the blocks would be smaller than a leaf of the tree
+            v = [np.float32(ol.dot(a[lo:hi], b[lo:hi], True)) for lo, hi in parts]
+            while len(v) > 1:
+                v = [np.float32(v[2 * k] + v[2 * k + 1]) for k in range(len(v) // 2)]
+            assert v[0].tobytes() == want.tobytes(), (n, P)
