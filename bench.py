@@ -292,7 +292,7 @@ def run_b200(args):
     setup_s = time.perf_counter() - t_setup
 
     opts = B._Options()
-    opts.reduction_mode = B.REDUCE_FAST
+    opts.reduction_mode = B.REDUCE_REFERENCE_TREE if args.reduction == "tree" else B.REDUCE_FAST
     opts.driver_mode = {"auto": B.DRIVER_AUTO, "chunked": B.DRIVER_GRAPH_CHUNKED, "while": B.DRIVER_GRAPH_WHILE, "stream": B.DRIVER_STREAM}[args.driver]
     opts.check_every = max(iters, 1)
     info = B._Info()
@@ -371,7 +371,7 @@ def run_b200(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"ConjugateGradient float, 3D 7-point Poisson {grid}^3, b=A*1, x0=0 (BASELINE configs[4])",
                    "grid": grid, "rows": rows, "nnz": nnz, "iterations_per_step": iters, "eps": 0.0,
-                   "parallelism": "1 GPU", "driver": args.driver, "reductions": "fast (fused, deterministic two-stage)",
+                   "parallelism": "1 GPU", "driver": args.driver, "reductions": "fast (fused, deterministic two-stage)" if args.reduction == "fast" else "reference tree (bit-identical to the reference's multithreaded build)",
                    "l2": f"working set {(8 * nnz + 24 * rows) / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
                    "setup_s": round(setup_s, 3)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * rows, "d2h_bytes_per_step": 4 * rows,
@@ -401,6 +401,8 @@ def main():
     ap.add_argument("--grid", type=int, default=512)
     ap.add_argument("--iters", type=int, default=200, help="CG iterations per step")
     ap.add_argument("--driver", default="auto", choices=["auto", "chunked", "while", "stream"])
+    ap.add_argument("--reduction", default="fast", choices=["fast", "tree"],
+                    help="tree: the reference's summation order (bit-identical to its multithreaded build), also across GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

@@ -232,10 +232,11 @@ def bench(args, metric, unit):
     dist.barrier()
     setup_s = time.perf_counter() - t_setup
     drv = {"auto": B.DRIVER_AUTO, "chunked": B.DRIVER_GRAPH_CHUNKED, "while": B.DRIVER_GRAPH_WHILE, "stream": B.DRIVER_STREAM}[args.driver]
+    red = B.REDUCE_REFERENCE_TREE if getattr(args, "reduction", "fast") == "tree" else B.REDUCE_FAST
 
     def step():
         x.zero_()
-        info = D.solve_cg_dev(b.data_ptr(), x.data_ptr(), x.data_ptr(), iters, 0.0, sp, driver_mode=drv, check_every=max(iters, 1))
+        info = D.solve_cg_dev(b.data_ptr(), x.data_ptr(), x.data_ptr(), iters, 0.0, sp, driver_mode=drv, check_every=max(iters, 1), reduction_mode=red)
         assert info.iterations == iters and int(info.status) == 2, (info.iterations, info.status)
         return info
 
@@ -277,7 +278,7 @@ def bench(args, metric, unit):
     def step_host():
         b.copy_(hb, non_blocking=True)
         x.copy_(hx0, non_blocking=True)
-        D.solve_cg_dev(b.data_ptr(), x.data_ptr(), x.data_ptr(), iters, 0.0, sp, driver_mode=drv, check_every=max(iters, 1))
+        D.solve_cg_dev(b.data_ptr(), x.data_ptr(), x.data_ptr(), iters, 0.0, sp, driver_mode=drv, check_every=max(iters, 1), reduction_mode=red)
         hx.copy_(x, non_blocking=True)
         torch.cuda.synchronize()
 
@@ -305,7 +306,7 @@ def bench(args, metric, unit):
             "config": {"workload": f"ConjugateGradient float, 3D 7-point Poisson {grid}^3, b=A*1, x0=0 (BASELINE configs[4])",
                        "grid": grid, "rows": rows, "nnz": nnz, "iterations_per_step": iters, "eps": 0.0,
                        "parallelism": f"{world} GPUs, z-slab row blocks, P2P halo exchange + fused P2P scalar all-reduce (no NCCL in the loop)",
-                       "rows_per_gpu": n, "driver": args.driver,
+                       "rows_per_gpu": n, "driver": args.driver, "reductions": getattr(args, "reduction", "fast"),
                        "l2": f"per-GPU working set {(8 * nnz + 24 * rows) / world / 1e9:.2f} GB >> 126 MB L2 (no flush needed)",
                        "setup_s": round(setup_s, 3)},
             "e2e": {"value": e2e_steps * iters / e2e_s, "unit": unit, "h2d_bytes_per_step": 8 * rows, "d2h_bytes_per_step": 4 * rows,
