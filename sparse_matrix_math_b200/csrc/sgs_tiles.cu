@@ -3,14 +3,15 @@
 // The row-level schedule of sgs.cu pays one producer->L2->consumer hand-off (340-530 ns, tools/hop_latency.cu) per
 // dependency level, and a 7-point stencil on an N^3 grid has 3N-2 of them.  Here rows are grouped into TILES of up to
 // 64 rows that one warp solves in shared memory, so that only the hand-offs BETWEEN tiles go through L2: a 4x4x4 tile
-// has 10 internal levels (about 50 ns each) and the tile graph of the same grid has 3N/4-2 levels.
+// has 10 internal levels (about 120 ns each when the warps of an SM solve together) and the tile graph of the same
+// grid has 3N/4-2 levels.
 //
 //   * Any grouping is legal as long as the tile graph stays acyclic; the per-row arithmetic (operand order, two
 //     roundings per term, one division) is that of the row-level kernel, so the result has the same bits for any
 //     grouping.  build() takes a PROPOSAL (geometric tiles when the column offsets of the matrix are those of a
 //     natural-order 2D / 3D grid stencil) and VERIFIES it generically: tiles of <= 64 rows, <= 4 stored operands
-//     per row and sweep, an acyclic tile graph (Kahn).  Anything else falls back to the
-//     row-level schedule.
+//     per row and sweep, <= 3 rows of the same tile consuming a row, an acyclic tile graph (Kahn).  Anything else falls
+//     back to the row-level schedule.
 //   * Layout: tiles sorted by tile level; position = 64 * tile + index, rows inside a tile sorted by internal level.
 //     Intermediate vectors are stored by position (as in sgs.cu), entries as [tile][operand slot][64].
 //   * Kernel: one warp per tile, lane l holds rows l and l + 32 of the tile in registers (loaded, with the next
