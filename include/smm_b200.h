@@ -199,7 +199,11 @@ int smm_gen_xstar_dev(int64_t n, int64_t offset, uint64_t seed, float* x_dev, vo
  *   smm_dist_connect  maps every peer's block and derives the halo send plan.
  * smm_dist_solve_cg then runs ConjugateGradient (H:2316-2398) on the partitioned system: b, x0, x are this rank's
  * DEVICE slices; halo exchange by P2P stores + flags, scalar reductions by a P2P all-reduce fused into the kernels'
- * epilogues (summed in rank order: identical bits, identical branches on every rank).  No NCCL inside the loop. */
+ * epilogues (summed in rank order: identical bits, identical branches on every rank).  No NCCL inside the loop.
+ * opts->reduction_mode == SMM_REDUCE_REFERENCE_TREE is accepted by smm_dist_solve_cg when the number of ranks is a power
+ * of two and every rank's row block is a node of the reference's reduction tree over [0, global_rows) (the range halved at
+ * lo + (hi - lo) / 2, H:308-320): the ranks' subtree sums are then joined pairwise and the solve is bit-identical to the
+ * reference's SMM_MULTITHREADING build; any other partition is refused with SMM_E_INVALID. */
 typedef struct smm_dist smm_dist_t;
 int smm_dist_create(int rank, int nranks, int64_t global_rows, int64_t row_begin, int64_t row_end, smm_csr_t* local,
                     smm_dist_t** out);
