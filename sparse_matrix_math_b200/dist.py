@@ -147,10 +147,12 @@ class DistMatrix:
                  "smm_dist_solve_cg")
         return B.SolveInfo(info)
 
-    def solve_dev(self, solver, b_ptr, x_ptr, max_iterations, eps, stream=None, driver_mode=B.DRIVER_AUTO, check_every=0):
-        """solver in {"bicgsym", "cgs", "bicgstab"}; x is initial guess and result (device slices of this rank)."""
+    def solve_dev(self, solver, b_ptr, x_ptr, max_iterations, eps, stream=None, driver_mode=B.DRIVER_AUTO, check_every=0,
+                  reduction_mode=B.REDUCE_FAST):
+        """solver in {"bicgsym", "cgs", "bicgstab"}; x is initial guess and result (device slices of this rank).
+        REDUCE_REFERENCE_TREE: bicgsym and cgs, with the row blocks of tbb_partition."""
         o = B._Options()
-        o.reduction_mode, o.driver_mode, o.check_every = B.REDUCE_FAST, driver_mode, check_every
+        o.reduction_mode, o.driver_mode, o.check_every = reduction_mode, driver_mode, check_every
         info = B._Info()
         fn = getattr(self.L, "smm_dist_solve_" + solver)
         B._check(fn(self.handle, b_ptr, x_ptr, int(max_iterations), float(eps), C.byref(o), C.byref(info), stream), "smm_dist_solve_" + solver)
