@@ -78,3 +78,27 @@ def test_dropin_tests_run_on_gpu(built_lib):
     print(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert " 0 failures" in r.stdout
+
+
+EXAMPLE = os.path.join(ROOT, "examples", "solve_mtx.cpp")
+
+
+def test_example_compiles(built_lib):
+    r = compile_cpp(EXAMPLE, os.path.join(BUILD, "solve_mtx"))
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("matrix,solver,order", [("mesh1em1.mtx", "cg", 1), ("mesh1e1.mtx", "bicgstab-sgs", 0), ("mesh1em6.mtx", "cg-ic0", 1),
+                                                 ("mesh1em1.mtx", "bicgstab-ilu0", 0), ("mesh1e1.mtx", "cgs", 0)])
+def test_example_runs_on_gpu(built_lib, matrix, solver, order):
+    """examples/solve_mtx.cpp: the reference's asset files through the drop-in header, end to end."""
+    exe = os.path.join(BUILD, "solve_mtx")
+    r = compile_cpp(EXAMPLE, exe)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe, os.path.join(HERE, "golden", matrix), solver, "1e-4", str(order)], capture_output=True, text=True, timeout=120)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "status 0" in r.stdout and "48 rows" in r.stdout
+    err = float(r.stdout.split("max |x - 1| = ")[1].split(",")[0])
+    assert err < 1e-3
