@@ -26,7 +26,9 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <future>
+#include <thread>
 #include <vector>
 
 #include "sgs_internal.cuh"
@@ -287,6 +289,19 @@ std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& st
     return cl;
 }
 
+// f(cluster) for every cluster, on a few threads (set-up code; the clusters are independent of each other)
+template <class F>
+void for_clusters(int ncl, F f) {
+    const unsigned int hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<unsigned int>(hw > 3 ? hw / 2 : 1, 8);       // the two sweeps are laid out side by side
+    if (ncl < 4096) nt = 1;
+    if (nt <= 1) { for (int a = 0; a < ncl; ++a) f(a); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&, t] { for (int a = (int)((long long)ncl * t / nt); a < (int)((long long)ncl * (t + 1) / nt); ++a) f(a); });
+    for (std::thread& x : th) x.join();
+}
+
 // Lay one sweep out by tiles.  Returns false when the proposal does not verify.
 bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag,
                   const std::vector<int32_t>& cl, int ncl, int width, SweepLayout* out) {
@@ -304,24 +319,29 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
         std::vector<int32_t> cur(cptr.begin(), cptr.end() - 1);
         for (int r = 0; r < rows; ++r) crow[(size_t)cur[cl[r]]++] = r;
     }
-    // distinct predecessor tiles
+    // distinct predecessor tiles (in the order the rows of the tile meet them)
     std::vector<int32_t> pred((size_t)ncl * MAX_PREDS, -1);
     std::vector<uint8_t> npred((size_t)ncl, 0);
-    for (int r = 0; r < rows; ++r) {
-        const int a = cl[r];
-        for (int k = dep_begin(r); k < dep_end(r); ++k) {
-            const int b = cl[pos[k]];
-            if (b == a) continue;
-            int32_t* pa = &pred[(size_t)a * MAX_PREDS];
-            int n = npred[a], i = 0;
-            while (i < n && pa[i] != b) ++i;
-            if (i == n) {
-                if (n == MAX_PREDS) return false;
-                pa[n] = b;
-                npred[a] = (uint8_t)(n + 1);
+    std::atomic<bool> bad(false);
+    for_clusters(ncl, [&](int a) {
+        int32_t* pa = &pred[(size_t)a * MAX_PREDS];
+        int n = 0;
+        for (int q = cptr[a]; q < cptr[a + 1]; ++q) {
+            const int r = crow[q];
+            for (int k = dep_begin(r); k < dep_end(r); ++k) {
+                const int b = cl[pos[k]];
+                if (b == a) continue;
+                int i = 0;
+                while (i < n && pa[i] != b) ++i;
+                if (i == n) {
+                    if (n == MAX_PREDS) { bad = true; return; }
+                    pa[n++] = b;
+                }
             }
         }
-    }
+        npred[a] = (uint8_t)n;
+    });
+    if (bad) return false;
     // Kahn: tile levels, cycle check
     std::vector<int32_t> sptr((size_t)ncl + 1, 0);
     for (int a = 0; a < ncl; ++a) for (int i = 0; i < npred[a]; ++i) sptr[(size_t)pred[(size_t)a * MAX_PREDS + i] + 1]++;
@@ -359,8 +379,7 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
     out->where.assign((size_t)rows, 0);
     out->steps.assign((size_t)ncl * TILE + (size_t)ncl, 255);    // [tiles * 64] step of every row, then [tiles] number of steps
     std::vector<int8_t> ilev((size_t)rows, 0);
-    std::vector<int32_t> tmp;
-    for (int a = 0; a < ncl; ++a) {
+    for_clusters(ncl, [&](int a) {
         const int n = cptr[a + 1] - cptr[a];
         const int32_t* R = &crow[(size_t)cptr[a]];
         int nl = 0;
@@ -368,45 +387,55 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
             const int r = forward ? R[q] : R[n - 1 - q];
             int l = 0;
             for (int k = dep_begin(r); k < dep_end(r); ++k) if (cl[pos[k]] == a) l = std::max(l, ilev[pos[k]] + 1);
-            if (l >= MAX_STEPS) return false;
+            if (l >= MAX_STEPS) { bad = true; return; }
             ilev[r] = (int8_t)l;
             nl = std::max(nl, l + 1);
         }
-        tmp.assign(R, R + n);
-        if (!forward) std::reverse(tmp.begin(), tmp.end());
-        std::stable_sort(tmp.begin(), tmp.end(), [&](int32_t p, int32_t q) { return ilev[p] < ilev[q]; });
+        int32_t tmp[TILE];                                     // rows by internal level, stable in the sweep's row order
+        int at[MAX_STEPS + 1] = {0};
+        for (int q = 0; q < n; ++q) at[ilev[R[q]] + 1]++;
+        for (int l = 0; l < nl; ++l) at[l + 1] += at[l];
+        for (int q = 0; q < n; ++q) { const int r = forward ? R[q] : R[n - 1 - q]; tmp[at[ilev[r]]++] = r; }
         const int t = tile_of[a];
         out->steps[(size_t)ncl * TILE + t] = (uint8_t)nl;       // a step = an internal level (lane l solves rows l and l + 32)
-        for (int i = 0; i < n; ++i) out->steps[(size_t)t * TILE + i] = (uint8_t)ilev[tmp[i]];
         for (int i = 0; i < n; ++i) {
+            out->steps[(size_t)t * TILE + i] = (uint8_t)ilev[tmp[i]];
             out->order[(size_t)t * TILE + i] = tmp[i];
             out->where[(size_t)tmp[i]] = t * TILE + i;
         }
-    }
+    });
+    if (bad) return false;
     // entries: [tile][slot][64], operand order = the reference's (ascending columns forward, descending backward);
-    // push lists: where inside the tile's operand staging a row's result has to go (unused entries point at the row's
-    // own first slot, which nobody reads once the row is solved)
+    // push lists: where inside the tile's operand staging a row's result has to go (bytes 0..2; a byte that is not needed
+    // points at the row's own first slot, which nobody reads once the row is solved)
     out->ecol.assign((size_t)ncl * width * TILE, -1);
     out->eidx.assign((size_t)ncl * width * TILE, -1);
     out->push.assign((size_t)ncl * TILE, 0u);
-    std::vector<uint8_t> npush((size_t)ncl * TILE, 0);
-    for (size_t p = 0; p < out->push.size(); ++p) { const uint32_t own = (uint32_t)((p & (TILE - 1)) * TILE_MAX_W); out->push[p] = own * 0x01010101u; }
-    for (int r = 0; r < rows; ++r) {
-        const int p = out->where[r], t = p >> 6, i = p & (TILE - 1);
-        const int cnt = dep_end(r) - dep_begin(r);
-        for (int e = 0; e < cnt; ++e) {
-            const int srci = forward ? start[r] + e : start[r + 1] - 1 - e;
-            const size_t at = ((size_t)t * width + e) * TILE + i;
-            const int q = out->where[pos[srci]];
-            out->ecol[at] = q;
-            out->eidx[at] = srci;
-            if ((q >> 6) == t) {                               // produced inside the tile: the producer pushes it
-                if (npush[q] == 3) return false;                   // a row with more than three consumers inside its tile
-                const int sh = 8 * npush[q]++;
-                out->push[q] = (out->push[q] & ~(0xFFu << sh)) | ((uint32_t)(i * TILE_MAX_W + e) << sh);
+    for_clusters(ncl, [&](int a) {                             // a row is only pushed to rows of its own tile: no sharing between tiles
+        const int t = tile_of[a];
+        uint8_t npush[TILE] = {0};
+        for (int i = 0; i < TILE; ++i) out->push[(size_t)t * TILE + i] = (uint32_t)(i * TILE_MAX_W) * 0x01010101u;
+        for (int q = cptr[a]; q < cptr[a + 1]; ++q) {
+            const int r = crow[q];
+            const int i = out->where[r] & (TILE - 1);
+            const int cnt = dep_end(r) - dep_begin(r);
+            for (int e = 0; e < cnt; ++e) {
+                const int srci = forward ? start[r] + e : start[r + 1] - 1 - e;
+                const size_t at = ((size_t)t * width + e) * TILE + i;
+                const int w = out->where[pos[srci]];
+                out->ecol[at] = w;
+                out->eidx[at] = srci;
+                if ((w >> 6) == t) {                           // produced inside the tile: the producer pushes it
+                    const int j = w & (TILE - 1);
+                    if (npush[j] == 3) { bad = true; return; } // a row with more than three consumers inside its tile
+                    const int sh = 8 * npush[j]++;
+                    uint32_t& pu = out->push[(size_t)t * TILE + j];
+                    pu = (pu & ~(0xFFu << sh)) | ((uint32_t)(i * TILE_MAX_W + e) << sh);
+                }
             }
         }
-    }
+    });
+    if (bad) return false;
     return true;
 }
 
