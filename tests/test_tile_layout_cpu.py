@@ -1,0 +1,46 @@
+"""Host side of the tile-level sweep schedule (csrc/sgs_tiles.cu: proposal, generic verification, layout), without a GPU:
+tools/layout_fingerprint.cu includes the source file and runs the set-up code on generated stencils.  The fingerprints
+pin every array the kernels read (row order, operand positions, steps, push lists) -- the arrays the GPU parity tests
+(`test_sweep_schedules_bit_exact`, the solver tests) were green with; a change of the set-up code must reproduce them."""
+import os
+import re
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+EXE = os.path.join(ROOT, "tools", "bin", "layout_fingerprint")
+
+GOLDEN = {
+    ("64",): (46, "3af65eb5649ada45", "5de0bdfdeda5a402"),                    # 64^3: 16^3 tiles, 3 * 16 - 2 tile levels
+    ("70", "45", "33"): (37, "80b94a34718a146f", "cbf3d109cd13d484"),         # ragged 3D grid
+    ("200", "150", "1"): (43, "0cf68e73ed3ec432", "8b05cb26ed34e36f"),        # 2D, 8 x 8 tiles
+}
+
+
+@pytest.fixture(scope="module")
+def exe():
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    cmd = ["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-ccbin", "/usr/bin/g++", f"-I{ROOT}/include", f"-I{ROOT}/sparse_matrix_math_b200/csrc",
+           "-gencode", "arch=compute_100a,code=sm_100a", "-o", EXE, os.path.join(ROOT, "tools", "layout_fingerprint.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return EXE
+
+
+@pytest.mark.parametrize("dims", sorted(GOLDEN))
+def test_tile_layout_fingerprints(exe, dims):
+    out = subprocess.run([exe, *dims], capture_output=True, text=True, timeout=300).stdout
+    levels, fwd, bwd = GOLDEN[dims]
+    got = re.findall(r"(forward|backward)\s+ok (\d) levels (\d+) time \S+ s fingerprint ([0-9a-f]{16})", out)
+    assert [g[0] for g in got] == ["forward", "backward"], out
+    assert all(g[1] == "1" and int(g[2]) == levels for g in got), out
+    assert got[0][3] == fwd and got[1][3] == bwd, out
+
+
+def test_tile_proposal_with_cycles_is_rejected(exe):
+    """A grid-like band matrix whose +-1 couplings run across the grid lines: tiles (0, J) and (last, J) need each other, the
+    verification (Kahn on the tile graph) must refuse the proposal, so the row-level schedule is used instead."""
+    out = subprocess.run([exe, "64", "48", "1", "1"], capture_output=True, text=True, timeout=300).stdout
+    assert re.search(r"forward\s+ok 0", out), out
