@@ -44,3 +44,43 @@ def test_tile_proposal_with_cycles_is_rejected(exe):
     verification (Kahn on the tile graph) must refuse the proposal, so the row-level schedule is used instead."""
     out = subprocess.run([exe, "64", "48", "1", "1"], capture_output=True, text=True, timeout=300).stdout
     assert re.search(r"forward\s+ok 0", out), out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the host-side factorisations of csrc/sgs.cu (IC(0): bit-identical to the reference's O(rows^2) algorithm; ILU(0):
+# extension) against the oracle, without a GPU: tools/factor_fingerprint.cu includes the source file
+# ---------------------------------------------------------------------------------------------------------------
+FEXE = os.path.join(ROOT, "tools", "bin", "factor_fingerprint")
+
+
+@pytest.fixture(scope="module")
+def fexe():
+    os.makedirs(os.path.dirname(FEXE), exist_ok=True)
+    cmd = ["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-ccbin", "/usr/bin/g++", f"-I{ROOT}/include", f"-I{ROOT}/sparse_matrix_math_b200/csrc",
+           "-gencode", "arch=compute_100a,code=sm_100a", "-o", FEXE, os.path.join(ROOT, "tools", "factor_fingerprint.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return FEXE
+
+
+def _fnv(buf):
+    h = 1469598103934665603
+    for b in buf:
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
+
+
+@pytest.mark.parametrize("dims,c", [((12, 10, 9), 0.0), ((12, 10, 9), 0.5), ((31, 17, 1), 0.0), ((7, 7, 7), 0.5)])
+def test_host_factorisations_match_the_oracle(fexe, dims, c):
+    import matgen
+    import oracle_lib as ol
+    nx, ny, nz = dims
+    g = matgen.convdiff3d(nx, c, ny, nz) if nz > 1 else matgen.poisson2d(nx, ny)
+    out = subprocess.run([fexe, str(nx), str(ny), str(nz), str(c)], capture_output=True, text=True, timeout=300).stdout
+    m = re.search(r"rows (\d+) nnz (\d+) valid 1 diag 1 ic0 rc (\d) ([0-9a-f]{16}) ilu0 rc (\d) ([0-9a-f]{16})", out)
+    assert m, out
+    assert int(m.group(1)) == g.rows and int(m.group(2)) == g.nnz
+    rc, f = ol.ic0_factorize(g)
+    assert rc == int(m.group(3)) == 0 and _fnv(f[: g.nnz].tobytes()) == m.group(4)
+    rc, lu = ol.ilu0_factorize(g)
+    assert rc == int(m.group(5)) == 0 and _fnv(lu[: g.nnz].tobytes()) == m.group(6)
