@@ -127,3 +127,40 @@ int main(int, char** argv) {
                 got[int(r_), int(c_)] = np.float32(v_)
         want = sp.coo_matrix(scipy.io.mmread(path, spmatrix=True)).astype(np.float32).toarray()
         np.testing.assert_array_equal(got, want)
+
+
+def test_extended_loader_random_files_match_scipy(tmp_path):
+    """Random coordinate files of every supported kind (seeded): same matrix as scipy.io.mmread."""
+    rng = np.random.default_rng(20261018)
+    for trial in range(40):
+        rows, cols = int(rng.integers(1, 12)), int(rng.integers(1, 12))
+        structure = ["general", "symmetric", "skew-symmetric"][trial % 3]
+        field = ["real", "integer", "pattern"][(trial // 3) % 3]
+        if structure != "general":
+            cols = rows
+        if structure == "skew-symmetric" and field == "pattern":
+            field = "real"                                    # not a Matrix Market combination
+        n = int(rng.integers(0, 20))
+        lines = []
+        seen = set()
+        for _ in range(n):
+            r, c = int(rng.integers(1, rows + 1)), int(rng.integers(1, cols + 1))
+            if structure != "general" and c > r:
+                r, c = c, r                                   # lower triangle only
+            if structure == "skew-symmetric" and r == c:
+                continue                                      # no diagonal in a skew-symmetric file
+            if (r, c) in seen:
+                continue                                      # duplicates are summed in float32, in file order (H:606-618), scipy sums in double
+            seen.add((r, c))
+            if field == "pattern":
+                lines.append(f"{r} {c}")
+            elif field == "integer":
+                lines.append(f"{r} {c} {int(rng.integers(-9, 10))}")
+            else:
+                lines.append(f"{r} {c} {np.float32(rng.standard_normal()):.9g}")
+        path = tmp_path / f"r{trial}.mtx"
+        path.write_text(f"%%MatrixMarket matrix coordinate {field} {structure}\n% trial {trial}\n{rows} {cols} {len(lines)}\n" + "\n".join(lines) + ("\n" if lines else ""))
+        t = smm.TripletMatrix()
+        assert smm.loadMatrix(str(path), t, extended=True) == smm.MatrixLoadStatus.SUCCESS, path.read_text()
+        want = sp.coo_matrix(scipy.io.mmread(str(path), spmatrix=True)).astype(np.float32).toarray()
+        np.testing.assert_array_equal(dense_from_triplet(t), want, err_msg=path.read_text())
