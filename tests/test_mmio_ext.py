@@ -114,12 +114,13 @@ int main(int, char** argv) {
     exe = str(tmp_path / "mm_ext")
     r = compile_cpp(str(src), exe)
     assert r.returncode == 0, r.stderr[-3000:]
-    for name in FILES:
-        path = str(tmp_path / (name + ".mtx"))
+    randoms = [str(q) for q in random_mm_files(tmp_path)]
+    for path in [str(tmp_path / (name + ".mtx")) for name in FILES] + randoms:
         out = subprocess.run([exe, path], capture_output=True, text=True).stdout.split("\n")
         strict, st, rows, cols = (int(v) for v in out[0].split())
-        assert st == 0
-        assert (strict == 0) == (name == "never")            # every file here is one the reference rejects or mis-parses
+        assert st == 0, path
+        if path not in randoms:
+            assert strict != 0                               # every hand-written file is one the reference's loader rejects
         got = np.zeros((rows, cols), np.float32)
         for line in out[1:]:
             if line.strip():
@@ -129,10 +130,12 @@ int main(int, char** argv) {
         np.testing.assert_array_equal(got, want)
 
 
-def test_extended_loader_random_files_match_scipy(tmp_path):
-    """Random coordinate files of every supported kind (seeded): same matrix as scipy.io.mmread."""
+def random_mm_files(tmp_path, count=40):
+    """Seeded random coordinate files of every supported kind (no duplicate entries: those are summed in float32, in file
+    order, H:606-618, while scipy sums in double)."""
     rng = np.random.default_rng(20261018)
-    for trial in range(40):
+    paths = []
+    for trial in range(count):
         rows, cols = int(rng.integers(1, 12)), int(rng.integers(1, 12))
         structure = ["general", "symmetric", "skew-symmetric"][trial % 3]
         field = ["real", "integer", "pattern"][(trial // 3) % 3]
@@ -150,7 +153,7 @@ def test_extended_loader_random_files_match_scipy(tmp_path):
             if structure == "skew-symmetric" and r == c:
                 continue                                      # no diagonal in a skew-symmetric file
             if (r, c) in seen:
-                continue                                      # duplicates are summed in float32, in file order (H:606-618), scipy sums in double
+                continue
             seen.add((r, c))
             if field == "pattern":
                 lines.append(f"{r} {c}")
@@ -160,6 +163,12 @@ def test_extended_loader_random_files_match_scipy(tmp_path):
                 lines.append(f"{r} {c} {np.float32(rng.standard_normal()):.9g}")
         path = tmp_path / f"r{trial}.mtx"
         path.write_text(f"%%MatrixMarket matrix coordinate {field} {structure}\n% trial {trial}\n{rows} {cols} {len(lines)}\n" + "\n".join(lines) + ("\n" if lines else ""))
+        paths.append(path)
+    return paths
+
+
+def test_extended_loader_random_files_match_scipy(tmp_path):
+    for path in random_mm_files(tmp_path):
         t = smm.TripletMatrix()
         assert smm.loadMatrix(str(path), t, extended=True) == smm.MatrixLoadStatus.SUCCESS, path.read_text()
         want = sp.coo_matrix(scipy.io.mmread(str(path), spmatrix=True)).astype(np.float32).toarray()
