@@ -77,6 +77,8 @@ def test_host_factorisations_match_the_oracle(fexe, dims, c):
     nx, ny, nz = dims
     g = matgen.convdiff3d(nx, c, ny, nz) if nz > 1 else matgen.poisson2d(nx, ny)
     out = subprocess.run([fexe, str(nx), str(ny), str(nz), str(c)], capture_output=True, text=True, timeout=300).stdout
+    lv = re.search(r"levels (\d+) (\d+) order_is_permutation 1", out)       # row-level analysis: nx + ny + nz - 2 levels per sweep
+    assert lv and int(lv.group(1)) == int(lv.group(2)) == nx + ny + nz - 2, out
     m = re.search(r"rows (\d+) nnz (\d+) valid 1 diag 1 ic0 rc (\d) ([0-9a-f]{16}) ilu0 rc (\d) ([0-9a-f]{16})", out)
     assert m, out
     assert int(m.group(1)) == g.rows and int(m.group(2)) == g.nnz

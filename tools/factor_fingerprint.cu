@@ -41,6 +41,16 @@ int main(int argc, char** argv) {
     std::vector<float> ic0, ilu0;
     const int rc_ic0 = ic0_factorize_host(rows, start, pos, d2, val, &ic0);
     const int rc_ilu0 = ilu0_factorize_host(rows, start, pos, d2, val, &ilu0);
+    std::vector<int32_t> of, ob;
+    int lf = 0, lb = 0;
+    level_orders(rows, start, pos, d2, &of, &ob, &lf, &lb);    // the row-level schedule's analysis
+    bool perm = of.size() % 32 == 0 && ob.size() % 32 == 0;
+    {
+        std::vector<char> seen(rows, 0);
+        for (int32_t r : of) if (r >= 0) { if (seen[r]) perm = false; seen[r] = 1; }
+        for (char c2 : seen) if (!c2) perm = false;
+    }
+    printf("levels %d %d order_is_permutation %d\n", lf, lb, (int)perm);
     printf("rows %d nnz %zu valid %d diag %d ic0 rc %d %016llx ilu0 rc %d %016llx\n", rows, pos.size(), (int)valid, (int)(d2 == diag), rc_ic0,
            (unsigned long long)fnv(ic0.data(), ic0.size() * 4), rc_ilu0, (unsigned long long)fnv(ilu0.data(), ilu0.size() * 4));
     return 0;
