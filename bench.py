@@ -41,6 +41,9 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+TRAFFIC_SOURCE = "committed ncu --set full capture of this command (not re-measured in this run)"
+
+
 def ncu_traffic_bytes(kernel_prefix, grid):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
     same command (profiles/r01h_spmv_rows_kernel_full.txt, 512^3); None for any other problem size."""
@@ -126,23 +129,39 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own implementation (oracle/_ref, SMM_MULTITHREADING build) on the host cores
 # ----------------------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def _cpu_libs():
+    """The CPU arm always uses every host core this process may run on: torch.distributed.run exports OMP_NUM_THREADS=1 to
+    its ranks, which is a default for GPU workers, not a statement about the reference's parallel path."""
     import oracle_lib as ol
+    n = host_cores()
+    olib = ol.oracle()
+    olib.smm_oracle_set_threads.argtypes = [C.c_int]
+    olib.smm_oracle_set_threads(n)
     if ol.ref_available():
-        return ol, ol.ref(1), "reference"
+        rlib = ol.ref(1)
+        rlib.smm_ref_set_threads.argtypes = [C.c_int]
+        rlib.smm_ref_set_threads(n)
+        return ol, rlib, "reference"
     return ol, None, "port"
 
 
 def cpu_problem(grid):
     """Build the grid^3 Poisson CSR on the host inside the reference library (no std::map); returns closures."""
     import oracle_lib as ol
+    _, rlib, kind = _cpu_libs()
     olib = ol.oracle()
     olib.smm_oracle_stencil_nnz.restype = C.c_int64
     olib.smm_oracle_stencil_nnz.argtypes = [C.c_int] * 4
     olib.smm_oracle_gen_stencil.argtypes = [C.c_int] * 4 + [C.c_float] * 3 + [C.c_void_p] * 3
     rows = grid ** 3
     nnz = olib.smm_oracle_stencil_nnz(grid, grid, grid, 1)
-    _, rlib, kind = _cpu_libs()
     if rlib is not None:
         rlib.smm_ref_alloc_int.restype = C.c_void_p
         rlib.smm_ref_alloc_int.argtypes = [C.c_int64]
@@ -217,38 +236,50 @@ def cpu_baseline(grid, budget_s=15.0):
     return {"value": rate * scale, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
 
 
+def workload_config(grid, iters):
+    """The keys both arms share (the driver compares them): the workload, not how an arm executes it."""
+    return {"workload": f"ConjugateGradient float, 3D 7-point Poisson {grid}^3, b=A*1, x0=0 (BASELINE configs[4])",
+            "grid": grid, "rows": grid ** 3, "nnz": stencil_nnz(grid), "iterations_per_step": iters, "eps": 0.0}
+
+
 def run_reference(args):
+    """The reference's own ConjugateGradient (oracle/_ref, SMM_MULTITHREADING build) on all host cores.  Same workload as
+    the GPU arm (a step = one solver call of --iters iterations); each timed step executes a BOUNDED SAMPLE of it -- k
+    iterations, k sized so that steps + warmup finish in ~2.5 minutes -- and the value is the marginal iteration rate
+    (start-up r0 = b - A x0, measured once, subtracted), which is what a --iters-iteration step sustains."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     g = pick_cpu_grid(args.grid)
     run, threads, kind, free = cpu_problem(g)
-    # same iterations per step as the GPU arm unless that would take more than ~2.5 minutes in total
     t2, t1 = run(2), run(1)
+    t1 = min(t1, run(1))                                      # start-up: r0, p, r.r and one iteration
     per_it = max(t2 - t1, 1e-6)
-    iters = int(max(2, min(args.iters, 150.0 / ((args.steps + args.warmup) * per_it))))
+    k = int(max(3, min(args.iters, 150.0 / ((args.steps + args.warmup) * per_it))))
     for _ in range(args.warmup):
-        run(iters)
+        run(k)
     t0 = time.perf_counter()
     total = 0.0
     for _ in range(args.steps):
-        total += run(iters)
+        total += run(k)
     wall = time.perf_counter() - t0
     free()
     scale = (g ** 3) / float(args.grid ** 3)
-    value = args.steps * iters / total * scale
-    sample = f"CG {g}^3 Poisson, {iters} iterations per step (each step includes r0 = b - A x0), {threads} host threads"
+    marginal = args.steps * (k - 1) / max(total - args.steps * t1, 1e-9) * scale
+    inclusive = args.steps * k / total * scale
+    sample = (f"CG {g}^3 Poisson on {threads} host threads: every step runs {k} of the workload's {args.iters} iterations; value = marginal rate "
+              f"(start-up of {t1 * 1e3:.0f} ms per call subtracted; including it: {inclusive:.3f} it/s)")
     if g != args.grid:
-        sample += f"; rate scaled by rows ratio {scale:.4f}"
+        sample += f"; host memory too small for {args.grid}^3: rate scaled by rows ratio {scale:.4f}"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": marginal, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ConjugateGradient float, 3D 7-point Poisson {args.grid}^3, b=A*1, x0=0 (BASELINE configs[4])",
-                   "grid": args.grid, "rows": args.grid ** 3, "nnz": stencil_nnz(args.grid), "iterations_per_step": iters,
-                   "cpu_grid": g},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(args.grid, args.iters),
+        "cpu_baseline": {"value": marginal, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "sample_iterations_per_step": k, "cpu_grid": g,
+                         "flags": "-O3 -fopenmp -DSMM_MULTITHREADING, no -march (the prebuilt .so must run on any host; FMA contraction would change the reference's bits)"},
+        "e2e": {"value": marginal, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     }
     print(json.dumps(line), flush=True)
@@ -257,6 +288,152 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
+def golden_fullsize():
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "fullsize_reference.json")))
+    except Exception:
+        return {}
+
+
+def x_checksum(x):
+    """Order-independent checksum of a float vector's bit patterns (what tests/golden/fullsize_reference.json records)."""
+    bits = x.view(np.uint32).astype(np.uint64)
+    return int(bits.sum() & np.uint64(0xFFFFFFFFFFFFFFFF)), int(np.bitwise_xor.reduce(bits))
+
+
+def parity_record(ref, status, iterations, residual, sum_bits, xor_bits, max_abs_error):
+    """Compare a REFERENCE_TREE-mode solve with the golden record of the reference's multithreaded arithmetic."""
+    rb = int(np.float32(residual).view(np.uint32))
+    rec = {"mode": "reference tree (H:305-328 summation order)", "status": int(status), "iterations": int(iterations), "residual_bits": rb,
+           "x_checksum": [int(sum_bits), int(xor_bits)], "max_abs_error": float(max_abs_error)}
+    if ref:
+        rec["golden_iterations"] = ref["iterations"]
+        rec["matches_golden"] = bool(int(status) == ref["status"] and int(iterations) == ref["iterations"] and rb == ref["residual_bits"]
+                                     and int(sum_bits) == ref["x"]["sum_bits"] and int(xor_bits) == ref["x"]["xor_bits"]
+                                     and float(max_abs_error) == ref["max_abs_error"])
+    else:
+        rec["matches_golden"] = None
+    return rec
+
+
+# SURVEY 8(d): fused-minimum algorithmic bytes per iteration
+def bytes_per_iteration(solver, rows, nnz, sgs=False):
+    base = {"cg": 8 * nnz + 48 * rows, "bicgsym": 8 * nnz + 48 * rows, "cgs": 16 * nnz + 80 * rows, "bicgstab": 16 * nnz + 84 * rows}[solver]
+    return base + (2 * (8 * nnz + 32 * rows) if sgs else 0)          # + two applies of B_sgs = 8 nnz + 32 n
+
+
+def bytes_spmv(rows, cols, nnz):
+    return 8 * nnz + 4 * (rows + 1) + 4 * cols + 4 * rows
+
+
+def run_config(smm, B, L, name, key, solver, A, M, rhs_kind, eps, maxit, modes, peak, golden, setup_s=None):
+    """One BASELINE configuration at full size: iterations, rate, the section 8(d) roofline fraction per mode, and the
+    bit-exact comparison with the golden record in the reference-order mode.  Device-timed (CUDA events inside the call)."""
+    n, nnz = A.rows, A.nnz
+    xs = smm.DeviceVector(n)
+    if rhs_kind == "ones":
+        xs.upload(np.ones(n, np.float32))
+    else:
+        B._check(L.smm_gen_xstar_dev(n, 0, 0xB200, xs.ptr, None), "xstar")
+    b = smm.DeviceVector(n)
+    A.spmv_dev(B.OP_ASSIGN, None, xs.ptr, b.ptr)
+    xs_h = xs.download()
+    bpi = bytes_per_iteration(solver, n, nnz, sgs=M is not None)
+    out = {"config": name, "rows": n, "nnz": nnz, "eps": eps, "algorithmic_bytes_per_iteration": bpi, "runs": []}
+    if setup_s is not None:
+        out["preconditioner_setup_s"] = round(setup_s, 4)
+    ref = golden.get(key) if key else None
+    if ref:
+        out["reference_mt_iterations"] = ref["iterations"]
+    # SpMV alone (rMult): effective GB/s over section 8(d)'s B_spmv
+    y = smm.DeviceVector(n)
+    reps = 20
+    t_spmv = spmv_ms(smm, B, L, A, xs, y, reps)
+    out["spmv"] = {"ms": t_spmv, "effective_gbs": bytes_spmv(n, A.cols, nnz) / (t_spmv * 1e-3) / 1e9,
+                   "frac": bytes_spmv(n, A.cols, nnz) / (t_spmv * 1e-3) / 1e9 / peak}
+    del y
+    for mode in modes:
+        m = {"fast": B.REDUCE_FAST, "tree": B.REDUCE_REFERENCE_TREE}[mode]
+        x = smm.DeviceVector(n)
+        best = None
+        for rep in range(2):                                  # second run: graphs instantiated, clocks up
+            x.zero()
+            o, _ = B._options(m, B.DRIVER_AUTO, 0, 0)
+            info = B._Info()
+            if solver == "cg":
+                rc = L.smm_solve_cg_dev(A.handle, b.ptr, x.ptr, x.ptr, maxit, eps, C.byref(o), C.byref(info), None)
+            elif solver == "bicgsym":
+                rc = L.smm_solve_bicgsym_dev(A.handle, b.ptr, x.ptr, maxit, eps, C.byref(o), C.byref(info), None)
+            elif solver == "cgs":
+                rc = L.smm_solve_cgs_dev(A.handle, b.ptr, x.ptr, maxit, eps, C.byref(o), C.byref(info), None)
+            else:
+                rc = L.smm_solve_bicgstab_dev(A.handle, None if M is None else M.handle, b.ptr, x.ptr, maxit, eps, C.byref(o), C.byref(info), None)
+            B._check(rc, solver)
+            if best is None or info.seconds_solve < best:
+                best = info.seconds_solve
+            if n > (1 << 26):
+                break                                         # the 512^3 solves take seconds: once
+        xh = x.download()
+        finite = bool(np.all(np.isfinite(xh)))
+        rate = info.iterations / best if best > 0 else None
+        rec = {"mode": mode, "status": int(info.status), "iterations": int(info.iterations), "solver_residual": float(info.residual),
+               "seconds_solve": best, "it_per_s": rate, "max_abs_error": float(np.max(np.abs(xh - xs_h))) if finite else None,
+               "driver": int(info.driver_mode), "kernel_launches": int(info.kernel_launches)}
+        if rate:
+            rec["iteration_gbs"] = bpi * rate / 1e9
+            rec["frac_of_peak"] = rec["iteration_gbs"] / peak
+        if ref and mode == "fast":
+            rec["iterations_vs_reference"] = info.iterations / ref["iterations"]
+        if mode == "tree" and ref:
+            sb, xb = x_checksum(xh)
+            rec["parity"] = parity_record(ref, info.status, info.iterations, info.residual, sb, xb, float(np.max(np.abs(xh - xs_h))) if finite else float("nan"))
+        out["runs"].append(rec)
+        del x
+    return out
+
+
+def spmv_ms(smm, B, L, A, xs, y, reps):
+    """Average device time of rMult (smm_spmv_dev) on the library's own stream, bracketed by host-timed synchronisation
+    of `reps` back-to-back launches (launch overhead is hidden behind the queue for anything but the smallest matrix)."""
+    for _ in range(3):
+        A.spmv_dev(B.OP_ASSIGN, None, xs.ptr, y.ptr)
+    B._check(L.smm_sync(), "sync")
+    t = time.perf_counter()
+    for _ in range(reps):
+        A.spmv_dev(B.OP_ASSIGN, None, xs.ptr, y.ptr)
+    B._check(L.smm_sync(), "sync")
+    return (time.perf_counter() - t) * 1e3 / reps
+
+
+def configs_report(smm, B, L, peak, which=(1, 2, 3, 4), modes=("fast", "tree")):
+    """BASELINE.json configs[0..3] at full size (config 5 is the headline above)."""
+    golden = golden_fullsize()
+    out = []
+    SGS = smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL
+    if 1 in which:
+        A = smm.CSRMatrix.generate(B.GEN_POISSON2D, 1024, 1024)
+        out.append(run_config(smm, B, L, "1: ConjugateGradient, 2D 5-point Poisson 1024^2, eps 1e-6, b=A*1", "1", "cg", A, None, "ones", 1e-6, -1, modes, peak, golden))
+        del A
+    if 2 in which:
+        A = smm.CSRMatrix.generate(B.GEN_CONVDIFF3D, 128, 128, 128, 0.5)
+        out.append(run_config(smm, B, L, "2: BiCGStab, 3D convection-diffusion 128^3, no preconditioner, eps 1e-6, b=A*x*", "2", "bicgstab", A, None, "xstar", 1e-6, -1, modes, peak, golden))
+        del A
+    if 3 in which:
+        A = smm.CSRMatrix.generate(B.GEN_CONVDIFF3D, 256, 256, 256, 0.5)
+        t = time.perf_counter()
+        M = A.getPreconditioner(SGS)
+        setup = time.perf_counter() - t
+        out.append(run_config(smm, B, L, "3: BiCGStab + getPreconditioner() (SGS), 3D convection-diffusion 256^3, eps 1e-6, b=A*x*", "3", "bicgstab", A, M, "xstar", 1e-6, -1, modes, peak, golden, setup_s=setup))
+        del M, A
+    if 4 in which:
+        A = smm.CSRMatrix.generate(B.GEN_POWERLAW, 8388608)
+        for fn in ("cgs", "bicgsym"):
+            out.append(run_config(smm, B, L, f"4: {fn} SpMV-bound sweep, power-law rows (8.4 M rows, 12..34755 entries per row), 100 iterations, eps 0, b=A*x*",
+                                  None, fn, A, None, "xstar", 0.0, 100, ("fast",), peak, golden))
+        del A
+    return out
+
+
 def run_b200(args):
     import torch
 
@@ -360,17 +537,41 @@ def run_b200(args):
     iter_gbs = iter_bytes * value / 1e9
     kernel_sum = ms_spmv + ms_xr + ms_p
 
+    # --- parity where the driver runs it: the same problem solved to convergence (eps 1e-6) in the reference's summation
+    # order, compared bit for bit with the golden record of the reference's multithreaded arithmetic
+    parity = None
+    if not args.no_parity:
+        x.zero_()
+        opts_t = B._Options()
+        opts_t.reduction_mode = B.REDUCE_REFERENCE_TREE
+        info_t = B._Info()
+        B._check(L.smm_solve_cg_dev(A.handle, b.data_ptr(), x.data_ptr(), x.data_ptr(), -1, 1e-6, C.byref(opts_t), C.byref(info_t), sp), "smm_solve_cg_dev (parity)")
+        torch.cuda.synchronize()
+        xh = x.cpu().numpy()
+        sb, xb = x_checksum(xh)
+        parity = parity_record(golden_fullsize().get("5") if grid == 512 else None, info_t.status, info_t.iterations, info_t.residual, sb, xb,
+                               float(np.max(np.abs(xh - 1.0))))
+        parity["it_per_s"] = info_t.iterations / info_t.seconds_solve if info_t.seconds_solve > 0 else None
+        if parity["it_per_s"]:
+            parity["frac_of_peak"] = bytes_cg_iteration(rows, nnz) * parity["it_per_s"] / 1e9 / measured_peak_gbs()[0]
+        del xh
+
+    del hb, hx, x, b
+    A = None
+    torch.cuda.empty_cache()
+    configs = None
+    if not args.no_configs:
+        configs = configs_report(smm, B, L, measured_peak_gbs()[0])
+
     cpu = None
     if not args.no_cpu:
-        del hb, hx
         cpu = cpu_baseline(grid, args.cpu_budget)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": solve_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ConjugateGradient float, 3D 7-point Poisson {grid}^3, b=A*1, x0=0 (BASELINE configs[4])",
-                   "grid": grid, "rows": rows, "nnz": nnz, "iterations_per_step": iters, "eps": 0.0,
+        "config": {**workload_config(grid, iters),
                    "parallelism": "1 GPU", "driver": args.driver, "reductions": "fast (fused, deterministic two-stage)" if args.reduction == "fast" else "reference tree (bit-identical to the reference's multithreaded build)",
                    "l2": f"working set {(8 * nnz + 24 * rows) / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
                    "setup_s": round(setup_s, 3)},
@@ -379,13 +580,18 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "spmv_rows_kernel<1> (Ap = A p, p.Ap fused; TMA-staged, 1 lane per row)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes("spmv_rows", grid), "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes("spmv_rows", grid),
+                     "traffic_source": TRAFFIC_SOURCE if grid == 512 else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": ms_spmv,
                      "share_of_iteration": ms_spmv / kernel_sum if kernel_sum > 0 else None},
         "iteration": {"algorithmic_bytes": iter_bytes, "achieved_gbs": iter_gbs, "frac_of_peak": iter_gbs / peak,
                       "ms_spmv_dot": ms_spmv, "ms_xr_update": ms_xr, "ms_p_update": ms_p,
                       "ms_per_iteration": solve_ms / iters, "final_rr": final_rr, "x_mid": x_host_check},
         "spmv_effective_gbs": achieved,
+        "parity": parity,
+        "configs": configs,
+        "fast_mode_note": "fast-mode iteration counts are at or below the reference's (fewer is allowed: SURVEY 7 hard part 1; the reference's own two "
+                          "builds differ by 2x); the reference-order mode reproduces its counts and bits exactly (parity / configs[].runs[].parity)",
         "cpu_baseline": cpu,
     }
     if rank == 0:
@@ -404,6 +610,8 @@ def main():
     ap.add_argument("--reduction", default="fast", choices=["fast", "tree"],
                     help="tree: the reference's summation order (bit-identical to its multithreaded build), also across GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the reference-order solve to convergence")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 1-4 (N = 1 only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -209,6 +209,12 @@ int smm_dist_create(int rank, int nranks, int64_t global_rows, int64_t row_begin
                     smm_dist_t** out);
 int smm_dist_info(const smm_dist_t* d, int64_t* ranges4, void* ipc_handle64);
 int smm_dist_connect(smm_dist_t* d, const int64_t* all_ranges /* [nranks][4] */, const void* all_handles /* [nranks][64] */);
+/* Single-process variant of smm_dist_connect: all[r] is rank r's handle, each created in THIS process on its own device
+ * (smm_set_device before smm_csr_create / smm_dist_create).  The devices are made peer-accessible and address each other's
+ * blocks directly: no IPC handles, no second process. */
+int smm_dist_connect_local(smm_dist_t** all, int nranks);
+/* y_local = A_local * x with the halo of x exchanged.  Calls need no barrier between them: every exchange is acknowledged
+ * by its consumers, and a rank pushes only after the previous halo it sent has been read. */
 int smm_dist_spmv_dev(smm_dist_t* d, const float* x_local_dev, float* y_local_dev, void* stream);
 int smm_dist_solve_cg(smm_dist_t* d, const float* b_dev, const float* x0_dev, float* x_dev, int maxIterations, float eps,
                       const smm_solve_options* opts, smm_solve_info* info, void* stream);

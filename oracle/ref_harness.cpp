@@ -53,6 +53,15 @@ int smm_ref_threads(void) {
 #endif
 }
 
+// torchrun exports OMP_NUM_THREADS=1 to every rank; the timing harness asks for all host cores explicitly
+void smm_ref_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int smm_ref_multithreaded(void) {
 #if defined(SMM_MULTITHREADING)
     return 1;

@@ -34,6 +34,14 @@ int smm_oracle_threads(void) {
 #endif
 }
 
+void smm_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 void smm_oracle_free(void *p) { free(p); }
 
 /* ------------------------------------------------------------------------------------------------

@@ -122,6 +122,8 @@ void smm_oracle_gen_xstar(int64_t n, uint64_t seed, float *x);
 
 /* Number of OpenMP threads the row/vector loops use (1 if built without OpenMP). */
 int smm_oracle_threads(void);
+/* Override OMP_NUM_THREADS (torchrun exports 1 to every rank; the timing legs want all host cores). */
+void smm_oracle_set_threads(int n);
 
 #ifdef __cplusplus
 }

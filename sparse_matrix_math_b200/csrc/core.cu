@@ -7,7 +7,10 @@
 #include "epilogue.cuh"
 #include "smm_internal.cuh"
 
-long long g_smm_launches = 0;
+std::atomic<long long> g_smm_launches{0};
+thread_local long long t_smm_launches = 0;
+thread_local bool t_smm_capturing = false;
+std::mutex g_smm_attr_mu;
 
 namespace {
 thread_local char g_err[512] = "";
@@ -102,7 +105,7 @@ extern "C" {
 
 int smm_abi_version(void) { return SMM_B200_ABI_VERSION; }
 const char* smm_last_error(void) { return g_err; }
-long long smm_kernel_launch_count(void) { return g_smm_launches; }
+long long smm_kernel_launch_count(void) { return g_smm_launches.load(); }
 
 int smm_device_count(int* count) {
     SMM_CUDA(cudaGetDeviceCount(count));

@@ -70,6 +70,36 @@ __global__ void halo_push_empty_kernel(DistComm* comm, const SolveState* st) {
     comm->push_seq = comm->push_seq + 1u;
 }
 
+// rows that read entries outside the owned part [own_lo, own_hi) of the extended vector
+__global__ void halo_rows_kernel(const int32_t* __restrict__ start, const int32_t* __restrict__ positions, int rows, int own_lo, int own_hi,
+                                 int* __restrict__ row_lo, int* __restrict__ row_hi) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    bool below = false, above = false;
+    for (int k = start[r]; k < start[r + 1]; ++k) { const int c = positions[k]; below |= c < own_lo; above |= c >= own_hi; }
+    if (below) atomicMax(row_lo, r + 1);
+    if (above) atomicMin(row_hi, r);
+}
+
+// stand-alone SpMV (no reduction between two exchanges): wait until every destination has consumed the previous halo
+__global__ void halo_credit_wait_kernel(DistComm* comm, const int* __restrict__ dests, int ndests) {
+    const int k = threadIdx.x;
+    if (k >= ndests) return;
+    const unsigned int want = comm->ack_seq;
+    const unsigned int* a = comm->acks[comm->rank] + dests[k];
+    unsigned int polls = 0;
+    while ((int)(ld_acquire_sys_u32(a) - want) < 0) {
+        if (++polls >= SMM_DIST_POLL_LIMIT) { comm->error = 1; break; }
+    }
+}
+// ... and tell every source that this rank's SpMV has read what they pushed
+__global__ void halo_ack_kernel(DistComm* comm, const int* __restrict__ sources, int nsources) {
+    const unsigned int seq = comm->ack_seq + 1u;
+    __syncthreads();
+    if ((int)threadIdx.x < nsources) st_release_sys_u32(comm->acks[sources[threadIdx.x]] + comm->rank, seq);
+    if (threadIdx.x == 0) comm->ack_seq = seq;
+}
+
 __global__ void halo_wait_kernel(DistComm* comm, const int* __restrict__ sources, int nsources, SolveState* st) {
     if (st != nullptr && st->done) return;
     const int k = threadIdx.x;
@@ -85,7 +115,7 @@ __global__ void halo_wait_kernel(DistComm* comm, const int* __restrict__ sources
 }  // namespace
 
 // ---- used by solvers.cu --------------------------------------------------------------------------------------
-int smm_dist_exchange_async(smm_dist* d, SolveState* st, cudaStream_t s) {
+int smm_dist_exchange_async(smm_dist* d, SolveState* st, cudaStream_t s, bool wait_kernel) {
     if (d->nranks == 1) return SMM_OK;
     if (!d->send.empty()) {
         long long blocks = 0;
@@ -95,8 +125,16 @@ int smm_dist_exchange_async(smm_dist* d, SolveState* st, cudaStream_t s) {
     } else {
         halo_push_empty_kernel<<<1, 1, 0, s>>>(d->comm_dev, st);
     }
+    if (wait_kernel) halo_wait_kernel<<<1, 32, 0, s>>>(d->comm_dev, d->sources_dev, (int)d->sources.size(), st);
+    SMM_COUNT_LAUNCH(wait_kernel ? 2 : 1);
+    SMM_CUDA(cudaGetLastError());
+    return SMM_OK;
+}
+
+int smm_dist_wait_async(smm_dist* d, SolveState* st, cudaStream_t s) {
+    if (d->nranks == 1) return SMM_OK;
     halo_wait_kernel<<<1, 32, 0, s>>>(d->comm_dev, d->sources_dev, (int)d->sources.size(), st);
-    SMM_COUNT_LAUNCH(2);
+    SMM_COUNT_LAUNCH(1);
     SMM_CUDA(cudaGetLastError());
     return SMM_OK;
 }
@@ -174,24 +212,18 @@ int smm_dist_info(const smm_dist_t* d, int64_t* ranges4, void* ipc_handle64) {
     return SMM_OK;
 }
 
-int smm_dist_connect(smm_dist_t* d, const int64_t* all_ranges, const void* all_handles) {
-    if (!d || !all_ranges || !all_handles) return SMM_E_INVALID;
-    SMM_CUDA(cudaSetDevice(d->device));
+// peer_base[] filled in (IPC-mapped or peer-accessible pointers): derive the mailbox / flag addresses, the send plan and
+// the rows that read halo entries
+static int dist_finish_connect(smm_dist_t* d, const int64_t* all_ranges) {
     const int P = d->nranks, me = d->rank;
     DistComm c;
     memset(&c, 0, sizeof c);
     c.rank = me; c.nranks = P;
-    for (int r = 0; r < P; ++r) {
-        if (r == me) { d->peer_base[r] = d->shared; }
-        else {
-            cudaIpcMemHandle_t h;
-            memcpy(&h, (const char*)all_handles + 64 * r, 64);
-            SMM_CUDA(cudaIpcOpenMemHandle(&d->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
-        }
-    }
-    // every rank lays its block out as [ext | mail | flags] with its own window length
+    // every rank lays its block out as [ext | mail | flags, acks] with its own window length
     d->send.clear(); d->dests.clear(); d->sources.clear();
     std::vector<SegDev> segs;
+    HaloPushDev hp;
+    memset(&hp, 0, sizeof hp);
     long long first_block = 0;
     for (int r = 0; r < P; ++r) {
         const long long rb = all_ranges[4 * r], re = all_ranges[4 * r + 1], lo = all_ranges[4 * r + 2], hi = all_ranges[4 * r + 3];
@@ -200,8 +232,8 @@ int smm_dist_connect(smm_dist_t* d, const int64_t* all_ranges, const void* all_h
         char* base = (char*)d->peer_base[r];
         c.mail[r] = reinterpret_cast<unsigned long long*>(base + ext_bytes);
         c.flags[r] = reinterpret_cast<unsigned int*>(base + ext_bytes + ((mail_bytes + 255) & ~(size_t)255));
+        c.acks[r] = c.flags[r] + 32;
         if (r == me) continue;
-        (void)rb; (void)re;
         // what rank r needs from me: my owned rows inside its window
         const long long a = d->row_begin > lo ? d->row_begin : lo;
         const long long b = d->row_end < hi ? d->row_end : hi;
@@ -215,12 +247,18 @@ int smm_dist_connect(smm_dist_t* d, const int64_t* all_ranges, const void* all_h
             sg.first_block = first_block;
             first_block += (sg.len + PUSH_ELEMS_PER_BLOCK - 1) / PUSH_ELEMS_PER_BLOCK;
             segs.push_back(sg);
+            hp.segs[hp.nsegs].dst = sg.dst;
+            hp.segs[hp.nsegs].begin = a - d->row_begin;        // relative to this rank's owned entries
+            hp.segs[hp.nsegs].len = b - a;
+            hp.dests[hp.nsegs] = r;
+            hp.nsegs++;
         }
         // what I need from rank r: its owned rows inside my window
         const long long a2 = rb > d->lo ? rb : d->lo;
         const long long b2 = re < d->hi ? re : d->hi;
         if (b2 > a2) d->sources.push_back(r);
     }
+    hp.ndests = hp.nsegs;
     if (!segs.empty()) {
         SMM_CUDA(cudaMalloc(&d->seg_dev, sizeof(SegDev) * segs.size()));
         SMM_CUDA(cudaMemcpy(d->seg_dev, segs.data(), sizeof(SegDev) * segs.size(), cudaMemcpyHostToDevice));
@@ -230,21 +268,103 @@ int smm_dist_connect(smm_dist_t* d, const int64_t* all_ranges, const void* all_h
     if (!d->dests.empty()) SMM_CUDA(cudaMemcpy(d->dests_dev, d->dests.data(), sizeof(int) * d->dests.size(), cudaMemcpyHostToDevice));
     if (!d->sources.empty()) SMM_CUDA(cudaMemcpy(d->sources_dev, d->sources.data(), sizeof(int) * d->sources.size(), cudaMemcpyHostToDevice));
     SMM_CUDA(cudaMemcpy(d->comm_dev, &c, sizeof c, cudaMemcpyHostToDevice));
+    // rows [0, halo_row_lo) and [halo_row_hi, rows) read halo entries: the SpMV multiplies the others while the pushes travel
+    const int rows = d->local->rows;
+    int bounds[2] = {0, rows};
+    if (rows > 0 && d->local->nnz > 0) {
+        int* bd = nullptr;
+        SMM_CUDA(cudaMalloc(&bd, sizeof bounds));
+        SMM_CUDA(cudaMemcpy(bd, bounds, sizeof bounds, cudaMemcpyHostToDevice));
+        halo_rows_kernel<<<(rows + 255) / 256, 256>>>(d->local->start, d->local->positions, rows, (int)d->own_off, (int)(d->own_off + rows), bd, bd + 1);
+        SMM_COUNT_LAUNCH(1);
+        SMM_CUDA(cudaMemcpy(bounds, bd, sizeof bounds, cudaMemcpyDeviceToHost));
+        cudaFree(bd);
+    }
+    d->halo_row_lo = bounds[0]; d->halo_row_hi = bounds[1];
+    hp.comm = d->comm_dev; hp.ticket = d->ticket;
+    HaloWaitDev hw;
+    memset(&hw, 0, sizeof hw);
+    hw.nsources = (int)d->sources.size();
+    for (int k = 0; k < hw.nsources; ++k) hw.sources[k] = d->sources[k];
+    hw.row_lo = bounds[0]; hw.row_hi = bounds[1]; hw.comm = d->comm_dev;
+    SMM_CUDA(cudaMalloc(&d->push_dev, sizeof hp));
+    SMM_CUDA(cudaMalloc(&d->wait_dev, sizeof hw));
+    SMM_CUDA(cudaMemcpy(d->push_dev, &hp, sizeof hp, cudaMemcpyHostToDevice));
+    SMM_CUDA(cudaMemcpy(d->wait_dev, &hw, sizeof hw, cudaMemcpyHostToDevice));
     d->connected = true;
     return SMM_OK;
 }
 
-// y_local = A_local * x (exchange of x's halo included); x_local_dev, y_local_dev hold this rank's owned rows
+int smm_dist_connect(smm_dist_t* d, const int64_t* all_ranges, const void* all_handles) {
+    if (!d || !all_ranges || !all_handles) return SMM_E_INVALID;
+    SMM_CUDA(cudaSetDevice(d->device));
+    for (int r = 0; r < d->nranks; ++r) {
+        if (r == d->rank) { d->peer_base[r] = d->shared; }
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)all_handles + 64 * r, 64);
+            SMM_CUDA(cudaIpcOpenMemHandle(&d->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    d->ipc_mapped = true;
+    return dist_finish_connect(d, all_ranges);
+}
+
+// Single-process variant: all[r] is rank r's handle, created in THIS process on its own device.  The devices are made
+// peer-accessible (cudaDeviceEnablePeerAccess) and every rank addresses the others' blocks directly: no IPC handles, no
+// second process, no torch.distributed.  The solvers then run one host thread per device (smm_group_*).
+int smm_dist_connect_local(smm_dist_t** all, int nranks) {
+    if (!all || nranks < 1 || nranks > SMM_MAX_RANKS) return SMM_E_INVALID;
+    std::vector<int64_t> ranges(4 * (size_t)nranks);
+    for (int r = 0; r < nranks; ++r) {
+        if (!all[r] || all[r]->rank != r || all[r]->nranks != nranks) { smm_set_error("smm_dist_connect_local: handle %d is not rank %d of %d", r, r, nranks); return SMM_E_INVALID; }
+        ranges[4 * r] = all[r]->row_begin; ranges[4 * r + 1] = all[r]->row_end; ranges[4 * r + 2] = all[r]->lo; ranges[4 * r + 3] = all[r]->hi;
+    }
+    for (int r = 0; r < nranks; ++r) {
+        SMM_CUDA(cudaSetDevice(all[r]->device));
+        for (int q = 0; q < nranks; ++q) {
+            if (q == r || all[q]->device == all[r]->device) continue;
+            int can = 0;
+            SMM_CUDA(cudaDeviceCanAccessPeer(&can, all[r]->device, all[q]->device));
+            if (!can) { smm_set_error("smm_dist_connect_local: device %d cannot access device %d", all[r]->device, all[q]->device); return SMM_E_CUDA; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(all[q]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return smm_cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        }
+    }
+    for (int r = 0; r < nranks; ++r) {
+        SMM_CUDA(cudaSetDevice(all[r]->device));
+        for (int q = 0; q < nranks; ++q) all[r]->peer_base[q] = all[q]->shared;
+        all[r]->ipc_mapped = false;
+        SMM_TRY(dist_finish_connect(all[r], ranges.data()));
+    }
+    return SMM_OK;
+}
+
+// y_local = A_local * x (exchange of x's halo included); x_local_dev, y_local_dev hold this rank's owned rows.
+// Calls need no barrier between them: the push waits until every destination has acknowledged the previous call's halo.
 int smm_dist_spmv_dev(smm_dist_t* d, const float* x_local_dev, float* y_local_dev, void* stream) {
     if (!d || !d->connected) { smm_set_error("smm_dist_spmv_dev: not connected"); return SMM_E_STATE; }
     SMM_CUDA(cudaSetDevice(d->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : smm_default_stream();
     const long long n = d->row_end - d->row_begin;
     if (n) SMM_CUDA(cudaMemcpyAsync(d->ext + d->own_off, x_local_dev, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, s));
-    SMM_TRY(smm_dist_exchange_async(d, nullptr, s));
+    const bool multi = d->nranks > 1;
+    if (multi) {
+        halo_credit_wait_kernel<<<1, 32, 0, s>>>(d->comm_dev, d->dests_dev, (int)d->dests.size());
+        SMM_COUNT_LAUNCH(1);
+    }
+    const bool fused = multi && smm_spmv_rows_lanes(d->local, 0) > 0;
+    SMM_TRY(smm_dist_exchange_async(d, nullptr, s, !fused));
     SpmvArgs a;
     a.m = d->local; a.op = SMM_OP_ASSIGN; a.mult = d->ext; a.out = y_local_dev;
+    a.halo_wait = fused ? d->wait_dev : nullptr;
     SMM_TRY(smm_launch_spmv(a, s));
+    if (multi) {
+        halo_ack_kernel<<<1, 32, 0, s>>>(d->comm_dev, d->sources_dev, (int)d->sources.size());
+        SMM_COUNT_LAUNCH(1);
+        SMM_CUDA(cudaGetLastError());
+    }
     return SMM_OK;
 }
 
@@ -287,8 +407,9 @@ int smm_dist_destroy(smm_dist_t* d) {
     if (!d) return SMM_OK;
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
-    for (int r = 0; r < d->nranks; ++r) if (r != d->rank && d->peer_base[r]) cudaIpcCloseMemHandle(d->peer_base[r]);
+    if (d->ipc_mapped) for (int r = 0; r < d->nranks; ++r) if (r != d->rank && d->peer_base[r]) cudaIpcCloseMemHandle(d->peer_base[r]);
     cudaFree(d->shared); cudaFree(d->comm_dev); cudaFree(d->ticket); cudaFree(d->seg_dev); cudaFree(d->dests_dev); cudaFree(d->sources_dev);
+    cudaFree(d->push_dev); cudaFree(d->wait_dev);
     delete d;
     return SMM_OK;
 }

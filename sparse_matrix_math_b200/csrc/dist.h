@@ -26,8 +26,15 @@ struct smm_dist {
     int* dests_dev = nullptr;
     int* sources_dev = nullptr;
     unsigned int* ticket = nullptr;
+    HaloPushDev* push_dev = nullptr;     // the send plan for kernels that push their own output (vecops.cu)
+    HaloWaitDev* wait_dev = nullptr;     // sources + the rows that read halo entries, for the SpMV that waits by itself (spmv.cu)
+    int halo_row_lo = 0, halo_row_hi = 0; // rows [0, lo) and [hi, rows) may read halo entries
+    bool ipc_mapped = false;             // peers mapped with CUDA IPC (one process per GPU) rather than peer access (one process)
     bool connected = false;
 };
 
-// push this rank's boundary entries of d->ext to the peers and wait for theirs (two launches on s)
-int smm_dist_exchange_async(smm_dist* d, SolveState* st, cudaStream_t s);
+// Push this rank's boundary entries of d->ext to the peers (one launch on s).  wait_kernel: also launch the kernel that
+// spins on the peers' flags; pass false when the consumer is an SpMV launched with SpmvArgs::halo_wait = d->wait_dev.
+int smm_dist_exchange_async(smm_dist* d, SolveState* st, cudaStream_t s, bool wait_kernel = true);
+// the wait kernel alone (the push was done by the kernel that produced the operand)
+int smm_dist_wait_async(smm_dist* d, SolveState* st, cudaStream_t s);

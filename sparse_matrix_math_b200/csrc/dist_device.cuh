@@ -7,9 +7,16 @@
 //     the same bits, so all ranks take the same branches without any further agreement.  Four mailbox sets cycle,
 //     and a rank cannot run two reductions ahead of a peer (it needs that peer's contribution), so a set is never
 //     overwritten before it has been read.
-//   * halo exchange: a push kernel stores the boundary entries of the local vector straight into the peers'
-//     extended vectors and then raises a per-source flag (release, system scope); a wait kernel spins on the flags
-//     (acquire, system scope) before the SpMV that gathers the halo.
+//   * halo exchange: the boundary entries of the local vector are stored straight into the peers' extended vectors
+//     and a per-source flag is raised (release, system scope) -- by the CTAs of the CG p-update themselves
+//     (HaloPushDev, vecops.cu) or by a push kernel for every other operand; the consumer is the SpMV: its rows kernel
+//     schedules the rows that read no halo FIRST and only the warps that reach a boundary row group spin on the flags
+//     (acquire, system scope; HaloWaitDev, spmv.cu), gathering those groups' operands past L1.  Other SpMV kernels
+//     are preceded by a wait kernel.
+//   * back-pressure: inside the solvers a fused all-reduce sits between two exchanges, so a rank cannot push again
+//     before every peer's SpMV has finished reading its halo.  The stand-alone smm_dist_spmv_dev has no such
+//     reduction: there the consumer acknowledges every exchange (acks[], release) and the pusher waits for the
+//     acknowledgement of the previous one before it overwrites a peer's halo.
 // Every spin is bounded; on expiry the error flag is set and the solve is marked done so nothing can hang.
 #pragma once
 #include <stdint.h>
@@ -25,6 +32,26 @@ struct DistComm {
     int tree_order;                             // 1: combine the ranks' values pairwise (reference-tree mode), 0: in rank order
     unsigned long long* mail[SMM_MAX_RANKS];    // mail[d]: rank d's mailbox [4 sets][nranks][2] (mail[rank] is local)
     unsigned int* flags[SMM_MAX_RANKS];         // flags[d]: rank d's flag array [nranks]; this rank writes flags[d][rank]
+    unsigned int* acks[SMM_MAX_RANKS];          // acks[d]: rank d's ack array [nranks]; this rank writes acks[d][rank] (stand-alone SpMV)
+    unsigned int ack_seq;                       // stand-alone SpMV calls completed
+};
+
+// halo push fused into an element-wise kernel: segment s covers elements [begin, begin + len) of the kernel's first
+// output (this rank's owned entries) and goes to dst[0 .. len) in a peer's extended vector
+struct HaloSeg { float* dst; long long begin; long long len; };
+struct HaloPushDev {
+    int nsegs, ndests;
+    HaloSeg segs[SMM_MAX_RANKS];
+    int dests[SMM_MAX_RANKS];
+    DistComm* comm;
+    unsigned int* ticket;
+};
+// halo wait fused into the SpMV: rows [0, row_lo) and [row_hi, rows) may read halo entries
+struct HaloWaitDev {
+    int nsources;
+    int sources[SMM_MAX_RANKS];
+    int row_lo, row_hi;
+    DistComm* comm;
 };
 
 #ifdef __CUDACC__
@@ -43,6 +70,20 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p
     unsigned int v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+// spin until every source rank has raised its flag for the current exchange; false when the bounded wait expired
+__device__ __forceinline__ bool dist_halo_wait(const HaloWaitDev* w) {
+    DistComm* c = w->comm;
+    const unsigned int want = c->push_seq;                  // my own push of this exchange is already counted
+    const unsigned int* f = c->flags[c->rank];
+    for (int k = 0; k < w->nsources; ++k) {
+        unsigned int polls = 0;
+        while ((int)(ld_acquire_sys_u32(f + w->sources[k]) - want) < 0) {
+            if (++polls >= SMM_DIST_POLL_LIMIT) { c->error = 1; return false; }
+        }
+    }
+    return true;
 }
 
 // Called by ONE thread per rank.  Sums t0 and t1 over all ranks: in rank order, or pairwise in reference-tree mode.

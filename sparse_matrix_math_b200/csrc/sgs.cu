@@ -395,8 +395,7 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
     }
     const long long nfill = std::max(p->threads_fwd, p->threads_bwd);
     sgs_fill_kernel<<<(unsigned)((nfill + 255) / 256), 256, 0, s>>>(p->yperm, p->threads_fwd, p->xperm, p->threads_bwd, p->tickets, state);
-    static int ctas_per_sm = 0;
-    if (!ctas_per_sm) { const char* e = getenv("SMM_B200_SGS_CTAS_PER_SM"); ctas_per_sm = e ? atoi(e) : 8; if (ctas_per_sm < 1) ctas_per_sm = 1; }
+    static const int ctas_per_sm = [] { const char* e = getenv("SMM_B200_SGS_CTAS_PER_SM"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : v; }();
     // SGS reads A's current values; an IC(0) factor is frozen at init() like the reference's ic0Val
     const unsigned long long want_version = p->kind != 0 ? 0ull : m->values_version;
     if (p->values_version != want_version) {                   // matrix values changed since the packed copies were gathered
@@ -411,13 +410,9 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
         SMM_COUNT_LAUNCH(2);
         pm->values_version = want_version;
     }
-    static unsigned int sleep_first = 0u, sleep_later = 64u;
-    static bool sleeps_read = false;
-    if (!sleeps_read) {                                        // tuning knobs (tools/sgs_bench.py)
-        if (const char* e = getenv("SMM_B200_SGS_SLEEP_FIRST")) sleep_first = (unsigned int)atoi(e);
-        if (const char* e = getenv("SMM_B200_SGS_SLEEP_LATER")) sleep_later = (unsigned int)atoi(e);
-        sleeps_read = true;
-    }
+    // tuning knobs (tools/sgs_bench.py), read once
+    static const unsigned int sleep_first = [] { const char* e = getenv("SMM_B200_SGS_SLEEP_FIRST"); return e ? (unsigned int)atoi(e) : 0u; }();
+    static const unsigned int sleep_later = [] { const char* e = getenv("SMM_B200_SGS_SLEEP_LATER"); return e ? (unsigned int)atoi(e) : 64u; }();
     if (p->tiled) {
         SMM_TRY(smm_sgs_tiles_launch(p, rhs_dev, x_dev, state, ctas_per_sm, sleep_first, sleep_later, s));
     } else {

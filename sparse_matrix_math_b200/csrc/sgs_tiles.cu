@@ -500,11 +500,17 @@ void launch_tiles(const smm_precond* p, const TileArgs& F, const TileArgs& B, co
                   cudaStream_t s) {
     const long long nblocks = (F.ntiles + TILE_WARPS - 1) / TILE_WARPS;
     // persistent grid: no more CTAs than can be resident (the rest would only find the tickets used up)
-    static int resident = 0;
-    if (!resident) {
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgs_tile_kernel<false, false, TILE_WARPS>, TILE_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-        resident = per_sm * p->m->sm_count;
+    static int resident_dev[SMM_MAX_DEVICES] = {0};            // occupancy is a per-device property
+    int resident;
+    {
+        std::lock_guard<std::mutex> lk(g_smm_attr_mu);
+        int& r = resident_dev[p->m->device % SMM_MAX_DEVICES];
+        if (!r) {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgs_tile_kernel<false, false, TILE_WARPS>, TILE_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+            r = per_sm * p->m->sm_count;
+        }
+        resident = r;
     }
     if (cap > resident) cap = resident;
     const unsigned grid = (unsigned)(nblocks < cap ? nblocks : cap);

@@ -4,6 +4,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "smm_b200.h"
 
 // ---------------------------------------------------------------------------------------------------
@@ -24,8 +27,20 @@ int smm_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         if (_rc != SMM_OK) return _rc; \
     } while (0)
 
-extern long long g_smm_launches;           // kernels launched by this library (host-side counter)
-#define SMM_COUNT_LAUNCH(n) (g_smm_launches += (n))
+// kernels launched by this library: process-wide (smm_kernel_launch_count) and by the calling thread (a solve's own count;
+// single-process multi-GPU solves run one host thread per device).  Launches recorded into a CUDA graph are not counted
+// while they are captured but once per graph launch.
+extern std::atomic<long long> g_smm_launches;
+extern thread_local long long t_smm_launches;
+extern thread_local bool t_smm_capturing;
+#define SMM_COUNT_LAUNCH(n)                                                   \
+    do {                                                                      \
+        if (!t_smm_capturing) { g_smm_launches.fetch_add((n), std::memory_order_relaxed); t_smm_launches += (n); } \
+    } while (0)
+
+// per-device caches of launch attributes (a process may drive several GPUs, from several threads)
+constexpr int SMM_MAX_DEVICES = 64;
+extern std::mutex g_smm_attr_mu;
 
 cudaStream_t smm_default_stream();
 
@@ -130,8 +145,10 @@ struct SpmvArgs {
     float* copy1 = nullptr;  // optional extra copies of out[row] (p = r, r0 = r, u = r ...)
     float* copy2 = nullptr;
     float* copy3 = nullptr;
+    const void* halo_wait = nullptr;   // HaloWaitDev* (device): fused halo wait of the multi-GPU SpMV (rows kernel only)
 };
 int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s);
+int smm_spmv_rows_lanes(const smm_csr* m, int exact);
 
 // fused element-wise kernels (vecops.cu); operand order per kind is documented at each functor
 enum VecKind {
@@ -148,6 +165,7 @@ enum VecKind {
     VEC_COPY3,         // in: a               out: o0 o1 o2
 };
 struct VecArgs {
+    const void* halo_push = nullptr;   // HaloPushDev* (device): out[0]'s boundary entries also go to the peers (VEC_CG_P / VEC_COPY3)
     long long n = 0;
     const float* in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float* out[3] = {nullptr, nullptr, nullptr};

@@ -48,26 +48,33 @@ struct Ctx {
     int kernels_per_iteration = 0;
 };
 
+// multi-GPU: can the SpMV wait for the halo itself (rows kernel), or does it need the wait kernel in front of it?
+bool fused_wait(const Ctx& c) { return c.dist && c.dist->nranks > 1 && c.dist->wait_dev && smm_spmv_rows_lanes(c.a, c.exact ? 1 : 0) > 0; }
+
 int spmv(Ctx& c, int op, const float* lhs, const float* mult, float* out, int reduce, int finish, const float* aux,
          float* c1 = nullptr, float* c2 = nullptr, float* c3 = nullptr) {
-    if (c.dist && mult != c.dist->ext) {
-        // multi-GPU: the operand's owned entries go into the extended vector, the halo comes from the peers
-        smm_dist* d = c.dist;
-        if (mult != d->ext + d->own_off)
-            SMM_CUDA(cudaMemcpyAsync(d->ext + d->own_off, mult, sizeof(float) * (size_t)c.n, cudaMemcpyDeviceToDevice, c.s));
-        SMM_TRY(smm_dist_exchange_async(d, c.st, c.s));
-        mult = d->ext;
-    }
     SpmvArgs a;
+    if (c.dist) {
+        smm_dist* d = c.dist;
+        if (mult != d->ext) {
+            // the operand's owned entries go into the extended vector, the halo comes from the peers
+            if (mult != d->ext + d->own_off)
+                SMM_CUDA(cudaMemcpyAsync(d->ext + d->own_off, mult, sizeof(float) * (size_t)c.n, cudaMemcpyDeviceToDevice, c.s));
+            SMM_TRY(smm_dist_exchange_async(d, c.st, c.s, !fused_wait(c)));
+            mult = d->ext;
+        }   // else: the kernel that produced the operand has pushed its boundary already (CG's p)
+        if (fused_wait(c)) a.halo_wait = d->wait_dev;
+    }
     a.m = c.a; a.op = op; a.lhs = lhs; a.mult = mult; a.out = out; a.exact = c.exact ? 1 : 0;
     a.reduce = reduce; a.finish = finish; a.slot = 0; a.aux = aux; a.state = c.st;
     a.copy1 = c1; a.copy2 = c2; a.copy3 = c3;
     return smm_launch_spmv(a, c.s);
 }
 
-int vec(Ctx& c, int kind, int finish, std::initializer_list<const float*> in, std::initializer_list<float*> out) {
+int vec(Ctx& c, int kind, int finish, std::initializer_list<const float*> in, std::initializer_list<float*> out, bool push_halo = false) {
     VecArgs v;
     v.n = c.n; v.state = c.st; v.finish = finish; v.slot = 1; v.ws = c.ws;
+    if (push_halo && c.dist && c.dist->nranks > 1) v.halo_push = c.dist->push_dev;
     int i = 0;
     for (const float* p : in) v.in[i++] = p;
     i = 0;
@@ -90,35 +97,39 @@ int dots(Ctx& c, int finish, const float* a0, const float* b0, const float* a1 =
 // Multi-GPU CG: p lives inside the extended vector (owned part + halo); every SpMV operand is exchanged first.
 // The reductions are summed over the ranks inside the kernels' epilogues (dist_device.cuh), so the scalar state --
 // and with it every branch -- is bit-identical on all ranks.
+// p lives in the extended vector; the kernel that writes it (p = r at the start, the p update afterwards) stores its boundary
+// entries into the peers' extended vectors as well and raises the flags, and the next SpMV multiplies its interior rows while
+// those stores travel, waiting for the peers' flags only in the warps that reach a boundary row group: 3 launches per
+// iteration, like the single-GPU solve.
 int cg_init_dist(Ctx& c, const float* x0) {
     smm_dist* d = c.dist;
-    SMM_CUDA(cudaMemcpyAsync(d->ext + d->own_off, x0, sizeof(float) * (size_t)c.n, cudaMemcpyDeviceToDevice, c.s));
-    SMM_TRY(smm_dist_exchange_async(d, c.st, c.s));
     if (c.exact) {                                             // reference-tree mode: local tree, ranks joined pairwise
-        SMM_TRY(spmv(c, SMM_OP_SUB, c.b, d->ext, c.r, RED_NONE, FIN_NONE, nullptr));
+        SMM_TRY(spmv(c, SMM_OP_SUB, c.b, x0, c.r, RED_NONE, FIN_NONE, nullptr));
         SMM_TRY(dots(c, FIN_CG_INIT, c.r, c.r));
     } else
-    SMM_TRY(spmv(c, SMM_OP_SUB, c.b, d->ext, c.r, RED_OUT_OUT, FIN_CG_INIT, nullptr));
-    SMM_TRY(vec(c, VEC_COPY3, FIN_NONE, {c.r}, {c.p, c.p, c.p}));
-    return smm_dist_exchange_async(d, c.st, c.s);
+    SMM_TRY(spmv(c, SMM_OP_SUB, c.b, x0, c.r, RED_OUT_OUT, FIN_CG_INIT, nullptr));
+    SMM_TRY(vec(c, VEC_COPY3, FIN_NONE, {c.r}, {c.p, c.p, c.p}, true));
+    if (!fused_wait(c)) SMM_TRY(smm_dist_wait_async(d, c.st, c.s));
+    return SMM_OK;
 }
 int cg_iter_dist(Ctx& c) {
     smm_dist* d = c.dist;
+    const int extra = fused_wait(c) ? 0 : 1;
     if (c.exact) {
         SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, d->ext, c.ap, RED_NONE, FIN_NONE, nullptr));
         SMM_TRY(dots(c, FIN_CG_ALPHA, c.ap, c.p));
         SMM_TRY(vec(c, VEC_CG_XR, FIN_NONE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
         SMM_TRY(dots(c, FIN_CG_UPDATE, c.r, c.r));
-        SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}));
-        SMM_TRY(smm_dist_exchange_async(d, c.st, c.s));
-        c.kernels_per_iteration = 7;
+        SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}, true));
+        if (extra) SMM_TRY(smm_dist_wait_async(d, c.st, c.s));
+        c.kernels_per_iteration = 5 + extra;
         return SMM_OK;
     }
     SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, d->ext, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));
     SMM_TRY(vec(c, VEC_CG_XR, FIN_CG_UPDATE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
-    SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}));
-    SMM_TRY(smm_dist_exchange_async(d, c.st, c.s));
-    c.kernels_per_iteration = 5;
+    SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}, true));
+    if (extra) SMM_TRY(smm_dist_wait_async(d, c.st, c.s));
+    c.kernels_per_iteration = 3 + extra;
     return SMM_OK;
 }
 
@@ -307,9 +318,9 @@ int run_stream(Ctx& c, IterFn iter, long long budget, int check_every, long long
 
 int capture_iteration(Ctx& c, IterFn iter, cudaGraph_t* graph) {
     SMM_CUDA(cudaStreamBeginCapture(c.s, cudaStreamCaptureModeThreadLocal));
-    const long long before = g_smm_launches;
+    t_smm_capturing = true;                                   // captured, not launched: counted per graph launch
     int rc = iter(c);
-    g_smm_launches = before;                                  // captured, not launched: counted per graph launch
+    t_smm_capturing = false;
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(c.s, &g);
     if (rc != SMM_OK) { if (g) cudaGraphDestroy(g); return rc; }
@@ -333,7 +344,7 @@ int run_graph_chunked(Ctx& c, IterFn iter, long long budget, int check_every, lo
             if (e != cudaSuccess) rc = smm_cuda_fail(e, "cudaGraphLaunch", __FILE__, __LINE__);
         }
         *launches += m * c.kernels_per_iteration;
-        g_smm_launches += m * c.kernels_per_iteration;
+        g_smm_launches.fetch_add(m * c.kernels_per_iteration, std::memory_order_relaxed);
         done_iters += m;
         if (rc == SMM_OK) rc = poll_state(c);
         if (rc == SMM_OK && c.ws->state_host->done) break;
@@ -360,13 +371,13 @@ int run_graph_while(Ctx& c, IterFn iter, long long* launches) {
     cudaGraph_t body = np.conditional.phGraph_out[0];
     e = cudaStreamBeginCaptureToGraph(c.s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) { cudaGraphDestroy(g); return smm_cuda_fail(e, "cudaStreamBeginCaptureToGraph", __FILE__, __LINE__); }
-    const long long before = g_smm_launches;
+    t_smm_capturing = true;
     int rc = iter(c);
     if (rc == SMM_OK) {
         while_condition_kernel<<<1, 1, 0, c.s>>>(c.st, h);
         if (cudaGetLastError() != cudaSuccess) rc = SMM_E_CUDA;
     }
-    g_smm_launches = before;
+    t_smm_capturing = false;
     e = cudaStreamEndCapture(c.s, nullptr);
     if (rc != SMM_OK || e != cudaSuccess) {
         cudaGraphDestroy(g);
@@ -382,7 +393,7 @@ int run_graph_while(Ctx& c, IterFn iter, long long* launches) {
         // the body ran once per iteration plus possibly one no-op pass
         const long long it = c.ws->state_host->iterations;
         *launches += (it + 1) * (c.kernels_per_iteration + 1);
-        g_smm_launches += (it + 1) * (c.kernels_per_iteration + 1);
+        g_smm_launches.fetch_add((it + 1) * (c.kernels_per_iteration + 1), std::memory_order_relaxed);
     }
     cudaGraphExecDestroy(exec);
     cudaGraphDestroy(g);
@@ -475,7 +486,7 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
     SMM_CUDA(cudaMemcpyAsync(c.st, h, sizeof *h, cudaMemcpyHostToDevice, s));
 
     long long launches = 0;
-    const long long launches_before = g_smm_launches;
+    const long long launches_before = t_smm_launches;
     SMM_CUDA(cudaEventRecord(ws->ev0, s));
     IterFn iter = nullptr;
     long long budget = 0;
@@ -506,7 +517,7 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
                 SMM_TRY(stab_init(c)); iter = stab_iter; budget = max_it > 1 ? max_it : 1;         // H:2232/2277
                 break;
         }
-        launches += g_smm_launches - launches_before;
+        launches += t_smm_launches - launches_before;
         int rc = SMM_OK;
         if (budget > 0) {
             if (driver == SMM_DRIVER_GRAPH_WHILE) rc = run_graph_while(c, iter, &launches);

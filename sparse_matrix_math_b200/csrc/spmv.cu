@@ -33,6 +33,8 @@
 
 #include "smm_internal.cuh"
 
+struct HaloWaitDev;   // dist_device.cuh
+
 namespace {
 
 struct SpmvParams {
@@ -58,6 +60,7 @@ struct SpmvParams {
     float* partials;
     size_t partials_stride;
     unsigned int* ticket;
+    const HaloWaitDev* halo;         // multi-GPU: the rows that read halo entries wait for the peers' flags (rows kernel only)
 };
 
 }  // namespace
@@ -288,26 +291,31 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // mult[] gathers issued together (one latency round for a stencil row), then added in the order of the entries
 // (V = 1: the reference's left-to-right sum with two roundings per term, H:1484-1489).
 // exactly L entries, no predicates (the interior rows of a stencil)
-template <int L, class VP, class CP>
+// COH: the operand vector is being written by peer GPUs while this kernel runs (halo rows of a multi-GPU SpMV, after the
+// flags have been acquired): gather past L1 (ld.global.cg), whose lines may predate the peers' stores
+template <bool COH>
+__device__ __forceinline__ float gather(const float* __restrict__ mult, const int c) { return COH ? __ldcg(mult + c) : __ldg(mult + c); }
+
+template <int L, bool COH, class VP, class CP>
 __device__ __forceinline__ float row_dot_fixed(const VP vs, const CP cs, const float* __restrict__ mult, const int j) {
     int c[L];
     float v[L], x[L];
 #pragma unroll
     for (int k = 0; k < L; ++k) { c[k] = cs[j + k]; v[k] = vs[j + k]; }
 #pragma unroll
-    for (int k = 0; k < L; ++k) x[k] = __ldg(mult + c[k]);
+    for (int k = 0; k < L; ++k) x[k] = gather<COH>(mult, c[k]);
     float dot = 0.0f;
 #pragma unroll
     for (int k = 0; k < L; ++k) dot = __fadd_rn(__fmul_rn(v[k], x[k]), dot);
     return dot;
 }
 
-template <int V, class VP, class CP>
+template <int V, bool COH, class VP, class CP>
 __device__ __forceinline__ float row_dot(const VP vs, const CP cs, const float* __restrict__ mult, int j, const int e) {
     if (V == 1) {                                                 // warp-uniform row length: same sum, fewer instructions
         const int len = e - j;
-        if (__all_sync(0xffffffffu, len == 7)) return row_dot_fixed<7>(vs, cs, mult, j);
-        if (__all_sync(0xffffffffu, len == 5)) return row_dot_fixed<5>(vs, cs, mult, j);
+        if (__all_sync(0xffffffffu, len == 7)) return row_dot_fixed<7, COH>(vs, cs, mult, j);
+        if (__all_sync(0xffffffffu, len == 5)) return row_dot_fixed<5, COH>(vs, cs, mult, j);
     }
     float dot = 0.0f;
     while (j < e) {
@@ -320,7 +328,7 @@ __device__ __forceinline__ float row_dot(const VP vs, const CP cs, const float* 
             v[k] = in ? vs[j + k * V] : 0.0f;
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = c[k] >= 0 ? __ldg(mult + c[k]) : 0.0f;
+        for (int k = 0; k < 8; ++k) x[k] = c[k] >= 0 ? gather<COH>(mult, c[k]) : 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if (c[k] >= 0) dot = __fadd_rn(__fmul_rn(v[k], x[k]), dot);
@@ -334,7 +342,8 @@ __device__ __forceinline__ float row_dot(const VP vs, const CP cs, const float* 
 // the slot is free (empty barrier), then has the TMA engine copy the group's values/positions window into the
 // slot, completion counted in bytes on the slot's full barrier.  Warps 0..7 are consumers: wait for the slot, take
 // one row per V lanes out of shared memory, release the slot.  No CTA-wide barrier inside the loop.
-template <int V, bool PLAIN>   // lanes per row; PLAIN: op == ASSIGN and no extra copies of the result
+// HALO: multi-GPU SpMV whose boundary row groups wait for the peers' halo pushes (compiled out of the single-GPU kernel)
+template <int V, bool PLAIN, bool HALO>   // lanes per row; PLAIN: op == ASSIGN and no extra copies of the result
 __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParams P, const int cap, const int nchunks, const int stages) {
     if (P.state != nullptr && P.state->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -361,13 +370,26 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
     const int G = gridDim.x;
     const int first = blockIdx.x;
     const int my_chunks = first < nchunks ? (nchunks - first + G - 1) / G : 0;
+    // Multi-GPU: groups [0, c_lo) and [c_hi, nchunks) hold rows that read halo entries.  The groups are walked in the order
+    // c_lo .. nchunks-1, 0 .. c_lo-1 (group = position + c_lo, wrapped), i.e. the interior first, so that the peers' pushes
+    // travel while the bulk of the rows is being multiplied; a warp spins on the flags only when it reaches a boundary group.
+    int c_lo = 0, c_hi = nchunks;
+    if (HALO) {
+        c_lo = min(nchunks, (P.halo->row_lo + R - 1) / R);
+        c_hi = max(c_lo, P.halo->row_hi / R);
+    }
+    auto group_of = [&](const int j) {
+        if (!HALO) return j;
+        const int q = j + c_lo;
+        return q >= nchunks ? q - nchunks : q;
+    };
 
     if (warp == ROWS_CONSUMERS / 32) {
         // ---------------- producer ----------------
         if (lane == 0) {
             int k0 = 0, k1 = 0;
             if (my_chunks > 0) {
-                const int rb = first * R, re = min(rb + R, P.rows);
+                const int rb = group_of(first) * R, re = min(rb + R, P.rows);
                 k0 = P.start[rb]; k1 = P.start[re];
             }
             int s = 0;                                             // ring slot and how often it has been used before
@@ -375,7 +397,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
             for (int it = 0; it < my_chunks; ++it) {
                 int n0 = 0, n1 = 0;                                // next group's window, fetched ahead of the wait
                 if (it + 1 < my_chunks) {
-                    const int rb = (first + (it + 1) * G) * R, re = min(rb + R, P.rows);
+                    const int rb = group_of(first + (it + 1) * G) * R, re = min(rb + R, P.rows);
                     n0 = P.start[rb]; n1 = P.start[re];
                 }
                 if (use > 0) mbar_wait(&empty[s], (use - 1) & 1u);
@@ -403,25 +425,36 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
         const int rloc = tid / V;                                 // row inside the group
         int my_s = 0, my_e = 0;
         if (my_chunks > 0) {
-            const int r = first * R + rloc;
+            const int r = group_of(first) * R + rloc;
             if (r < P.rows) { my_s = P.start[r]; my_e = P.start[r + 1]; }
         }
         int s = 0;
         uint32_t phase = 0;
-        int q = first;
-        for (int it = 0; it < my_chunks; ++it, q += G) {
+        int j = first;
+        bool halo_here = !HALO;                                   // the peers' halo entries have been acquired by this warp
+        for (int it = 0; it < my_chunks; ++it, j += G) {
+            const int q = group_of(j);
             int nx_s = 0, nx_e = 0;                               // next group's row bounds, fetched ahead
             if (it + 1 < my_chunks) {
-                const int rn = (q + G) * R + rloc;
+                const int rn = group_of(j + G) * R + rloc;
                 if (rn < P.rows) { nx_s = P.start[rn]; nx_e = P.start[rn + 1]; }
             }
             const int row = q * R + rloc;
+            const bool boundary = HALO && (q < c_lo || q >= c_hi);
+            if (boundary && !halo_here) {
+                if (lane == 0 && !dist_halo_wait(P.halo) && P.state != nullptr) { P.state->done = 1; P.state->precond_error |= 8; }
+                __syncwarp();
+                halo_here = true;
+            }
             mbar_wait(&full[s], phase);
             const int a0 = win[2 * s];
             float dot;
             // rows past the end have my_s == my_e == 0: their lanes fall through and only join the shuffles
-            if (win[2 * s + 1]) dot = row_dot<V>(vals_s + (size_t)s * cap - a0, cols_s + (size_t)s * cap - a0, P.mult, my_s + sub, my_e);
-            else dot = row_dot<V>(P.values, P.positions, P.mult, my_s + sub, my_e);
+            if (HALO && boundary) {
+                if (win[2 * s + 1]) dot = row_dot<V, true>(vals_s + (size_t)s * cap - a0, cols_s + (size_t)s * cap - a0, P.mult, my_s + sub, my_e);
+                else dot = row_dot<V, true>(P.values, P.positions, P.mult, my_s + sub, my_e);
+            } else if (win[2 * s + 1]) dot = row_dot<V, false>(vals_s + (size_t)s * cap - a0, cols_s + (size_t)s * cap - a0, P.mult, my_s + sub, my_e);
+            else dot = row_dot<V, false>(P.values, P.positions, P.mult, my_s + sub, my_e);
             if (V > 1) {
 #pragma unroll
                 for (int o = V / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
@@ -529,6 +562,9 @@ int smm_first_active_start(const smm_csr* m, int* out_host, cudaStream_t s) {
     return SMM_OK;
 }
 
+// lanes per row of the TMA rows kernel for this matrix and mode, 0 when the product-staging kernel runs instead
+int smm_spmv_rows_lanes(const smm_csr* m, int exact) { return (exact && m->rows_kernel_lanes > 1) ? 0 : m->rows_kernel_lanes; }
+
 int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
     const smm_csr* m = a.m;
     if (m->rows == 0) return SMM_OK;
@@ -539,6 +575,7 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
     P.copy1 = a.copy1; P.copy2 = a.copy2; P.copy3 = a.copy3;
     P.aux = a.aux; P.reduce = a.reduce; P.finish = a.finish; P.state = a.state;
     P.partials = nullptr; P.partials_stride = 0; P.ticket = nullptr;
+    P.halo = nullptr;
     if (a.reduce != RED_NONE) {
         smm_workspace* ws = m->ws;
         if (!ws || ws->partials_cap < (size_t)m->num_blocks) { smm_set_error("spmv: reduction workspace too small"); return SMM_E_STATE; }
@@ -546,15 +583,18 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
         P.partials_stride = ws->partials_cap;
         P.ticket = ws->tickets + a.slot;
     }
-    const int V = (a.exact && m->rows_kernel_lanes > 1) ? 0 : m->rows_kernel_lanes;   // exact mode needs one lane per row
+    const int V = smm_spmv_rows_lanes(m, a.exact);             // exact mode needs one lane per row
+    if (a.halo_wait != nullptr && V <= 0) { smm_set_error("spmv: the fused halo wait needs the rows kernel"); return SMM_E_STATE; }
     if (V > 0) {
-        static int stages_env = -1, cap_env = 0;
-        if (stages_env < 0) {
+        P.halo = static_cast<const HaloWaitDev*>(a.halo_wait);
+        struct RowsEnv { int stages, cap; };
+        static const RowsEnv env = [] {                                  // read once (thread-safe initialisation)
             const char* e1 = getenv("SMM_B200_ROWS_STAGES");
             const char* e2 = getenv("SMM_B200_ROWS_CAP");
-            stages_env = e1 ? atoi(e1) : 0;                              // 0: as many stages as five resident CTAs per SM allow
-            cap_env = e2 ? (atoi(e2) & ~3) : 0;                          // 0: per-matrix window from the analysis
-        }
+            return RowsEnv{e1 ? atoi(e1) : 0,                            // 0: as many stages as five resident CTAs per SM allow
+                           e2 ? (atoi(e2) & ~3) : 0};                    // 0: per-matrix window from the analysis
+        }();
+        const int stages_env = env.stages, cap_env = env.cap;
         const int cap = cap_env ? cap_env : m->rows_kernel_cap;
         // Five resident CTAs per SM hide the gather latency best (measured: 7-point stencil 3 stages x 14.8 KB, 5 CTAs 1.46 ms
         // vs 3 CTAs with 4 stages 1.97 ms; 5-point stencil 4 stages x 10.8 KB, 5 CTAs 14.4 us vs 6 CTAs with 3 stages 18.4 us on
@@ -570,18 +610,23 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
         int grid = m->sm_count * per_sm;
         if (grid > nchunks) grid = nchunks;
         if (a.reduce != RED_NONE && m->ws->partials_cap < (size_t)grid) { smm_set_error("spmv: reduction workspace too small"); return SMM_E_STATE; }
-        static size_t attr_smem = 0;
-        if (attr_smem != smem) {
-#define SMM_ROWS_ATTR(V_, PL_) SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<V_, PL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+        static size_t attr_smem[SMM_MAX_DEVICES] = {0};                  // function attributes are per device
+        std::lock_guard<std::mutex> attr_lock(g_smm_attr_mu);
+        if (attr_smem[m->device % SMM_MAX_DEVICES] != smem) {
+#define SMM_ROWS_ATTR(V_, PL_) SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<V_, PL_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    SMM_CUDA(cudaFuncSetAttribute(spmv_rows_kernel<V_, PL_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
             SMM_ROWS_ATTR(1, true); SMM_ROWS_ATTR(2, true); SMM_ROWS_ATTR(4, true); SMM_ROWS_ATTR(8, true);
             SMM_ROWS_ATTR(1, false); SMM_ROWS_ATTR(2, false); SMM_ROWS_ATTR(4, false); SMM_ROWS_ATTR(8, false);
 #undef SMM_ROWS_ATTR
-            attr_smem = smem;
+            attr_smem[m->device % SMM_MAX_DEVICES] = smem;
         }
         const bool plain = a.op == SMM_OP_ASSIGN && !a.copy1 && !a.copy2 && !a.copy3;
 #define SMM_ROWS_LAUNCH(V_) \
-    if (plain) spmv_rows_kernel<V_, true><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); \
-    else spmv_rows_kernel<V_, false><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages)
+    if (P.halo != nullptr) { \
+        if (plain) spmv_rows_kernel<V_, true, true><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); \
+        else spmv_rows_kernel<V_, false, true><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); \
+    } else if (plain) spmv_rows_kernel<V_, true, false><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); \
+    else spmv_rows_kernel<V_, false, false><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages)
         switch (V) {
             case 1: SMM_ROWS_LAUNCH(1); break;
             case 2: SMM_ROWS_LAUNCH(2); break;

@@ -26,13 +26,30 @@ struct VecParams {
     float* partials;
     size_t partials_stride;
     unsigned int* ticket;
+    const HaloPushDev* halo;   // multi-GPU: boundary entries of out[0] are also stored into the peers' extended vectors
 };
+
+// out[0][e .. e + cnt) has just been computed: the part that lies in a send segment goes to the peer as well (P2P stores)
+__device__ __forceinline__ void halo_store(const HaloSeg* segs, const int nsegs, const long long e, const float* v, const int cnt, bool& pushed) {
+    for (int s = 0; s < nsegs; ++s) {
+        const long long b = segs[s].begin, len = segs[s].len;
+        if (e + cnt <= b || e >= b + len) continue;
+        float* dst = segs[s].dst + (e - b);
+        if (cnt == 4 && e >= b && e + 4 <= b + len && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int c = 0; c < cnt; ++c) if (e + c >= b && e + c < b + len) dst[c] = v[c];
+        }
+        pushed = true;
+    }
+}
 
 // ---- functors: NIN inputs, NOUT outputs, NRED reductions; sc = scalars read once per thread -------------------
 struct Scal { float a, b, c; };
 
 // CG  x = fma(alpha,p,x); r = fma(-alpha,Ap,r); t0 = r.r            (H:2363-2375)   in: x p r Ap  out: x r
 struct FCgXR {
+    static constexpr bool HALO_OK = false;
     static constexpr int NIN = 4, NOUT = 2, NRED = 1;
     static __device__ Scal scal(const SolveState* s) { return {s->alpha, 0.f, 0.f}; }
     static __device__ void apply(const Scal& sc, const float* in, float* out, float* red) {
@@ -44,12 +61,14 @@ struct FCgXR {
 };
 // CG  p = fma(beta,p,r)                                              (H:2385-2393)   in: p r  out: p
 struct FCgP {
+    static constexpr bool HALO_OK = true;
     static constexpr int NIN = 2, NOUT = 1, NRED = 0;
     static __device__ Scal scal(const SolveState* s) { return {s->beta, 0.f, 0.f}; }
     static __device__ void apply(const Scal& sc, const float* in, float* out, float*) { out[0] = smm_fma2(sc.a, in[0], in[1]); }
 };
 // BiCGSymmetric  x += alpha*p; r -= alpha*ap; t0 = r.r               (H:2061-2075)   in: x p r ap  out: x r
 struct FBsXR {
+    static constexpr bool HALO_OK = false;
     static constexpr int NIN = 4, NOUT = 2, NRED = 1;
     static __device__ Scal scal(const SolveState* s) { return {s->alpha, 0.f, 0.f}; }
     static __device__ void apply(const Scal& sc, const float* in, float* out, float* red) {
@@ -61,12 +80,14 @@ struct FBsXR {
 };
 // BiCGSymmetric  p = r + beta*p                                      (H:2084-2092)   in: p r  out: p
 struct FBsP {
+    static constexpr bool HALO_OK = false;
     static constexpr int NIN = 2, NOUT = 1, NRED = 0;
     static __device__ Scal scal(const SolveState* s) { return {s->beta, 0.f, 0.f}; }
     static __device__ void apply(const Scal& sc, const float* in, float* out, float*) { out[0] = __fadd_rn(in[1], __fmul_rn(sc.a, in[0])); }
 };
 // CGS  q = fma(-alpha,ap,u); auq = alpha*(u+q); x = x + auq          (H:2137-2149)   in: ap u x  out: q auq x
 struct FCgsQX {
+    static constexpr bool HALO_OK = false;
     static constexpr int NIN = 3, NOUT = 3, NRED = 0;
     static __device__ Scal scal(const SolveState* s) { return {s->alpha, 0.f, 0.f}; }
     static __device__ void apply(const Scal& sc, const float* in, float* out, float*) {
@@ -79,6 +100,7 @@ struct FCgsQX {
 };
 // CGS  u = fma(beta,q,r); p = fma(beta, fma(beta,p,q), u)            (H:2157-2167)   in: q r p  out: u p
 struct FCgsUP {
+    static constexpr bool HALO_OK = false;
     static constexpr int NIN = 3, NOUT = 2, NRED = 0;
     static __device__ Scal scal(const SolveState* s) { return {s->beta, 0.f, 0.f}; }
     static __device__ void apply(const Scal& sc, const float* in, float* out, float*) {
@@ -89,6 +111,7 @@ struct FCgsUP {
 };
 // BiCGStab  s = fma(-alpha,ap,r)                                     (H:2245-2247)   in: ap r  out: s
 struct FStabS {
+    static constexpr bool HALO_OK = false;
     static constexpr int NIN = 2, NOUT = 1, NRED = 0;
     static __device__ Scal scal(const SolveState* s) { return {s->alpha, 0.f, 0.f}; }
     static __device__ void apply(const Scal& sc, const float* in, float* out, float*) { out[0] = smm_fma2(-sc.a, in[0], in[1]); }
@@ -96,6 +119,7 @@ struct FStabS {
 // BiCGStab  x = fma(alpha,p,fma(omega,s,x)); r = fma(-omega,as,s); t0 = r.r; t1 = r.r0   (H:2263-2269)
 //                                                                     in: x p s as r0  out: x r
 struct FStabXR {
+    static constexpr bool HALO_OK = false;
     static constexpr int NIN = 5, NOUT = 2, NRED = 2;
     static __device__ Scal scal(const SolveState* s) { return {s->alpha, s->omega, 0.f}; }
     static __device__ void apply(const Scal& sc, const float* in, float* out, float* red) {
@@ -108,6 +132,7 @@ struct FStabXR {
 };
 // BiCGStab  p = fma(beta, fma(-omega,ap,p), r)                       (H:2272-2274)   in: p ap r  out: p
 struct FStabP {
+    static constexpr bool HALO_OK = false;
     static constexpr int NIN = 3, NOUT = 1, NRED = 0;
     static __device__ Scal scal(const SolveState* s) { return {s->beta, s->omega, 0.f}; }
     static __device__ void apply(const Scal& sc, const float* in, float* out, float*) {
@@ -116,6 +141,7 @@ struct FStabP {
 };
 // dot products: t0 = a.b, t1 = a.a                                                    in: a b
 struct FDot2 {
+    static constexpr bool HALO_OK = false;
     static constexpr int NIN = 2, NOUT = 0, NRED = 2;
     static __device__ Scal scal(const SolveState*) { return {0.f, 0.f, 0.f}; }
     static __device__ void apply(const Scal&, const float* in, float*, float* red) {
@@ -125,16 +151,27 @@ struct FDot2 {
 };
 // copies: out0 = out1 = out2 = in0 (r0 = p = r after the preconditioned start, H:2221-2227)   in: a
 struct FCopy3 {
+    static constexpr bool HALO_OK = true;
     static constexpr int NIN = 1, NOUT = 3, NRED = 0;
     static __device__ Scal scal(const SolveState*) { return {0.f, 0.f, 0.f}; }
     static __device__ void apply(const Scal&, const float* in, float* out, float*) { out[0] = in[0]; out[1] = in[0]; out[2] = in[0]; }
 };
 
-template <class F, bool VEC4>
+// HALO (multi-GPU CG, F = FCgP / FCopy3): the kernel that produces the next SpMV operand also pushes its boundary entries
+// to the peers and, once every CTA is through, raises this rank's flag on them -- no separate push kernel.
+template <class F, bool VEC4, bool HALO>
 __global__ void __launch_bounds__(VEC_THREADS) vec_kernel(const VecParams P) {
     if (P.state != nullptr && P.state->done) return;
     __shared__ float red_sh[96];
     __shared__ int sh_flag;
+    __shared__ HaloSeg sh_segs[HALO ? SMM_MAX_RANKS : 1];
+    int nsegs = 0;
+    bool pushed = false;
+    if (HALO) {
+        nsegs = P.halo->nsegs;
+        if (threadIdx.x < nsegs) sh_segs[threadIdx.x] = P.halo->segs[threadIdx.x];
+        __syncthreads();
+    }
     const Scal sc = F::scal(P.state);
     float red[2] = {0.f, 0.f};
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -156,6 +193,7 @@ __global__ void __launch_bounds__(VEC_THREADS) vec_kernel(const VecParams P) {
 #undef SMM_LANE
 #pragma unroll
             for (int k = 0; k < F::NOUT; ++k) reinterpret_cast<float4*>(P.out[k])[i] = vout[k];
+            if (HALO) { const float v4[4] = {vout[0].x, vout[0].y, vout[0].z, vout[0].w}; halo_store(sh_segs, nsegs, i << 2, v4, 4, pushed); }
         }
         // tail (n % 4 elements) by the first threads of CTA 0
         const long long t = (n4 << 2) + gid;
@@ -166,6 +204,7 @@ __global__ void __launch_bounds__(VEC_THREADS) vec_kernel(const VecParams P) {
             F::apply(sc, ein, eout, red);
 #pragma unroll
             for (int k = 0; k < F::NOUT; ++k) P.out[k][t] = eout[k];
+            if (HALO) halo_store(sh_segs, nsegs, t, eout, 1, pushed);
         }
     } else {
         for (long long i = gid; i < P.n; i += stride) {
@@ -175,6 +214,20 @@ __global__ void __launch_bounds__(VEC_THREADS) vec_kernel(const VecParams P) {
             F::apply(sc, ein, eout, red);
 #pragma unroll
             for (int k = 0; k < F::NOUT; ++k) P.out[k][i] = eout[k];
+            if (HALO) halo_store(sh_segs, nsegs, i, eout, 1, pushed);
+        }
+    }
+
+    if (HALO) {
+        if (pushed) __threadfence_system();                    // my peer stores are visible before my CTA's ticket
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(P.halo->ticket, 1u) == gridDim.x - 1) {
+            __threadfence_system();
+            DistComm* comm = P.halo->comm;
+            const unsigned int seq = comm->push_seq + 1u;
+            for (int k = 0; k < P.halo->ndests; ++k) st_release_sys_u32(comm->flags[P.halo->dests[k]] + comm->rank, seq);
+            comm->push_seq = seq;
+            *P.halo->ticket = 0u;
         }
     }
 
@@ -196,11 +249,16 @@ int launch(const VecArgs& a, cudaStream_t s) {
     for (int k = 0; k < 3; ++k) { P.out[k] = a.out[k]; if (k < F::NOUT && ((uintptr_t)a.out[k] & 15)) aligned = false; }
     P.state = a.state; P.finish = a.finish;
     P.partials = nullptr; P.partials_stride = 0; P.ticket = nullptr;
+    P.halo = static_cast<const HaloPushDev*>(a.halo_push);
+    if (P.halo != nullptr && !(F::NOUT >= 1 && F::NRED == 0 && F::HALO_OK)) { smm_set_error("vecops: this kernel cannot push a halo"); return SMM_E_INVALID; }
     smm_workspace* ws = a.ws;
     long long work = aligned ? ((a.n + 3) >> 2) : a.n;
     long long want = (work + VEC_THREADS - 1) / VEC_THREADS;
-    static int per_sm_env = -1;                                // tuning knob; the workspace is sized for VEC_CTAS_PER_SM
-    if (per_sm_env < 0) { const char* e = getenv("SMM_B200_VEC_CTAS_PER_SM"); per_sm_env = e ? atoi(e) : 0; if (per_sm_env > VEC_CTAS_PER_SM) per_sm_env = VEC_CTAS_PER_SM; }
+    static const int per_sm_env = [] {                         // tuning knob, read once; the workspace is sized for VEC_CTAS_PER_SM
+        const char* e = getenv("SMM_B200_VEC_CTAS_PER_SM");
+        const int v = e ? atoi(e) : 0;
+        return v > VEC_CTAS_PER_SM ? VEC_CTAS_PER_SM : v;
+    }();
     // vectors of up to two waves (L2-resident sizes) are latency-bound: half as many CTAs doing two rounds each leave
     // the last CTA half as many partial sums to fold (2 M rows: 12.3 -> 10.3 us); long vectors want every slot filled
     const int per_sm = per_sm_env > 0 ? per_sm_env : (want <= 2ll * ws->sm_count * VEC_CTAS_PER_SM ? VEC_CTAS_PER_SM / 2 : VEC_CTAS_PER_SM);
@@ -212,8 +270,11 @@ int launch(const VecArgs& a, cudaStream_t s) {
         P.partials_stride = ws->partials_cap;
         P.ticket = ws->tickets + a.slot;
     }
-    if (aligned) vec_kernel<F, true><<<grid, VEC_THREADS, 0, s>>>(P);
-    else vec_kernel<F, false><<<grid, VEC_THREADS, 0, s>>>(P);
+    if (F::HALO_OK && P.halo != nullptr) {
+        if (aligned) vec_kernel<F, true, F::HALO_OK><<<grid, VEC_THREADS, 0, s>>>(P);
+        else vec_kernel<F, false, F::HALO_OK><<<grid, VEC_THREADS, 0, s>>>(P);
+    } else if (aligned) vec_kernel<F, true, false><<<grid, VEC_THREADS, 0, s>>>(P);
+    else vec_kernel<F, false, false><<<grid, VEC_THREADS, 0, s>>>(P);
     SMM_COUNT_LAUNCH(1);
     SMM_CUDA(cudaGetLastError());
     return SMM_OK;

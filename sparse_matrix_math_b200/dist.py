@@ -210,7 +210,7 @@ def bench(args, metric, unit):
     import torch
     import torch.distributed as dist
 
-    from bench import ClockSampler, bytes_cg_iteration, measured_peak_gbs, stencil_nnz
+    from bench import ClockSampler, bytes_cg_iteration, golden_fullsize, measured_peak_gbs, parity_record, stencil_nnz, workload_config, x_checksum
 
     rank, world, local = init_process_group()
     grid, iters = args.grid, args.iters
@@ -293,6 +293,29 @@ def bench(args, metric, unit):
     e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e.item())
+    # parity where the driver runs it: the same system solved to convergence (eps 1e-6) in the reference's summation order --
+    # every rank sums its own node of the reference's reduction tree, the ranks are joined pairwise -- compared bit for bit
+    # with the golden record of the reference's multithreaded arithmetic (iterations, residual bits, checksum of x)
+    parity = None
+    if not getattr(args, "no_parity", False) and world & (world - 1) == 0 and tbb_partition(rows, world)[rank] == (rb, re):
+        x.zero_()
+        info_t = D.solve_cg_dev(b.data_ptr(), x.data_ptr(), x.data_ptr(), -1, 1e-6, sp, driver_mode=drv, reduction_mode=B.REDUCE_REFERENCE_TREE)
+        torch.cuda.synchronize()
+        xh = x.cpu().numpy()
+        sb, xb = x_checksum(xh)
+        parts = all_gather_object((sb, xb, float(np.max(np.abs(xh - 1.0))), int(info_t.status), info_t.iterations, info_t.residual, info_t.seconds_solve))
+        if rank == 0:
+            sum_bits, xor_bits = 0, 0
+            for p_ in parts:
+                sum_bits = (sum_bits + p_[0]) & 0xFFFFFFFFFFFFFFFF
+                xor_bits ^= p_[1]
+            same = all(p_[3:6] == parts[0][3:6] for p_ in parts)           # every rank took the same branches
+            parity = parity_record(golden_fullsize().get("5") if grid == 512 else None, parts[0][3], parts[0][4], parts[0][5], sum_bits, xor_bits,
+                                   max(p_[2] for p_ in parts))
+            parity["ranks_agree"] = same
+            secs = max(p_[6] for p_ in parts)
+            parity["it_per_s"] = parts[0][4] / secs if secs > 0 else None
+        del xh
     err = D.error()
     clocks = sampler.stop(tm0, tm1) if rank == 0 else None
 
@@ -305,8 +328,7 @@ def bench(args, metric, unit):
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"ConjugateGradient float, 3D 7-point Poisson {grid}^3, b=A*1, x0=0 (BASELINE configs[4])",
-                       "grid": grid, "rows": rows, "nnz": nnz, "iterations_per_step": iters, "eps": 0.0,
+            "config": {**workload_config(grid, iters),
                        "parallelism": f"{world} GPUs, z-slab row blocks, P2P halo exchange + fused P2P scalar all-reduce (no NCCL in the loop)",
                        "rows_per_gpu": n, "driver": args.driver, "reductions": getattr(args, "reduction", "fast"),
                        "l2": f"per-GPU working set {(8 * nnz + 24 * rows) / world / 1e9:.2f} GB >> 126 MB L2 (no flush needed)",
@@ -320,6 +342,7 @@ def bench(args, metric, unit):
                          "unit": "GB/s", "frac": gbs / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
                          "algorithmic_bytes_per_launch": iter_bytes},
             "iteration": {"ms_per_iteration": dev_ms / args.steps / iters, "final_rr": float(info.residual), "comm_error": err},
+            "parity": parity,
             "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)

@@ -50,6 +50,18 @@ def main():
         y = dy.download()
         b_glob = ol.spmv(g, 0, None, xs)
         check(y.tobytes() == b_glob[rb:re].tobytes(), f"{name}: distributed SpMV differs from the oracle")
+        # back-to-back calls with NO barrier between them and one rank running behind: every exchange is acknowledged by its
+        # consumers, so a fast rank cannot overwrite a halo its neighbour is still reading (smm_dist_spmv_dev's contract)
+        seq_ok = True
+        for k in range(6):
+            xk = (xs * np.float32(k + 1)).astype(np.float32)
+            dx.upload(xk[rb:re])
+            if rank == world - 1:
+                torch.cuda._sleep(20_000_000)                    # ~10 ms of GPU time on the legacy stream ...
+                torch.cuda.synchronize()                         # ... and the host waits: this rank's call is issued late
+            D.spmv_dev(dx.ptr, dy.ptr)
+            seq_ok = seq_ok and dy.download().tobytes() == ol.spmv(g, 0, None, xk)[rb:re].tobytes()
+        check(seq_ok, f"{name}: back-to-back distributed SpMV without barriers differs from the oracle")
         # CG to convergence; compare with the oracle's multithreaded build on the global problem
         o = ol.solve("cg", g, b_glob, np.zeros(g.rows, np.float32), -1, 1e-5, 1)
         db, dxx = smm.DeviceVector(re - rb, b_glob[rb:re]), smm.DeviceVector(re - rb, np.zeros(re - rb, np.float32))

@@ -5,8 +5,12 @@
   iteration count, same residual bits, same checksum of x.  Config 1's and config 5's counts (2265, 1570) are also the
   numbers measured with the real reference header during the survey.
 * FAST mode: status, the solver's own stopping quantity, accuracy of x, iteration count against the documented bar.
-* config 4 (power-law, 8.4 M rows, ~2e8 entries): size-independent properties (generator statistics, linearity, exact
-  vs fast row accumulation, fast vs reference-order solver steps).
+* config 4 (power-law, 8.4 M rows, ~2e8 entries): (a) against the CPU oracle at FULL size -- the device-generated CSR is
+  downloaded and handed to oracle/smm_oracle.c: rMult / rMultSub bit-identical in exact mode and within 1e-5 in both
+  SURVEY 8(d) norms in the fast mode (the long rows are tree-summed there); x, residual and iteration count after 8
+  iterations of ConjugateGradientSquared and BiCGSymmetric bit-identical to the oracle's multithreaded arithmetic in
+  REFERENCE_TREE mode; (b) size-independent properties (generator statistics, linearity, exact vs fast row
+  accumulation, fast vs reference-order solver steps).
 """
 import ctypes as C
 import json
@@ -139,3 +143,64 @@ def test_config4_powerlaw_properties(smm):
             res.append(x.download())
         assert np.max(np.abs(res[0] - res[1])) < 1e-5
         assert np.max(np.abs(res[0] - xs.download())) < 1e-2
+
+
+def test_config4_powerlaw_fullsize_against_the_oracle(smm):
+    """SpMV parity and x after k <= 10 iterations against the oracle at 8.4 M rows / ~197 M entries.
+    Row sums of the reference are strictly sequential (H:1484-1489); the longest row here has 34755 entries."""
+    import matgen
+    import oracle_lib as ol
+    from sparse_matrix_math_b200 import binding as B
+    n = 8388608
+    A = smm.CSRMatrix.generate(B.GEN_POWERLAW, n)
+    start, positions, values = A.download()
+    g = ol.CSR(n, n, start, positions, values, 0)
+    assert g.nnz == A.nnz and int(np.diff(start).max()) > 30000
+    xs_h = matgen.xstar(n)
+    xs = smm.DeviceVector(n)
+    B._check(smm.lib().smm_gen_xstar_dev(n, 0, 0xB200, xs.ptr, None), "xstar")
+    assert xs.download().tobytes() == xs_h.tobytes()                     # device generator == tests/matgen.py
+
+    # ---- rMult (H:1501-1505) and rMultSub (H:1512-1515) ----
+    y_ref = ol.spmv(g, 0, None, xs_h)
+    gabs = ol.CSR(n, n, start, positions, np.abs(values), 0)
+    scale = ol.spmv(gabs, 0, None, np.abs(xs_h))                         # sum_k |a_ik| |x_k|, the denominator of 8(d)'s row norm
+    del gabs
+    assert scale.min() > 0
+    y, ye = smm.DeviceVector(n), smm.DeviceVector(n)
+    A.spmv_dev(B.OP_ASSIGN, None, xs.ptr, ye.ptr, exact=True)
+    assert ye.download().tobytes() == y_ref.tobytes()                    # exact mode: the reference's bits in every row
+    A.spmv_dev(B.OP_ASSIGN, None, xs.ptr, y.ptr)
+    yf = y.download()
+    assert float(np.max(np.abs(yf - y_ref) / scale)) <= 1e-5
+    assert float(np.linalg.norm((yf - y_ref).astype(np.float64)) / np.linalg.norm(y_ref.astype(np.float64))) <= 1e-5
+    lhs_h = np.random.default_rng(44).uniform(-1, 1, n).astype(np.float32)
+    lhs = smm.DeviceVector(n, lhs_h)
+    s_ref = ol.spmv(g, 2, lhs_h, xs_h)
+    A.spmv_dev(B.OP_SUB, lhs.ptr, xs.ptr, ye.ptr, exact=True)
+    assert ye.download().tobytes() == s_ref.tobytes()
+    A.spmv_dev(B.OP_SUB, lhs.ptr, xs.ptr, y.ptr)
+    sf = y.download()
+    assert float(np.max(np.abs(sf - s_ref) / (scale + np.abs(lhs_h)))) <= 1e-5
+    assert float(np.linalg.norm((sf - s_ref).astype(np.float64)) / np.linalg.norm(s_ref.astype(np.float64))) <= 1e-5
+    del lhs, ye, y
+
+    # ---- 8 iterations of CGS (H:2109-2178) and BiCGSymmetric (H:2021-2102): b = A x*, x0 = 0, eps = 0 ----
+    b = smm.DeviceVector(n, y_ref)
+    L = smm.lib()
+    for name, fn in (("cgs", L.smm_solve_cgs_dev), ("bicgsym", L.smm_solve_bicgsym_dev)):
+        o = ol.solve(name, g, y_ref, np.zeros(n, np.float32), 8, 0.0, 1)
+        assert o["iterations"] == 8
+        for mode in (B.REDUCE_REFERENCE_TREE, B.REDUCE_FAST):
+            x = smm.DeviceVector(n); x.zero()
+            opts, _ = B._options(mode, B.DRIVER_AUTO, 0, 0)
+            info = B._Info()
+            B._check(fn(A.handle, b.ptr, x.ptr, 8, 0.0, C.byref(opts), C.byref(info), None), name)
+            xh = x.download()
+            assert info.iterations == 8 and info.status == o["status"]
+            if mode == B.REDUCE_REFERENCE_TREE:                          # the multithreaded reference's bits
+                assert xh.tobytes() == o["x"].tobytes(), name
+                assert np.float32(info.residual).tobytes() == np.float32(o["residual"]).tobytes(), name
+            else:                                                        # throughput mode: same iterate up to rounding
+                assert float(np.max(np.abs(xh - o["x"]))) <= 1e-5, name
+            assert float(np.max(np.abs(xh - xs_h))) < 1e-2
