@@ -231,6 +231,25 @@ int smm_dist_destroy(smm_dist_t* d);
 /* rows [row_begin,row_end) of a generated stencil matrix, global column indices (kinds POISSON2D / CONVDIFF3D) */
 int smm_gen_csr_rows(int kind, int nx, int ny, int nz, float c, int64_t row_begin, int64_t row_end, smm_csr_t** out);
 
+/* ---- multi-GPU in ONE process (additive): what the C++ drop-in header binds when SMM::b200::devices() > 1 ----
+ * smm_group_create cuts a host CSR (square) into `ndevices` contiguous row blocks -- partition 0: equal numbers of stored
+ * entries; partition 1: the nodes of the reference's reduction tree (H:308-320; power-of-two device counts), which the
+ * reference-order reduction mode needs -- uploads block r to devices[r] (NULL: devices 0 .. ndevices-1), enables peer access
+ * and connects the blocks (smm_dist_connect_local).  Every later call runs one host thread per device; all pointers are
+ * HOST pointers of the global system, like the reference's functions.  No torch, no launcher, no IPC. */
+typedef struct smm_group smm_group_t;
+int smm_group_create(int rows, int cols, const int32_t* start, const int32_t* positions, const float* values, int ndevices,
+                     const int* devices, int partition, smm_group_t** out);
+int smm_group_info(const smm_group_t* g, int* ndevices, int64_t* row_cuts /* [ndevices + 1] */);
+int smm_group_update_values(smm_group_t* g, const float* values);
+/* CSRMatrix::rMult / rMultAdd / rMultSub, H:1501-1515 */
+int smm_group_spmv(smm_group_t* g, int op, const float* lhs, const float* mult, float* out);
+/* solver: 0 ConjugateGradient H:2316 (b, x0, x), 1 BiCGSymmetric H:2021, 2 ConjugateGradientSquared H:2109, 3 BiCGStab without
+ * preconditioner H:2294 (b, x; x0 ignored).  Status, clamping and stopping tests as in smm_solve_*. */
+int smm_group_solve(smm_group_t* g, int solver, const float* b, const float* x0, float* x, int maxIterations, float eps,
+                    const smm_solve_options* opts, smm_solve_info* info);
+int smm_group_destroy(smm_group_t* g);
+
 /* ---- measurement hook (bench.py): average device time, in ms, of each of the three kernels of one fused CG
  * iteration (SpMV + p.Ap | x,r update + r.r | p update), `reps` launches each, CUDA events on `stream` ---- */
 int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_spmv, float* ms_xr, float* ms_p, void* stream);

@@ -15,6 +15,10 @@
 // Additive (not in the reference): CSRMatrix::init(rows, cols, start, positions, values) for direct CSR ingest,
 // SMM::SolveInfo / SMM::b200::lastSolveInfo() for iteration counts, SMM::b200::options() for the reduction and
 // driver modes, the README spellings ConjugateGradientSqared and SYMMETRIC_GAUSS_SEIDEL.
+// Multi-GPU: SMM::b200::devices() = N (default 1) row-partitions the matrix over the first N GPUs of the box inside THIS
+// process (smm_group_*, one host thread per GPU, P2P halo exchange and reductions between the kernels): rMult*, ConjugateGradient,
+// BiCGSymmetric, ConjugateGradientSquared and the unpreconditioned BiCGStab then run on N GPUs with the same signatures.
+// Preconditioned solves stay on one GPU (triangular sweeps do not shard exactly).
 #pragma once
 
 #include <algorithm>
@@ -63,6 +67,11 @@ namespace b200 {
 inline smm_solve_options& options() {
     static smm_solve_options o = {SMM_REDUCE_FAST, SMM_DRIVER_AUTO, 0, 0, nullptr, {0, 0, 0, 0}};
     return o;
+}
+// number of GPUs the unpreconditioned hot path uses (one process, row blocks; see the header comment)
+inline int& devices() {
+    static int n = 1;
+    return n;
 }
 inline SolveInfo& lastSolveInfo() {
     static thread_local SolveInfo info;
@@ -486,15 +495,15 @@ public:
     void rMult(const T* const mult, T* const out) const noexcept {
         b200::requireFloat<T>();
         assert(mult != out);
-        b200::check(smm_spmv(device(), SMM_OP_ASSIGN, nullptr, mult, out), "smm_spmv");
+        spmv(SMM_OP_ASSIGN, nullptr, mult, out);
     }
     void rMultAdd(const T* const lhs, const T* const mult, T* const out) const noexcept {
         b200::requireFloat<T>();
-        b200::check(smm_spmv(device(), SMM_OP_ADD, lhs, mult, out), "smm_spmv");
+        spmv(SMM_OP_ADD, lhs, mult, out);
     }
     void rMultSub(const T* const lhs, const T* const mult, T* const out) const noexcept {
         b200::requireFloat<T>();
-        b200::check(smm_spmv(device(), SMM_OP_SUB, lhs, mult, out), "smm_spmv");
+        spmv(SMM_OP_SUB, lhs, mult, out);
     }
 
     // ---- host-side arithmetic and element access (ref H:1525-1604); each marks the device mirror stale ----
@@ -683,9 +692,31 @@ public:
         }
         return dev;
     }
-    void touchValues() const noexcept { valuesStale = true; }
+    void touchValues() const noexcept { valuesStale = true; groupStale = true; }
+
+    // ---- the same matrix row-partitioned over b200::devices() GPUs (created on first use) ----
+    bool multiDevice() const noexcept { return b200::devices() > 1 && denseRowCount == denseColCount && denseRowCount > 0; }
+    smm_group_t* group() const {
+        b200::requireFloat<T>();
+        const int want = b200::devices();
+        // the reference-order reduction modes need row blocks that are nodes of the reference's reduction tree (H:308-320)
+        const int part = b200::options().reduction_mode == SMM_REDUCE_FAST ? 0 : 1;
+        if (grp && (grpDevices != want || grpPartition != part)) { smm_group_destroy(grp); grp = nullptr; }
+        if (!grp) {
+            b200::check(smm_group_create(denseRowCount, denseColCount, start.get(), positions.get(), values.get(), want, nullptr, part, &grp), "smm_group_create");
+            grpDevices = want; grpPartition = part; groupStale = false;
+        } else if (groupStale) {
+            b200::check(smm_group_update_values(grp, values.get()), "smm_group_update_values");
+            groupStale = false;
+        }
+        return grp;
+    }
 
 private:
+    void spmv(int op, const T* lhs, const T* mult, T* out) const {
+        if (multiDevice()) b200::check(smm_group_spmv(group(), op, lhs, mult, out), "smm_group_spmv");
+        else b200::check(smm_spmv(device(), op, lhs, mult, out), "smm_spmv");
+    }
     int find(const int row, const int col) const {     // binary search: columns ascend inside a row
         assert(row >= 0 && row < denseRowCount && col >= 0 && col < denseColCount);
         const int* b = positions.get() + start[row];
@@ -696,13 +727,16 @@ private:
     void releaseDevice() noexcept {
         if (dev) smm_csr_destroy(dev);
         dev = nullptr;
+        if (grp) smm_group_destroy(grp);
+        grp = nullptr;
         ++structureStamp;
     }
     void moveFrom(CSRMatrix& o) noexcept {
         values = std::move(o.values); positions = std::move(o.positions); start = std::move(o.start);
         denseRowCount = o.denseRowCount; denseColCount = o.denseColCount; firstActiveStart = o.firstActiveStart;
         dev = o.dev; valuesStale = o.valuesStale; structureStamp = o.structureStamp + 1;
-        o.dev = nullptr; o.denseRowCount = o.denseColCount = 0; o.firstActiveStart = 0;
+        grp = o.grp; grpDevices = o.grpDevices; grpPartition = o.grpPartition; groupStale = o.groupStale;
+        o.dev = nullptr; o.grp = nullptr; o.denseRowCount = o.denseColCount = 0; o.firstActiveStart = 0;
     }
 
     std::unique_ptr<T[]> values;        // [nnz]
@@ -713,6 +747,9 @@ private:
     int firstActiveStart = 0;           // first non-empty row, or rows
     mutable smm_csr_t* dev = nullptr;
     mutable bool valuesStale = false;
+    mutable smm_group_t* grp = nullptr;   // row blocks on b200::devices() GPUs
+    mutable int grpDevices = 0, grpPartition = 0;
+    mutable bool groupStale = false;
     mutable unsigned long long structureStamp = 1;
 };
 
@@ -758,7 +795,8 @@ template <typename T>
 inline SolverStatus BiCGSymmetric(const CSRMatrix<T>& a, T* b, T* x, int maxIterations, T eps) {
     b200::requireFloat<T>();
     smm_solve_info info;
-    b200::check(smm_solve_bicgsym(a.device(), b, x, maxIterations, eps, &b200::options(), &info), "smm_solve_bicgsym");
+    if (a.multiDevice()) b200::check(smm_group_solve(a.group(), 1, b, nullptr, x, maxIterations, eps, &b200::options(), &info), "smm_group_solve");
+    else b200::check(smm_solve_bicgsym(a.device(), b, x, maxIterations, eps, &b200::options(), &info), "smm_solve_bicgsym");
     b200::record(info);
     return static_cast<SolverStatus>(info.status);
 }
@@ -767,7 +805,8 @@ template <typename T>
 inline SolverStatus ConjugateGradientSquared(const CSRMatrix<T>& a, T* b, T* x, int maxIterations, T eps) {
     b200::requireFloat<T>();
     smm_solve_info info;
-    b200::check(smm_solve_cgs(a.device(), b, x, maxIterations, eps, &b200::options(), &info), "smm_solve_cgs");
+    if (a.multiDevice()) b200::check(smm_group_solve(a.group(), 2, b, nullptr, x, maxIterations, eps, &b200::options(), &info), "smm_group_solve");
+    else b200::check(smm_solve_cgs(a.device(), b, x, maxIterations, eps, &b200::options(), &info), "smm_solve_cgs");
     b200::record(info);
     return static_cast<SolverStatus>(info.status);
 }
@@ -799,7 +838,9 @@ inline SolverStatus BiCGStab(const CSRMatrix<T>& a, T* b, T* x, int maxIteration
         }
     }
     smm_solve_info info;
-    b200::check(smm_solve_bicgstab(a.device(), p, b, x, maxIterations, eps, &b200::options(), &info), "smm_solve_bicgstab");
+    // without a preconditioner the solve shards over b200::devices() GPUs; the triangular sweeps of a preconditioner do not
+    if (p == nullptr && a.multiDevice()) b200::check(smm_group_solve(a.group(), 3, b, nullptr, x, maxIterations, eps, &b200::options(), &info), "smm_group_solve");
+    else b200::check(smm_solve_bicgstab(a.device(), p, b, x, maxIterations, eps, &b200::options(), &info), "smm_solve_bicgstab");
     b200::record(info);
     return static_cast<SolverStatus>(info.status);
 }
@@ -813,7 +854,8 @@ template <typename T>
 inline SolverStatus ConjugateGradient(const CSRMatrix<T>& a, const T* const b, const T* const x0, T* const x, int maxIterations, T eps) {
     b200::requireFloat<T>();
     smm_solve_info info;
-    b200::check(smm_solve_cg(a.device(), b, x0, x, maxIterations, eps, &b200::options(), &info), "smm_solve_cg");
+    if (a.multiDevice()) b200::check(smm_group_solve(a.group(), 0, b, x0, x, maxIterations, eps, &b200::options(), &info), "smm_group_solve");
+    else b200::check(smm_solve_cg(a.device(), b, x0, x, maxIterations, eps, &b200::options(), &info), "smm_solve_cg");
     b200::record(info);
     return static_cast<SolverStatus>(info.status);
 }

@@ -12,6 +12,7 @@
 //       streams products into shared memory ahead of it.
 //   SMM_REDUCE_FAST             vecops.cu's fused two-stage reduction (VEC_DOT2).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "epilogue.cuh"
 #include "smm_internal.cuh"
@@ -74,9 +75,42 @@ struct TreeParams {
     float* out_dev;        // optional: totals written here too
 };
 
+// every CTA has stored its depth-D' node values: the last one to arrive combines them by a perfect pairwise tree (ping-pong
+// between the two halves of each dot's node buffer) -- the joins of the reference's reduction, left + right -- and hands
+// the totals to the scalar step.  Called by all threads of the CTA.
+__device__ __forceinline__ void tree_finish(const TreeParams& P) {
+    __shared__ int sh_last;
+    const long long nn = 1ll << P.depth;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) sh_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    float totals[2] = {0.f, 0.f};
+    for (int d = 0; d < P.ndots; ++d) {
+        float* cur = P.nodes + (size_t)d * 2 * nn;
+        float* nxt = cur + nn;
+        for (long long w = nn >> 1; w >= 1; w >>= 1) {
+            for (long long k = threadIdx.x; k < w; k += blockDim.x) {
+                const float2 pr = __ldcg(reinterpret_cast<const float2*>(cur) + k);
+                nxt[k] = __fadd_rn(pr.x, pr.y);
+            }
+            __threadfence_block();
+            __syncthreads();
+            float* t = cur; cur = nxt; nxt = t;
+        }
+        totals[d] = __ldcg(cur);
+    }
+    if (threadIdx.x == 0) {
+        *P.ticket = 0u;
+        if (P.out_dev) { P.out_dev[0] = totals[0]; P.out_dev[1] = totals[1]; }
+        if (P.state) smm_finish(P.finish, P.state, totals[0], totals[1]);
+    }
+}
+
 __global__ void __launch_bounds__(TREE_WARPS * 32) dot_tree_kernel(const TreeParams P) {
     if (P.state != nullptr && P.state->done) return;
-    __shared__ int sh_last;
     __shared__ __align__(16) float sh_buf[TREE_WARPS][LEAF_CHUNK];
     const long long nn = 1ll << P.depth;
     const int warp = threadIdx.x >> 5;
@@ -99,33 +133,105 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) dot_tree_kernel(const TreePar
         }
         if ((threadIdx.x & 31) == 0) P.nodes[(size_t)d * 2 * nn + i] = v;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) sh_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!sh_last) return;
-    __threadfence();
-    // perfect pairwise tree, ping-pong between the two halves of each dot's node buffer
-    float totals[2] = {0.f, 0.f};
-    for (int d = 0; d < P.ndots; ++d) {
-        float* cur = P.nodes + (size_t)d * 2 * nn;
-        float* nxt = cur + nn;
-        for (long long w = nn >> 1; w >= 1; w >>= 1) {
-            for (long long k = threadIdx.x; k < w; k += blockDim.x) {
-                const float2 pr = __ldcg(reinterpret_cast<const float2*>(cur) + k);
-                nxt[k] = __fadd_rn(pr.x, pr.y);
-            }
-            __threadfence_block();
-            __syncthreads();
-            float* t = cur; cur = nxt; nxt = t;
+    tree_finish(P);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Long vectors: one LANE per depth-D' node, R nodes per warp.
+//
+// dot_tree_kernel spends one warp on a node and has lane 0 add its 8192 products: about 1.4 warp instructions per element,
+// which is what bounds it (377 us for 134 M elements; the fused fast-mode dot streams the same bytes in 193 us).  Here a warp
+// takes R consecutive nodes; their windows of a[] and b[] are brought in by cp.async (16-byte chunks, three stages in
+// flight per warp, rows of 1024 / R elements padded by 4 so that the per-lane 128-bit reads are conflict-free), and lane l
+// adds the products of node l left to right from 0 -- the reference's leaf loop (H:312-316), R chains per warp instead of
+// one, about 0.2 warp instructions per element for R = 16.  A node of 8193 elements is two leaves (H:308-320: the range is
+// halved while it exceeds the grain): the lane restarts from 0 at the split point and joins left + right at the end.
+// ---------------------------------------------------------------------------------------------------
+constexpr int ROWS_TILE = 1024;        // elements per stage and array, all R rows together
+constexpr int ROWS_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, int src_bytes) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(TREE_WARPS * 32) dot_tree_rows_kernel(const TreeParams P) {
+    if (P.state != nullptr && P.state->done) return;
+    extern __shared__ __align__(16) float rows_smem[];
+    constexpr int C = ROWS_TILE / R, CP = C + 4, ARR = R * CP;               // elements per row, padded row, one array of a stage
+    constexpr int CHUNKS_PER_ROW = C / 4;
+    const long long nn = 1ll << P.depth;
+    const long long groups = nn / R;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* const mine = rows_smem + (size_t)warp * ROWS_STAGES * 2 * ARR;
+    const long long job = (long long)blockIdx.x * TREE_WARPS + warp;         // (dot, group of R nodes)
+    if (job < groups * P.ndots) {
+        const int d = (int)(job / groups);
+        const long long node = (job - (long long)d * groups) * R + (lane % R);
+        const float* __restrict__ a = P.a[d];
+        const float* __restrict__ b = P.b[d];
+        long long lo = 0, hi = P.n;
+        for (int level = P.depth - 1; level >= 0; --level) {
+            const long long mid = lo + (hi - lo) / 2;
+            if ((node >> level) & 1) lo = mid; else hi = mid;
         }
-        totals[d] = __ldcg(cur);
+        const long long split = hi - lo > TBB_GRAIN ? lo + (hi - lo) / 2 : -1;   // two leaves
+        const long long a4 = lo & ~3ll;                                        // 16-byte aligned start of the node's window
+        int nstages = (int)((hi - a4 + C - 1) / C);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nstages = max(nstages, __shfl_xor_sync(0xFFFFFFFFu, nstages, o));
+        auto issue = [&](const int t) {
+            if (t < nstages) {
+                float* sa = mine + (size_t)(t % ROWS_STAGES) * 2 * ARR;
+                float* sb = sa + ARR;
+#pragma unroll
+                for (int k = 0; k < (R * CHUNKS_PER_ROW) / 32; ++k) {
+                    const int q = lane + 32 * k, row = q / CHUNKS_PER_ROW, col = (q % CHUNKS_PER_ROW) * 4;
+                    const long long g0 = __shfl_sync(0xFFFFFFFFu, a4, row) + (long long)t * C + col;
+                    const long long left = P.n - g0;
+                    if (left > 0) {
+                        const int bytes = left >= 4 ? 16 : (int)left * 4;
+                        cp_async16(sa + row * CP + col, a + g0, bytes);
+                        cp_async16(sb + row * CP + col, b + g0, bytes);
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        issue(0);
+        issue(1);
+        float acc = 0.0f, first = 0.0f;                                       // identity, H:312
+        for (int t = 0; t < nstages; ++t) {
+            issue(t + 2);
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+            __syncwarp();
+            if (lane < R) {
+                const float* sa = mine + (size_t)(t % ROWS_STAGES) * 2 * ARR + lane * CP;
+                const float* sb = sa + ARR;
+                const long long g0 = a4 + (long long)t * C;
+                if (g0 >= lo && g0 + C <= hi && !(split >= g0 && split < g0 + C)) {
+#pragma unroll 4
+                    for (int c = 0; c < C; c += 4) {
+                        const float4 va = *reinterpret_cast<const float4*>(sa + c), vb = *reinterpret_cast<const float4*>(sb + c);
+                        acc = __fadd_rn(acc, __fmul_rn(va.x, vb.x)); acc = __fadd_rn(acc, __fmul_rn(va.y, vb.y));   // H:314-316
+                        acc = __fadd_rn(acc, __fmul_rn(va.z, vb.z)); acc = __fadd_rn(acc, __fmul_rn(va.w, vb.w));
+                    }
+                } else {
+                    for (int c = 0; c < C; ++c) {
+                        const long long g = g0 + c;
+                        if (g < lo || g >= hi) continue;
+                        if (g == split) { first = acc; acc = 0.0f; }
+                        acc = __fadd_rn(acc, __fmul_rn(sa[c], sb[c]));
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (lane < R) P.nodes[(size_t)d * 2 * nn + node] = split >= 0 ? __fadd_rn(first, acc) : acc;
     }
-    if (threadIdx.x == 0) {
-        *P.ticket = 0u;
-        if (P.out_dev) { P.out_dev[0] = totals[0]; P.out_dev[1] = totals[1]; }
-        if (P.state) smm_finish(P.finish, P.state, totals[0], totals[1]);
-    }
+    tree_finish(P);
 }
 
 struct SerialParams {
@@ -445,7 +551,36 @@ int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const 
         DotScratch* sc = nullptr;
         SMM_TRY(scratch_for(1ll << P.depth, &sc));
         P.nodes = sc->nodes; P.ticket = sc->ticket; P.state = state; P.finish = finish; P.out_dev = out_dev;
-        const long long jobs = (1ll << P.depth) * ndots;       // one warp per (dot, depth-D' node)
+        const long long jobs = (1ll << P.depth) * ndots;       // (dot, depth-D' node)
+        // long vectors: a lane per node, R nodes per warp (as many as still leave four warps for every SM)
+        int R = 0;
+        const bool aligned16 = ((reinterpret_cast<uintptr_t>(a0) | reinterpret_cast<uintptr_t>(b0) | reinterpret_cast<uintptr_t>(a1) | reinterpret_cast<uintptr_t>(b1)) & 15) == 0;
+        static const bool rows_off = [] { const char* e = getenv("SMM_B200_DOT_ROWS"); return e && atoi(e) == 0; }();
+        if (aligned16 && !rows_off) for (int r = 16; r >= 2 && !R; r >>= 1) if ((1ll << P.depth) >= r && jobs / r >= 592) R = r;
+        if (R) {
+            const size_t smem = (size_t)TREE_WARPS * ROWS_STAGES * 2 * (ROWS_TILE + 4 * R) * sizeof(float);
+            {
+                static bool attr_done[SMM_MAX_DEVICES] = {false};
+                int dev = 0;
+                SMM_CUDA(cudaGetDevice(&dev));
+                std::lock_guard<std::mutex> lk(g_smm_attr_mu);
+                if (!attr_done[dev % SMM_MAX_DEVICES]) {
+                    const int most = (int)((size_t)TREE_WARPS * ROWS_STAGES * 2 * (ROWS_TILE + 4 * 16) * sizeof(float));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    attr_done[dev % SMM_MAX_DEVICES] = true;
+                }
+            }
+            const unsigned grid = (unsigned)((jobs / R + TREE_WARPS - 1) / TREE_WARPS);
+            switch (R) {
+                case 16: dot_tree_rows_kernel<16><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+                case 8: dot_tree_rows_kernel<8><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+                case 4: dot_tree_rows_kernel<4><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+                default: dot_tree_rows_kernel<2><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+            }
+        } else
         dot_tree_kernel<<<(unsigned)((jobs + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, 0, s>>>(P);
     } else {
         // left to right.  Dots of a vector with itself are sums of squares: exact in parallel (sum_squares_serial_kernel)

@@ -38,6 +38,7 @@ struct smm_precond {
     uint8_t* tile_steps[2] = {nullptr, nullptr};   // [tiles * 64] step of every row, then [tiles] number of steps
     uint32_t* tile_push[2] = {nullptr, nullptr};   // [tiles * 64] operand slots inside the tile that consume the row's result
     int tile_levels[2] = {0, 0};
+    int tile_chain[2] = {1, 1};      // tiles per chain (one warp solves a chain from end to end), per sweep
 };
 
 // sgs_tiles.cu

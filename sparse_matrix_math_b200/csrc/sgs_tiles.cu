@@ -20,8 +20,13 @@
 //     level s, operands inside the tile coming from shared memory (pushed there by their producer).  A tile publishes
 //     its 64 results together after its last step.  The step loop is kept to about 30 instructions: the warps of an SM
 //     solve at the same time and share its issue slots.
-//     Tiles are handed out in order by an atomic ticket (a block of TILE_WARPS tiles per CTA claim), so every
-//     awaited producer belongs to a tile that a running warp already owns: no deadlock.
+//   * Schedule: tiles are grouped into CHAINS (for a grid: the tiles of one (J, K) column, marched along i) that ONE warp
+//     solves from end to end; chains are handed out in dependency order by an atomic ticket, so every awaited producer
+//     belongs to a chain that a running warp already owns (no deadlock).  A tile's rows are published one by one as
+//     they are solved and a consumer only waits, step by step, for the operands of the rows that are due, so that
+//     neighbouring chains settle into a pipeline a few steps apart instead of a whole tile plus a hand-off per tile
+//     level; the proposal's chains are verified generically (dependencies inside a chain point backwards, the chain
+//     graph is acyclic) and anything else falls back to single-tile chains in tile-level order.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -53,6 +58,8 @@ struct TileArgs {
     const float* eval;
     const float* dval;          // [tiles * 64]
     long long ntiles;
+    long long nchains;          // ntiles / chain_len
+    int chain_len;              // tiles per chain (consecutive tile indices)
     int width;
     unsigned int sleep_first, sleep_later;
     unsigned long long* trace;  // debug (SMM_B200_SGS_TRACE): [tiles][4] globaltimer at claim / first step / solved, and the SM
@@ -81,21 +88,18 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
     // are put there by the row's own lane once they have been published; operands from the same tile are PUSHED
     // there by the lane that solves them, so a row needs a single 128-bit shared-memory load when its step comes
     __shared__ __align__(16) float stage[TILE_WARPS][TILE * TILE_MAX_W];
-    __shared__ unsigned int sh_bid[2];
     unsigned int* abort_flag = tickets + 2;
     unsigned int* ticket = tickets + (FORWARD ? 0 : 1);
-    const long long nblocks = (A.ntiles + TILE_WARPS - 1) / TILE_WARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* src = FORWARD ? yperm : xperm;
     float* dst = FORWARD ? yperm : xperm;
     float* mine = stage[warp];
 
-    auto load_head = [&](long long bid) {
+    auto load_head = [&](const long long tile) {
         TileHead h;
         h.row[0] = h.row[1] = -1;
         h.yp[0] = h.yp[1] = 0;
-        const long long tile = bid * TILE_WARPS + warp;
-        if (bid < nblocks && tile < A.ntiles) {
+        if (tile < A.ntiles) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 h.row[k] = A.order[tile * TILE + k * 32 + lane];
@@ -104,10 +108,9 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
         }
         return h;
     };
-    auto load_body = [&](long long bid, const TileHead& h) {
+    auto load_body = [&](const long long tile, const TileHead& h) {
         TileBody b;
-        const long long tile = bid * TILE_WARPS + warp;
-        const bool live = bid < nblocks && tile < A.ntiles;
+        const bool live = tile < A.ntiles;
         b.nsteps = live ? A.nsteps[tile] : 0;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -126,13 +129,11 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
         }
         return b;
     };
-    auto solve_tile = [&](long long bid, const TileHead& h, const TileBody& b) {
-        const int tile = (int)(bid * TILE_WARPS + warp);
+    auto solve_tile = [&](const long long tile_ll, const TileHead& h, const TileBody& b) {
+        const int tile = (int)tile_ll;
         if (A.trace && lane == 0) A.trace[4ll * tile] = tile_clock();
-        // Operands from other tiles (both rows of this lane) are requested up front, all at once, and whatever has not
-        // been published yet is requested again until everything is there: predecessors publish their rows together
-        // after their last step, so there is nothing to gain from starting early, and the step loop below stays free of
-        // any waiting logic (every instruction in it is paid ten times per tile by warps that share an SM's issue slots)
+        // Operands from other tiles (both rows of this lane) are requested up front, all at once; what has not been
+        // published yet is requested again, but only when a row that needs it is due (wait_for below)
         unsigned int pend = 0u;                                // bit 4 k + e: operand e of row k is still awaited
         unsigned int first[2 * TILE_MAX_W];
 #pragma unroll
@@ -150,23 +151,26 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
             if (FORWARD && !IC0 && h.row[k] >= 0 && fabsf(b.d[k]) < 1e-5) atomicOr(tickets + 3, 1u);   // H:1691-1693 (reported, not fatal here)
         }
         unsigned int polls = 0;
-        while (__any_sync(0xFFFFFFFFu, pend != 0u)) {
-            if (!poll_pause(&polls, abort_flag, A.sleep_first, A.sleep_later)) pend = 0u;
-            unsigned int bits[2 * TILE_MAX_W];
+        // the rows k of the lanes flagged `due` are about to be solved: get the operands they still miss (and, in the same
+        // round trip, whatever else this warp still misses)
+        auto wait_for = [&](const unsigned int need) {
+            while (__any_sync(0xFFFFFFFFu, (pend & need) != 0u)) {
+                if (!poll_pause(&polls, abort_flag, A.sleep_first, A.sleep_later)) pend = 0u;
+                unsigned int bits[2 * TILE_MAX_W];
 #pragma unroll
-            for (int q = 0; q < 2 * TILE_MAX_W; ++q)                              // all requests first: one L2 round trip per round
-                bits[q] = (pend >> q) & 1u ? peek(src + b.c[q / TILE_MAX_W][q % TILE_MAX_W]) : SENTINEL;
+                for (int q = 0; q < 2 * TILE_MAX_W; ++q)                          // all requests first: one L2 round trip per round
+                    bits[q] = (pend >> q) & 1u ? peek(src + b.c[q / TILE_MAX_W][q % TILE_MAX_W]) : SENTINEL;
 #pragma unroll
-            for (int q = 0; q < 2 * TILE_MAX_W; ++q) {
-                if (bits[q] != SENTINEL) { pend &= ~(1u << q); mine[4 * ((q / TILE_MAX_W) * 32 + lane) + (q % TILE_MAX_W)] = __uint_as_float(bits[q]); }
+                for (int q = 0; q < 2 * TILE_MAX_W; ++q) {
+                    if (bits[q] != SENTINEL) { pend &= ~(1u << q); mine[4 * ((q / TILE_MAX_W) * 32 + lane) + (q % TILE_MAX_W)] = __uint_as_float(bits[q]); }
+                }
             }
-        }
+        };
         __syncwarp();
-        if (A.trace && lane == 0) A.trace[4ll * tile + 1] = tile_clock();         // operands complete
+        if (A.trace && lane == 0) A.trace[4ll * tile + 1] = tile_clock();         // first requests issued
         float* const out = dst + ((long long)tile * TILE + lane);
-        float solved[2] = {0.0f, 0.0f};
-        // one row of the lane in one step: operands out of the staging slots, the sum in operand order, the division, and
-        // the result handed to the (up to three) rows of this tile that use it
+        // one row of the lane in one step: operands out of the staging slots, the sum in operand order, the division, the
+        // result handed to the (up to three) rows of this tile that use it and published for the other tiles
         auto solve_row = [&](const int k) {
             const float4 xo = *reinterpret_cast<const float4*>(mine + 4 * (k * 32 + lane));
             // same operand order and roundings as the row-level kernel (H:1685, H:1704, H:1813, H:1829); only the
@@ -179,7 +183,8 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
                                                : __fsub_rn(b.init[k], __fdiv_rn(acc, b.d[k]));   // H:1710
             const unsigned int pu = b.push[k];
             mine[pu & 255u] = res; mine[(pu >> 8) & 255u] = res; mine[(pu >> 16) & 255u] = res;
-            solved[k] = res;
+            publish(out + k * 32, res);                                           // off the dependent chain: nothing here waits for it
+            if (!FORWARD) x[h.row[k]] = res;
         };
         // rows l (k = 0) belong to the early steps and rows l + 32 (k = 1) to the late ones (a tile's rows are sorted by
         // step): three loops, so that a step only tests the rows that can be due
@@ -187,26 +192,23 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
         const int last0 = __reduce_max_sync(0xFFFFFFFFu, b.step[0] == 255 ? -1 : b.step[0]);
         int s = 0;
         for (; s < b.nsteps && s < first1; ++s) {
-            if (s == b.step[0]) solve_row(0);
+            const bool due0 = s == b.step[0];
+            wait_for(due0 ? 0x0Fu : 0u);
+            if (due0) solve_row(0);
             __syncwarp();
         }
         for (; s < b.nsteps && s <= last0; ++s) {
-            if (s == b.step[0]) solve_row(0);
-            if (s == b.step[1]) solve_row(1);
+            const bool due0 = s == b.step[0], due1 = s == b.step[1];
+            wait_for((due0 ? 0x0Fu : 0u) | (due1 ? 0xF0u : 0u));
+            if (due0) solve_row(0);
+            if (due1) solve_row(1);
             __syncwarp();
         }
         for (; s < b.nsteps; ++s) {
-            if (s == b.step[1]) solve_row(1);
+            const bool due1 = s == b.step[1];
+            wait_for(due1 ? 0xF0u : 0u);
+            if (due1) solve_row(1);
             __syncwarp();
-        }
-        // the tile's rows are published together, after its last step: the stores stay off the step chain, and a
-        // successor that waits for this tile finds all of it in one poll
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            if (h.row[k] >= 0) {
-                publish(out + k * 32, solved[k]);
-                if (!FORWARD) x[h.row[k]] = solved[k];
-            }
         }
         if (A.trace && lane == 0) {
             unsigned int sm;
@@ -215,26 +217,30 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
         }
     };
 
-    unsigned int pending = 0u;
-    if (threadIdx.x == 0) {
-        sh_bid[0] = atomicAdd(ticket, 1u);
-        sh_bid[1] = atomicAdd(ticket, 1u);
-        pending = atomicAdd(ticket, 1u);
-    }
-    __syncthreads();
-    long long b0 = sh_bid[0], b1 = sh_bid[1];
-    __syncthreads();
-    TileHead h0 = load_head(b0), h1 = load_head(b1);
-    TileBody r0 = load_body(b0, h0);
-    for (unsigned int it = 0; b0 < nblocks; ++it) {
-        if (threadIdx.x == 0) sh_bid[it & 1u] = pending;
-        __syncthreads();
-        const long long b2 = sh_bid[it & 1u];
-        if (threadIdx.x == 0) pending = atomicAdd(ticket, 1u);
-        const TileHead h2 = load_head(b2);
-        const TileBody r1 = load_body(b1, h1);
-        solve_tile(b0, h0, r0);
-        b0 = b1; b1 = b2; h0 = h1; h1 = h2; r0 = r1;
+    // this warp's stream of tiles: chain after chain (claimed in dependency order), every chain from its first tile to its last
+    long long chain = 0;
+    int at = 0;
+    auto claim = [&]() {
+        unsigned int v = 0u;
+        if (lane == 0) v = atomicAdd(ticket, 1u);
+        return (long long)__shfl_sync(0xFFFFFFFFu, v, 0);
+    };
+    auto next_tile = [&]() {
+        if (chain >= A.nchains) return A.ntiles;
+        const long long t = chain * A.chain_len + at;
+        if (++at == A.chain_len) { at = 0; chain = claim(); }
+        return t;
+    };
+    chain = claim();
+    long long t0 = next_tile(), t1 = next_tile();
+    TileHead h0 = load_head(t0), h1 = load_head(t1);
+    TileBody r0 = load_body(t0, h0);
+    while (t0 < A.ntiles) {
+        const long long t2 = next_tile();
+        const TileHead h2 = load_head(t2);
+        const TileBody r1 = load_body(t1, h1);
+        solve_tile(t0, h0, r0);
+        t0 = t1; t1 = t2; h0 = h1; h1 = h2; r0 = r1;
     }
 }
 
@@ -246,10 +252,12 @@ struct SweepLayout {
     std::vector<uint8_t> steps;
     std::vector<uint32_t> push;
     int levels = 0;
+    int chain_len = 1;                               // tiles per chain (consecutive tile indices); 1: tiles in tile-level order
 };
 
 // cluster ids for a natural-order grid stencil, or empty when the column offsets are not of that kind
-std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int* nclusters) {
+// *chain_len: clusters [c * chain_len, (c + 1) * chain_len) are proposed as chain c (the tiles of one grid column along i)
+std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int* nclusters, int* chain_len = nullptr) {
     // distinct |col - row| > 0 over a sample of the rows (head, middle, tail): this is only a proposal, what it leads to
     // is verified on every row by layout_sweep
     std::vector<long long> offs;
@@ -286,6 +294,7 @@ std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& st
         cl[(size_t)r] = (int32_t)(((k / tk) * TJ + j / tj) * TI + i / ti);
     }
     *nclusters = (int)(TI * TJ * TK);
+    if (chain_len) *chain_len = (int)TI;
     return cl;
 }
 
@@ -304,7 +313,7 @@ void for_clusters(int ncl, F f) {
 
 // Lay one sweep out by tiles.  Returns false when the proposal does not verify.
 bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag,
-                  const std::vector<int32_t>& cl, int ncl, int width, SweepLayout* out) {
+                  const std::vector<int32_t>& cl, int ncl, int width, SweepLayout* out, int chain_len = 1) {
     auto dep_begin = [&](int r) { return forward ? start[r] : diag[r] + 1; };
     auto dep_end = [&](int r) { return forward ? diag[r] : start[r + 1]; };
     // rows of every cluster, ascending
@@ -366,11 +375,70 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
     }
     if ((int)queue.size() != ncl) return false;                // the tile graph has a cycle
     out->levels = maxl + 1;
-    // tiles in level order (stable in the cluster id; the backward sweep runs the ids downwards for locality)
-    std::vector<int32_t> lptr((size_t)out->levels + 1, 0), tile_of((size_t)ncl);
-    for (int a = 0; a < ncl; ++a) lptr[(size_t)level[a] + 1]++;
-    for (int l = 0; l < out->levels; ++l) lptr[(size_t)l + 1] += lptr[l];
-    {
+    // Tile order.  Proposed chains (clusters [c * chain_len, (c + 1) * chain_len), walked upwards by the forward sweep and
+    // downwards by the backward one) are verified: a dependency inside a chain must point to an earlier tile of the chain,
+    // and the graph of the chains must be acyclic; chains are then ordered by their level in that graph, a chain's tiles
+    // are consecutive.  Otherwise: single-tile chains in tile-level order.
+    std::vector<int32_t> tile_of((size_t)ncl);
+    out->chain_len = 1;
+    if (chain_len > 1 && ncl % chain_len == 0) {
+        const int nch = ncl / chain_len;
+        auto chain_of = [&](int a) { return a / chain_len; };
+        auto at_of = [&](int a) { return forward ? a % chain_len : chain_len - 1 - a % chain_len; };
+        std::vector<int32_t> cpred((size_t)nch * MAX_PREDS, -1);
+        std::vector<uint8_t> ncp((size_t)nch, 0);
+        bool ok = true;
+        for (int a = 0; a < ncl && ok; ++a) {
+            const int ca = chain_of(a);
+            for (int i = 0; i < npred[a] && ok; ++i) {
+                const int b = pred[(size_t)a * MAX_PREDS + i], cb = chain_of(b);
+                if (cb == ca) { ok = at_of(b) < at_of(a); continue; }
+                int32_t* pc = &cpred[(size_t)ca * MAX_PREDS];
+                int j = 0;
+                while (j < ncp[ca] && pc[j] != cb) ++j;
+                if (j == ncp[ca]) {
+                    if (ncp[ca] == MAX_PREDS) ok = false; else pc[ncp[ca]++] = cb;
+                }
+            }
+        }
+        std::vector<int32_t> clevel((size_t)nch, 0);
+        if (ok) {                                              // Kahn on the chain graph
+            std::vector<int32_t> cs((size_t)nch + 1, 0), indeg2((size_t)nch), q2;
+            for (int c = 0; c < nch; ++c) for (int i = 0; i < ncp[c]; ++i) cs[(size_t)cpred[(size_t)c * MAX_PREDS + i] + 1]++;
+            for (int c = 0; c < nch; ++c) cs[(size_t)c + 1] += cs[c];
+            std::vector<int32_t> csucc((size_t)cs[nch]);
+            {
+                std::vector<int32_t> cur(cs.begin(), cs.end() - 1);
+                for (int c = 0; c < nch; ++c) for (int i = 0; i < ncp[c]; ++i) csucc[(size_t)cur[cpred[(size_t)c * MAX_PREDS + i]]++] = c;
+            }
+            q2.reserve((size_t)nch);
+            for (int c = 0; c < nch; ++c) { indeg2[c] = ncp[c]; if (!indeg2[c]) q2.push_back(c); }
+            for (size_t q = 0; q < q2.size(); ++q) {
+                const int c = q2[q];
+                for (int i = cs[c]; i < cs[c + 1]; ++i) {
+                    const int d = csucc[i];
+                    clevel[d] = std::max(clevel[d], clevel[c] + 1);
+                    if (--indeg2[d] == 0) q2.push_back(d);
+                }
+            }
+            ok = (int)q2.size() == nch;
+        }
+        if (ok) {
+            int maxc = 0;
+            for (int c = 0; c < nch; ++c) maxc = std::max(maxc, clevel[c]);
+            std::vector<int32_t> lp((size_t)maxc + 2, 0), rank((size_t)nch);
+            for (int c = 0; c < nch; ++c) lp[(size_t)clevel[c] + 1]++;
+            for (int l = 0; l <= maxc; ++l) lp[(size_t)l + 1] += lp[l];
+            if (forward) { for (int c = 0; c < nch; ++c) rank[c] = lp[clevel[c]]++; }
+            else { for (int c = nch - 1; c >= 0; --c) rank[c] = lp[clevel[c]]++; }
+            for (int a = 0; a < ncl; ++a) tile_of[a] = rank[chain_of(a)] * chain_len + at_of(a);
+            out->chain_len = chain_len;
+        }
+    }
+    if (out->chain_len == 1) {                                 // tiles in level order (stable in the cluster id; the backward sweep runs the ids downwards)
+        std::vector<int32_t> lptr((size_t)out->levels + 1, 0);
+        for (int a = 0; a < ncl; ++a) lptr[(size_t)level[a] + 1]++;
+        for (int l = 0; l < out->levels; ++l) lptr[(size_t)l + 1] += lptr[l];
         std::vector<int32_t> cur(lptr.begin(), lptr.end() - 1);
         if (forward) { for (int a = 0; a < ncl; ++a) tile_of[a] = cur[level[a]]++; }
         else { for (int a = ncl - 1; a >= 0; --a) tile_of[a] = cur[level[a]]++; }
@@ -455,12 +523,13 @@ bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& s
     for (int r = 0; r < rows; ++r) width = std::max(width, std::max(diag[r] - start[r], start[r + 1] - 1 - diag[r]));
     if (width > TILE_MAX_W) return false;
     if (width == 0) width = 1;
-    int ncl = 0;
-    const std::vector<int32_t> cl = propose_grid_tiles(rows, start, pos, &ncl);
+    int ncl = 0, chain_len = 1;
+    const std::vector<int32_t> cl = propose_grid_tiles(rows, start, pos, &ncl, &chain_len);
     if (cl.empty()) return false;
+    if (const char* e = getenv("SMM_B200_SGS_CHAINS")) { if (atoi(e) == 0) chain_len = 1; }   // A/B: tiles in tile-level order
     SweepLayout L[2];                                          // the two sweeps are laid out side by side (set-up time)
-    std::future<bool> bwd = std::async(std::launch::async, [&] { return layout_sweep(false, rows, start, pos, diag, cl, ncl, width, &L[1]); });
-    const bool fwd_ok = layout_sweep(true, rows, start, pos, diag, cl, ncl, width, &L[0]);
+    std::future<bool> bwd = std::async(std::launch::async, [&] { return layout_sweep(false, rows, start, pos, diag, cl, ncl, width, &L[1], chain_len); });
+    const bool fwd_ok = layout_sweep(true, rows, start, pos, diag, cl, ncl, width, &L[0], chain_len);
     if (!bwd.get() || !fwd_ok) return false;
     std::vector<int32_t> yp(L[1].order.size(), 0);
     for (size_t t = 0; t < yp.size(); ++t) if (L[1].order[t] >= 0) yp[t] = L[0].where[(size_t)L[1].order[t]];
@@ -469,6 +538,8 @@ bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& s
     p->tile_width = width;
     p->tile_levels[0] = L[0].levels;
     p->tile_levels[1] = L[1].levels;
+    p->tile_chain[0] = L[0].chain_len;
+    p->tile_chain[1] = L[1].chain_len;
     bool ok = upload(L[0].order, &p->order_fwd) == SMM_OK && upload(L[1].order, &p->order_bwd) == SMM_OK && upload(yp, &p->ypos) == SMM_OK &&
               cudaMalloc(&p->yperm, sizeof(float) * npos) == cudaSuccess && cudaMalloc(&p->xperm, sizeof(float) * npos) == cudaSuccess;
     for (int w = 0; w < 2 && ok; ++w) {
@@ -498,7 +569,8 @@ namespace {
 template <int TILE_WARPS>
 void launch_tiles(const smm_precond* p, const TileArgs& F, const TileArgs& B, const float* rhs_dev, float* x_dev, SolveState* state, long long cap,
                   cudaStream_t s) {
-    const long long nblocks = (F.ntiles + TILE_WARPS - 1) / TILE_WARPS;
+    const long long nchains = F.nchains > B.nchains ? F.nchains : B.nchains;
+    const long long nblocks = (nchains + TILE_WARPS - 1) / TILE_WARPS;   // one warp per chain at a time
     // persistent grid: no more CTAs than can be resident (the rest would only find the tickets used up)
     static int resident_dev[SMM_MAX_DEVICES] = {0};            // occupancy is a per-device property
     int resident;
@@ -540,8 +612,9 @@ int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_de
     }
     const uint8_t* nsf = p->tile_steps[0] + ntiles * TILE;
     const uint8_t* nsb = p->tile_steps[1] + ntiles * TILE;
-    TileArgs F{nsf, p->tile_steps[0], p->tile_push[0], p->order_fwd, nullptr, p->ecol[0], p->eval[0], p->dval[0], ntiles, p->tile_width, sleep_first, sleep_later, trace};
-    TileArgs B{nsb, p->tile_steps[1], p->tile_push[1], p->order_bwd, p->ypos, p->ecol[1], p->eval[1], p->dval[1], ntiles, p->tile_width, sleep_first, sleep_later, nullptr};
+    const int cf = p->tile_chain[0] > 0 ? p->tile_chain[0] : 1, cb = p->tile_chain[1] > 0 ? p->tile_chain[1] : 1;
+    TileArgs F{nsf, p->tile_steps[0], p->tile_push[0], p->order_fwd, nullptr, p->ecol[0], p->eval[0], p->dval[0], ntiles, ntiles / cf, cf, p->tile_width, sleep_first, sleep_later, trace};
+    TileArgs B{nsb, p->tile_steps[1], p->tile_push[1], p->order_bwd, p->ypos, p->ecol[1], p->eval[1], p->dval[1], ntiles, ntiles / cb, cb, p->tile_width, sleep_first, sleep_later, nullptr};
     launch_tiles<4>(p, F, B, rhs_dev, x_dev, state, cap, s);   // 1, 2 and 8 tiles per CTA claim measured the same
     SMM_CUDA(cudaGetLastError());
     if (trace) {

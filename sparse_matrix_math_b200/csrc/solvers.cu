@@ -22,6 +22,7 @@
 // In the REFERENCE_* reduction modes the reductions are un-fused and use dots.cu so that every float operation
 // happens in the reference's order.
 #include <chrono>
+#include <stdlib.h>
 #include <string.h>
 
 #include "dist.h"
@@ -49,7 +50,9 @@ struct Ctx {
 };
 
 // multi-GPU: can the SpMV wait for the halo itself (rows kernel), or does it need the wait kernel in front of it?
-bool fused_wait(const Ctx& c) { return c.dist && c.dist->nranks > 1 && c.dist->wait_dev && smm_spmv_rows_lanes(c.a, c.exact ? 1 : 0) > 0; }
+// (SMM_B200_DIST_FUSED=0: separate push and wait kernels around every exchange, for A/B measurements)
+bool dist_fused() { static const bool on = [] { const char* e = getenv("SMM_B200_DIST_FUSED"); return !e || atoi(e) != 0; }(); return on; }
+bool fused_wait(const Ctx& c) { return dist_fused() && c.dist && c.dist->nranks > 1 && c.dist->wait_dev && smm_spmv_rows_lanes(c.a, c.exact ? 1 : 0) > 0; }
 
 int spmv(Ctx& c, int op, const float* lhs, const float* mult, float* out, int reduce, int finish, const float* aux,
          float* c1 = nullptr, float* c2 = nullptr, float* c3 = nullptr) {
@@ -74,7 +77,7 @@ int spmv(Ctx& c, int op, const float* lhs, const float* mult, float* out, int re
 int vec(Ctx& c, int kind, int finish, std::initializer_list<const float*> in, std::initializer_list<float*> out, bool push_halo = false) {
     VecArgs v;
     v.n = c.n; v.state = c.st; v.finish = finish; v.slot = 1; v.ws = c.ws;
-    if (push_halo && c.dist && c.dist->nranks > 1) v.halo_push = c.dist->push_dev;
+    if (push_halo && c.dist && c.dist->nranks > 1 && dist_fused()) v.halo_push = c.dist->push_dev;
     int i = 0;
     for (const float* p : in) v.in[i++] = p;
     i = 0;
@@ -101,6 +104,12 @@ int dots(Ctx& c, int finish, const float* a0, const float* b0, const float* a1 =
 // entries into the peers' extended vectors as well and raises the flags, and the next SpMV multiplies its interior rows while
 // those stores travel, waiting for the peers' flags only in the warps that reach a boundary row group: 3 launches per
 // iteration, like the single-GPU solve.
+// after the kernel that wrote p: whatever part of the exchange that kernel and the next SpMV do not do themselves
+int dist_after_p(Ctx& c) {
+    if (!dist_fused()) return smm_dist_exchange_async(c.dist, c.st, c.s, true);
+    if (!fused_wait(c)) return smm_dist_wait_async(c.dist, c.st, c.s);
+    return SMM_OK;
+}
 int cg_init_dist(Ctx& c, const float* x0) {
     smm_dist* d = c.dist;
     if (c.exact) {                                             // reference-tree mode: local tree, ranks joined pairwise
@@ -109,26 +118,25 @@ int cg_init_dist(Ctx& c, const float* x0) {
     } else
     SMM_TRY(spmv(c, SMM_OP_SUB, c.b, x0, c.r, RED_OUT_OUT, FIN_CG_INIT, nullptr));
     SMM_TRY(vec(c, VEC_COPY3, FIN_NONE, {c.r}, {c.p, c.p, c.p}, true));
-    if (!fused_wait(c)) SMM_TRY(smm_dist_wait_async(d, c.st, c.s));
-    return SMM_OK;
+    return dist_after_p(c);
 }
 int cg_iter_dist(Ctx& c) {
     smm_dist* d = c.dist;
-    const int extra = fused_wait(c) ? 0 : 1;
+    const int extra = !dist_fused() ? 2 : (fused_wait(c) ? 0 : 1);
     if (c.exact) {
         SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, d->ext, c.ap, RED_NONE, FIN_NONE, nullptr));
         SMM_TRY(dots(c, FIN_CG_ALPHA, c.ap, c.p));
         SMM_TRY(vec(c, VEC_CG_XR, FIN_NONE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
         SMM_TRY(dots(c, FIN_CG_UPDATE, c.r, c.r));
         SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}, true));
-        if (extra) SMM_TRY(smm_dist_wait_async(d, c.st, c.s));
+        SMM_TRY(dist_after_p(c));
         c.kernels_per_iteration = 5 + extra;
         return SMM_OK;
     }
     SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, d->ext, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));
     SMM_TRY(vec(c, VEC_CG_XR, FIN_CG_UPDATE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
     SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}, true));
-    if (extra) SMM_TRY(smm_dist_wait_async(d, c.st, c.s));
+    SMM_TRY(dist_after_p(c));
     c.kernels_per_iteration = 3 + extra;
     return SMM_OK;
 }
@@ -589,6 +597,24 @@ int solve_host(int solver, const smm_csr* a, const smm_precond* precond, const f
 }
 
 }  // namespace
+
+// every allocation a solve on `a` may need (workspace, work vectors, reference-order dot scratch, residual history), so that
+// the solve itself allocates nothing: the single-process multi-GPU driver calls this on all devices before any kernel runs
+int smm_solve_prepare(const smm_csr* a, const smm_solve_options* opts) {
+    SMM_CUDA(cudaSetDevice(a->device));
+    smm_workspace* ws = nullptr;
+    SMM_TRY(smm_workspace_get(a, &ws));
+    SMM_TRY(smm_workspace_vectors(ws, 10, (size_t)a->rows));
+    if (opts && opts->reduction_mode != SMM_REDUCE_FAST) SMM_TRY(smm_dot_ref_prepare(a->rows));
+    const int hist_cap = opts && opts->history && opts->history_cap > 0 ? opts->history_cap : 0;
+    if (hist_cap > ws->history_cap) {
+        cudaFree(ws->history);
+        ws->history = nullptr;
+        SMM_CUDA(cudaMalloc(&ws->history, sizeof(float) * (size_t)hist_cap));
+        ws->history_cap = hist_cap;
+    }
+    return SMM_OK;
+}
 
 int smm_solve_dist_cg_impl(smm_dist* d, const float* b_dev, const float* x0_dev, float* x_dev, int maxIterations, float eps,
                            const smm_solve_options* opts, smm_solve_info* info, cudaStream_t s) {

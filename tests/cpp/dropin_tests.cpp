@@ -415,4 +415,75 @@ TEST_CASE("Vector: dot product and norms run on the device") {
     CHECK_EQ(d[1], 2.5f);
 }
 
+// ---- the SAME calls on N GPUs of one box, one process (SMM::b200::devices(), smm_group_*) -------------------
+TEST_CASE("Row-partitioned over N GPUs behind the reference's calls (skipped on a single-GPU box)") {
+    int have = 0;
+    REQUIRE_EQ(smm_device_count(&have), 0);
+    int ngpu = 1;
+    while (ngpu * 2 <= have && ngpu * 2 <= 8) ngpu *= 2;
+    if (ngpu < 2) { std::printf("    (1 GPU visible: multi-GPU scenario skipped)\n"); return; }
+    const int nx = 300, ny = 256, n = nx * ny;                 // 2D 5-point Poisson, natural order: 9600 rows per GPU on 8 GPUs
+    SMM::TripletMatrix<T> t(n, n);
+    for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+        const int r = j * nx + i;
+        t.addEntry(r, r, 4.0f);
+        if (i > 0) t.addEntry(r, r - 1, -1.0f);
+        if (i < nx - 1) t.addEntry(r, r + 1, -1.0f);
+        if (j > 0) t.addEntry(r, r - nx, -1.0f);
+        if (j < ny - 1) t.addEntry(r, r + nx, -1.0f);
+    }
+    SMM::CSRMatrix<T> m(t);
+    SMM::Vector<T> rhs = sumColumsPerRow(m);
+    SMM::Vector<T> xs(n, 0);
+    for (int i = 0; i < n; ++i) xs[i] = T((i * 2654435761u) >> 8) / T(1 << 24);
+    // rMult / rMultSub: bit-identical to the single-GPU result (rows are summed left to right on either path)
+    SMM::Vector<T> y1(n, 0), yN(n, 0), s1(n, 0), sN(n, 0);
+    m.rMult(xs, y1); m.rMultSub(rhs, xs, s1);
+    SMM::b200::devices() = ngpu;
+    m.rMult(xs, yN); m.rMultSub(rhs, xs, sN);
+    int diff = 0;
+    for (int i = 0; i < n; ++i) diff += (y1[i] != yN[i]) + (s1[i] != sN[i]);
+    CHECK_EQ(diff, 0);
+    // reference-order reductions: every GPU sums its node of the reference's reduction tree, the GPUs are joined pairwise --
+    // the same bits and iteration counts as one GPU (which equal the reference's multithreaded build)
+    SMM::b200::options().reduction_mode = SMM_REDUCE_REFERENCE_TREE;
+    for (int solver = 0; solver < 3; ++solver) {
+        int its[2] = {0, 0};
+        SMM::Vector<T> xa(n, 0), xb(n, 0);
+        for (int pass = 0; pass < 2; ++pass) {
+            SMM::b200::devices() = pass == 0 ? 1 : ngpu;
+            SMM::Vector<T>& x = pass == 0 ? xa : xb;
+            SMM::SolverStatus st = SMM::SolverStatus::DIVERGED;
+            if (solver == 0) st = SMM::ConjugateGradient<T>(m, rhs, x, x, -1, kL2Eps);
+            else if (solver == 1) st = SMM::BiCGSymmetric<T>(m, rhs, x, -1, kL2Eps);
+            else st = SMM::ConjugateGradientSquared<T>(m, rhs, x, -1, kL2Eps);
+            CHECK_EQ(st, SMM::SolverStatus::SUCCESS);
+            its[pass] = SMM::b200::lastSolveInfo().iterations;
+        }
+        CHECK_EQ(its[0], its[1]);
+        int d = 0;
+        for (int i = 0; i < n; ++i) d += xa[i] != xb[i];
+        CHECK_EQ(d, 0);
+    }
+    // throughput mode on N GPUs: converges to the known solution (x = 1); BiCGStab without preconditioner shards as well
+    SMM::b200::options().reduction_mode = SMM_REDUCE_FAST;
+    SMM::b200::devices() = ngpu;
+    {
+        SMM::Vector<T> x(n, 0);
+        REQUIRE_EQ(SMM::ConjugateGradient<T>(m, rhs, x, x, -1, kL2Eps), SMM::SolverStatus::SUCCESS);
+        for (const T ri : x) CHECK_APPROX(T(1), ri, 1e-3);
+        SMM::Vector<T> x2(n, 0);
+        REQUIRE_EQ(SMM::BiCGStab<T>(m, rhs, x2, -1, kL2Eps), SMM::SolverStatus::SUCCESS);
+        for (const T ri : x2) CHECK_APPROX(T(1), ri, 1e-3);
+    }
+    // host-side mutation reaches every GPU's rows
+    m *= 2.0f;
+    m.rMult(xs, yN);
+    diff = 0;
+    for (int i = 0; i < n; ++i) diff += yN[i] != 2.0f * y1[i];
+    CHECK_EQ(diff, 0);
+    SMM::b200::devices() = 1;
+    std::printf("    (%d GPUs)\n", ngpu);
+}
+
 int main() { return mini_main(); }

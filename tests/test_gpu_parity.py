@@ -224,6 +224,19 @@ def test_dot_modes(smm, n):
         assert np.float32(smm.dot(a, b, smm.REDUCE_REFERENCE_SERIAL)) == np.float32(ol.dot(a, b, 0))
 
 
+@pytest.mark.parametrize("n", [9_800_001,                 # 2048 nodes of ~4785: two nodes per warp
+                               8192 * 2048 + 1000,        # nodes of 8192 and of 8193 elements (the latter split once more, H:308-320)
+                               20_000_003, 40_000_001,    # four / eight nodes per warp
+                               8192 * 16384 + 5000])      # sixteen nodes per warp, two-leaf nodes, windows at every misalignment
+def test_reference_tree_dot_long_vectors(smm, n):
+    """Vector::operator* (H:305-328) on long vectors: the lane-per-node kernel (cp.async staged rows) has the reference's bits;
+    two different operands, and a vector with itself (the residual norms of the solvers)."""
+    rng = np.random.default_rng(n % 1000003)
+    a = rng.uniform(-1, 1, n).astype(np.float32); b = rng.uniform(-1, 1, n).astype(np.float32)
+    assert np.float32(smm.dot(a, b, smm.REDUCE_REFERENCE_TREE)).tobytes() == np.float32(ol.dot(a, b, 1)).tobytes()
+    assert np.float32(smm.dot(a, a, smm.REDUCE_REFERENCE_TREE)).tobytes() == np.float32(ol.dot(a, a, 1)).tobytes()
+
+
 # ---------------------------------------------------------------------------------------------
 # solvers
 # ---------------------------------------------------------------------------------------------

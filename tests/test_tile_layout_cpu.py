@@ -12,10 +12,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 EXE = os.path.join(ROOT, "tools", "bin", "layout_fingerprint")
 
+# (tile levels, tiles per chain, forward fingerprint, backward fingerprint).  Chains: one warp marches along a grid column of
+# tiles; "0" as the fifth argument lays the tiles out in tile-level order instead (single-tile chains, the round-1 order).
 GOLDEN = {
-    ("64",): (46, "3af65eb5649ada45", "5de0bdfdeda5a402"),                    # 64^3: 16^3 tiles, 3 * 16 - 2 tile levels
-    ("70", "45", "33"): (37, "80b94a34718a146f", "cbf3d109cd13d484"),         # ragged 3D grid
-    ("200", "150", "1"): (43, "0cf68e73ed3ec432", "8b05cb26ed34e36f"),        # 2D, 8 x 8 tiles
+    ("64",): (46, 16, "a92db4e914f3e2b9", "c6740e91fb1c60a2"),                # 64^3: 16^3 tiles, 3 * 16 - 2 tile levels
+    ("64", "64", "64", "0", "0"): (46, 1, "3af65eb5649ada45", "5de0bdfdeda5a402"),
+    ("70", "45", "33"): (37, 18, "e26b9f3a74916599", "1f94717455d29427"),     # ragged 3D grid
+    ("200", "150", "1"): (43, 25, "e24e55652b9de722", "625e836d02b6c2bf"),    # 2D, 8 x 8 tiles
 }
 
 
@@ -23,7 +26,7 @@ GOLDEN = {
 def exe():
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     cmd = ["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-ccbin", "/usr/bin/g++", f"-I{ROOT}/include", f"-I{ROOT}/sparse_matrix_math_b200/csrc",
-           "-gencode", "arch=compute_100a,code=sm_100a", "-o", EXE, os.path.join(ROOT, "tools", "layout_fingerprint.cu")]
+           "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared", "-o", EXE, os.path.join(ROOT, "tools", "layout_fingerprint.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return EXE
@@ -32,10 +35,12 @@ def exe():
 @pytest.mark.parametrize("dims", sorted(GOLDEN))
 def test_tile_layout_fingerprints(exe, dims):
     out = subprocess.run([exe, *dims], capture_output=True, text=True, timeout=300).stdout
-    levels, fwd, bwd = GOLDEN[dims]
-    got = re.findall(r"(forward|backward)\s+ok (\d) levels (\d+) time \S+ s fingerprint ([0-9a-f]{16})", out)
+    levels, chain, fwd, bwd = GOLDEN[dims]
+    got = re.findall(r"(forward|backward)\s+ok (\d) levels (\d+) time \S+ s fingerprint ([0-9a-f]{16}) chain (\d+) schedule_ok (\d)", out)
     assert [g[0] for g in got] == ["forward", "backward"], out
-    assert all(g[1] == "1" and int(g[2]) == levels for g in got), out
+    assert all(g[1] == "1" and int(g[2]) == levels and int(g[4]) == chain for g in got), out
+    # every operand comes from an earlier step of the tile, an earlier tile of the chain or a chain handed out earlier: no deadlock
+    assert all(g[5] == "1" for g in got), out
     assert got[0][3] == fwd and got[1][3] == bwd, out
 
 
@@ -57,7 +62,7 @@ FEXE = os.path.join(ROOT, "tools", "bin", "factor_fingerprint")
 def fexe():
     os.makedirs(os.path.dirname(FEXE), exist_ok=True)
     cmd = ["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-ccbin", "/usr/bin/g++", f"-I{ROOT}/include", f"-I{ROOT}/sparse_matrix_math_b200/csrc",
-           "-gencode", "arch=compute_100a,code=sm_100a", "-o", FEXE, os.path.join(ROOT, "tools", "factor_fingerprint.cu")]
+           "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared", "-o", FEXE, os.path.join(ROOT, "tools", "factor_fingerprint.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return FEXE
