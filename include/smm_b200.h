@@ -96,7 +96,8 @@ int smm_sync(void);
  * this uploads the three arrays and analyses row lengths for the SpMV kernels. */
 int smm_csr_create(int rows, int cols, const int32_t* start, const int32_t* positions, const float* values,
                    smm_csr_t** out);
-/* same, from DEVICE arrays; copy != 0 copies them, copy == 0 adopts them (freed with cudaFree on destroy) */
+/* same, from DEVICE arrays; copy != 0 copies them, copy == 0 adopts them (freed with cudaFree on destroy).  Adopted arrays
+ * change hands only when the call SUCCEEDS: on failure they are untouched and still the caller's. */
 int smm_csr_create_dev(int rows, int cols, int32_t* start_dev, int32_t* positions_dev, float* values_dev,
                        int copy, smm_csr_t** out);
 /* values changed on the host (operator*=, inplaceAdd, updateEntry, setValue ... H:1525-1604, H:846-849) */
@@ -204,6 +205,9 @@ int smm_gen_xstar_dev(int64_t n, int64_t offset, uint64_t seed, float* x_dev, vo
  * of two and every rank's row block is a node of the reference's reduction tree over [0, global_rows) (the range halved at
  * lo + (hi - lo) / 2, H:308-320): the ranks' subtree sums are then joined pairwise and the solve is bit-identical to the
  * reference's SMM_MULTITHREADING build; any other partition is refused with SMM_E_INVALID. */
+/* smm_dist_create re-indexes local's column indices IN PLACE (global -> window) and sets its column count to the window
+ * length; `local` must outlive the smm_dist_t and must not be used for single-GPU calls afterwards.  On failure nothing the
+ * function allocated is kept. */
 typedef struct smm_dist smm_dist_t;
 int smm_dist_create(int rank, int nranks, int64_t global_rows, int64_t row_begin, int64_t row_end, smm_csr_t* local,
                     smm_dist_t** out);

@@ -961,6 +961,10 @@ inline MatrixLoadStatus loadSMMDTMatrix(const char* filepath, TripletMatrix<T>& 
         }
         skipTo('\n');
     }
+    // the closing line: a file that ends with its last row (no trailing newline, or truncated there) has already hit the
+    // end of the stream and fails here, as in the reference (H:2640-2643)
+    skipTo('\n');
+    if (in.fail()) return MatrixLoadStatus::FAILED_TO_PARSE_FILE;
     return MatrixLoadStatus::SUCCESS;
 }
 

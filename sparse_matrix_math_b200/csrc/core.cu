@@ -92,6 +92,7 @@ void smm_workspace_free(smm_workspace* ws) {
     cudaFree(ws->state);
     cudaFreeHost(ws->state_host);
     cudaFree(ws->history);
+    smm_dot_scratch_free(&ws->dot);
     for (int i = 0; i < 10; ++i) cudaFree(ws->vec[i]);
     if (ws->ev0) cudaEventDestroy(ws->ev0);
     if (ws->ev1) cudaEventDestroy(ws->ev1);
@@ -172,7 +173,7 @@ static int csr_finish_create(smm_csr* m) {
 int smm_csr_create(int rows, int cols, const int32_t* start, const int32_t* positions, const float* values, smm_csr_t** out) {
     if (!out || rows < 0 || cols < 0 || (rows > 0 && !start)) { smm_set_error("smm_csr_create: bad arguments"); return SMM_E_INVALID; }
     smm_csr* m = new smm_csr();
-    SMM_CUDA(cudaGetDevice(&m->device));
+    if (cudaGetDevice(&m->device) != cudaSuccess) { delete m; return smm_cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__); }
     m->rows = rows; m->cols = cols;
     m->nnz = start ? start[rows] : 0;
     if (m->nnz < 0 || (m->nnz > 0 && (!positions || !values))) { delete m; smm_set_error("smm_csr_create: bad arrays"); return SMM_E_INVALID; }
@@ -201,29 +202,42 @@ int smm_csr_create(int rows, int cols, const int32_t* start, const int32_t* posi
 
 int smm_csr_create_dev(int rows, int cols, int32_t* start_dev, int32_t* positions_dev, float* values_dev, int copy, smm_csr_t** out) {
     if (!out || rows < 0 || cols < 0 || !start_dev) { smm_set_error("smm_csr_create_dev: bad arguments"); return SMM_E_INVALID; }
+    // Ownership: with copy == 0 the caller's arrays become the handle's ONLY when the call succeeds; on any failure they are
+    // left untouched and still belong to the caller.  Everything this function allocated itself is released on failure.
     smm_csr* m = new smm_csr();
-    SMM_CUDA(cudaGetDevice(&m->device));
     m->rows = rows; m->cols = cols;
+    int rc = SMM_OK;
     int32_t nnz32 = 0;
-    SMM_CUDA(cudaMemcpy(&nnz32, start_dev + rows, sizeof(int32_t), cudaMemcpyDeviceToHost));
-    m->nnz = nnz32;
-    m->nnz_alloc = m->nnz;                                     // adopted arrays: nothing is known beyond nnz entries
-    if (copy) {
-        const size_t npad = ((size_t)m->nnz + 3) & ~(size_t)3;
-        m->nnz_alloc = (int64_t)(npad ? npad : 4);
-        SMM_CUDA(cudaMalloc(&m->start, sizeof(int32_t) * ((size_t)rows + 1)));
-        SMM_CUDA(cudaMalloc(&m->positions, sizeof(int32_t) * (npad ? npad : 4)));
-        SMM_CUDA(cudaMalloc(&m->values, sizeof(float) * (npad ? npad : 4)));
-        SMM_CUDA(cudaMemcpy(m->start, start_dev, sizeof(int32_t) * ((size_t)rows + 1), cudaMemcpyDeviceToDevice));
-        SMM_CUDA(cudaMemcpy(m->positions, positions_dev, sizeof(int32_t) * (size_t)m->nnz, cudaMemcpyDeviceToDevice));
-        SMM_CUDA(cudaMemcpy(m->values, values_dev, sizeof(float) * (size_t)m->nnz, cudaMemcpyDeviceToDevice));
-    } else {
-        if (((uintptr_t)positions_dev & 15) || ((uintptr_t)values_dev & 15)) { delete m; smm_set_error("smm_csr_create_dev: adopted arrays must be 16-byte aligned"); return SMM_E_INVALID; }
-        m->start = start_dev; m->positions = positions_dev; m->values = values_dev;
+    do {
+        if (cudaGetDevice(&m->device) != cudaSuccess ||
+            cudaMemcpy(&nnz32, start_dev + rows, sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = smm_cuda_fail(cudaGetLastError(), "smm_csr_create_dev: read nnz", __FILE__, __LINE__); break; }
+        m->nnz = nnz32;
+        m->nnz_alloc = m->nnz;                                 // adopted arrays: nothing is known beyond nnz entries
+        if (m->nnz < 0 || (m->nnz > 0 && (!positions_dev || !values_dev))) { smm_set_error("smm_csr_create_dev: bad arrays"); rc = SMM_E_INVALID; break; }
+        if (copy) {
+            const size_t npad = ((size_t)m->nnz + 3) & ~(size_t)3;
+            m->nnz_alloc = (int64_t)(npad ? npad : 4);
+            if (cudaMalloc(&m->start, sizeof(int32_t) * ((size_t)rows + 1)) != cudaSuccess ||
+                cudaMalloc(&m->positions, sizeof(int32_t) * (npad ? npad : 4)) != cudaSuccess ||
+                cudaMalloc(&m->values, sizeof(float) * (npad ? npad : 4)) != cudaSuccess ||
+                cudaMemcpy(m->start, start_dev, sizeof(int32_t) * ((size_t)rows + 1), cudaMemcpyDeviceToDevice) != cudaSuccess ||
+                (m->nnz && cudaMemcpy(m->positions, positions_dev, sizeof(int32_t) * (size_t)m->nnz, cudaMemcpyDeviceToDevice) != cudaSuccess) ||
+                (m->nnz && cudaMemcpy(m->values, values_dev, sizeof(float) * (size_t)m->nnz, cudaMemcpyDeviceToDevice) != cudaSuccess)) {
+                rc = smm_cuda_fail(cudaGetLastError(), "smm_csr_create_dev: copy", __FILE__, __LINE__);
+                break;
+            }
+        } else {
+            if (((uintptr_t)positions_dev & 15) || ((uintptr_t)values_dev & 15)) { smm_set_error("smm_csr_create_dev: adopted arrays must be 16-byte aligned"); rc = SMM_E_INVALID; break; }
+            m->start = start_dev; m->positions = positions_dev; m->values = values_dev;
+        }
+        m->owns_arrays = true;
+        rc = csr_finish_create(m);
+    } while (0);
+    if (rc != SMM_OK) {
+        if (!copy) { m->start = nullptr; m->positions = nullptr; m->values = nullptr; }   // still the caller's
+        smm_csr_destroy(m);
+        return rc;
     }
-    m->owns_arrays = true;
-    int rc = csr_finish_create(m);
-    if (rc != SMM_OK) { if (!copy) { m->start = nullptr; m->positions = nullptr; m->values = nullptr; } smm_csr_destroy(m); return rc; }
     *out = m;
     return SMM_OK;
 }

@@ -159,41 +159,50 @@ int smm_dist_create(int rank, int nranks, int64_t global_rows, int64_t row_begin
     smm_dist* d = new smm_dist();
     d->rank = rank; d->nranks = nranks; d->device = local->device; d->local = local;
     d->global_rows = global_rows; d->row_begin = row_begin; d->row_end = row_end;
-    // window of the global vector the local rows read
-    int mm[2] = {0x7fffffff, -1};
     int* mm_dev = nullptr;
-    SMM_CUDA(cudaMalloc(&mm_dev, 2 * sizeof(int)));
-    SMM_CUDA(cudaMemcpyAsync(mm_dev, mm, sizeof mm, cudaMemcpyHostToDevice, s));
-    if (local->nnz > 0) {
-        minmax_col_kernel<<<1184, 256, 0, s>>>(local->positions, local->nnz, mm_dev, mm_dev + 1);
-        SMM_COUNT_LAUNCH(1);
-    }
-    SMM_CUDA(cudaMemcpyAsync(mm, mm_dev, sizeof mm, cudaMemcpyDeviceToHost, s));
-    SMM_CUDA(cudaStreamSynchronize(s));
+    const int rc = [&]() -> int {
+        // window of the global vector the local rows read
+        int mm[2] = {0x7fffffff, -1};
+        SMM_CUDA(cudaMalloc(&mm_dev, 2 * sizeof(int)));
+        SMM_CUDA(cudaMemcpyAsync(mm_dev, mm, sizeof mm, cudaMemcpyHostToDevice, s));
+        if (local->nnz > 0) {
+            minmax_col_kernel<<<1184, 256, 0, s>>>(local->positions, local->nnz, mm_dev, mm_dev + 1);
+            SMM_COUNT_LAUNCH(1);
+        }
+        SMM_CUDA(cudaMemcpyAsync(mm, mm_dev, sizeof mm, cudaMemcpyDeviceToHost, s));
+        SMM_CUDA(cudaStreamSynchronize(s));
+        long long lo = row_begin, hi = row_end;
+        if (local->nnz > 0) { if (mm[0] < lo) lo = mm[0]; if ((long long)mm[1] + 1 > hi) hi = (long long)mm[1] + 1; }
+        if (hi > global_rows || lo < 0) { smm_set_error("smm_dist_create: column index outside the global vector"); return SMM_E_INVALID; }
+        lo = row_begin - (((row_begin - lo) + 3) / 4) * 4;        // keep the owned part 16-byte aligned (may dip below 0: unused pad)
+        d->lo = lo; d->hi = hi; d->own_off = row_begin - lo;
+        // shared block (allocated before the matrix is touched: a failure up to here leaves `local` as it was)
+        const size_t ext_bytes = (((size_t)(hi - lo) * sizeof(float)) + 255) & ~(size_t)255;
+        const size_t mail_bytes = (size_t)4 * nranks * 2 * sizeof(unsigned long long);
+        const size_t flag_bytes = 256;                            // flags [nranks] at +0, acknowledgements [nranks] at +128
+        d->mail_off = ext_bytes; d->flag_off = ext_bytes + ((mail_bytes + 255) & ~(size_t)255);
+        d->shared_bytes = d->flag_off + flag_bytes;
+        SMM_CUDA(cudaMalloc(&d->shared, d->shared_bytes));
+        SMM_CUDA(cudaMemsetAsync(d->shared, 0, d->shared_bytes, s));
+        d->ext = reinterpret_cast<float*>(d->shared);
+        SMM_CUDA(cudaMalloc(&d->comm_dev, sizeof(DistComm)));
+        SMM_CUDA(cudaMalloc(&d->ticket, sizeof(unsigned int)));
+        SMM_CUDA(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned int), s));
+        // the local CSR is re-indexed IN PLACE: columns become indices into the extended vector (documented in smm_b200.h)
+        if (local->nnz > 0 && lo != 0) {
+            shift_cols_kernel<<<1184, 256, 0, s>>>(local->positions, local->nnz, (int)lo);
+            SMM_COUNT_LAUNCH(1);
+        }
+        local->cols = (int)(hi - lo);
+        SMM_CUDA(cudaStreamSynchronize(s));
+        return SMM_OK;
+    }();
     cudaFree(mm_dev);
-    long long lo = row_begin, hi = row_end;
-    if (local->nnz > 0) { if (mm[0] < lo) lo = mm[0]; if ((long long)mm[1] + 1 > hi) hi = (long long)mm[1] + 1; }
-    if (hi > global_rows || lo < 0) { delete d; smm_set_error("smm_dist_create: column index outside the global vector"); return SMM_E_INVALID; }
-    lo = row_begin - (((row_begin - lo) + 3) / 4) * 4;            // keep the owned part 16-byte aligned (may dip below 0: unused pad)
-    d->lo = lo; d->hi = hi; d->own_off = row_begin - lo;
-    if (local->nnz > 0 && lo != 0) {
-        shift_cols_kernel<<<1184, 256, 0, s>>>(local->positions, local->nnz, (int)lo);
-        SMM_COUNT_LAUNCH(1);
+    if (rc != SMM_OK) {
+        cudaFree(d->shared); cudaFree(d->comm_dev); cudaFree(d->ticket);
+        delete d;
+        return rc;
     }
-    local->cols = (int)(hi - lo);
-    // shared block
-    const size_t ext_bytes = (((size_t)(hi - lo) * sizeof(float)) + 255) & ~(size_t)255;
-    const size_t mail_bytes = (size_t)4 * nranks * 2 * sizeof(unsigned long long);
-    const size_t flag_bytes = 256;
-    d->mail_off = ext_bytes; d->flag_off = ext_bytes + ((mail_bytes + 255) & ~(size_t)255);
-    d->shared_bytes = d->flag_off + flag_bytes;
-    SMM_CUDA(cudaMalloc(&d->shared, d->shared_bytes));
-    SMM_CUDA(cudaMemsetAsync(d->shared, 0, d->shared_bytes, s));
-    d->ext = reinterpret_cast<float*>(d->shared);
-    SMM_CUDA(cudaMalloc(&d->comm_dev, sizeof(DistComm)));
-    SMM_CUDA(cudaMalloc(&d->ticket, sizeof(unsigned int)));
-    SMM_CUDA(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned int), s));
-    SMM_CUDA(cudaStreamSynchronize(s));
     if (nranks == 1) d->connected = true;
     *out = d;
     return SMM_OK;

@@ -493,22 +493,17 @@ __global__ void __cluster_dims__(SQ_CTAS, 1, 1) __launch_bounds__(SQ_THREADS, 1)
     }
 }
 
-struct DotScratch {
-    float* nodes = nullptr;
-    size_t nodes_cap = 0;
-    unsigned int* ticket = nullptr;
-    float* out = nullptr;        // 2 floats
-    float* sq = nullptr;         // 2 floats: totals of sum_squares_serial_kernel on their way to dot_serial_kernel
-};
-DotScratch g_scratch[64];
+typedef smm_dot_scratch DotScratch;
+DotScratch g_scratch[SMM_MAX_DEVICES];     // stand-alone smm_dot (no handle): one per device, used under g_scratch_mu
+std::mutex g_scratch_mu;
 }  // namespace
 int smm_tree_depth(long long n);
 namespace {
 
-int scratch_for(long long nn, DotScratch** out) {
+int scratch_for(long long nn, smm_workspace* ws, DotScratch** out) {
     int dev = 0;
     SMM_CUDA(cudaGetDevice(&dev));
-    DotScratch& sc = g_scratch[dev];
+    DotScratch& sc = ws ? ws->dot : g_scratch[dev % SMM_MAX_DEVICES];
     if (!sc.ticket) {
         SMM_CUDA(cudaMalloc(&sc.ticket, sizeof(unsigned int)));
         SMM_CUDA(cudaMemset(sc.ticket, 0, sizeof(unsigned int)));
@@ -519,6 +514,7 @@ int scratch_for(long long nn, DotScratch** out) {
     const size_t need = (size_t)nn * 4;
     if (sc.nodes_cap < need) {
         cudaFree(sc.nodes);
+        sc.nodes = nullptr; sc.nodes_cap = 0;
         SMM_CUDA(cudaMalloc(&sc.nodes, need * sizeof(float)));
         sc.nodes_cap = need;
     }
@@ -528,10 +524,15 @@ int scratch_for(long long nn, DotScratch** out) {
 
 }  // namespace
 
+void smm_dot_scratch_free(smm_dot_scratch* sc) {
+    cudaFree(sc->nodes); cudaFree(sc->ticket); cudaFree(sc->out); cudaFree(sc->sq);
+    *sc = smm_dot_scratch();
+}
+
 // allocate the node scratch for vectors of length n now (cudaMalloc is not allowed while a stream is capturing)
-int smm_dot_ref_prepare(long long n) {
+int smm_dot_ref_prepare(long long n, smm_workspace* ws) {
     DotScratch* sc = nullptr;
-    return scratch_for(1ll << smm_tree_depth(n), &sc);
+    return scratch_for(1ll << smm_tree_depth(n), ws, &sc);
 }
 
 int smm_tree_depth(long long n) {
@@ -543,13 +544,13 @@ int smm_tree_depth(long long n) {
 // t0 = a0.b0 [, t1 = a1.b1] in the requested reference order; the totals go to smm_finish(finish, state, t0, t1)
 // and/or out_dev[0..1].  mode: SMM_REDUCE_REFERENCE_TREE or SMM_REDUCE_REFERENCE_SERIAL.
 int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const float* b0, const float* a1, const float* b1,
-                       SolveState* state, int finish, float* out_dev, cudaStream_t s) {
+                       SolveState* state, int finish, float* out_dev, cudaStream_t s, smm_workspace* ws) {
     if (mode == SMM_REDUCE_REFERENCE_TREE) {
         TreeParams P;
         P.n = n; P.depth = smm_tree_depth(n); P.ndots = ndots;
         P.a[0] = a0; P.b[0] = b0; P.a[1] = a1; P.b[1] = b1;
         DotScratch* sc = nullptr;
-        SMM_TRY(scratch_for(1ll << P.depth, &sc));
+        SMM_TRY(scratch_for(1ll << P.depth, ws, &sc));
         P.nodes = sc->nodes; P.ticket = sc->ticket; P.state = state; P.finish = finish; P.out_dev = out_dev;
         const long long jobs = (1ll << P.depth) * ndots;       // (dot, depth-D' node)
         // long vectors: a lane per node, R nodes per warp (as many as still leave four warps for every SM)
@@ -585,7 +586,7 @@ int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const 
     } else {
         // left to right.  Dots of a vector with itself are sums of squares: exact in parallel (sum_squares_serial_kernel)
         DotScratch* sc = nullptr;
-        SMM_TRY(scratch_for(1, &sc));
+        SMM_TRY(scratch_for(1, ws, &sc));
         const float* aa[2] = {a0, a1};
         const float* bb[2] = {b0, b1};
         if (ndots == 1 && a0 == b0) {
@@ -651,9 +652,10 @@ int smm_dot_dev(int64_t n, const float* a_dev, const float* b_dev, int reduction
         SMM_CUDA(cudaMemcpyAsync(res, (const char*)ws->state + offsetof(SolveState, scratch), 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
         SMM_CUDA(cudaStreamSynchronize(s));
     } else if (reduction_mode == SMM_REDUCE_REFERENCE_TREE || reduction_mode == SMM_REDUCE_REFERENCE_SERIAL) {
+        std::lock_guard<std::mutex> lk(g_scratch_mu);          // the per-device scratch: one stand-alone dot at a time
         DotScratch* sc = nullptr;
-        SMM_TRY(scratch_for(1ll << smm_tree_depth(n), &sc));
-        SMM_TRY(smm_launch_dot_ref(reduction_mode, n, 1, a_dev, b_dev, a_dev, b_dev, nullptr, FIN_NONE, sc->out, s));
+        SMM_TRY(scratch_for(1ll << smm_tree_depth(n), nullptr, &sc));
+        SMM_TRY(smm_launch_dot_ref(reduction_mode, n, 1, a_dev, b_dev, a_dev, b_dev, nullptr, FIN_NONE, sc->out, s, nullptr));
         SMM_CUDA(cudaMemcpyAsync(res, sc->out, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
         SMM_CUDA(cudaStreamSynchronize(s));
     } else {

@@ -104,8 +104,19 @@ struct SolveState {
     int pad[6];
 };
 
+// scratch of the reference-order dot products (dots.cu): per handle, so that two handles solving on different streams of
+// one device never share the node buffer or the last-block ticket
+struct smm_dot_scratch {
+    float* nodes = nullptr;
+    size_t nodes_cap = 0;
+    unsigned int* ticket = nullptr;
+    float* out = nullptr;        // 2 floats
+    float* sq = nullptr;         // 2 floats: totals of sum_squares_serial_kernel on their way to dot_serial_kernel
+};
+
 struct smm_workspace {
     int device = 0;
+    smm_dot_scratch dot;
     int sm_count = 148;
     // partial sums of fused reductions: [RED_SLOTS][2][partials_cap] floats
     float* partials = nullptr;
@@ -179,9 +190,11 @@ int smm_vec_max_grid(const smm_workspace* ws);
 
 // dot products in the reference's summation orders (dots.cu)
 int smm_tree_depth(long long n);
-int smm_dot_ref_prepare(long long n);
+// ws: the handle's workspace (its own scratch); null: the stand-alone smm_dot's per-device scratch
+int smm_dot_ref_prepare(long long n, smm_workspace* ws);
 int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const float* b0, const float* a1, const float* b1,
-                       SolveState* state, int finish, float* out_dev, cudaStream_t s);
+                       SolveState* state, int finish, float* out_dev, cudaStream_t s, smm_workspace* ws);
+void smm_dot_scratch_free(smm_dot_scratch* sc);
 
 // SGS preconditioner (sgs.cu)
 int smm_sgs_apply_async(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, cudaStream_t s);

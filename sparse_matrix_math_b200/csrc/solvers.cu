@@ -91,7 +91,7 @@ int dots(Ctx& c, int finish, const float* a0, const float* b0, const float* a1 =
         // VEC_DOT2 computes (a.b, a.a): callers in FAST mode only use shapes it covers
         return vec(c, VEC_DOT2, finish, {a0, b0}, {});
     }
-    return smm_launch_dot_ref(c.mode, c.n, a1 ? 2 : 1, a0, b0, a1 ? a1 : a0, b1 ? b1 : b0, c.st, finish, nullptr, c.s);
+    return smm_launch_dot_ref(c.mode, c.n, a1 ? 2 : 1, a0, b0, a1 ? a1 : a0, b1 ? b1 : b0, c.st, finish, nullptr, c.s, c.ws);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -171,7 +171,7 @@ int pcg_init(Ctx& c, const float* x0) {
     SMM_TRY(vec(c, VEC_COPY3, FIN_NONE, {c.sv}, {c.p, c.p, c.p}));                                 // p = z, H:2447
     // rz and ||r||^2 are accumulated by a plain loop in BOTH builds of the reference (H:2444-2448)
     if (c.mode == SMM_REDUCE_FAST) return vec(c, VEC_DOT2, FIN_PCG_INIT, {c.r, c.sv}, {});
-    return smm_launch_dot_ref(SMM_REDUCE_REFERENCE_SERIAL, c.n, 2, c.r, c.sv, c.r, c.r, c.st, FIN_PCG_INIT, nullptr, c.s);
+    return smm_launch_dot_ref(SMM_REDUCE_REFERENCE_SERIAL, c.n, 2, c.r, c.sv, c.r, c.r, c.st, FIN_PCG_INIT, nullptr, c.s, c.ws);
 }
 int pcg_iter(Ctx& c) {
     if (!c.exact) {
@@ -287,7 +287,7 @@ int stab_iter(Ctx& c) {
         SMM_TRY(dots(c, FIN_BICGSTAB_OMEGA, c.as, c.sv, c.as, c.as));
         SMM_TRY(vec(c, VEC_STAB_XR, FIN_NONE, {c.x, c.p, c.sv, c.as, c.r0}, {c.x, c.r}));
         // resL2Norm is a serial left-to-right sum in BOTH builds of the reference (H:2262-2267); r.r0 follows the build
-        SMM_TRY(smm_launch_dot_ref(SMM_REDUCE_REFERENCE_SERIAL, c.n, 1, c.r, c.r, c.r, c.r, c.st, FIN_STASH0, nullptr, c.s));
+        SMM_TRY(smm_launch_dot_ref(SMM_REDUCE_REFERENCE_SERIAL, c.n, 1, c.r, c.r, c.r, c.r, c.st, FIN_STASH0, nullptr, c.s, c.ws));
         SMM_TRY(dots(c, FIN_BICGSTAB_UPDATE_STASHED, c.r, c.r0));
         k += 6;
     }
@@ -457,7 +457,7 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
         SMM_CUDA(cudaStreamSynchronize(s));                    // the source is a stack variable
     }
     c.exact = c.mode != SMM_REDUCE_FAST;
-    if (c.exact) SMM_TRY(smm_dot_ref_prepare(a->rows));        // scratch must exist before the iteration graph is captured
+    if (c.exact) SMM_TRY(smm_dot_ref_prepare(a->rows, ws));        // scratch must exist before the iteration graph is captured
     c.b = b_dev; c.x = x_dev;
     const int nvec = solver == S_CG || solver == S_BICGSYM ? 3 : (solver == S_CGS ? 7 : 7);
     // work vectors live behind the three host-I/O staging slots (vec[0..2])
@@ -605,7 +605,7 @@ int smm_solve_prepare(const smm_csr* a, const smm_solve_options* opts) {
     smm_workspace* ws = nullptr;
     SMM_TRY(smm_workspace_get(a, &ws));
     SMM_TRY(smm_workspace_vectors(ws, 10, (size_t)a->rows));
-    if (opts && opts->reduction_mode != SMM_REDUCE_FAST) SMM_TRY(smm_dot_ref_prepare(a->rows));
+    if (opts && opts->reduction_mode != SMM_REDUCE_FAST) SMM_TRY(smm_dot_ref_prepare(a->rows, ws));
     const int hist_cap = opts && opts->history && opts->history_cap > 0 ? opts->history_cap : 0;
     if (hist_cap > ws->history_cap) {
         cudaFree(ws->history);

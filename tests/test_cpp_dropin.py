@@ -54,6 +54,53 @@ int main() {
     assert subprocess.run([out]).returncode == 0        # host-only code: runs without a GPU
 
 
+def test_smmdt_loader_status_codes_match_the_reference(built_lib, tmp_path):
+    """loadSMMDTMatrix (H:2611-2646) on well-formed and cut-off files: same MatrixLoadStatus and entries as the real reference
+    (oracle/_ref) -- including FAILED_TO_PARSE_FILE for a file that ends with its last row (the trailing ignore + fail check)."""
+    import sys
+    sys.path.insert(0, HERE)
+    import oracle_lib as ol
+    if not ol.ref_available():
+        pytest.skip("oracle/_ref not built")
+    files = {
+        "ok.smmdt": "2 3\n{\n{1.5,0,2},\n{0,-3,0}\n}",
+        "ok_newline.smmdt": "2 3\n{\n{1.5,0,2},\n{0,-3,0}\n}\n",
+        "no_closing_line.smmdt": "2 3\n{\n{1.5,0,2},\n{0,-3,0}\n",
+        "ends_with_last_row.smmdt": "2 3\n{\n{1.5,0,2},\n{0,-3,0}",
+        "cut_in_row.smmdt": "2 3\n{\n{1.5,0,2},\n{0,-3",
+        "bad_header.smmdt": "x 3\n{\n{1}\n}",
+    }
+    src = tmp_path / "smmdt.cpp"
+    src.write_text('''
+#include <cstdio>
+#include "sparse_matrix_math.h"
+int main(int argc, char** argv) {
+    for (int i = 1; i < argc; ++i) {
+        SMM::TripletMatrix<float> t;
+        const int st = (int)SMM::loadMatrix(argv[i], t);
+        std::printf("%d %d\\n", st, st == 0 ? t.getNonZeroCount() : -1);
+    }
+    return 0;
+}
+''')
+    out = str(tmp_path / "smmdt")
+    r = compile_cpp(str(src), out)
+    assert r.returncode == 0, r.stderr[-3000:]
+    paths = []
+    for name, text in files.items():
+        p = tmp_path / name
+        p.write_text(text)
+        paths.append(str(p))
+    got = [tuple(int(v) for v in line.split()) for line in subprocess.run([out, *paths], capture_output=True, text=True).stdout.splitlines()]
+    assert len(got) == len(paths)
+    for path, (st, nnz) in zip(paths, got):
+        rst, m = ol.ref_load_matrix(path)
+        assert st == rst, (path, st, rst)
+        if st == 0:
+            assert nnz == m.nnz, path
+    assert got[3][0] != 0 and got[0][0] == 0          # the case ADVICE named: ends with its last row -> FAILED_TO_PARSE_FILE
+
+
 def test_hot_path_refuses_other_scalars_at_compile_time(built_lib, tmp_path):
     src = tmp_path / "dbl.cpp"
     src.write_text('''
