@@ -599,6 +599,7 @@ int smm_precond_tile_levels(const smm_precond_t* p, int* forward_levels, int* ba
 int smm_precond_destroy(smm_precond_t* p) {
     if (!p) return SMM_OK;
     cudaFree(p->tile_steps[0]); cudaFree(p->tile_steps[1]); cudaFree(p->tile_push[0]); cudaFree(p->tile_push[1]);
+    cudaFree(p->tile_push2[0]); cudaFree(p->tile_push2[1]);
     cudaFree(p->order_fwd); cudaFree(p->order_bwd); cudaFree(p->diag_pos); cudaFree(p->yperm); cudaFree(p->xperm); cudaFree(p->ypos); cudaFree(p->tickets); cudaFree(p->factor);
     for (int w = 0; w < 2; ++w) { cudaFree(p->slice_ptr[w]); cudaFree(p->ecol[w]); cudaFree(p->eidx[w]); cudaFree(p->eval[w]); cudaFree(p->dval[w]); }
     cudaFree(p->io[0]); cudaFree(p->io[1]);

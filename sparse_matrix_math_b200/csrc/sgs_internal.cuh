@@ -39,6 +39,8 @@ struct smm_precond {
     uint32_t* tile_push[2] = {nullptr, nullptr};   // [tiles * 64] operand slots inside the tile that consume the row's result
     int tile_levels[2] = {0, 0};
     int tile_chain[2] = {1, 1};      // tiles per chain (one warp solves a chain from end to end), per sweep
+    int tile_blocks = 0;             // cluster schedule: blocks of 32 chains, one thread-block cluster per block at a time (0: off)
+    uint32_t* tile_push2[2] = {nullptr, nullptr};  // cluster schedule: [tiles * 64] pushes that leave the tile (next tile of the chain, other chains of the block)
 };
 
 // sgs_tiles.cu

@@ -36,7 +36,11 @@
 #include <thread>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "sgs_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -45,6 +49,21 @@ namespace {
 #endif
 constexpr int TILE = 64;
 constexpr int TILE_MAX_W = 4;
+// Cluster schedule: a BLOCK of CLUSTER_CHAINS neighbouring chains is solved by one thread-block cluster (8 CTAs x 4 warps,
+// one warp per chain); operands that cross from one chain of the block to another travel through distributed shared memory.
+constexpr int CLUSTER_CTAS = 8;
+constexpr int CLUSTER_WARPS = 4;
+constexpr int CLUSTER_CHAINS = CLUSTER_CTAS * CLUSTER_WARPS;
+constexpr int INBOX_SLOTS = 32;                      // operands per tile that may arrive from other chains of the block
+constexpr int CLUSTER_MAX_CHAIN = 160;               // longest chain the inbox is sized for (4 warps x 160 tiles x 128 B = 80 KB per CTA)
+// operand codes in ecol for the cluster schedule (>= 0: position in the intermediate vector, polled through L2)
+constexpr int E_NONE = -1;                           // no operand (0 * 0)
+constexpr int E_LOCAL = -2;                          // pushed into the warp's own staging (same tile, or the previous tile of the chain)
+constexpr int E_INBOX = -16;                         // -16 - slot: arrives in the warp's inbox [tile of the chain][slot]
+// push2 word of a producer row: [7:0] staging slot of the consumer in the NEXT tile of the chain (0xFF: none),
+// [18:8] and [29:19]: (target warp of the cluster block << 5 | inbox slot) (0x7FF: none)
+constexpr uint32_t PUSH2_NONE = 0xFFu | (0x7FFu << 8) | (0x7FFu << 19);
+
 constexpr int MAX_STEPS = 64;
 constexpr int MAX_PREDS = 8;
 
@@ -60,6 +79,8 @@ struct TileArgs {
     long long ntiles;
     long long nchains;          // ntiles / chain_len
     int chain_len;              // tiles per chain (consecutive tile indices)
+    int nblocks;                // cluster schedule: blocks of CLUSTER_CHAINS chains (0: not laid out for clusters)
+    const uint32_t* push2;      // cluster schedule: [tiles * 64] pushes that leave the tile (PUSH2_*)
     int width;
     unsigned int sleep_first, sleep_later;
     unsigned long long* trace;  // debug (SMM_B200_SGS_TRACE): [tiles][4] globaltimer at claim / first step / solved, and the SM
@@ -248,6 +269,210 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / TILE_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Cluster schedule.  The trace of the chain schedule above (tools/sgs_trace.py, 256^3) shows where a sweep's time goes:
+// a tile is solved in 1.2 us, but the hand-off of its results through L2 (publish -> visible -> polled) costs another
+// 1.1 us, per tile along a chain and per hop from chain to chain: 126 hops x 2.5 us + 64 tiles x 2.4 us = 0.47 ms.
+// Here a thread-block CLUSTER (8 CTAs x 4 warps) takes a block of 32 neighbouring chains, one warp each, and results move
+// by PUSH through shared memory: to the rows of the same tile and of the chain's next tile in the warp's own staging
+// (double-buffered), to the other chains of the block straight into the consumer warp's INBOX over distributed shared
+// memory (mapa + st.shared::cluster; one slot per operand and tile of the chain, written once per sweep, so no flow
+// control is needed).  A consumer's operand fetch is a shared-memory load, and waiting is re-loading it: cheap enough to
+// wait row by row, so the chains of a block run three steps plus a DSMEM hop apart instead of a tile plus an L2 round
+// trip.  Only operands from OTHER blocks are still polled through L2 (whole-tile wait, as above).  Blocks are claimed in
+// dependency order by the resident clusters (no deadlock); the per-row arithmetic is unchanged (same bits).
+// ---------------------------------------------------------------------------------------------------------------
+struct ClusterBody {
+    int nsteps, step[2];
+    unsigned int push[2], push2[2];
+    float d[2], init[2];
+    int c[2][TILE_MAX_W];       // operand codes (E_*) or positions
+    float v[2][TILE_MAX_W];
+};
+
+__device__ __forceinline__ float lds_volatile(uint32_t addr) {
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void st_cluster_f32(uint32_t local_addr, unsigned int cta_rank, float v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta_rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
+template <bool FORWARD, bool IC0>
+__global__ void __cluster_dims__(CLUSTER_CTAS, 1, 1) __launch_bounds__(CLUSTER_WARPS * 32, SMM_TILE_MIN_CTAS * 4 / CLUSTER_WARPS)
+sgs_cluster_kernel(const TileArgs A, const float* __restrict__ rhs, float* yperm, float* xperm, float* __restrict__ x, unsigned int* tickets, const SolveState* st) {
+    if (st != nullptr && st->done) return;
+    extern __shared__ __align__(16) float cluster_smem[];      // stage [warp][2][256] | inbox [warp][chain_len][INBOX_SLOTS]
+    __shared__ unsigned int sh_block;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int crank = cluster.block_rank();
+    unsigned int* abort_flag = tickets + 2;
+    unsigned int* ticket = tickets + (FORWARD ? 0 : 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* src = FORWARD ? yperm : xperm;
+    float* dst = FORWARD ? yperm : xperm;
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(cluster_smem) + (uint32_t)warp * 2u * 1024u;
+    const uint32_t inbox_all = (uint32_t)__cvta_generic_to_shared(cluster_smem) + CLUSTER_WARPS * 2u * 1024u;   // same offset in every CTA
+    const uint32_t inbox_bytes = (uint32_t)A.chain_len * INBOX_SLOTS * 4u;                                       // per warp
+    float* const my_inbox = cluster_smem + CLUSTER_WARPS * 512 + (size_t)warp * A.chain_len * INBOX_SLOTS;
+
+    auto load_head = [&](const long long tile, const bool live) {
+        TileHead h;
+        h.row[0] = h.row[1] = -1;
+        h.yp[0] = h.yp[1] = 0;
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                h.row[k] = A.order[tile * TILE + k * 32 + lane];
+                if (!FORWARD) h.yp[k] = A.ypos[tile * TILE + k * 32 + lane];
+            }
+        }
+        return h;
+    };
+    auto load_body = [&](const long long tile, const bool live, const TileHead& h) {
+        ClusterBody b;
+        b.nsteps = live ? A.nsteps[tile] : 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const long long at = tile * TILE + k * 32 + lane;
+            b.step[k] = live ? A.row_step[at] : 255;
+            b.push[k] = live ? A.push[at] : 0u;
+            b.push2[k] = live ? A.push2[at] : PUSH2_NONE;
+            b.d[k] = live ? A.dval[at] : 1.0f;
+#pragma unroll
+            for (int e = 0; e < TILE_MAX_W; ++e) {
+                const bool in = live && e < A.width;
+                b.c[k][e] = in ? A.ecol[(tile * A.width + e) * TILE + k * 32 + lane] : E_NONE;
+                b.v[k][e] = in ? A.eval[(tile * A.width + e) * TILE + k * 32 + lane] : 0.0f;
+            }
+            b.init[k] = h.row[k] >= 0 ? (FORWARD ? rhs[h.row[k]] : yperm[h.yp[k]]) : 0.0f;
+        }
+        return b;
+    };
+    // tile `at` of the warp's chain
+    auto solve_tile = [&](const long long tile, const int at, const TileHead& h, const ClusterBody& b) {
+        const uint32_t mine = stage_addr + (uint32_t)(at & 1) * 1024u, next = stage_addr + (uint32_t)((at & 1) ^ 1) * 1024u;
+        const uint32_t inbox_row = inbox_all + (uint32_t)warp * inbox_bytes + (uint32_t)at * (INBOX_SLOTS * 4u);
+        // operands that come through L2 (other blocks): requested all at once, re-requested until everything is there
+        unsigned int pend = 0u;
+        unsigned int first[2 * TILE_MAX_W];
+#pragma unroll
+        for (int q = 0; q < 2 * TILE_MAX_W; ++q) {
+            const int c = b.c[q / TILE_MAX_W][q % TILE_MAX_W];
+            first[q] = c >= 0 ? peek(src + c) : 0u;
+        }
+        uint32_t addr[2][TILE_MAX_W];                          // where each operand is read from when the row's step comes
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+#pragma unroll
+            for (int e = 0; e < TILE_MAX_W; ++e) {
+                const int c = b.c[k][e];
+                const uint32_t slot = mine + 4u * (uint32_t)(4 * (k * 32 + lane) + e);
+                addr[k][e] = c <= E_INBOX ? inbox_row + 4u * (uint32_t)(E_INBOX - c) : slot;
+                if (c >= 0 && first[4 * k + e] == SENTINEL) pend |= 1u << (4 * k + e);
+                if (c >= 0 || c == E_NONE) sts_f32(slot, __uint_as_float(first[4 * k + e]));     // pushed slots (E_LOCAL) are left alone
+            }
+            if (FORWARD && !IC0 && h.row[k] >= 0 && fabsf(b.d[k]) < 1e-5) atomicOr(tickets + 3, 1u);   // H:1691-1693 (reported, not fatal here)
+        }
+        unsigned int polls = 0;
+        while (__any_sync(0xFFFFFFFFu, pend != 0u)) {
+            if (!poll_pause(&polls, abort_flag, A.sleep_first, A.sleep_later)) pend = 0u;
+            unsigned int bits[2 * TILE_MAX_W];
+#pragma unroll
+            for (int q = 0; q < 2 * TILE_MAX_W; ++q)
+                bits[q] = (pend >> q) & 1u ? peek(src + b.c[q / TILE_MAX_W][q % TILE_MAX_W]) : SENTINEL;
+#pragma unroll
+            for (int q = 0; q < 2 * TILE_MAX_W; ++q) {
+                if (bits[q] != SENTINEL) { pend &= ~(1u << q); sts_f32(mine + 4u * (uint32_t)(4 * ((q / TILE_MAX_W) * 32 + lane) + (q % TILE_MAX_W)), __uint_as_float(bits[q])); }
+            }
+        }
+        __syncwarp();
+        float solved[2] = {0.0f, 0.0f};
+        unsigned int spins = 0;
+        // One step: the rows that are due fetch their operands (staging or inbox: shared memory either way) and fetch them
+        // again for as long as one of them has not arrived from its neighbour chain; then the sum in operand order, the
+        // division, and the result pushed to every consumer that does not go through L2.
+        auto step_rows = [&](const bool due0, const bool due1) {
+            float o[2][TILE_MAX_W];
+            for (;;) {
+                bool missing = false;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (k == 0 ? due0 : due1) {
+#pragma unroll
+                        for (int e = 0; e < TILE_MAX_W; ++e) { o[k][e] = lds_volatile(addr[k][e]); missing |= __float_as_uint(o[k][e]) == SENTINEL; }
+                    }
+                }
+                if (!__any_sync(0xFFFFFFFFu, missing)) break;
+                if ((++spins & 1023u) == 0u) {
+                    if (peek(reinterpret_cast<const float*>(abort_flag)) != 0u || spins >= (POLL_LIMIT << 4)) { atomicExch(abort_flag, 1u); break; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k == 0 ? due0 : due1) {
+                    // same operand order and roundings as the row-level kernel (H:1685, H:1704, H:1813, H:1829)
+                    const float p0 = __fmul_rn(b.v[k][0], o[k][0]), p1 = __fmul_rn(b.v[k][1], o[k][1]), p2 = __fmul_rn(b.v[k][2], o[k][2]), p3 = __fmul_rn(b.v[k][3], o[k][3]);
+                    float acc = (FORWARD || IC0) ? b.init[k] : 0.0f;
+                    if (FORWARD || IC0) { acc = __fsub_rn(acc, p0); acc = __fsub_rn(acc, p1); acc = __fsub_rn(acc, p2); acc = __fsub_rn(acc, p3); }
+                    else { acc = __fadd_rn(p0, acc); acc = __fadd_rn(p1, acc); acc = __fadd_rn(p2, acc); acc = __fadd_rn(p3, acc); }
+                    const float res = (FORWARD || IC0) ? __fdiv_rn(acc, b.d[k]) : __fsub_rn(b.init[k], __fdiv_rn(acc, b.d[k]));
+                    const unsigned int pu = b.push[k], p2w = b.push2[k];
+                    sts_f32(mine + 4u * (pu & 255u), res); sts_f32(mine + 4u * ((pu >> 8) & 255u), res); sts_f32(mine + 4u * ((pu >> 16) & 255u), res);
+                    if ((p2w & 0xFFu) != 0xFFu) sts_f32(next + 4u * (p2w & 0xFFu), res);              // the chain's next tile
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {                                                     // other chains of the block: their inbox, over DSMEM
+                        const unsigned int r = (p2w >> (8 + 11 * j)) & 0x7FFu;
+                        if (r != 0x7FFu) {
+                            const unsigned int tw = r >> 5;
+                            st_cluster_f32(inbox_all + (tw & (CLUSTER_WARPS - 1)) * inbox_bytes + (uint32_t)at * (INBOX_SLOTS * 4u) + 4u * (r & 31u), tw / CLUSTER_WARPS, res);
+                        }
+                    }
+                    solved[k] = res;
+                }
+            }
+        };
+        const int first1 = __reduce_min_sync(0xFFFFFFFFu, b.step[1]);
+        const int last0 = __reduce_max_sync(0xFFFFFFFFu, b.step[0] == 255 ? -1 : b.step[0]);
+        int s = 0;
+        for (; s < b.nsteps && s < first1; ++s) { step_rows(s == b.step[0], false); __syncwarp(); }
+        for (; s < b.nsteps && s <= last0; ++s) { step_rows(s == b.step[0], s == b.step[1]); __syncwarp(); }
+        for (; s < b.nsteps; ++s) { step_rows(false, s == b.step[1]); __syncwarp(); }
+        // every row is also published to the intermediate vector: other blocks poll it, the backward sweep starts from it
+        float* const out = dst + (tile * TILE + lane);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (h.row[k] >= 0) {
+                publish(out + k * 32, solved[k]);
+                if (!FORWARD) x[h.row[k]] = solved[k];
+            }
+        }
+    };
+
+    for (;;) {
+        if (crank == 0 && threadIdx.x == 0) sh_block = atomicAdd(ticket, 1u);
+        cluster.sync();                                        // the previous block is finished everywhere; the claim is visible
+        const unsigned int blk = *cluster.map_shared_rank(&sh_block, 0);
+        if (blk >= (unsigned int)A.nblocks) break;
+        for (int i = lane; i < A.chain_len * INBOX_SLOTS; i += 32) my_inbox[i] = __uint_as_float(SENTINEL);
+        cluster.sync();                                        // every inbox of the cluster is empty before anybody pushes
+        const long long t0 = (((long long)blk * CLUSTER_CTAS + crank) * CLUSTER_WARPS + warp) * A.chain_len;
+        TileHead h0 = load_head(t0, true), h1 = load_head(t0 + 1, A.chain_len > 1);
+        ClusterBody r0 = load_body(t0, true, h0);
+        for (int at = 0; at < A.chain_len; ++at) {
+            const bool l1 = at + 1 < A.chain_len, l2 = at + 2 < A.chain_len;
+            const TileHead h2 = load_head(t0 + at + 2, l2);
+            const ClusterBody r1 = load_body(t0 + at + 1, l1, h1);
+            solve_tile(t0 + at, at, h0, r0);
+            h0 = h1; h1 = h2; r0 = r1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host: proposal + generic verification + layout
 // ---------------------------------------------------------------------------------------------------------------
 struct SweepLayout {
@@ -256,11 +481,21 @@ struct SweepLayout {
     std::vector<uint32_t> push;
     int levels = 0;
     int chain_len = 1;                               // tiles per chain (consecutive tile indices); 1: tiles in tile-level order
+    // cluster schedule (sgs_cluster_kernel): CLUSTER_CHAINS chains per block, a block per thread-block cluster at a time
+    int nblocks = 0;                                 // 0: not laid out for clusters
+    long long ntiles = 0;                            // tiles the arrays hold (padding chains of incomplete blocks included)
+    std::vector<uint32_t> push2;                     // [tiles * 64] where a row's result goes outside its tile (see PUSH2_*)
+};
+
+struct ClusterPlan {                                  // proposal: which block a chain belongs to and which warp of the cluster takes it
+    int nblocks = 0;
+    std::vector<int32_t> block_of_chain, warp_of_chain;
 };
 
 // cluster ids for a natural-order grid stencil, or empty when the column offsets are not of that kind
 // *chain_len: clusters [c * chain_len, (c + 1) * chain_len) are proposed as chain c (the tiles of one grid column along i)
-std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int* nclusters, int* chain_len = nullptr) {
+std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int* nclusters, int* chain_len = nullptr,
+                                        ClusterPlan* plan = nullptr) {
     // distinct |col - row| > 0 over a sample of the rows (head, middle, tail): this is only a proposal, what it leads to
     // is verified on every row by layout_sweep
     std::vector<long long> offs;
@@ -298,6 +533,18 @@ std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& st
     }
     *nclusters = (int)(TI * TJ * TK);
     if (chain_len) *chain_len = (int)TI;
+    if (plan) {
+        // blocks of 4 x 8 neighbouring columns (32 x 1 for a 2D grid): most hand-offs between chains stay inside a block
+        const long long BJ = TK > 1 ? 4 : CLUSTER_CHAINS, BK = TK > 1 ? 8 : 1;
+        const long long NBJ = (TJ + BJ - 1) / BJ, NBK = (TK + BK - 1) / BK;
+        plan->nblocks = (int)(NBJ * NBK);
+        plan->block_of_chain.resize((size_t)(TJ * TK));
+        plan->warp_of_chain.resize((size_t)(TJ * TK));
+        for (long long K = 0; K < TK; ++K) for (long long J = 0; J < TJ; ++J) {
+            plan->block_of_chain[(size_t)(K * TJ + J)] = (int32_t)((K / BK) * NBJ + J / BJ);
+            plan->warp_of_chain[(size_t)(K * TJ + J)] = (int32_t)((K % BK) * BJ + J % BJ);
+        }
+    }
     return cl;
 }
 
@@ -316,7 +563,7 @@ void for_clusters(int ncl, F f) {
 
 // Lay one sweep out by tiles.  Returns false when the proposal does not verify.
 bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag,
-                  const std::vector<int32_t>& cl, int ncl, int width, SweepLayout* out, int chain_len = 1) {
+                  const std::vector<int32_t>& cl, int ncl, int width, SweepLayout* out, int chain_len = 1, const ClusterPlan* plan = nullptr) {
     auto dep_begin = [&](int r) { return forward ? start[r] : diag[r] + 1; };
     auto dep_end = [&](int r) { return forward ? diag[r] : start[r + 1]; };
     // rows of every cluster, ascending
@@ -436,8 +683,45 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
             else { for (int c = nch - 1; c >= 0; --c) rank[c] = lp[clevel[c]]++; }
             for (int a = 0; a < ncl; ++a) tile_of[a] = rank[chain_of(a)] * chain_len + at_of(a);
             out->chain_len = chain_len;
+            // Cluster schedule: the proposed blocks of chains are verified -- the graph of the blocks must be acyclic -- and
+            // ordered by their level in it; chain rank = 32 * block rank + warp.  (Chains of one block run concurrently, one
+            // per warp of the cluster, so dependencies inside a block need no order.)
+            if (plan && plan->nblocks > 0 && (int)plan->block_of_chain.size() == nch) {
+                const int nb = plan->nblocks;
+                std::vector<std::vector<int32_t>> bsucc((size_t)nb);
+                std::vector<int32_t> bdeg((size_t)nb, 0), blevel((size_t)nb, 0), bq;
+                for (int c = 0; c < nch; ++c) for (int i = 0; i < ncp[c]; ++i) {
+                    const int bb = plan->block_of_chain[cpred[(size_t)c * MAX_PREDS + i]], b = plan->block_of_chain[c];
+                    if (bb != b && std::find(bsucc[bb].begin(), bsucc[bb].end(), b) == bsucc[bb].end()) { bsucc[bb].push_back(b); bdeg[b]++; }
+                }
+                for (int b = 0; b < nb; ++b) if (!bdeg[b]) bq.push_back(b);
+                for (size_t q = 0; q < bq.size(); ++q) for (int b : bsucc[bq[q]]) { blevel[b] = std::max(blevel[b], blevel[bq[q]] + 1); if (--bdeg[b] == 0) bq.push_back(b); }
+                bool okb = (int)bq.size() == nb;
+                std::vector<uint8_t> seen((size_t)nb * CLUSTER_CHAINS, 0);
+                for (int c = 0; c < nch && okb; ++c) {          // every chain its own warp of its block
+                    const int w = plan->warp_of_chain[c];
+                    okb = w >= 0 && w < CLUSTER_CHAINS && !seen[(size_t)plan->block_of_chain[c] * CLUSTER_CHAINS + w];
+                    if (okb) seen[(size_t)plan->block_of_chain[c] * CLUSTER_CHAINS + w] = 1;
+                }
+                if (okb) {
+                    std::vector<int32_t> order_b((size_t)nb), brank((size_t)nb);
+                    for (int b = 0; b < nb; ++b) order_b[b] = b;
+                    std::stable_sort(order_b.begin(), order_b.end(), [&](int x, int y) {
+                        if (blevel[x] != blevel[y]) return blevel[x] < blevel[y];
+                        return forward ? x < y : x > y;
+                    });
+                    for (int i = 0; i < nb; ++i) brank[order_b[i]] = i;
+                    for (int a = 0; a < ncl; ++a) {
+                        const int c = chain_of(a);
+                        tile_of[a] = (brank[plan->block_of_chain[c]] * CLUSTER_CHAINS + plan->warp_of_chain[c]) * chain_len + at_of(a);
+                    }
+                    out->nblocks = nb;
+                }
+            }
         }
     }
+    const int ntl = out->nblocks > 0 ? out->nblocks * CLUSTER_CHAINS * out->chain_len : ncl;   // tiles the arrays hold
+    out->ntiles = ntl;
     if (out->chain_len == 1) {                                 // tiles in level order (stable in the cluster id; the backward sweep runs the ids downwards)
         std::vector<int32_t> lptr((size_t)out->levels + 1, 0);
         for (int a = 0; a < ncl; ++a) lptr[(size_t)level[a] + 1]++;
@@ -446,9 +730,10 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
         if (forward) { for (int a = 0; a < ncl; ++a) tile_of[a] = cur[level[a]]++; }
         else { for (int a = ncl - 1; a >= 0; --a) tile_of[a] = cur[level[a]]++; }
     }
-    out->order.assign((size_t)ncl * TILE, -1);
+    out->order.assign((size_t)ntl * TILE, -1);
     out->where.assign((size_t)rows, 0);
-    out->steps.assign((size_t)ncl * TILE + (size_t)ncl, 255);    // [tiles * 64] step of every row, then [tiles] number of steps
+    out->steps.assign((size_t)ntl * TILE + (size_t)ntl, 255);    // [tiles * 64] step of every row, then [tiles] number of steps
+    if (out->nblocks > 0) std::fill(out->steps.begin() + (size_t)ntl * TILE, out->steps.end(), (uint8_t)0);   // padding tiles: no steps
     std::vector<int8_t> ilev((size_t)rows, 0);
     for_clusters(ncl, [&](int a) {
         const int n = cptr[a + 1] - cptr[a];
@@ -468,7 +753,7 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
         for (int l = 0; l < nl; ++l) at[l + 1] += at[l];
         for (int q = 0; q < n; ++q) { const int r = forward ? R[q] : R[n - 1 - q]; tmp[at[ilev[r]]++] = r; }
         const int t = tile_of[a];
-        out->steps[(size_t)ncl * TILE + t] = (uint8_t)nl;       // a step = an internal level (lane l solves rows l and l + 32)
+        out->steps[(size_t)ntl * TILE + t] = (uint8_t)nl;       // a step = an internal level (lane l solves rows l and l + 32)
         for (int i = 0; i < n; ++i) {
             out->steps[(size_t)t * TILE + i] = (uint8_t)ilev[tmp[i]];
             out->order[(size_t)t * TILE + i] = tmp[i];
@@ -479,12 +764,25 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
     // entries: [tile][slot][64], operand order = the reference's (ascending columns forward, descending backward);
     // push lists: where inside the tile's operand staging a row's result has to go (bytes 0..2; a byte that is not needed
     // points at the row's own first slot, which nobody reads once the row is solved)
-    out->ecol.assign((size_t)ncl * width * TILE, -1);
-    out->eidx.assign((size_t)ncl * width * TILE, -1);
-    out->push.assign((size_t)ncl * TILE, 0u);
-    for_clusters(ncl, [&](int a) {                             // a row is only pushed to rows of its own tile: no sharing between tiles
+    out->ecol.assign((size_t)ntl * width * TILE, -1);
+    out->eidx.assign((size_t)ntl * width * TILE, -1);
+    out->push.assign((size_t)ntl * TILE, 0u);
+    const bool clustered = out->nblocks > 0;
+    const int clen = out->chain_len;
+    if (clustered) out->push2.assign((size_t)ntl * TILE, PUSH2_NONE);
+    // claim a field of a producer row's push2 word (other consumer tiles are laid out by other threads): CAS
+    auto claim_push2 = [&](uint32_t* word, int shift, uint32_t mask, uint32_t value) {
+        uint32_t cur = __atomic_load_n(word, __ATOMIC_RELAXED);
+        for (;;) {
+            if (((cur >> shift) & mask) != mask) return false;                    // taken
+            const uint32_t want = (cur & ~(mask << shift)) | (value << shift);
+            if (__atomic_compare_exchange_n(word, &cur, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return true;
+        }
+    };
+    for_clusters(ncl, [&](int a) {                             // in-tile pushes touch the tile's own rows only; push2 words are claimed atomically
         const int t = tile_of[a];
         uint8_t npush[TILE] = {0};
+        int ninbox = 0;
         for (int i = 0; i < TILE; ++i) out->push[(size_t)t * TILE + i] = (uint32_t)(i * TILE_MAX_W) * 0x01010101u;
         for (int q = cptr[a]; q < cptr[a + 1]; ++q) {
             const int r = crow[q];
@@ -502,11 +800,29 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
                     const int sh = 8 * npush[j]++;
                     uint32_t& pu = out->push[(size_t)t * TILE + j];
                     pu = (pu & ~(0xFFu << sh)) | ((uint32_t)(i * TILE_MAX_W + e) << sh);
+                    if (clustered) out->ecol[at] = E_LOCAL;
+                } else if (clustered) {
+                    // the previous tile of the same chain (same warp: its staging), or the same tile index of another chain
+                    // of the block (another warp of the cluster: its inbox); everything else stays a polled position
+                    const int tp = w >> 6, chain_t = t / clen, chain_p = tp / clen;
+                    uint32_t* word = &out->push2[(size_t)w];
+                    if (chain_p == chain_t && tp == t - 1) {
+                        if (claim_push2(word, 0, 0xFFu, (uint32_t)(i * TILE_MAX_W + e))) out->ecol[at] = E_LOCAL;
+                    } else if (chain_p / CLUSTER_CHAINS == chain_t / CLUSTER_CHAINS && tp % clen == t % clen && ninbox < INBOX_SLOTS) {
+                        const uint32_t v = ((uint32_t)(chain_t % CLUSTER_CHAINS) << 5) | (uint32_t)ninbox;
+                        if (claim_push2(word, 8, 0x7FFu, v) || claim_push2(word, 19, 0x7FFu, v)) out->ecol[at] = E_INBOX - ninbox++;
+                    }
                 }
             }
         }
     });
     if (bad) return false;
+    if (clustered) {                                           // the two remote fields in a canonical order (they were claimed by racing threads)
+        for (uint32_t& v : out->push2) {
+            const uint32_t r0 = (v >> 8) & 0x7FFu, r1 = (v >> 19) & 0x7FFu;
+            if (r0 > r1) v = (v & 0xFFu) | (r1 << 8) | (r0 << 19);
+        }
+    }
     return true;
 }
 
@@ -527,16 +843,29 @@ bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& s
     if (width > TILE_MAX_W) return false;
     if (width == 0) width = 1;
     int ncl = 0, chain_len = 1;
-    const std::vector<int32_t> cl = propose_grid_tiles(rows, start, pos, &ncl, &chain_len);
+    ClusterPlan plan;
+    const std::vector<int32_t> cl = propose_grid_tiles(rows, start, pos, &ncl, &chain_len, &plan);
     if (cl.empty()) return false;
-    if (const char* e = getenv("SMM_B200_SGS_CHAINS")) { if (atoi(e) == 0) chain_len = 1; }   // A/B: tiles in tile-level order
+    // A/B knobs: SMM_B200_SGS_CHAINS=0 tiles in tile-level order; SMM_B200_SGS_CLUSTERS=0 chains without the cluster schedule
+    if (const char* e = getenv("SMM_B200_SGS_CHAINS")) { if (atoi(e) == 0) chain_len = 1; }
+    bool want_clusters = chain_len > 1 && chain_len <= CLUSTER_MAX_CHAIN;
+    if (const char* e = getenv("SMM_B200_SGS_CLUSTERS")) { if (atoi(e) == 0) want_clusters = false; }
     SweepLayout L[2];                                          // the two sweeps are laid out side by side (set-up time)
-    std::future<bool> bwd = std::async(std::launch::async, [&] { return layout_sweep(false, rows, start, pos, diag, cl, ncl, width, &L[1], chain_len); });
-    const bool fwd_ok = layout_sweep(true, rows, start, pos, diag, cl, ncl, width, &L[0], chain_len);
-    if (!bwd.get() || !fwd_ok) return false;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const ClusterPlan* pl = want_clusters ? &plan : nullptr;
+        L[0] = SweepLayout(); L[1] = SweepLayout();
+        std::future<bool> bwd = std::async(std::launch::async, [&] { return layout_sweep(false, rows, start, pos, diag, cl, ncl, width, &L[1], chain_len, pl); });
+        const bool fwd_ok = layout_sweep(true, rows, start, pos, diag, cl, ncl, width, &L[0], chain_len, pl);
+        if (!bwd.get() || !fwd_ok) return false;
+        // both sweeps must agree on the schedule kind and on the padded size (they share the position space)
+        if ((L[0].nblocks > 0) == (L[1].nblocks > 0) && L[0].ntiles == L[1].ntiles) break;
+        if (!want_clusters) return false;
+        want_clusters = false;
+    }
     std::vector<int32_t> yp(L[1].order.size(), 0);
     for (size_t t = 0; t < yp.size(); ++t) if (L[1].order[t] >= 0) yp[t] = L[0].where[(size_t)L[1].order[t]];
-    const size_t npos = (size_t)ncl * TILE;
+    const size_t npos = (size_t)L[0].ntiles * TILE;
+    p->tile_blocks = L[0].nblocks;
     p->threads_fwd = p->threads_bwd = (long long)npos;
     p->tile_width = width;
     p->tile_levels[0] = L[0].levels;
@@ -548,7 +877,8 @@ bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& s
     for (int w = 0; w < 2 && ok; ++w) {
         p->esize[w] = (long long)L[w].ecol.size();
         ok = upload(L[w].ecol, &p->ecol[w]) == SMM_OK && upload(L[w].eidx, &p->eidx[w]) == SMM_OK && upload(L[w].steps, &p->tile_steps[w]) == SMM_OK &&
-             upload(L[w].push, &p->tile_push[w]) == SMM_OK && cudaMalloc(&p->eval[w], sizeof(float) * L[w].ecol.size()) == cudaSuccess &&
+             upload(L[w].push, &p->tile_push[w]) == SMM_OK && (L[w].push2.empty() || upload(L[w].push2, &p->tile_push2[w]) == SMM_OK) &&
+             cudaMalloc(&p->eval[w], sizeof(float) * L[w].ecol.size()) == cudaSuccess &&
              cudaMalloc(&p->dval[w], sizeof(float) * npos) == cudaSuccess;
     }
     if (!ok) {                                                  // out of memory: leave the handle as it was, the row-level schedule needs less
@@ -557,11 +887,12 @@ bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& s
         p->order_fwd = p->order_bwd = p->ypos = nullptr;
         p->yperm = p->xperm = nullptr;
         for (int w = 0; w < 2; ++w) {
-            cudaFree(p->ecol[w]); cudaFree(p->eidx[w]); cudaFree(p->tile_steps[w]); cudaFree(p->tile_push[w]); cudaFree(p->eval[w]); cudaFree(p->dval[w]);
-            p->ecol[w] = p->eidx[w] = nullptr; p->tile_steps[w] = nullptr; p->tile_push[w] = nullptr; p->eval[w] = p->dval[w] = nullptr;
+            cudaFree(p->ecol[w]); cudaFree(p->eidx[w]); cudaFree(p->tile_steps[w]); cudaFree(p->tile_push[w]); cudaFree(p->tile_push2[w]); cudaFree(p->eval[w]); cudaFree(p->dval[w]);
+            p->ecol[w] = p->eidx[w] = nullptr; p->tile_steps[w] = nullptr; p->tile_push[w] = nullptr; p->tile_push2[w] = nullptr; p->eval[w] = p->dval[w] = nullptr;
             p->esize[w] = 0;
         }
         p->threads_fwd = p->threads_bwd = 0;
+        p->tile_blocks = 0;
         return false;
     }
     p->tiled = true;
@@ -599,6 +930,56 @@ void launch_tiles(const smm_precond* p, const TileArgs& F, const TileArgs& B, co
 }
 }  // namespace
 
+namespace {
+size_t cluster_smem_bytes(int chain_len) { return (size_t)CLUSTER_WARPS * 2 * 1024 + (size_t)CLUSTER_WARPS * chain_len * INBOX_SLOTS * sizeof(float); }
+
+template <bool FORWARD, bool IC0>
+int launch_cluster_sweep(const smm_precond* p, const TileArgs& A, const float* rhs_dev, float* x_dev, SolveState* state, cudaStream_t s) {
+    const size_t smem = cluster_smem_bytes(A.chain_len);
+    // persistent grid: as many clusters as can be resident (the rest would only find the ticket used up)
+    static int resident_dev[SMM_MAX_DEVICES][2][2] = {};
+    int resident;
+    {
+        std::lock_guard<std::mutex> lk(g_smm_attr_mu);
+        int& r = resident_dev[p->m->device % SMM_MAX_DEVICES][FORWARD ? 1 : 0][IC0 ? 1 : 0];
+        if (!r) {
+            SMM_CUDA(cudaFuncSetAttribute(sgs_cluster_kernel<FORWARD, IC0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes(CLUSTER_MAX_CHAIN)));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(CLUSTER_CTAS * 1024); cfg.blockDim = dim3(CLUSTER_WARPS * 32); cfg.dynamicSmemBytes = cluster_smem_bytes(CLUSTER_MAX_CHAIN);
+            cudaLaunchAttribute at;
+            at.id = cudaLaunchAttributeClusterDimension;
+            at.val.clusterDim.x = CLUSTER_CTAS; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+            cfg.attrs = &at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, sgs_cluster_kernel<FORWARD, IC0>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = p->m->sm_count / CLUSTER_CTAS; }
+            r = n;
+        }
+        resident = r;
+    }
+    // the occupancy was queried for the largest inbox; shorter chains leave room for more clusters, bounded by the warps per SM
+    long long fit = resident;
+    if (A.chain_len < CLUSTER_MAX_CHAIN) {
+        const long long by_smem = (long long)((227 * 1024) / (smem + 1024)), by_warps = 2048 / (CLUSTER_WARPS * 32), by_regs = SMM_TILE_MIN_CTAS * 4 / CLUSTER_WARPS + 1;
+        const long long per_sm = std::min(by_smem, std::min(by_warps, by_regs));
+        fit = std::max<long long>(resident, per_sm * p->m->sm_count / CLUSTER_CTAS * 7 / 8);
+    }
+    const unsigned clusters = (unsigned)std::min<long long>(fit, A.nblocks);
+    sgs_cluster_kernel<FORWARD, IC0><<<clusters * CLUSTER_CTAS, CLUSTER_WARPS * 32, smem, s>>>(A, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+    return SMM_OK;
+}
+
+int launch_clusters(const smm_precond* p, const TileArgs& F, const TileArgs& B, const float* rhs_dev, float* x_dev, SolveState* state, cudaStream_t s) {
+    if (p->kind != 0) {
+        SMM_TRY((launch_cluster_sweep<true, true>(p, F, rhs_dev, x_dev, state, s)));
+        SMM_TRY((launch_cluster_sweep<false, true>(p, B, rhs_dev, x_dev, state, s)));
+    } else {
+        SMM_TRY((launch_cluster_sweep<true, false>(p, F, rhs_dev, x_dev, state, s)));
+        SMM_TRY((launch_cluster_sweep<false, false>(p, B, rhs_dev, x_dev, state, s)));
+    }
+    return SMM_OK;
+}
+}  // namespace
+
 int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, int ctas_per_sm, unsigned int sleep_first,
                          unsigned int sleep_later, cudaStream_t s) {
     const long long ntiles = p->threads_fwd / TILE;
@@ -616,9 +997,12 @@ int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_de
     const uint8_t* nsf = p->tile_steps[0] + ntiles * TILE;
     const uint8_t* nsb = p->tile_steps[1] + ntiles * TILE;
     const int cf = p->tile_chain[0] > 0 ? p->tile_chain[0] : 1, cb = p->tile_chain[1] > 0 ? p->tile_chain[1] : 1;
-    TileArgs F{nsf, p->tile_steps[0], p->tile_push[0], p->order_fwd, nullptr, p->ecol[0], p->eval[0], p->dval[0], ntiles, ntiles / cf, cf, p->tile_width, sleep_first, sleep_later, trace};
-    TileArgs B{nsb, p->tile_steps[1], p->tile_push[1], p->order_bwd, p->ypos, p->ecol[1], p->eval[1], p->dval[1], ntiles, ntiles / cb, cb, p->tile_width, sleep_first, sleep_later, nullptr};
-    launch_tiles<4>(p, F, B, rhs_dev, x_dev, state, cap, s);   // 1, 2 and 8 tiles per CTA claim measured the same
+    TileArgs F{nsf, p->tile_steps[0], p->tile_push[0], p->order_fwd, nullptr, p->ecol[0], p->eval[0], p->dval[0], ntiles, ntiles / cf, cf, p->tile_blocks,
+               p->tile_push2[0], p->tile_width, sleep_first, sleep_later, trace};
+    TileArgs B{nsb, p->tile_steps[1], p->tile_push[1], p->order_bwd, p->ypos, p->ecol[1], p->eval[1], p->dval[1], ntiles, ntiles / cb, cb, p->tile_blocks,
+               p->tile_push2[1], p->tile_width, sleep_first, sleep_later, nullptr};
+    if (p->tile_blocks > 0) SMM_TRY(launch_clusters(p, F, B, rhs_dev, x_dev, state, s));
+    else launch_tiles<4>(p, F, B, rhs_dev, x_dev, state, cap, s);   // 1, 2 and 8 tiles per CTA claim measured the same
     SMM_CUDA(cudaGetLastError());
     if (trace) {
         std::vector<unsigned long long> h(4 * (size_t)ntiles);

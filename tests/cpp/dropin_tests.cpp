@@ -465,16 +465,19 @@ TEST_CASE("Row-partitioned over N GPUs behind the reference's calls (skipped on 
         for (int i = 0; i < n; ++i) d += xa[i] != xb[i];
         CHECK_EQ(d, 0);
     }
-    // throughput mode on N GPUs: converges to the known solution (x = 1); BiCGStab without preconditioner shards as well
+    // throughput mode on N GPUs: converges (true residual b - A x, computed on the N GPUs as well, below the tolerance; the
+    // solution itself is only determined to ||r|| / lambda_min ~ 0.4 on this grid); BiCGStab without preconditioner shards too
     SMM::b200::options().reduction_mode = SMM_REDUCE_FAST;
     SMM::b200::devices() = ngpu;
     {
-        SMM::Vector<T> x(n, 0);
+        SMM::Vector<T> x(n, 0), res(n, 0);
         REQUIRE_EQ(SMM::ConjugateGradient<T>(m, rhs, x, x, -1, kL2Eps), SMM::SolverStatus::SUCCESS);
-        for (const T ri : x) CHECK_APPROX(T(1), ri, 1e-3);
+        m.rMultSub(rhs, x, res);
+        CHECK(res.secondNorm() < 5 * kL2Eps);
         SMM::Vector<T> x2(n, 0);
         REQUIRE_EQ(SMM::BiCGStab<T>(m, rhs, x2, -1, kL2Eps), SMM::SolverStatus::SUCCESS);
-        for (const T ri : x2) CHECK_APPROX(T(1), ri, 1e-3);
+        m.rMultSub(rhs, x2, res);
+        CHECK(res.secondNorm() < 5 * kL2Eps);
     }
     // host-side mutation reaches every GPU's rows
     m *= 2.0f;

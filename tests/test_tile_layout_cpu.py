@@ -19,6 +19,10 @@ GOLDEN = {
     ("64", "64", "64", "0", "0"): (46, 1, "3af65eb5649ada45", "5de0bdfdeda5a402"),
     ("70", "45", "33"): (37, 18, "e26b9f3a74916599", "1f94717455d29427"),     # ragged 3D grid
     ("200", "150", "1"): (43, 25, "e24e55652b9de722", "625e836d02b6c2bf"),    # 2D, 8 x 8 tiles
+    # cluster schedule (sixth argument 1): blocks of 32 chains, pushes through shared memory / DSMEM; the tool also EMULATES it
+    ("64", "64", "64", "0", "1", "1"): (46, 16, "02fa02a7b0c79573", "ff4be9ebd2480348"),
+    ("70", "45", "33", "0", "1", "1"): (37, 18, "1d933aedc1993fc0", "46952ecfb209f4c8"),
+    ("200", "150", "1", "0", "1", "1"): (43, 25, "22027ff9aedf6757", "0b7611ae10617423"),
 }
 
 
@@ -42,6 +46,20 @@ def test_tile_layout_fingerprints(exe, dims):
     # every operand comes from an earlier step of the tile, an earlier tile of the chain or a chain handed out earlier: no deadlock
     assert all(g[5] == "1" for g in got), out
     assert got[0][3] == fwd and got[1][3] == bwd, out
+    if len(dims) > 5 and dims[5] == "1":
+        # the host emulation of the cluster kernel's data flow (staging, inboxes, published vector) reproduces a plain
+        # triangular solve bit for bit and solves every row (no deadlock)
+        emu = re.findall(r"(forward|backward)\s+cluster blocks (\d+) tiles (\d+) emulation_ok (\d)", out)
+        assert [e[0] for e in emu] == ["forward", "backward"] and all(e[3] == "1" and int(e[1]) > 0 for e in emu), out
+
+
+@pytest.mark.parametrize("dims", [("24", "20", "16"), ("129", "67", "40"), ("520", "300", "1"), ("33", "9", "70")])
+def test_cluster_schedule_emulation(exe, dims):
+    """Ragged and thin grids: incomplete blocks (padding chains), short chains, 2D."""
+    out = subprocess.run([exe, *dims, "0", "1", "1"], capture_output=True, text=True, timeout=300).stdout
+    emu = re.findall(r"(forward|backward)\s+cluster blocks (\d+) tiles (\d+) emulation_ok (\d)", out)
+    assert [e[0] for e in emu] == ["forward", "backward"] and all(e[3] == "1" for e in emu), out
+    assert len(re.findall(r"schedule_ok 1", out)) == 2, out
 
 
 def test_tile_proposal_with_cycles_is_rejected(exe):
