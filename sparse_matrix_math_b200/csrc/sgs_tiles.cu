@@ -356,6 +356,7 @@ sgs_cluster_kernel(const TileArgs A, const float* __restrict__ rhs, float* yperm
     auto solve_tile = [&](const long long tile, const int at, const TileHead& h, const ClusterBody& b) {
         const uint32_t mine = stage_addr + (uint32_t)(at & 1) * 1024u, next = stage_addr + (uint32_t)((at & 1) ^ 1) * 1024u;
         const uint32_t inbox_row = inbox_all + (uint32_t)warp * inbox_bytes + (uint32_t)at * (INBOX_SLOTS * 4u);
+        if (A.trace && lane == 0) A.trace[4ll * tile] = tile_clock();
         // operands that come through L2 (other blocks): requested all at once, re-requested until everything is there
         unsigned int pend = 0u;
         unsigned int first[2 * TILE_MAX_W];
@@ -364,14 +365,20 @@ sgs_cluster_kernel(const TileArgs A, const float* __restrict__ rhs, float* yperm
             const int c = b.c[q / TILE_MAX_W][q % TILE_MAX_W];
             first[q] = c >= 0 ? peek(src + c) : 0u;
         }
-        uint32_t addr[2][TILE_MAX_W];                          // where each operand is read from when the row's step comes
+        // up to two operands per row arrive in the inbox (other chains of the block): their shared-memory addresses and
+        // which operand they are; everything else is in the row's four staging slots (one conflict-free 128-bit load)
+        uint32_t ibaddr[2][2] = {{0u, 0u}, {0u, 0u}};
+        int ibe[2][2] = {{-1, -1}, {-1, -1}};
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
 #pragma unroll
             for (int e = 0; e < TILE_MAX_W; ++e) {
                 const int c = b.c[k][e];
                 const uint32_t slot = mine + 4u * (uint32_t)(4 * (k * 32 + lane) + e);
-                addr[k][e] = c <= E_INBOX ? inbox_row + 4u * (uint32_t)(E_INBOX - c) : slot;
+                if (c <= E_INBOX) {
+                    const uint32_t a_ = inbox_row + 4u * (uint32_t)(E_INBOX - c);
+                    if (ibe[k][0] < 0) { ibaddr[k][0] = a_; ibe[k][0] = e; } else { ibaddr[k][1] = a_; ibe[k][1] = e; }
+                }
                 if (c >= 0 && first[4 * k + e] == SENTINEL) pend |= 1u << (4 * k + e);
                 if (c >= 0 || c == E_NONE) sts_f32(slot, __uint_as_float(first[4 * k + e]));     // pushed slots (E_LOCAL) are left alone
             }
@@ -390,47 +397,56 @@ sgs_cluster_kernel(const TileArgs A, const float* __restrict__ rhs, float* yperm
             }
         }
         __syncwarp();
+        if (A.trace && lane == 0) A.trace[4ll * tile + 1] = tile_clock();         // L2 operands complete
         float solved[2] = {0.0f, 0.0f};
         unsigned int spins = 0;
-        // One step: the rows that are due fetch their operands (staging or inbox: shared memory either way) and fetch them
-        // again for as long as one of them has not arrived from its neighbour chain; then the sum in operand order, the
-        // division, and the result pushed to every consumer that does not go through L2.
+        // One step: a row that is due takes the operands that arrive from neighbour chains out of its inbox -- re-reading them,
+        // with a short pause, for as long as one has not arrived -- and the rest out of its staging slots; then the sum in
+        // operand order, the division, and the result pushed to every consumer that does not go through L2.
         auto step_rows = [&](const bool due0, const bool due1) {
-            float o[2][TILE_MAX_W];
+            float in0[2] = {0.0f, 0.0f}, in1[2] = {0.0f, 0.0f};
             for (;;) {
                 bool missing = false;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     if (k == 0 ? due0 : due1) {
-#pragma unroll
-                        for (int e = 0; e < TILE_MAX_W; ++e) { o[k][e] = lds_volatile(addr[k][e]); missing |= __float_as_uint(o[k][e]) == SENTINEL; }
+                        if (ibe[k][0] >= 0) { in0[k] = lds_volatile(ibaddr[k][0]); missing |= __float_as_uint(in0[k]) == SENTINEL; }
+                        if (ibe[k][1] >= 0) { in1[k] = lds_volatile(ibaddr[k][1]); missing |= __float_as_uint(in1[k]) == SENTINEL; }
                     }
                 }
                 if (!__any_sync(0xFFFFFFFFu, missing)) break;
+                __nanosleep(32);
                 if ((++spins & 1023u) == 0u) {
-                    if (peek(reinterpret_cast<const float*>(abort_flag)) != 0u || spins >= (POLL_LIMIT << 4)) { atomicExch(abort_flag, 1u); break; }
+                    if (peek(reinterpret_cast<const float*>(abort_flag)) != 0u || spins >= (POLL_LIMIT << 2)) { atomicExch(abort_flag, 1u); break; }
                 }
             }
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (k == 0 ? due0 : due1) {
+                    float4 xo;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(xo.x), "=f"(xo.y), "=f"(xo.z), "=f"(xo.w) : "r"(mine + 16u * (uint32_t)(k * 32 + lane)) : "memory");
+                    const int e0 = ibe[k][0], e1 = ibe[k][1];
+                    xo.x = e0 == 0 ? in0[k] : (e1 == 0 ? in1[k] : xo.x);
+                    xo.y = e0 == 1 ? in0[k] : (e1 == 1 ? in1[k] : xo.y);
+                    xo.z = e0 == 2 ? in0[k] : (e1 == 2 ? in1[k] : xo.z);
+                    xo.w = e0 == 3 ? in0[k] : (e1 == 3 ? in1[k] : xo.w);
                     // same operand order and roundings as the row-level kernel (H:1685, H:1704, H:1813, H:1829)
-                    const float p0 = __fmul_rn(b.v[k][0], o[k][0]), p1 = __fmul_rn(b.v[k][1], o[k][1]), p2 = __fmul_rn(b.v[k][2], o[k][2]), p3 = __fmul_rn(b.v[k][3], o[k][3]);
+                    const float p0 = __fmul_rn(b.v[k][0], xo.x), p1 = __fmul_rn(b.v[k][1], xo.y), p2 = __fmul_rn(b.v[k][2], xo.z), p3 = __fmul_rn(b.v[k][3], xo.w);
                     float acc = (FORWARD || IC0) ? b.init[k] : 0.0f;
                     if (FORWARD || IC0) { acc = __fsub_rn(acc, p0); acc = __fsub_rn(acc, p1); acc = __fsub_rn(acc, p2); acc = __fsub_rn(acc, p3); }
                     else { acc = __fadd_rn(p0, acc); acc = __fadd_rn(p1, acc); acc = __fadd_rn(p2, acc); acc = __fadd_rn(p3, acc); }
                     const float res = (FORWARD || IC0) ? __fdiv_rn(acc, b.d[k]) : __fsub_rn(b.init[k], __fdiv_rn(acc, b.d[k]));
                     const unsigned int pu = b.push[k], p2w = b.push2[k];
-                    sts_f32(mine + 4u * (pu & 255u), res); sts_f32(mine + 4u * ((pu >> 8) & 255u), res); sts_f32(mine + 4u * ((pu >> 16) & 255u), res);
-                    if ((p2w & 0xFFu) != 0xFFu) sts_f32(next + 4u * (p2w & 0xFFu), res);              // the chain's next tile
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {                                                     // other chains of the block: their inbox, over DSMEM
+                    for (int j = 0; j < 2; ++j) {                                                     // other chains of the block first (the longest way): their inbox, over DSMEM
                         const unsigned int r = (p2w >> (8 + 11 * j)) & 0x7FFu;
                         if (r != 0x7FFu) {
                             const unsigned int tw = r >> 5;
                             st_cluster_f32(inbox_all + (tw & (CLUSTER_WARPS - 1)) * inbox_bytes + (uint32_t)at * (INBOX_SLOTS * 4u) + 4u * (r & 31u), tw / CLUSTER_WARPS, res);
                         }
                     }
+                    sts_f32(mine + 4u * (pu & 255u), res); sts_f32(mine + 4u * ((pu >> 8) & 255u), res); sts_f32(mine + 4u * ((pu >> 16) & 255u), res);
+                    if ((p2w & 0xFFu) != 0xFFu) sts_f32(next + 4u * (p2w & 0xFFu), res);              // the chain's next tile
                     solved[k] = res;
                 }
             }
@@ -441,6 +457,11 @@ sgs_cluster_kernel(const TileArgs A, const float* __restrict__ rhs, float* yperm
         for (; s < b.nsteps && s < first1; ++s) { step_rows(s == b.step[0], false); __syncwarp(); }
         for (; s < b.nsteps && s <= last0; ++s) { step_rows(s == b.step[0], s == b.step[1]); __syncwarp(); }
         for (; s < b.nsteps; ++s) { step_rows(false, s == b.step[1]); __syncwarp(); }
+        if (A.trace && lane == 0) {
+            unsigned int sm;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+            A.trace[4ll * tile + 2] = tile_clock(); A.trace[4ll * tile + 3] = sm;
+        }
         // every row is also published to the intermediate vector: other blocks poll it, the backward sweep starts from it
         float* const out = dst + (tile * TILE + lane);
 #pragma unroll
@@ -456,7 +477,10 @@ sgs_cluster_kernel(const TileArgs A, const float* __restrict__ rhs, float* yperm
         if (crank == 0 && threadIdx.x == 0) sh_block = atomicAdd(ticket, 1u);
         cluster.sync();                                        // the previous block is finished everywhere; the claim is visible
         const unsigned int blk = *cluster.map_shared_rank(&sh_block, 0);
-        if (blk >= (unsigned int)A.nblocks) break;
+        if (blk >= (unsigned int)A.nblocks) {
+            cluster.sync();                                    // nobody may leave while a peer still reads its shared memory (the claim above)
+            break;
+        }
         for (int i = lane; i < A.chain_len * INBOX_SLOTS; i += 32) my_inbox[i] = __uint_as_float(SENTINEL);
         cluster.sync();                                        // every inbox of the cluster is empty before anybody pushes
         const long long t0 = (((long long)blk * CLUSTER_CTAS + crank) * CLUSTER_WARPS + warp) * A.chain_len;
@@ -846,10 +870,14 @@ bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& s
     ClusterPlan plan;
     const std::vector<int32_t> cl = propose_grid_tiles(rows, start, pos, &ncl, &chain_len, &plan);
     if (cl.empty()) return false;
-    // A/B knobs: SMM_B200_SGS_CHAINS=0 tiles in tile-level order; SMM_B200_SGS_CLUSTERS=0 chains without the cluster schedule
-    if (const char* e = getenv("SMM_B200_SGS_CHAINS")) { if (atoi(e) == 0) chain_len = 1; }
-    bool want_clusters = chain_len > 1 && chain_len <= CLUSTER_MAX_CHAIN;
-    if (const char* e = getenv("SMM_B200_SGS_CLUSTERS")) { if (atoi(e) == 0) want_clusters = false; }
+    // Schedule.  Default: tiles in tile-level order, one warp per tile -- the fastest of the three on every grid measured
+    // (256^3 apply: 0.96 ms; chains 0.99 ms; clusters 1.43-1.94 ms, profiles/r02_sgs_schedules.txt).  The other two are kept
+    // selectable for measurements: SMM_B200_SGS_CHAINS=1 (a warp marches along a column of tiles), SMM_B200_SGS_CLUSTERS=1
+    // (chains in blocks of 32, hand-offs inside a block pushed through shared memory / DSMEM by a thread-block cluster).
+    const char* e_chains = getenv("SMM_B200_SGS_CHAINS");
+    const char* e_clusters = getenv("SMM_B200_SGS_CLUSTERS");
+    bool want_clusters = e_clusters && atoi(e_clusters) != 0 && chain_len > 1 && chain_len <= CLUSTER_MAX_CHAIN;
+    if (!want_clusters && !(e_chains && atoi(e_chains) != 0)) chain_len = 1;
     SweepLayout L[2];                                          // the two sweeps are laid out side by side (set-up time)
     for (int attempt = 0; attempt < 2; ++attempt) {
         const ClusterPlan* pl = want_clusters ? &plan : nullptr;
