@@ -169,6 +169,11 @@ __device__ __forceinline__ void row_path(const SpmvParams& P, int r0, int r1, Wr
     }
 }
 
+// DEPTH: 128-bit index/value vectors a thread has in flight before its gathers (4 * DEPTH gathers of mult[] per thread);
+// HINTS: L2 eviction priorities -- the streamed values/positions are marked evict-first and the gathered vector evict-last, so
+// that on matrices whose gathers have no locality (power-law rows, config 4) the 8 * nnz bytes passing through do not push
+// the 4 * cols bytes that are gathered again and again out of L2.
+template <int DEPTH, bool HINTS>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const SpmvParams P) {
     if (P.state != nullptr && P.state->done) return;
 
@@ -197,20 +202,50 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const SpmvParams P) 
             const int4* pos4 = reinterpret_cast<const int4*>(P.positions + a0);
             const float4* val4 = reinterpret_cast<const float4*>(P.values + a0);
             const int nvec = span >> 2;                       // full vectors inside [a0, k1)
-            // two vectors per thread in flight before the dependent gathers
-            for (int v = tid; v < nvec; v += 2 * SPMV_THREADS) {
-                const int v2 = v + SPMV_THREADS;
-                const bool has2 = v2 < nvec;
-                const int4 c = ldg_stream_i4(pos4 + v);
-                const float4 a = ldg_stream_f4(val4 + v);
-                int4 c2 = make_int4(0, 0, 0, 0);
-                float4 a2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has2) { c2 = ldg_stream_i4(pos4 + v2); a2 = ldg_stream_f4(val4 + v2); }
-                const float x0 = __ldg(P.mult + c.x), x1 = __ldg(P.mult + c.y), x2 = __ldg(P.mult + c.z), x3 = __ldg(P.mult + c.w);
-                float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
-                if (has2) { y0 = __ldg(P.mult + c2.x); y1 = __ldg(P.mult + c2.y); y2 = __ldg(P.mult + c2.z); y3 = __ldg(P.mult + c2.w); }
-                reinterpret_cast<float4*>(prod)[v] = make_float4(__fmul_rn(a.x, x0), __fmul_rn(a.y, x1), __fmul_rn(a.z, x2), __fmul_rn(a.w, x3));
-                if (has2) reinterpret_cast<float4*>(prod)[v2] = make_float4(__fmul_rn(a2.x, y0), __fmul_rn(a2.y, y1), __fmul_rn(a2.z, y2), __fmul_rn(a2.w, y3));
+            // DEPTH vectors per thread in flight before the dependent gathers
+            unsigned long long pol_stream = 0ull, pol_keep = 0ull;
+            if (HINTS) {
+                asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+                asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            }
+            auto load_c = [&](const int4* p) {
+                if (!HINTS) return ldg_stream_i4(p);
+                int4 r;
+                asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol_stream));
+                return r;
+            };
+            auto load_a = [&](const float4* p) {
+                if (!HINTS) return ldg_stream_f4(p);
+                float4 r;
+                asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol_stream));
+                return r;
+            };
+            auto load_x = [&](const int c) {
+                if (!HINTS) return __ldg(P.mult + c);
+                float r;
+                asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(P.mult + c), "l"(pol_keep));
+                return r;
+            };
+            for (int v = tid; v < nvec; v += DEPTH * SPMV_THREADS) {
+                int4 c[DEPTH];
+                float4 a[DEPTH];
+#pragma unroll
+                for (int d = 0; d < DEPTH; ++d) {
+                    const int vd = v + d * SPMV_THREADS;
+                    if (vd < nvec) { c[d] = load_c(pos4 + vd); a[d] = load_a(val4 + vd); }
+                    else { c[d] = make_int4(0, 0, 0, 0); a[d] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                }
+                float4 x[DEPTH];
+#pragma unroll
+                for (int d = 0; d < DEPTH; ++d) {
+                    const bool in = v + d * SPMV_THREADS < nvec;
+                    x[d] = in ? make_float4(load_x(c[d].x), load_x(c[d].y), load_x(c[d].z), load_x(c[d].w)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int d = 0; d < DEPTH; ++d) {
+                    const int vd = v + d * SPMV_THREADS;
+                    if (vd < nvec) reinterpret_cast<float4*>(prod)[vd] = make_float4(__fmul_rn(a[d].x, x[d].x), __fmul_rn(a[d].y, x[d].y), __fmul_rn(a[d].z, x[d].z), __fmul_rn(a[d].w, x[d].w));
+                }
             }
             {   // tail of the window (fewer than 4 entries)
                 const int k = a0 + (nvec << 2) + tid;
@@ -635,7 +670,11 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
         }
 #undef SMM_ROWS_LAUNCH
     } else {
-        spmv_kernel<<<m->num_blocks, SPMV_THREADS, 0, s>>>(P);
+        // knobs for measurements: SMM_B200_SPMV_DEPTH = 2 | 4 (vectors in flight per thread), SMM_B200_SPMV_HINTS = 0 | 1 (L2 eviction priorities)
+        static const int depth = [] { const char* e = getenv("SMM_B200_SPMV_DEPTH"); const int v = e ? atoi(e) : 2; return v == 4 ? 4 : 2; }();
+        static const bool hints = [] { const char* e = getenv("SMM_B200_SPMV_HINTS"); return e ? atoi(e) != 0 : false; }();
+        if (depth == 4) { if (hints) spmv_kernel<4, true><<<m->num_blocks, SPMV_THREADS, 0, s>>>(P); else spmv_kernel<4, false><<<m->num_blocks, SPMV_THREADS, 0, s>>>(P); }
+        else { if (hints) spmv_kernel<2, true><<<m->num_blocks, SPMV_THREADS, 0, s>>>(P); else spmv_kernel<2, false><<<m->num_blocks, SPMV_THREADS, 0, s>>>(P); }
     }
     SMM_COUNT_LAUNCH(1);
     SMM_CUDA(cudaGetLastError());
