@@ -352,6 +352,14 @@ def run_config(smm, B, L, name, key, solver, A, M, rhs_kind, eps, maxit, modes, 
     out["spmv"] = {"ms": t_spmv, "effective_gbs": bytes_spmv(n, A.cols, nnz) / (t_spmv * 1e-3) / 1e9,
                    "frac": bytes_spmv(n, A.cols, nnz) / (t_spmv * 1e-3) / 1e9 / peak}
     del y
+    if solver in ("cgs", "bicgsym") and key is None:
+        # Config 4's gathers have no locality (hash-placed columns): every stored entry costs its own 32-byte sector of x, and an SM's
+        # L1 looks up one sector per clock.  That, not HBM, is the ceiling of this SpMV: sectors / (SMs x clock).
+        sectors = nnz + (8 * nnz + 12 * n) // 32
+        sms, clk = smm.device_info()["sm_count"], 1.965e9
+        bound_ms = sectors / (sms * clk) * 1e3
+        out["spmv"]["second_ceiling"] = {"what": "L1 tag stage, one 32-byte sector per clock and SM (x gathers without locality: one sector per stored entry)",
+                                         "sectors": int(sectors), "bound_ms": bound_ms, "frac": bound_ms / t_spmv}
     for mode in modes:
         m = {"fast": B.REDUCE_FAST, "tree": B.REDUCE_REFERENCE_TREE}[mode]
         x = smm.DeviceVector(n)
@@ -382,6 +390,8 @@ def run_config(smm, B, L, name, key, solver, A, M, rhs_kind, eps, maxit, modes, 
         if rate:
             rec["iteration_gbs"] = bpi * rate / 1e9
             rec["frac_of_peak"] = rec["iteration_gbs"] / peak
+        if setup_s is not None:
+            rec["solve_plus_setup_s"] = best + setup_s              # getPreconditioner() is host analysis + layout: part of a first solve
         if ref and mode == "fast":
             rec["iterations_vs_reference"] = info.iterations / ref["iterations"]
         if mode == "tree" and ref:

@@ -31,6 +31,8 @@
 #include <time.h>
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <cmath>
 #include <future>
 #include <vector>
@@ -252,16 +254,38 @@ bool find_diagonals(int rows, const std::vector<int32_t>& start, const std::vect
 }
 
 // dependency levels of the two triangles and the level-ordered row lists of the row-level schedule
-void level_orders(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag,
-                  std::vector<int32_t>* order_f, std::vector<int32_t>* order_b, int* lf, int* lb) {
-    std::vector<int32_t> lev((size_t)rows, 0);
-    int maxl = -1;
-    for (int r = 0; r < rows; ++r) {
-        int l = 0;
-        for (int k = start[r]; k < diag[r]; ++k) l = std::max(l, lev[pos[k]] + 1);
-        lev[r] = l;
-        maxl = std::max(maxl, l);
+// dependency level of every row in the lower (forward sweep) and in the upper triangle (backward sweep)
+void row_levels(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag,
+                std::vector<int32_t>* lev_f, std::vector<int32_t>* lev_b, int* lf, int* lb) {
+    lev_f->assign((size_t)rows, 0);
+    lev_b->assign((size_t)rows, 0);
+    int maxf = -1, maxb = -1;
+    std::thread back([&] {                                     // the two triangles are independent of each other
+        std::vector<int32_t>& lev = *lev_b;
+        for (int r = rows - 1; r >= 0; --r) {
+            int l = 0;
+            for (int k = start[r + 1] - 1; k > diag[r]; --k) l = std::max(l, lev[pos[k]] + 1);
+            lev[r] = l;
+            maxb = std::max(maxb, l);
+        }
+    });
+    {
+        std::vector<int32_t>& lev = *lev_f;
+        for (int r = 0; r < rows; ++r) {
+            int l = 0;
+            for (int k = start[r]; k < diag[r]; ++k) l = std::max(l, lev[pos[k]] + 1);
+            lev[r] = l;
+            maxf = std::max(maxf, l);
+        }
     }
+    back.join();
+    *lf = maxf + 1;
+    *lb = maxb + 1;
+}
+
+// the two row orders of the row-level schedule: rows sorted by level, every level padded to a warp
+void level_orders(int rows, const std::vector<int32_t>& lev_f, const std::vector<int32_t>& lev_b, int lf, int lb,
+                  std::vector<int32_t>* order_f, std::vector<int32_t>* order_b) {
     auto build_order = [&](const std::vector<int32_t>& level, int nlev, bool descending, std::vector<int32_t>* out) {
         std::vector<long long> count((size_t)nlev + 1, 0);
         for (int r = 0; r < rows; ++r) count[(size_t)level[r] + 1]++;
@@ -272,18 +296,20 @@ void level_orders(int rows, const std::vector<int32_t>& start, const std::vector
         if (!descending) { for (int r = 0; r < rows; ++r) (*out)[(size_t)cur[level[r]]++] = r; }
         else { for (int r = rows - 1; r >= 0; --r) (*out)[(size_t)cur[level[r]]++] = r; }
     };
-    *lf = maxl + 1;
-    build_order(lev, *lf, false, order_f);
-    maxl = -1;
-    for (int r = rows - 1; r >= 0; --r) {
-        int l = 0;
-        for (int k = start[r + 1] - 1; k > diag[r]; --k) l = std::max(l, lev[pos[k]] + 1);   // lev[] of rows > r already hold backward levels
-        lev[r] = l;
-        maxl = std::max(maxl, l);
-    }
-    *lb = maxl + 1;
-    build_order(lev, *lb, true, order_b);
+    build_order(lev_f, lf, false, order_f);
+    build_order(lev_b, lb, true, order_b);
 }
+
+struct SetupClock {                                            // SMM_B200_SETUP_TRACE=1: where getPreconditioner()'s time goes (stderr)
+    const bool on = [] { const char* e = getenv("SMM_B200_SETUP_TRACE"); return e && atoi(e) != 0; }();
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    void mark(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[smm set-up] %-34s %7.3f s (total %.3f s)\n", what, std::chrono::duration<double>(now - last).count(), std::chrono::duration<double>(now - t0).count());
+        last = now;
+    }
+};
 
 // Zero-fill incomplete Cholesky in A's pattern, IC0Preconditioner::factorize (H:1839-1928), on the host (set-up code).
 // The reference walks column by column and scans every later row for each column (O(rows^2)); this walks row by row.
@@ -450,17 +476,20 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
     p->m = m;
     p->kind = kind;
     p->rows = m->rows;
+    SetupClock clock;
     std::vector<int32_t> start((size_t)m->rows + 1), pos((size_t)m->nnz);
     SMM_CUDA(cudaDeviceSynchronize());
     SMM_CUDA(cudaMemcpy(start.data(), m->start, sizeof(int32_t) * start.size(), cudaMemcpyDeviceToHost));
     if (m->nnz) SMM_CUDA(cudaMemcpy(pos.data(), m->positions, sizeof(int32_t) * pos.size(), cudaMemcpyDeviceToHost));
-    std::vector<int32_t> diag, of, ob;
+    clock.mark("download start / positions");
+    std::vector<int32_t> diag, of, ob, lev_f, lev_b;
     p->valid = find_diagonals(m->rows, start, pos, m->first_active_start, &diag);
-    // the level analysis (row-level schedule, and the level counts smm_precond_levels reports) runs beside the factorisation
-    // and the tile layout below: all of it is set-up time
+    clock.mark("find diagonals");
+    // the level analysis (the level counts smm_precond_levels reports, and the row-level schedule when no tile schedule is
+    // found) runs beside the factorisation and the tile layout below: all of it is set-up time
     std::future<void> levels;
     if (p->valid && m->rows > 0 && kind != 3)
-        levels = std::async(std::launch::async, [&] { level_orders(m->rows, start, pos, diag, &of, &ob, &p->levels_fwd, &p->levels_bwd); });
+        levels = std::async(std::launch::async, [&] { row_levels(m->rows, start, pos, diag, &lev_f, &lev_b, &p->levels_fwd, &p->levels_bwd); });
     struct Join { std::future<void>& f; ~Join() { if (f.valid()) f.wait(); } } join{levels};   // never leave with the task running
     if (rc_out) *rc_out = p->valid ? 0 : 1;
     if (kind != 0 && kind != 3 && p->valid && m->nnz > 0) {
@@ -482,9 +511,13 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
         SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
     }
     // tile-level schedule when the matrix admits one (sgs_tiles.cu), else the row-level schedule below
+    clock.mark("factorisation, diagonal upload");
     const bool tiles = kind != 3 && p->valid && m->rows > 0 && smm_sgs_tiles_build(p, m->rows, start, pos, diag);
+    clock.mark(tiles ? "tile schedule: layout + upload" : "tile schedule: not applicable");
     if (levels.valid()) levels.get();
+    clock.mark("row levels (ran beside the above)");
     if (kind != 3 && p->valid && m->rows > 0 && !tiles) {
+        level_orders(m->rows, lev_f, lev_b, p->levels_fwd, p->levels_bwd, &of, &ob);
         p->threads_fwd = (long long)of.size();
         p->threads_bwd = (long long)ob.size();
         SMM_CUDA(cudaMalloc(&p->order_fwd, sizeof(int32_t) * of.size()));
@@ -520,6 +553,7 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
             }
         }
     }
+    clock.mark("row-level schedule");
     *out = p;
     guard.p = nullptr;
     return SMM_OK;

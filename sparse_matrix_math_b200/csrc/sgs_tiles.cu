@@ -31,6 +31,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <future>
 #include <thread>
@@ -499,16 +500,46 @@ sgs_cluster_kernel(const TileArgs A, const float* __restrict__ rhs, float* yperm
 // ---------------------------------------------------------------------------------------------------------------
 // host: proposal + generic verification + layout
 // ---------------------------------------------------------------------------------------------------------------
+// vectors whose resize() leaves the new elements uninitialised: the big layout arrays are filled by several threads right
+// after (first touch in parallel instead of a single-threaded fill of several hundred MB)
+template <class T>
+struct raw_allocator : std::allocator<T> {
+    template <class U> struct rebind { using other = raw_allocator<U>; };
+    template <class U, class... Args>
+    void construct(U* p, Args&&... args) {
+        if constexpr (sizeof...(Args) == 0) ::new (static_cast<void*>(p)) U;
+        else ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+    }
+};
+template <class T> using raw_vector = std::vector<T, raw_allocator<T>>;
+
+// f(begin, end) over [0, n) on the host's threads (set-up code)
+template <class F>
+void for_range(long long n, F f) {
+    const unsigned int hw = std::thread::hardware_concurrency();
+    const int nt = n < (1 << 20) ? 1 : (int)std::min<unsigned int>(hw ? hw : 1, 16);
+    if (nt <= 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back([&, t] { f(n * t / nt, n * (t + 1) / nt); });
+    for (std::thread& x : th) x.join();
+}
+template <class V, class T>
+void fill_parallel(V& v, size_t n, T value) {
+    v.resize(n);
+    auto* p = v.data();
+    for_range((long long)n, [&](long long a, long long b) { std::fill(p + a, p + b, value); });
+}
+
 struct SweepLayout {
-    std::vector<int32_t> order, ecol, eidx, where;   // where[row] = position
-    std::vector<uint8_t> steps;
-    std::vector<uint32_t> push;
+    raw_vector<int32_t> order, ecol, eidx, where;    // where[row] = position
+    raw_vector<uint8_t> steps;
+    raw_vector<uint32_t> push;
     int levels = 0;
     int chain_len = 1;                               // tiles per chain (consecutive tile indices); 1: tiles in tile-level order
     // cluster schedule (sgs_cluster_kernel): CLUSTER_CHAINS chains per block, a block per thread-block cluster at a time
     int nblocks = 0;                                 // 0: not laid out for clusters
     long long ntiles = 0;                            // tiles the arrays hold (padding chains of incomplete blocks included)
-    std::vector<uint32_t> push2;                     // [tiles * 64] where a row's result goes outside its tile (see PUSH2_*)
+    raw_vector<uint32_t> push2;                      // [tiles * 64] where a row's result goes outside its tile (see PUSH2_*)
 };
 
 struct ClusterPlan {                                  // proposal: which block a chain belongs to and which warp of the cluster takes it
@@ -551,10 +582,12 @@ std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& st
     const long long TI = (nx + ti - 1) / ti, TJ = (ny + tj - 1) / tj, TK = (nz + tk - 1) / tk;
     if (TI * TJ * TK >= (1ll << 25)) return {};                // positions are int32: 64 * tiles < 2^31
     std::vector<int32_t> cl((size_t)rows);
-    for (int r = 0; r < rows; ++r) {
-        const long long i = r % nx, j = (r / nx) % ny, k = r / (nx * ny);
-        cl[(size_t)r] = (int32_t)(((k / tk) * TJ + j / tj) * TI + i / ti);
-    }
+    for_range(rows, [&](long long r0, long long r1) {
+        for (long long r = r0; r < r1; ++r) {
+            const long long i = r % nx, j = (r / nx) % ny, k = r / (nx * ny);
+            cl[(size_t)r] = (int32_t)(((k / tk) * TJ + j / tj) * TI + i / ti);
+        }
+    });
     *nclusters = (int)(TI * TJ * TK);
     if (chain_len) *chain_len = (int)TI;
     if (plan) {
@@ -590,18 +623,55 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
                   const std::vector<int32_t>& cl, int ncl, int width, SweepLayout* out, int chain_len = 1, const ClusterPlan* plan = nullptr) {
     auto dep_begin = [&](int r) { return forward ? start[r] : diag[r] + 1; };
     auto dep_end = [&](int r) { return forward ? diag[r] : start[r + 1]; };
+    static const bool trace_on = [] { const char* e = getenv("SMM_B200_SETUP_TRACE"); return e && atoi(e) != 0; }();
+    auto tl = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace_on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[smm set-up]   %s sweep: %-28s %7.3f s\n", forward ? "forward " : "backward", what, std::chrono::duration<double>(now - tl).count());
+        tl = now;
+    };
     // rows of every cluster, ascending
     std::vector<int32_t> cptr((size_t)ncl + 1, 0);
-    for (int r = 0; r < rows; ++r) cptr[(size_t)cl[r] + 1]++;
-    for (int a = 0; a < ncl; ++a) {
-        if (cptr[(size_t)a + 1] > TILE) return false;
-        cptr[(size_t)a + 1] += cptr[a];
-    }
     std::vector<int32_t> crow((size_t)rows);
     {
-        std::vector<int32_t> cur(cptr.begin(), cptr.end() - 1);
-        for (int r = 0; r < rows; ++r) crow[(size_t)cur[cl[r]]++] = r;
+        // counting sort of the rows by cluster, stable, on a few threads: thread t counts its slice of the rows, the counts
+        // are prefix-summed cluster by cluster and slice by slice, and every thread scatters its slice
+        const unsigned int hw = std::thread::hardware_concurrency();
+        const int nt = rows < (1 << 20) ? 1 : (int)std::min<unsigned int>(hw > 3 ? hw / 2 : 1, 8);
+        std::vector<std::vector<uint8_t>> cnt((size_t)nt);       // a cluster holds at most TILE rows: 8 bits, saturating
+        std::atomic<bool> too_many(false);
+        auto slice = [&](int t) { return std::make_pair((long long)rows * t / nt, (long long)rows * (t + 1) / nt); };
+        {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; ++t) th.emplace_back([&, t] {
+                cnt[t].assign((size_t)ncl, 0);
+                const auto [r0, r1] = slice(t);
+                for (long long r = r0; r < r1; ++r) { uint8_t& c = cnt[t][(size_t)cl[r]]; if (c == 255) too_many = true; else ++c; }
+            });
+            for (std::thread& x : th) x.join();
+        }
+        if (too_many) return false;
+        std::vector<std::vector<int32_t>> base((size_t)nt, std::vector<int32_t>());
+        for (int t = 0; t < nt; ++t) base[t].resize((size_t)ncl);
+        int32_t run = 0;
+        for (int a = 0; a < ncl; ++a) {
+            cptr[a] = run;
+            int total = 0;
+            for (int t = 0; t < nt; ++t) { base[t][a] = run + total; total += cnt[t][a]; }
+            if (total > TILE) return false;
+            run += total;
+        }
+        cptr[ncl] = run;
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back([&, t] {
+            const auto [r0, r1] = slice(t);
+            std::vector<int32_t>& cur = base[t];
+            for (long long r = r0; r < r1; ++r) crow[(size_t)cur[(size_t)cl[r]]++] = (int32_t)r;
+        });
+        for (std::thread& x : th) x.join();
     }
+    mark("rows by tile (counting sort)");
     // distinct predecessor tiles (in the order the rows of the tile meet them)
     std::vector<int32_t> pred((size_t)ncl * MAX_PREDS, -1);
     std::vector<uint8_t> npred((size_t)ncl, 0);
@@ -625,6 +695,7 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
         npred[a] = (uint8_t)n;
     });
     if (bad) return false;
+    mark("predecessor tiles");
     // Kahn: tile levels, cycle check
     std::vector<int32_t> sptr((size_t)ncl + 1, 0);
     for (int a = 0; a < ncl; ++a) for (int i = 0; i < npred[a]; ++i) sptr[(size_t)pred[(size_t)a * MAX_PREDS + i] + 1]++;
@@ -744,6 +815,7 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
             }
         }
     }
+    mark("tile levels and order");
     const int ntl = out->nblocks > 0 ? out->nblocks * CLUSTER_CHAINS * out->chain_len : ncl;   // tiles the arrays hold
     out->ntiles = ntl;
     if (out->chain_len == 1) {                                 // tiles in level order (stable in the cluster id; the backward sweep runs the ids downwards)
@@ -754,11 +826,12 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
         if (forward) { for (int a = 0; a < ncl; ++a) tile_of[a] = cur[level[a]]++; }
         else { for (int a = ncl - 1; a >= 0; --a) tile_of[a] = cur[level[a]]++; }
     }
-    out->order.assign((size_t)ntl * TILE, -1);
-    out->where.assign((size_t)rows, 0);
-    out->steps.assign((size_t)ntl * TILE + (size_t)ntl, 255);    // [tiles * 64] step of every row, then [tiles] number of steps
+    fill_parallel(out->order, (size_t)ntl * TILE, (int32_t)-1);
+    fill_parallel(out->where, (size_t)rows, (int32_t)0);
+    fill_parallel(out->steps, (size_t)ntl * TILE + (size_t)ntl, (uint8_t)255);   // [tiles * 64] step of every row, then [tiles] number of steps
     if (out->nblocks > 0) std::fill(out->steps.begin() + (size_t)ntl * TILE, out->steps.end(), (uint8_t)0);   // padding tiles: no steps
-    std::vector<int8_t> ilev((size_t)rows, 0);
+    raw_vector<int8_t> ilev;
+    fill_parallel(ilev, (size_t)rows, (int8_t)0);
     for_clusters(ncl, [&](int a) {
         const int n = cptr[a + 1] - cptr[a];
         const int32_t* R = &crow[(size_t)cptr[a]];
@@ -785,15 +858,16 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
         }
     });
     if (bad) return false;
+    mark("rows inside the tiles (steps)");
     // entries: [tile][slot][64], operand order = the reference's (ascending columns forward, descending backward);
     // push lists: where inside the tile's operand staging a row's result has to go (bytes 0..2; a byte that is not needed
     // points at the row's own first slot, which nobody reads once the row is solved)
-    out->ecol.assign((size_t)ntl * width * TILE, -1);
-    out->eidx.assign((size_t)ntl * width * TILE, -1);
-    out->push.assign((size_t)ntl * TILE, 0u);
+    fill_parallel(out->ecol, (size_t)ntl * width * TILE, (int32_t)-1);
+    fill_parallel(out->eidx, (size_t)ntl * width * TILE, (int32_t)-1);
+    fill_parallel(out->push, (size_t)ntl * TILE, 0u);
     const bool clustered = out->nblocks > 0;
     const int clen = out->chain_len;
-    if (clustered) out->push2.assign((size_t)ntl * TILE, PUSH2_NONE);
+    if (clustered) fill_parallel(out->push2, (size_t)ntl * TILE, PUSH2_NONE);
     // claim a field of a producer row's push2 word (other consumer tiles are laid out by other threads): CAS
     auto claim_push2 = [&](uint32_t* word, int shift, uint32_t mask, uint32_t value) {
         uint32_t cur = __atomic_load_n(word, __ATOMIC_RELAXED);
@@ -841,6 +915,7 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
         }
     });
     if (bad) return false;
+    mark("entries and push lists");
     if (clustered) {                                           // the two remote fields in a canonical order (they were claimed by racing threads)
         for (uint32_t& v : out->push2) {
             const uint32_t r0 = (v >> 8) & 0x7FFu, r1 = (v >> 19) & 0x7FFu;
@@ -850,8 +925,8 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
     return true;
 }
 
-template <class V>
-int upload(const std::vector<V>& h, V** d) {
+template <class V, class A>
+int upload(const std::vector<V, A>& h, V** d) {
     SMM_CUDA(cudaMalloc(d, sizeof(V) * (h.empty() ? 1 : h.size())));
     if (!h.empty()) SMM_CUDA(cudaMemcpy(*d, h.data(), sizeof(V) * h.size(), cudaMemcpyHostToDevice));
     return SMM_OK;
@@ -890,8 +965,11 @@ bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& s
         if (!want_clusters) return false;
         want_clusters = false;
     }
-    std::vector<int32_t> yp(L[1].order.size(), 0);
-    for (size_t t = 0; t < yp.size(); ++t) if (L[1].order[t] >= 0) yp[t] = L[0].where[(size_t)L[1].order[t]];
+    raw_vector<int32_t> yp;
+    yp.resize(L[1].order.size());
+    for_range((long long)yp.size(), [&](long long a, long long b) {
+        for (long long t = a; t < b; ++t) yp[(size_t)t] = L[1].order[(size_t)t] >= 0 ? L[0].where[(size_t)L[1].order[(size_t)t]] : 0;
+    });
     const size_t npos = (size_t)L[0].ntiles * TILE;
     p->tile_blocks = L[0].nblocks;
     p->threads_fwd = p->threads_bwd = (long long)npos;

@@ -46,7 +46,9 @@ int main(int argc, char** argv) {
     const int rc_ilu0 = ilu0_factorize_host(rows, start, pos, d2, val, &ilu0);
     std::vector<int32_t> of, ob;
     int lf = 0, lb = 0;
-    level_orders(rows, start, pos, d2, &of, &ob, &lf, &lb);    // the row-level schedule's analysis
+    std::vector<int32_t> lev_f, lev_b;
+    row_levels(rows, start, pos, d2, &lev_f, &lev_b, &lf, &lb);    // the row-level schedule's analysis
+    level_orders(rows, lev_f, lev_b, lf, lb, &of, &ob);
     bool perm = of.size() % 32 == 0 && ob.size() % 32 == 0;
     {
         std::vector<char> seen(rows, 0);
