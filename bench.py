@@ -41,15 +41,15 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-TRAFFIC_SOURCE = "committed ncu --set full capture of this command (not re-measured in this run)"
+TRAFFIC_SOURCE = "profiles/r02_spmv_rows_kernel_full.txt: committed ncu --set full capture of this kernel in this command (a constant, not re-measured in this run)"
 
 
 def ncu_traffic_bytes(kernel_prefix, grid):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
-    same command (profiles/r01h_spmv_rows_kernel_full.txt, 512^3); None for any other problem size."""
-    p = os.path.join(ROOT, "profiles", "r01h_spmv_rows_kernel_full.txt")
+    same command (profiles/r02_spmv_rows_kernel_full.txt, 512^3); None for any other problem size."""
+    p = os.path.join(ROOT, "profiles", "r02_spmv_rows_kernel_full.txt")
     if not os.path.exists(p):
-        p = os.path.join(ROOT, "profiles", "r01d_spmv_rows_kernel_full.txt")
+        p = os.path.join(ROOT, "profiles", "r01h_spmv_rows_kernel_full.txt")
     if grid != 512 or not os.path.exists(p):
         return None
     rd = wr = None

@@ -49,3 +49,14 @@ if which in ("all", "sgs"):
     info = B._Info()
     B._check(L.smm_solve_bicgstab_dev(A.handle, M.handle, b.ptr, x.ptr, 2, 0.0, C.byref(o), C.byref(info), None), "bicgstab")
     print("bicgstab+sgs 2 iterations:", info.iterations, flush=True)
+
+if which in ("all", "dots"):
+    # the reference-order dot on a long vector: lane-per-node kernel (dot_tree_rows_kernel<16>) at 134 M elements
+    n = 134217728
+    a = smm.DeviceVector(n); b2 = smm.DeviceVector(n)
+    B._check(L.smm_gen_xstar_dev(n, 0, 1, a.ptr, None), "x")
+    B._check(L.smm_gen_xstar_dev(n, 0, 2, b2.ptr, None), "x")
+    out = C.c_float()
+    for _ in range(2):
+        B._check(L.smm_dot_dev(n, a.ptr, b2.ptr, B.REDUCE_REFERENCE_TREE, C.byref(out), None), "dot")
+    print("tree dot 134M:", out.value, flush=True)
