@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <utility>
 
 #include "smm_b200.h"
 
@@ -203,6 +204,33 @@ int smm_sgs_kernels_per_apply(const smm_precond* p);
 extern "C" int smm_precond_kind(const smm_precond* p);   // 0 SGS, 1 IC(0)
 int smm_csr_analyse(smm_csr* m, cudaStream_t s);
 int smm_first_active_start(const smm_csr* m, int* out_host, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  The kernels of an iteration form a chain (each reads what the previous one wrote, down
+// to the scalars of the recurrence); launched with cudaLaunchAttributeProgrammaticStreamSerialization a kernel may start
+// while its predecessor drains -- its CTAs become resident and run their prologue (shared-memory ring, barriers, index
+// arithmetic) -- and blocks in smm_pdl_wait() until the predecessor has completed and its writes are visible.  A kernel
+// calls smm_pdl_trigger() once its main loop is done, which is what lets the successor start early.  Same kernels, same
+// results; only the launch / ramp-up latency between dependent kernels is taken off the critical path, which is what an
+// iteration on an L2-resident problem mostly consists of.  (SMM_B200_PDL=0 launches the plain way.)
+// ---------------------------------------------------------------------------------------------------
+bool smm_pdl_enabled();
+#ifdef __CUDACC__
+template <class... KArgs, class... Args>
+cudaError_t smm_launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = smm_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+// every kernel that may be launched through smm_launch_chain calls this before it reads anything a predecessor wrote
+__device__ __forceinline__ void smm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void smm_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // device helpers

@@ -175,6 +175,7 @@ __device__ __forceinline__ void row_path(const SpmvParams& P, int r0, int r1, Wr
 // the 4 * cols bytes that are gathered again and again out of L2.
 template <int DEPTH, bool HINTS>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const SpmvParams P) {
+    smm_pdl_wait();
     if (P.state != nullptr && P.state->done) return;
 
     __shared__ __align__(16) float prod[SPMV_CAP];
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const SpmvParams P) 
         }
     }
 
+    smm_pdl_trigger();
     if (P.reduce != RED_NONE) {
         float v[2] = {write.acc0, write.acc1};
         __syncthreads();
@@ -380,7 +382,6 @@ __device__ __forceinline__ float row_dot(const VP vs, const CP cs, const float* 
 // HALO: multi-GPU SpMV whose boundary row groups wait for the peers' halo pushes (compiled out of the single-GPU kernel)
 template <int V, bool PLAIN, bool HALO>   // lanes per row; PLAIN: op == ASSIGN and no extra copies of the result
 __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParams P, const int cap, const int nchunks, const int stages) {
-    if (P.state != nullptr && P.state->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: vals[stages][cap] | cols[stages][cap] | full[4] | empty[4] | win[4][2]
     float* vals_s = reinterpret_cast<float*>(smem_raw);
@@ -401,6 +402,10 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // everything above is independent of the previous kernel of the chain; the done flag, the operand vector and (for the
+    // multi-GPU case) the exchange counter are not
+    smm_pdl_wait();
+    if (P.state != nullptr && P.state->done) return;
 
     const int G = gridDim.x;
     const int first = blockIdx.x;
@@ -502,6 +507,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
         }
     }
 
+    smm_pdl_trigger();
     if (P.reduce != RED_NONE) {
         float v[2] = {write.acc0, write.acc1};
         __syncthreads();
@@ -619,6 +625,7 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
         P.ticket = ws->tickets + a.slot;
     }
     const int V = smm_spmv_rows_lanes(m, a.exact);             // exact mode needs one lane per row
+    cudaError_t le = cudaSuccess;
     if (a.halo_wait != nullptr && V <= 0) { smm_set_error("spmv: the fused halo wait needs the rows kernel"); return SMM_E_STATE; }
     if (V > 0) {
         P.halo = static_cast<const HaloWaitDev*>(a.halo_wait);
@@ -658,10 +665,10 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
         const bool plain = a.op == SMM_OP_ASSIGN && !a.copy1 && !a.copy2 && !a.copy3;
 #define SMM_ROWS_LAUNCH(V_) \
     if (P.halo != nullptr) { \
-        if (plain) spmv_rows_kernel<V_, true, true><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); \
-        else spmv_rows_kernel<V_, false, true><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); \
-    } else if (plain) spmv_rows_kernel<V_, true, false><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages); \
-    else spmv_rows_kernel<V_, false, false><<<grid, ROWS_THREADS, smem, s>>>(P, cap, nchunks, stages)
+        if (plain) le = smm_launch_chain(spmv_rows_kernel<V_, true, true>, grid, ROWS_THREADS, smem, s, P, cap, nchunks, stages); \
+        else le = smm_launch_chain(spmv_rows_kernel<V_, false, true>, grid, ROWS_THREADS, smem, s, P, cap, nchunks, stages); \
+    } else if (plain) le = smm_launch_chain(spmv_rows_kernel<V_, true, false>, grid, ROWS_THREADS, smem, s, P, cap, nchunks, stages); \
+    else le = smm_launch_chain(spmv_rows_kernel<V_, false, false>, grid, ROWS_THREADS, smem, s, P, cap, nchunks, stages)
         switch (V) {
             case 1: SMM_ROWS_LAUNCH(1); break;
             case 2: SMM_ROWS_LAUNCH(2); break;
@@ -673,10 +680,11 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
         // knobs for measurements: SMM_B200_SPMV_DEPTH = 2 | 4 (vectors in flight per thread), SMM_B200_SPMV_HINTS = 0 | 1 (L2 eviction priorities)
         static const int depth = [] { const char* e = getenv("SMM_B200_SPMV_DEPTH"); const int v = e ? atoi(e) : 2; return v == 4 ? 4 : 2; }();
         static const bool hints = [] { const char* e = getenv("SMM_B200_SPMV_HINTS"); return e ? atoi(e) != 0 : false; }();
-        if (depth == 4) { if (hints) spmv_kernel<4, true><<<m->num_blocks, SPMV_THREADS, 0, s>>>(P); else spmv_kernel<4, false><<<m->num_blocks, SPMV_THREADS, 0, s>>>(P); }
-        else { if (hints) spmv_kernel<2, true><<<m->num_blocks, SPMV_THREADS, 0, s>>>(P); else spmv_kernel<2, false><<<m->num_blocks, SPMV_THREADS, 0, s>>>(P); }
+        if (depth == 4) { if (hints) le = smm_launch_chain(spmv_kernel<4, true>, m->num_blocks, SPMV_THREADS, 0, s, P); else le = smm_launch_chain(spmv_kernel<4, false>, m->num_blocks, SPMV_THREADS, 0, s, P); }
+        else { if (hints) le = smm_launch_chain(spmv_kernel<2, true>, m->num_blocks, SPMV_THREADS, 0, s, P); else le = smm_launch_chain(spmv_kernel<2, false>, m->num_blocks, SPMV_THREADS, 0, s, P); }
     }
     SMM_COUNT_LAUNCH(1);
+    SMM_CUDA(le);
     SMM_CUDA(cudaGetLastError());
     return SMM_OK;
 }

@@ -161,6 +161,7 @@ struct FCopy3 {
 // to the peers and, once every CTA is through, raises this rank's flag on them -- no separate push kernel.
 template <class F, bool VEC4, bool HALO>
 __global__ void __launch_bounds__(VEC_THREADS) vec_kernel(const VecParams P) {
+    smm_pdl_wait();                                            // the scalars and vectors below come from the previous kernel
     if (P.state != nullptr && P.state->done) return;
     __shared__ float red_sh[96];
     __shared__ int sh_flag;
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(VEC_THREADS) vec_kernel(const VecParams P) {
         }
     }
 
+    smm_pdl_trigger();                                         // main loop done: the next kernel of the chain may start its prologue
     if (HALO) {
         if (pushed) __threadfence_system();                    // my peer stores are visible before my CTA's ticket
         __syncthreads();
@@ -270,12 +272,14 @@ int launch(const VecArgs& a, cudaStream_t s) {
         P.partials_stride = ws->partials_cap;
         P.ticket = ws->tickets + a.slot;
     }
+    cudaError_t le;
     if (F::HALO_OK && P.halo != nullptr) {
-        if (aligned) vec_kernel<F, true, F::HALO_OK><<<grid, VEC_THREADS, 0, s>>>(P);
-        else vec_kernel<F, false, F::HALO_OK><<<grid, VEC_THREADS, 0, s>>>(P);
-    } else if (aligned) vec_kernel<F, true, false><<<grid, VEC_THREADS, 0, s>>>(P);
-    else vec_kernel<F, false, false><<<grid, VEC_THREADS, 0, s>>>(P);
+        if (aligned) le = smm_launch_chain(vec_kernel<F, true, F::HALO_OK>, grid, VEC_THREADS, 0, s, P);
+        else le = smm_launch_chain(vec_kernel<F, false, F::HALO_OK>, grid, VEC_THREADS, 0, s, P);
+    } else if (aligned) le = smm_launch_chain(vec_kernel<F, true, false>, grid, VEC_THREADS, 0, s, P);
+    else le = smm_launch_chain(vec_kernel<F, false, false>, grid, VEC_THREADS, 0, s, P);
     SMM_COUNT_LAUNCH(1);
+    SMM_CUDA(le);
     SMM_CUDA(cudaGetLastError());
     return SMM_OK;
 }
