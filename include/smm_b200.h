@@ -53,8 +53,12 @@ enum { SMM_REDUCE_FAST = 0, SMM_REDUCE_REFERENCE_TREE = 1, SMM_REDUCE_REFERENCE_
  *   GRAPH_CHUNKED  one CUDA graph per iteration, enqueued `check_every` at a time; kernels no-op once the
  *                  device-side convergence flag is set; host polls the flag once per chunk
  *   GRAPH_WHILE    one launch: a conditional WHILE graph node loops on the device until the convergence test
- *   STREAM         plain stream launches, flag polled every check_every iterations (debug) */
-enum { SMM_DRIVER_AUTO = 0, SMM_DRIVER_GRAPH_CHUNKED = 1, SMM_DRIVER_GRAPH_WHILE = 2, SMM_DRIVER_STREAM = 3 };
+ *   STREAM         plain stream launches, flag polled every check_every iterations (debug)
+ *   PERSISTENT     ConjugateGradient only (fast reductions, one GPU, stencil-like matrices): the whole loop in ONE
+ *                  cooperative kernel with grid barriers instead of kernel boundaries -- for problems that live in L2, where
+ *                  an iteration is mostly launch latency.  Same bits as the graph drivers (it executes their kernels' CTAs as
+ *                  virtual CTAs); any other solve asked for in this mode runs GRAPH_CHUNKED and says so in smm_solve_info. */
+enum { SMM_DRIVER_AUTO = 0, SMM_DRIVER_GRAPH_CHUNKED = 1, SMM_DRIVER_GRAPH_WHILE = 2, SMM_DRIVER_STREAM = 3, SMM_DRIVER_PERSISTENT = 4 };
 
 typedef struct smm_csr smm_csr_t;          /* device-resident CSRMatrix<float> (H:1243-1259) + analysis */
 typedef struct smm_precond smm_precond_t;  /* CSRMatrix::SGSPreconditioner (H:1172-1186) + level analysis */

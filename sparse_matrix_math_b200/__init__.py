@@ -39,4 +39,5 @@ from .binding import (  # noqa: F401
     DRIVER_GRAPH_CHUNKED,
     DRIVER_GRAPH_WHILE,
     DRIVER_STREAM,
+    DRIVER_PERSISTENT,
 )

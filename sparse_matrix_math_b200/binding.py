@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 REDUCE_FAST, REDUCE_REFERENCE_TREE, REDUCE_REFERENCE_SERIAL = 0, 1, 2
-DRIVER_AUTO, DRIVER_GRAPH_CHUNKED, DRIVER_GRAPH_WHILE, DRIVER_STREAM = 0, 1, 2, 3
+DRIVER_AUTO, DRIVER_GRAPH_CHUNKED, DRIVER_GRAPH_WHILE, DRIVER_STREAM, DRIVER_PERSISTENT = 0, 1, 2, 3, 4
 OP_ASSIGN, OP_ADD, OP_SUB = 0, 1, 2
 GEN_POISSON2D, GEN_CONVDIFF3D, GEN_POWERLAW = 0, 1, 2
 

@@ -71,6 +71,8 @@ int smm_workspace_get(const smm_csr* mc, smm_workspace** out) {
         SMM_CUDA(cudaMalloc(&ws->partials, sizeof(float) * cap * 2 * RED_SLOTS));
         SMM_CUDA(cudaMalloc(&ws->tickets, sizeof(unsigned int) * RED_SLOTS));
         SMM_CUDA(cudaMemset(ws->tickets, 0, sizeof(unsigned int) * RED_SLOTS));
+        SMM_CUDA(cudaMalloc(&ws->grid_barrier, sizeof(unsigned int) * 2));
+        SMM_CUDA(cudaMemset(ws->grid_barrier, 0, sizeof(unsigned int) * 2));
         SMM_CUDA(cudaMalloc(&ws->state, sizeof(SolveState)));
         SMM_CUDA(cudaMemset(ws->state, 0, sizeof(SolveState)));
         SMM_CUDA(cudaMallocHost(&ws->state_host, sizeof(SolveState)));
@@ -99,6 +101,7 @@ void smm_workspace_free(smm_workspace* ws) {
     if (!ws) return;
     cudaFree(ws->partials);
     cudaFree(ws->tickets);
+    cudaFree(ws->grid_barrier);
     cudaFree(ws->state);
     cudaFreeHost(ws->state_host);
     cudaFree(ws->history);

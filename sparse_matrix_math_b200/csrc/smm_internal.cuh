@@ -131,6 +131,7 @@ struct smm_workspace {
     float* vec[10] = {nullptr};
     size_t vec_len = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned int* grid_barrier = nullptr;   // [2] arrival count and generation of the persistent iteration's grid barrier
 };
 
 constexpr int RED_SLOTS = 4;
@@ -188,6 +189,10 @@ struct VecArgs {
 };
 int smm_launch_vec(int kind, const VecArgs& a, cudaStream_t s);
 int smm_vec_max_grid(const smm_workspace* ws);
+int smm_vec_grid(const smm_workspace* ws, long long n, bool aligned);
+// persistent CG iteration (spmv.cu): the whole loop of ConjugateGradient (H:2352-2396) in ONE cooperative kernel
+bool smm_cg_persistent_fits(const smm_csr* m, const float* x, const float* r, const float* p, const float* ap);
+int smm_launch_cg_persistent(const smm_csr* m, SolveState* state, float* x, float* r, float* p, float* ap, cudaStream_t s);
 
 // dot products in the reference's summation orders (dots.cu)
 int smm_tree_depth(long long n);

@@ -29,6 +29,12 @@
 #include "epilogue.cuh"
 #include "smm_internal.cuh"
 
+// AUTO takes the persistent CG iteration for L2-resident problems when this is 1 (set from the measurement in
+// profiles/r02_driver_bench.txt)
+#ifndef SMM_PERSISTENT_AUTO
+#define SMM_PERSISTENT_AUTO 0
+#endif
+
 namespace {
 
 struct Ctx {
@@ -470,7 +476,19 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
     if (solver == S_CG_IC0) { c.sv = w[3]; }
 
     const int driver_req = opts ? opts->driver_mode : SMM_DRIVER_AUTO;
+    if (driver_req < SMM_DRIVER_AUTO || driver_req > SMM_DRIVER_PERSISTENT) { smm_set_error("solve: unknown driver mode"); return SMM_E_INVALID; }
     int driver = driver_req == SMM_DRIVER_AUTO ? SMM_DRIVER_GRAPH_CHUNKED : driver_req;
+    // the persistent iteration exists for ConjugateGradient with fast reductions on one GPU; AUTO takes it when the whole
+    // working set (matrix + the four vectors of the loop) lives in L2 (SMM_B200_PERSISTENT=0 / 1 forces the choice for AUTO)
+    const bool persistent_ok = solver == S_CG && !dist && !c.exact && a->rows > 0;
+    if (driver == SMM_DRIVER_PERSISTENT && !persistent_ok) driver = SMM_DRIVER_GRAPH_CHUNKED;
+    if (driver_req == SMM_DRIVER_AUTO && persistent_ok) {
+        static const int forced = [] { const char* e = getenv("SMM_B200_PERSISTENT"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+        int l2 = 0;
+        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, a->device);
+        const double working = 8.0 * (double)a->nnz + 4.0 * ((double)a->rows + 1) + 16.0 * (double)a->rows;
+        if (forced == 1 || (forced < 0 && SMM_PERSISTENT_AUTO && working <= 0.75 * (double)l2)) driver = SMM_DRIVER_PERSISTENT;
+    }
     int check_every = opts && opts->check_every > 0 ? opts->check_every : 32;
     const int hist_cap = opts && opts->history && opts->history_cap > 0 ? opts->history_cap : 0;
     if (hist_cap > ws->history_cap) {
@@ -527,7 +545,12 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
         }
         launches += t_smm_launches - launches_before;
         int rc = SMM_OK;
-        if (budget > 0) {
+        if (driver == SMM_DRIVER_PERSISTENT && !smm_cg_persistent_fits(a, c.x, c.r, c.p, c.ap)) driver = SMM_DRIVER_GRAPH_CHUNKED;
+        if (budget > 0 && driver == SMM_DRIVER_PERSISTENT) {
+            rc = smm_launch_cg_persistent(a, c.st, c.x, c.r, c.p, c.ap, s);
+            launches += 1;
+            if (rc == SMM_OK) rc = poll_state(c);
+        } else if (budget > 0) {
             if (driver == SMM_DRIVER_GRAPH_WHILE) rc = run_graph_while(c, iter, &launches);
             else if (driver == SMM_DRIVER_GRAPH_CHUNKED) rc = run_graph_chunked(c, iter, budget, check_every, &launches);
             else rc = run_stream(c, iter, budget, check_every, &launches);

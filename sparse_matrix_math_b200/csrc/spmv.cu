@@ -66,6 +66,7 @@ struct SpmvParams {
 }  // namespace
 
 #include "epilogue.cuh"
+#include "vec_functors.cuh"
 
 namespace {
 
@@ -379,36 +380,15 @@ __device__ __forceinline__ float row_dot(const VP vs, const CP cs, const float* 
 // the slot is free (empty barrier), then has the TMA engine copy the group's values/positions window into the
 // slot, completion counted in bytes on the slot's full barrier.  Warps 0..7 are consumers: wait for the slot, take
 // one row per V lanes out of shared memory, release the slot.  No CTA-wide barrier inside the loop.
-// HALO: multi-GPU SpMV whose boundary row groups wait for the peers' halo pushes (compiled out of the single-GPU kernel)
-template <int V, bool PLAIN, bool HALO>   // lanes per row; PLAIN: op == ASSIGN and no extra copies of the result
-__global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParams P, const int cap, const int nchunks, const int stages) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: vals[stages][cap] | cols[stages][cap] | full[4] | empty[4] | win[4][2]
-    float* vals_s = reinterpret_cast<float*>(smem_raw);
-    int* cols_s = reinterpret_cast<int*>(smem_raw + (size_t)stages * cap * sizeof(float));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * cap * 8);
-    uint64_t* empty = full + ROWS_MAX_STAGES;
-    int* win = reinterpret_cast<int*>(empty + ROWS_MAX_STAGES);   // [stage][2]: window start a0, staged flag
-    __shared__ float red_sh[96];
-    __shared__ int sh_flag;
-
+// One pass of a (virtual) CTA over its row groups first, first + G, ... : the body of spmv_rows_kernel, also run -- once per
+// virtual CTA and iteration -- by the persistent CG kernel below.  ring_s / ring_k: the thread's position in the shared-memory
+// ring (slot; uses of the slot for the producer, phase parity for a consumer), carried from one pass to the next.
+template <int V, bool HALO, class Writer>
+__device__ __forceinline__ void rows_sweep(const SpmvParams& P, const int cap, const int nchunks, const int stages, float* vals_s, int* cols_s,
+                                           uint64_t* full, uint64_t* empty, int* win, Writer& write, const int first, const int G, int& ring_s, uint32_t& ring_k) {
     constexpr int R = ROWS_CONSUMERS / V;                         // rows per group
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    typename std::conditional<PLAIN, PlainWriter, RowWriter>::type write(P);
-
-    if (tid == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ROWS_CONSUMERS / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    // everything above is independent of the previous kernel of the chain; the done flag, the operand vector and (for the
-    // multi-GPU case) the exchange counter are not
-    smm_pdl_wait();
-    if (P.state != nullptr && P.state->done) return;
-
-    const int G = gridDim.x;
-    const int first = blockIdx.x;
     const int my_chunks = first < nchunks ? (nchunks - first + G - 1) / G : 0;
     // Multi-GPU: groups [0, c_lo) and [c_hi, nchunks) hold rows that read halo entries.  The groups are walked in the order
     // c_lo .. nchunks-1, 0 .. c_lo-1 (group = position + c_lo, wrapped), i.e. the interior first, so that the peers' pushes
@@ -432,8 +412,8 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
                 const int rb = group_of(first) * R, re = min(rb + R, P.rows);
                 k0 = P.start[rb]; k1 = P.start[re];
             }
-            int s = 0;                                             // ring slot and how often it has been used before
-            uint32_t use = 0;
+            int s = ring_s;                                        // ring slot and how often it has been used before
+            uint32_t use = ring_k;
             for (int it = 0; it < my_chunks; ++it) {
                 int n0 = 0, n1 = 0;                                // next group's window, fetched ahead of the wait
                 if (it + 1 < my_chunks) {
@@ -458,6 +438,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
                 k0 = n0; k1 = n1;
                 if (++s == stages) { s = 0; ++use; }
             }
+            ring_s = s; ring_k = use;
         }
     } else {
         // ---------------- consumers ----------------
@@ -468,8 +449,8 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
             const int r = group_of(first) * R + rloc;
             if (r < P.rows) { my_s = P.start[r]; my_e = P.start[r + 1]; }
         }
-        int s = 0;
-        uint32_t phase = 0;
+        int s = ring_s;
+        uint32_t phase = ring_k;
         int j = first;
         bool halo_here = !HALO;                                   // the peers' halo entries have been acquired by this warp
         for (int it = 0; it < my_chunks; ++it, j += G) {
@@ -505,7 +486,39 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
             my_s = nx_s; my_e = nx_e;
             if (++s == stages) { s = 0; phase ^= 1u; }
         }
+        ring_s = s; ring_k = phase;
     }
+}
+
+// HALO: multi-GPU SpMV whose boundary row groups wait for the peers' halo pushes (compiled out of the single-GPU kernel)
+template <int V, bool PLAIN, bool HALO>   // lanes per row; PLAIN: op == ASSIGN and no extra copies of the result
+__global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParams P, const int cap, const int nchunks, const int stages) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: vals[stages][cap] | cols[stages][cap] | full[4] | empty[4] | win[4][2]
+    float* vals_s = reinterpret_cast<float*>(smem_raw);
+    int* cols_s = reinterpret_cast<int*>(smem_raw + (size_t)stages * cap * sizeof(float));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * cap * 8);
+    uint64_t* empty = full + ROWS_MAX_STAGES;
+    int* win = reinterpret_cast<int*>(empty + ROWS_MAX_STAGES);   // [stage][2]: window start a0, staged flag
+    __shared__ float red_sh[96];
+    __shared__ int sh_flag;
+
+    const int tid = threadIdx.x;
+    typename std::conditional<PLAIN, PlainWriter, RowWriter>::type write(P);
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ROWS_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // everything above is independent of the previous kernel of the chain; the done flag, the operand vector and (for the
+    // multi-GPU case) the exchange counter are not
+    smm_pdl_wait();
+    if (P.state != nullptr && P.state->done) return;
+
+    int ring_s = 0;
+    uint32_t ring_k = 0;
+    rows_sweep<V, HALO>(P, cap, nchunks, stages, vals_s, cols_s, full, empty, win, write, (int)blockIdx.x, (int)gridDim.x, ring_s, ring_k);
 
     smm_pdl_trigger();
     if (P.reduce != RED_NONE) {
@@ -514,6 +527,188 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
         if (grid_sum_last_block<2>(v, P.partials, P.partials_stride, P.ticket, red_sh, &sh_flag)) {
             if (tid == 0) smm_finish(P.finish, P.state, v[0], v[1]);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cg_persistent_kernel: the whole loop of ConjugateGradient (H:2352-2396) in ONE cooperative launch, for problems that live
+// in L2, where an iteration of three kernels is mostly launch ramp-up, tail and the last CTA folding the partial sums
+// (1024^2: 25 us per iteration for 90 MB of L2 traffic).  The resident CTAs run the three phases of an iteration --
+//   Ap = A p with p.Ap  |  x += alpha p, r -= alpha Ap with r.r  |  p = r + beta p
+// -- separated by grid barriers, and every CTA folds the partial sums itself, so the scalars (alpha, beta, the stopping test)
+// are known everywhere without a second barrier.
+// RESULTS ARE THE SAME BITS AS THE GRAPH DRIVERS': the phases are executed as the VIRTUAL CTAs of the kernels they replace
+// (virtual CTA v of spmv_rows_kernel's grid G1 = rows_sweep(first = v, G = G1); virtual CTA v of vec_kernel's grid G2 =
+// threads 0..255 with gid = v * 256 + tid), each leaves the partial sum the real CTA would have left, and the fold walks the
+// partial sums in the order of grid_sum_last_block (thread t adds partials t, t + T, ...; then the block tree over T threads).
+// ---------------------------------------------------------------------------------------------------
+struct PersistParams {
+    SpmvParams sp;                 // Ap = A p, RED_OUT_AUX with aux = p; partials = reduction slot 0
+    int cap, nchunks, stages, G1;  // spmv_rows_kernel's launch configuration
+    VecParams xr, pu;              // FCgXR (partials = slot 1) and FCgP
+    int G2;                        // vec_kernel's grid
+    unsigned int* barrier;         // [0] arrivals, [1] generation (both 0 at launch)
+};
+
+// block_sum of smm_internal.cuh for a (virtual) CTA of nw warps inside this CTA: threads of warps >= nw pass zeros
+template <int NV>
+__device__ __forceinline__ void block_sum_nw(float (&v)[NV], float* sh, const int nw) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sh[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float t = lane < nw ? sh[i * 32 + lane] : 0.0f;
+            v[i] = warp_sum(t);
+        }
+    }
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, const unsigned int nblocks, unsigned int& generation) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&bar[0], 1u) == nblocks - 1u) {
+            bar[0] = 0u;                                       // everybody has arrived: nobody touches the count until released
+            __threadfence();
+            atomicExch(&bar[1], generation + 1u);
+        } else {
+            unsigned int g;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(bar + 1) : "memory"); } while (g == generation);
+        }
+        __threadfence();
+    }
+    ++generation;
+    __syncthreads();
+}
+
+// the element-wise phase of virtual CTA vb of a grid of G2 CTAs x 256 threads (the body of vec_kernel<F, VEC4 = true, false>)
+template <class F>
+__device__ __forceinline__ void vec_phase(const VecParams& P, const Scal sc, const int vb, const int G2, float (&red)[2]) {
+    if (threadIdx.x >= VEC_THREADS) return;
+    const long long stride = (long long)G2 * VEC_THREADS;
+    const long long gid = (long long)vb * VEC_THREADS + threadIdx.x;
+    const long long n4 = P.n >> 2;
+    for (long long i = gid; i < n4; i += stride) {
+        float4 vin[F::NIN];
+#pragma unroll
+        for (int k = 0; k < F::NIN; ++k) vin[k] = reinterpret_cast<const float4*>(P.in[k])[i];
+        float4 vout[F::NOUT > 0 ? F::NOUT : 1];
+        float ein[F::NIN], eout[F::NOUT > 0 ? F::NOUT : 1];
+#define SMM_LANE(c)                                                        \
+    _Pragma("unroll") for (int k = 0; k < F::NIN; ++k) ein[k] = vin[k].c;   \
+    F::apply(sc, ein, eout, red);                                           \
+    _Pragma("unroll") for (int k = 0; k < F::NOUT; ++k) vout[k].c = eout[k];
+        SMM_LANE(x) SMM_LANE(y) SMM_LANE(z) SMM_LANE(w)
+#undef SMM_LANE
+#pragma unroll
+        for (int k = 0; k < F::NOUT; ++k) reinterpret_cast<float4*>(P.out[k])[i] = vout[k];
+    }
+    const long long t = (n4 << 2) + gid;                       // tail (n % 4 elements) by the first threads of virtual CTA 0
+    if (gid < 4 && t < P.n) {
+        float ein[F::NIN], eout[F::NOUT > 0 ? F::NOUT : 1];
+#pragma unroll
+        for (int k = 0; k < F::NIN; ++k) ein[k] = P.in[k][t];
+        F::apply(sc, ein, eout, red);
+#pragma unroll
+        for (int k = 0; k < F::NOUT; ++k) P.out[k][t] = eout[k];
+    }
+}
+
+// totals of `count` partial sums, walked like the last CTA of a kernel of T threads does (grid_sum_last_block); in thread 0
+__device__ __forceinline__ void fold_partials(const float* partials, const size_t stride, const int count, const int T, float (&tot)[2], float* sh) {
+    float acc[2] = {0.0f, 0.0f};
+    if ((int)threadIdx.x < T) {
+        for (int b = threadIdx.x; b < count; b += T) {
+            acc[0] += __ldcg(&partials[b]);
+            acc[1] += __ldcg(&partials[stride + b]);
+        }
+    }
+    __syncthreads();                                           // sh is reused
+    block_sum_nw<2>(acc, sh, T / 32);
+    tot[0] = acc[0]; tot[1] = acc[1];
+}
+
+template <int V>
+__global__ void __launch_bounds__(ROWS_THREADS, 5) cg_persistent_kernel(const PersistParams A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* vals_s = reinterpret_cast<float*>(smem_raw);
+    int* cols_s = reinterpret_cast<int*>(smem_raw + (size_t)A.stages * A.cap * sizeof(float));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)A.stages * A.cap * 8);
+    uint64_t* empty = full + ROWS_MAX_STAGES;
+    int* win = reinterpret_cast<int*>(empty + ROWS_MAX_STAGES);
+    __shared__ float red_sh[96];
+    __shared__ SolveState st;                                  // this CTA's copy of the scalar state: every CTA computes the same one
+    const int tid = threadIdx.x;
+    const int Gp = gridDim.x;
+    SolveState* const global_state = A.sp.state;
+
+    if (tid == 0) {
+        for (int s = 0; s < A.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ROWS_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        st = *global_state;
+        if (blockIdx.x != 0) { st.history = nullptr; st.history_cap = 0; }   // one writer for the residual history
+    }
+    __syncthreads();
+    int ring_s = 0;
+    uint32_t ring_k = 0;
+    unsigned int generation = 0;
+
+    while (!st.done) {
+        // ---- Ap = A p, p.Ap -> alpha (H:2353-2358) ----
+        for (int v = blockIdx.x; v < A.G1; v += Gp) {
+            PlainWriter write(A.sp);
+            rows_sweep<V, false>(A.sp, A.cap, A.nchunks, A.stages, vals_s, cols_s, full, empty, win, write, v, A.G1, ring_s, ring_k);
+            float part[2] = {write.acc0, write.acc1};
+            __syncthreads();
+            block_sum_nw<2>(part, red_sh, ROWS_THREADS / 32);
+            if (tid == 0) { A.sp.partials[v] = part[0]; A.sp.partials[A.sp.partials_stride + v] = part[1]; }
+            __syncthreads();
+        }
+        grid_barrier(A.barrier, Gp, generation);
+        {
+            float tot[2];
+            fold_partials(A.sp.partials, A.sp.partials_stride, A.G1, ROWS_THREADS, tot, red_sh);
+            if (tid == 0) smm_finish(FIN_CG_ALPHA, &st, tot[0], tot[1]);
+            __syncthreads();
+        }
+        // ---- x = fma(alpha, p, x); r = fma(-alpha, Ap, r); r.r -> beta, stopping test (H:2363-2382) ----
+        {
+            const Scal sc = FCgXR::scal(&st);
+            for (int v = blockIdx.x; v < A.G2; v += Gp) {
+                float red[2] = {0.0f, 0.0f};
+                vec_phase<FCgXR>(A.xr, sc, v, A.G2, red);
+                block_sum_nw<2>(red, red_sh, VEC_THREADS / 32);
+                if (tid == 0) { A.xr.partials[v] = red[0]; A.xr.partials[A.xr.partials_stride + v] = red[1]; }
+                __syncthreads();
+            }
+        }
+        grid_barrier(A.barrier, Gp, generation);
+        {
+            float tot[2];
+            fold_partials(A.xr.partials, A.xr.partials_stride, A.G2, VEC_THREADS, tot, red_sh);
+            if (tid == 0) smm_finish(FIN_CG_UPDATE, &st, tot[0], tot[1]);
+            __syncthreads();
+        }
+        if (st.done) break;                                    // the p update of the last iteration is a no-op in the graph drivers too
+        // ---- p = fma(beta, p, r) (H:2385-2393) ----
+        {
+            const Scal sc = FCgP::scal(&st);
+            float none[2] = {0.0f, 0.0f};
+            for (int v = blockIdx.x; v < A.G2; v += Gp) vec_phase<FCgP>(A.pu, sc, v, A.G2, none);
+        }
+        grid_barrier(A.barrier, Gp, generation);
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        global_state->done = st.done; global_state->status = st.status; global_state->iterations = st.iterations;
+        global_state->residual = st.residual; global_state->rr = st.rr; global_state->denom = st.denom;
+        global_state->alpha = st.alpha; global_state->beta = st.beta;
     }
 }
 
@@ -605,6 +800,86 @@ int smm_first_active_start(const smm_csr* m, int* out_host, cudaStream_t s) {
 
 // lanes per row of the TMA rows kernel for this matrix and mode, 0 when the product-staging kernel runs instead
 int smm_spmv_rows_lanes(const smm_csr* m, int exact) { return (exact && m->rows_kernel_lanes > 1) ? 0 : m->rows_kernel_lanes; }
+
+
+// ---------------------------------------------------------------------------------------------------
+// persistent CG iteration: configuration shared with smm_launch_spmv / smm_launch_vec (the virtual grids must be theirs)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct RowsConfig { int cap, stages, nchunks, grid; size_t smem; };
+RowsConfig rows_config(const smm_csr* m, const int V) {
+    static const int stages_env = [] { const char* e = getenv("SMM_B200_ROWS_STAGES"); return e ? atoi(e) : 0; }();
+    static const int cap_env = [] { const char* e = getenv("SMM_B200_ROWS_CAP"); return e ? (atoi(e) & ~3) : 0; }();
+    RowsConfig c;
+    c.cap = cap_env ? cap_env : m->rows_kernel_cap;
+    c.stages = stages_env ? stages_env : (int)(((227 * 1024) / 5 - 1024 - ROWS_MAX_STAGES * 24) / ((size_t)c.cap * 8));
+    if (c.stages < 2) c.stages = 2;
+    if (c.stages > ROWS_MAX_STAGES) c.stages = ROWS_MAX_STAGES;
+    c.smem = (size_t)c.stages * c.cap * 8 + ROWS_MAX_STAGES * 8 * 2 + ROWS_MAX_STAGES * 8;
+    const int R = ROWS_CONSUMERS / V;
+    c.nchunks = (m->rows + R - 1) / R;
+    int per_sm = (int)((227 * 1024) / (c.smem + 1024));
+    if (per_sm > 2048 / ROWS_THREADS) per_sm = 2048 / ROWS_THREADS;
+    c.grid = m->sm_count * per_sm;
+    if (c.grid > c.nchunks) c.grid = c.nchunks;
+    return c;
+}
+}  // namespace
+
+// the persistent iteration applies to matrices of the rows kernel with one lane per row, 16-byte aligned vectors
+bool smm_cg_persistent_fits(const smm_csr* m, const float* x, const float* r, const float* p, const float* ap) {
+    if (m->rows_kernel_lanes != 1 || m->rows < 4096 || !m->ws) return false;
+    return ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(ap)) & 15) == 0;
+}
+
+int smm_launch_cg_persistent(const smm_csr* m, SolveState* state, float* x, float* r, float* p, float* ap, cudaStream_t s) {
+    smm_workspace* ws = m->ws;
+    const RowsConfig rc = rows_config(m, 1);
+    PersistParams A;
+    SpmvParams& P = A.sp;
+    P.start = m->start; P.positions = m->positions; P.values = m->values; P.block_row = m->block_row;
+    P.rows = m->rows; P.nnz = (int)m->nnz; P.nnz_alloc = (int)m->nnz_alloc; P.op = SMM_OP_ASSIGN; P.exact = 0;
+    P.lhs = nullptr; P.mult = p; P.out = ap; P.copy1 = P.copy2 = P.copy3 = nullptr;
+    P.aux = p; P.reduce = RED_OUT_AUX; P.finish = FIN_CG_ALPHA; P.state = state;
+    P.partials = ws->partials; P.partials_stride = ws->partials_cap; P.ticket = nullptr; P.halo = nullptr;
+    A.cap = rc.cap; A.nchunks = rc.nchunks; A.stages = rc.stages; A.G1 = rc.grid;
+    A.G2 = smm_vec_grid(ws, m->rows, true);
+    if (ws->partials_cap < (size_t)A.G1 || ws->partials_cap < (size_t)A.G2) { smm_set_error("persistent CG: reduction workspace too small"); return SMM_E_STATE; }
+    auto vec = [&](VecParams& V) {
+        V.n = m->rows; V.state = state; V.finish = FIN_NONE; V.ticket = nullptr; V.halo = nullptr;
+        for (int k = 0; k < 5; ++k) V.in[k] = nullptr;
+        for (int k = 0; k < 3; ++k) V.out[k] = nullptr;
+        V.partials = ws->partials + (size_t)1 * 2 * ws->partials_cap;     // reduction slot 1, as in the graph drivers
+        V.partials_stride = ws->partials_cap;
+    };
+    vec(A.xr); A.xr.in[0] = x; A.xr.in[1] = p; A.xr.in[2] = r; A.xr.in[3] = ap; A.xr.out[0] = x; A.xr.out[1] = r;
+    vec(A.pu); A.pu.in[0] = p; A.pu.in[1] = r; A.pu.out[0] = p;
+    A.barrier = ws->grid_barrier;
+    static int per_sm_dev[SMM_MAX_DEVICES] = {0};
+    static size_t attr_dev[SMM_MAX_DEVICES] = {0};
+    int per_sm;
+    {
+        std::lock_guard<std::mutex> lk(g_smm_attr_mu);
+        const int d = m->device % SMM_MAX_DEVICES;
+        if (attr_dev[d] != rc.smem) {
+            SMM_CUDA(cudaFuncSetAttribute(cg_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rc.smem));
+            int n = 0;
+            SMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, cg_persistent_kernel<1>, ROWS_THREADS, rc.smem));
+            per_sm_dev[d] = n;
+            attr_dev[d] = rc.smem;
+        }
+        per_sm = per_sm_dev[d];
+    }
+    if (per_sm < 1) { smm_set_error("persistent CG: the kernel does not fit an SM"); return SMM_E_STATE; }
+    int grid = per_sm * m->sm_count;                           // every CTA resident (cooperative launch): the grid barrier relies on it
+    const int most = A.G1 > A.G2 ? A.G1 : A.G2;
+    if (grid > most) grid = most;
+    SMM_CUDA(cudaMemsetAsync(ws->grid_barrier, 0, 2 * sizeof(unsigned int), s));
+    void* args[] = {&A};
+    SMM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cg_persistent_kernel<1>), dim3(grid), dim3(ROWS_THREADS), args, rc.smem, s));
+    SMM_COUNT_LAUNCH(1);
+    return SMM_OK;
+}
 
 int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
     const smm_csr* m = a.m;

@@ -329,6 +329,26 @@ def test_drivers_agree(smm, golden, solver):
     assert res[0] == res[1] == res[2]
 
 
+@pytest.mark.parametrize("shape", [(96, 100), (300, 256), (1024, 200), (512, 512)])
+def test_persistent_cg_has_the_graph_drivers_bits(smm, shape):
+    """SMM_DRIVER_PERSISTENT (one cooperative kernel for the whole ConjugateGradient loop, H:2352-2396) executes the CTAs of the
+    graph drivers' kernels as virtual CTAs: same partial sums, same scalars, same x, same residual history, bit for bit --
+    converged runs, capped runs (MAX_ITERATIONS_REACHED) and the zero-iteration exit."""
+    g = matgen.poisson2d(*shape)
+    m = upload(smm, g)
+    xs = matgen.xstar(g.rows)
+    b = ol.spmv(g, 0, None, xs)
+    for maxit, eps in ((-1, 1e-5), (37, 0.0), (1, 1e-6), (-1, 1e9)):
+        res = []
+        for drv in (smm.DRIVER_GRAPH_CHUNKED, smm.DRIVER_PERSISTENT):
+            x = np.zeros(g.rows, np.float32)
+            info = smm.ConjugateGradient(m, b, x, x, maxit, np.float32(eps), driver_mode=drv, check_every=16, history_cap=64)
+            assert info.driver_mode == drv
+            hist = info.history[: min(info.iterations, 64)]
+            res.append((int(info.status), info.iterations, np.float32(info.residual).tobytes(), x.tobytes(), hist.tobytes()))
+        assert res[0] == res[1], (shape, maxit, eps, res[0][:2], res[1][:2])
+
+
 def test_cg_quirks(smm, golden):
     g = gold_csr(golden, "poisson2d_96x100")
     m = upload(smm, g)

@@ -14,7 +14,8 @@ n = A.rows
 ones = smm.DeviceVector(n, np.ones(n, np.float32)); b = smm.DeviceVector(n); x = smm.DeviceVector(n)
 A.spmv_dev(B.OP_ASSIGN, None, ones.ptr, b.ptr)
 L = smm.lib()
-for name, drv, ce in [("chunked/32", B.DRIVER_GRAPH_CHUNKED, 32), ("chunked/256", B.DRIVER_GRAPH_CHUNKED, 256), ("while", B.DRIVER_GRAPH_WHILE, 0), ("stream/256", B.DRIVER_STREAM, 256)]:
+for name, drv, ce in [("chunked/32", B.DRIVER_GRAPH_CHUNKED, 32), ("chunked/256", B.DRIVER_GRAPH_CHUNKED, 256), ("while", B.DRIVER_GRAPH_WHILE, 0), ("stream/256", B.DRIVER_STREAM, 256),
+                      ("persistent", B.DRIVER_PERSISTENT, 0)]:
     for rep in range(2):
         x.zero()
         o, _ = B._options(B.REDUCE_FAST, drv, ce, 0)
