@@ -208,7 +208,8 @@ int smm_gen_xstar_dev(int64_t n, int64_t offset, uint64_t seed, float* x_dev, vo
  * opts->reduction_mode == SMM_REDUCE_REFERENCE_TREE is accepted by smm_dist_solve_cg when the number of ranks is a power
  * of two and every rank's row block is a node of the reference's reduction tree over [0, global_rows) (the range halved at
  * lo + (hi - lo) / 2, H:308-320): the ranks' subtree sums are then joined pairwise and the solve is bit-identical to the
- * reference's SMM_MULTITHREADING build; any other partition is refused with SMM_E_INVALID. */
+ * reference's SMM_MULTITHREADING build; any other partition is refused with SMM_E_INVALID.  The same holds for the other
+ * three solvers below (BiCGStab's serial ||r||^2, H:2262-2267, is chained through the ranks). */
 /* smm_dist_create re-indexes local's column indices IN PLACE (global -> window) and sets its column count to the window
  * length; `local` must outlive the smm_dist_t and must not be used for single-GPU calls afterwards.  On failure nothing the
  * function allocated is kept. */

@@ -242,6 +242,7 @@ static int dist_finish_connect(smm_dist_t* d, const int64_t* all_ranges) {
         c.mail[r] = reinterpret_cast<unsigned long long*>(base + ext_bytes);
         c.flags[r] = reinterpret_cast<unsigned int*>(base + ext_bytes + ((mail_bytes + 255) & ~(size_t)255));
         c.acks[r] = c.flags[r] + 32;
+        c.chain[r] = reinterpret_cast<unsigned long long*>(c.flags[r] + 16);     // flags [nranks] at +0, chain word at +64, acks at +128
         if (r == me) continue;
         // what rank r needs from me: my owned rows inside its window
         const long long a = d->row_begin > lo ? d->row_begin : lo;

@@ -13,6 +13,10 @@
 //     schedules the rows that read no halo FIRST and only the warps that reach a boundary row group spin on the flags
 //     (acquire, system scope; HaloWaitDev, spmv.cu), gathering those groups' operands past L1.  Other SpMV kernels
 //     are preceded by a wait kernel.
+//   * chained sums: BiCGStab's ||r||^2 is ONE left-to-right sum over the whole vector in both builds of the reference
+//     (H:2262-2267), not a per-rank quantity: rank r starts its part from the running sum rank r - 1 hands it (one 64-bit
+//     word, value + sequence tag, into chain[r]) and hands its own on; the last rank's total reaches everybody through the
+//     ordinary all-reduce with zeros from the others (x + 0 = x).
 //   * back-pressure: inside the solvers a fused all-reduce sits between two exchanges, so a rank cannot push again
 //     before every peer's SpMV has finished reading its halo.  The stand-alone smm_dist_spmv_dev has no such
 //     reduction: there the consumer acknowledges every exchange (acks[], release) and the pusher waits for the
@@ -34,6 +38,8 @@ struct DistComm {
     unsigned int* flags[SMM_MAX_RANKS];         // flags[d]: rank d's flag array [nranks]; this rank writes flags[d][rank]
     unsigned int* acks[SMM_MAX_RANKS];          // acks[d]: rank d's ack array [nranks]; this rank writes acks[d][rank] (stand-alone SpMV)
     unsigned int ack_seq;                       // stand-alone SpMV calls completed
+    unsigned long long* chain[SMM_MAX_RANKS];   // chain[d]: rank d's inbound word of a sum that is CHAINED through the ranks
+    unsigned int chain_seq;                     // chained sums completed (same on every rank)
 };
 
 // halo push fused into an element-wise kernel: segment s covers elements [begin, begin + len) of the kernel's first

@@ -364,6 +364,24 @@ __global__ void __cluster_dims__(SQ_CTAS, 1, 1) __launch_bounds__(SQ_THREADS, 1)
     const int rank = (int)cluster.block_rank();
     const unsigned int g = (unsigned int)rank * SQ_THREADS + tid;              // thread index inside the window
     unsigned int sbits = 0u;                                 // the running sum (H:2262: res = 0)
+    // Multi-GPU: the sum runs through the ranks in order -- this rank's rows continue the sum of the ranks before it
+    DistComm* const chain = (P.state != nullptr) ? P.state->comm : nullptr;
+    if (chain != nullptr && chain->rank > 0) {
+        if (rank == 0 && tid == 0) {
+            const unsigned int want = chain->chain_seq + 1u;
+            unsigned long long w = 0ull;
+            unsigned int polls = 0;
+            for (;;) {
+                w = ld_sys_u64(chain->chain[chain->rank]);
+                if ((unsigned int)(w >> 32) == want) break;
+                if (++polls >= SMM_DIST_POLL_LIMIT) { chain->error = 1; break; }
+            }
+            for (int c = 0; c < SQ_CTAS; ++c) *cluster.map_shared_rank(&sh_bits, c) = (unsigned int)w;
+        }
+        cluster.sync();
+        sbits = sh_bits;
+        cluster.sync();                                      // sh_bits is written again inside the loop
+    }
     long long base = 0;
     bool open_ended = false;                                 // the sum has become infinite or NaN
     // values of this CTA's part of the window, coalesced, all loads of a thread in flight; the NEXT window is requested
@@ -487,7 +505,15 @@ __global__ void __cluster_dims__(SQ_CTAS, 1, 1) __launch_bounds__(SQ_THREADS, 1)
         if (sh_flag) sbits = 0x7FFFFFFFu;
     }
     if (tid == 0) {
-        const float total = __uint_as_float(sbits);
+        float total = __uint_as_float(sbits);
+        if (chain != nullptr) {
+            const unsigned int seq = chain->chain_seq + 1u;
+            if (chain->rank + 1 < chain->nranks) {             // hand the running sum on; the total comes back through the all-reduce
+                st_sys_u64(chain->chain[chain->rank + 1], ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(total));
+                total = 0.0f;
+            }
+            chain->chain_seq = seq;
+        }
         if (P.out_dev) P.out_dev[0] = total;
         if (P.state) smm_finish(P.finish, P.state, total, 0.0f);
     }

@@ -441,8 +441,9 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
     if (dist && c.mode != SMM_REDUCE_FAST) {
         // The reference-tree mode distributes when every rank owns one node of the reference's reduction tree (the range
         // [0, n) halved log2(P) times at lo + (hi - lo) / 2, H:308-320): local trees, then the ranks joined pairwise.
-        // (BiCGStab's ||r||^2 is one serial sum over the whole vector in the reference, H:2262-2267: not a per-rank quantity.)
-        bool aligned = solver != S_BICGSTAB && c.mode == SMM_REDUCE_REFERENCE_TREE && (dist->nranks & (dist->nranks - 1)) == 0;
+        // (BiCGStab's ||r||^2 is one serial sum over the whole vector in the reference, H:2262-2267: it is chained through the
+        // ranks, dots.cu / dist_device.cuh.)
+        bool aligned = c.mode == SMM_REDUCE_REFERENCE_TREE && (dist->nranks & (dist->nranks - 1)) == 0;
         if (aligned) {
             long long lo = 0, hi = dist->global_rows;
             for (int bit = dist->nranks >> 1; bit >= 1; bit >>= 1) {
@@ -452,7 +453,7 @@ int solve_dev(int solver, const smm_csr* a, const smm_precond* precond, const fl
             aligned = lo == dist->row_begin && hi == dist->row_end && hi - lo > 8192;
         }
         if (!aligned) {
-            smm_set_error("multi-GPU solve: of the reference-order modes only REFERENCE_TREE distributes (not for BiCGStab), with a power-of-two "
+            smm_set_error("multi-GPU solve: of the reference-order modes only REFERENCE_TREE distributes, with a power-of-two "
                           "number of ranks and row blocks that are the nodes of the reference's reduction tree (dist.tbb_partition)");
             return SMM_E_INVALID;
         }

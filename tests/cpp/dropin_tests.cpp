@@ -448,7 +448,7 @@ TEST_CASE("Row-partitioned over N GPUs behind the reference's calls (skipped on 
     // reference-order reductions: every GPU sums its node of the reference's reduction tree, the GPUs are joined pairwise --
     // the same bits and iteration counts as one GPU (which equal the reference's multithreaded build)
     SMM::b200::options().reduction_mode = SMM_REDUCE_REFERENCE_TREE;
-    for (int solver = 0; solver < 3; ++solver) {
+    for (int solver = 0; solver < 4; ++solver) {
         int its[2] = {0, 0};
         SMM::Vector<T> xa(n, 0), xb(n, 0);
         for (int pass = 0; pass < 2; ++pass) {
@@ -457,7 +457,8 @@ TEST_CASE("Row-partitioned over N GPUs behind the reference's calls (skipped on 
             SMM::SolverStatus st = SMM::SolverStatus::DIVERGED;
             if (solver == 0) st = SMM::ConjugateGradient<T>(m, rhs, x, x, -1, kL2Eps);
             else if (solver == 1) st = SMM::BiCGSymmetric<T>(m, rhs, x, -1, kL2Eps);
-            else st = SMM::ConjugateGradientSquared<T>(m, rhs, x, -1, kL2Eps);
+            else if (solver == 2) st = SMM::ConjugateGradientSquared<T>(m, rhs, x, -1, kL2Eps);
+            else st = SMM::BiCGStab<T>(m, rhs, x, -1, kL2Eps);   // its serial ||r||^2 (H:2262-2267) is chained through the GPUs
             CHECK_EQ(st, SMM::SolverStatus::SUCCESS);
             its[pass] = SMM::b200::lastSolveInfo().iterations;
         }
