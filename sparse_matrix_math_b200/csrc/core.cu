@@ -60,24 +60,28 @@ int smm_workspace_get(const smm_csr* mc, smm_workspace** out) {
     if (!m->ws) {
         smm_workspace* ws = new smm_workspace();
         ws->device = m->device;
-        cudaDeviceProp prop;
-        SMM_CUDA(cudaGetDeviceProperties(&prop, m->device));
-        ws->sm_count = prop.multiProcessorCount;
-        size_t cap = (size_t)m->num_blocks;
-        const size_t vg = (size_t)smm_vec_max_grid(ws);
-        if (cap < vg) cap = vg;
-        cap = (cap + 63) & ~(size_t)63;
-        ws->partials_cap = cap;
-        SMM_CUDA(cudaMalloc(&ws->partials, sizeof(float) * cap * 2 * RED_SLOTS));
-        SMM_CUDA(cudaMalloc(&ws->tickets, sizeof(unsigned int) * RED_SLOTS));
-        SMM_CUDA(cudaMemset(ws->tickets, 0, sizeof(unsigned int) * RED_SLOTS));
-        SMM_CUDA(cudaMalloc(&ws->grid_barrier, sizeof(unsigned int) * 2));
-        SMM_CUDA(cudaMemset(ws->grid_barrier, 0, sizeof(unsigned int) * 2));
-        SMM_CUDA(cudaMalloc(&ws->state, sizeof(SolveState)));
-        SMM_CUDA(cudaMemset(ws->state, 0, sizeof(SolveState)));
-        SMM_CUDA(cudaMallocHost(&ws->state_host, sizeof(SolveState)));
-        SMM_CUDA(cudaEventCreate(&ws->ev0));
-        SMM_CUDA(cudaEventCreate(&ws->ev1));
+        const int rc = [&]() -> int {                          // a workspace is attached whole or not at all
+            cudaDeviceProp prop;
+            SMM_CUDA(cudaGetDeviceProperties(&prop, m->device));
+            ws->sm_count = prop.multiProcessorCount;
+            size_t cap = (size_t)m->num_blocks;
+            const size_t vg = (size_t)smm_vec_max_grid(ws);
+            if (cap < vg) cap = vg;
+            cap = (cap + 63) & ~(size_t)63;
+            ws->partials_cap = cap;
+            SMM_CUDA(cudaMalloc(&ws->partials, sizeof(float) * cap * 2 * RED_SLOTS));
+            SMM_CUDA(cudaMalloc(&ws->tickets, sizeof(unsigned int) * RED_SLOTS));
+            SMM_CUDA(cudaMemset(ws->tickets, 0, sizeof(unsigned int) * RED_SLOTS));
+            SMM_CUDA(cudaMalloc(&ws->grid_barrier, sizeof(unsigned int) * 2));
+            SMM_CUDA(cudaMemset(ws->grid_barrier, 0, sizeof(unsigned int) * 2));
+            SMM_CUDA(cudaMalloc(&ws->state, sizeof(SolveState)));
+            SMM_CUDA(cudaMemset(ws->state, 0, sizeof(SolveState)));
+            SMM_CUDA(cudaMallocHost(&ws->state_host, sizeof(SolveState)));
+            SMM_CUDA(cudaEventCreate(&ws->ev0));
+            SMM_CUDA(cudaEventCreate(&ws->ev1));
+            return SMM_OK;
+        }();
+        if (rc != SMM_OK) { smm_workspace_free(ws); return rc; }
         m->ws = ws;
     }
     *out = m->ws;
