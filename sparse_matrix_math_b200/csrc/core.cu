@@ -272,6 +272,7 @@ int smm_csr_destroy(smm_csr_t* m) {
     cudaSetDevice(m->device);
     if (m->owns_arrays) { cudaFree(m->start); cudaFree(m->positions); cudaFree(m->values); }
     cudaFree(m->block_row);
+    cudaFree(m->row_perm);
     smm_workspace_free(m->ws);
     delete m;
     return SMM_OK;

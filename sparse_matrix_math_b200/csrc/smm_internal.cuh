@@ -53,6 +53,7 @@ constexpr int SPMV_CHUNK = 4096;           // nnz per CTA: CTA q owns the rows w
 constexpr int SPMV_CAP = 6144;             // products staged in shared memory (24 KB): CHUNK + longest row streamed
 constexpr int SPMV_MIN_STREAM_ROWS = 48;   // fewer rows than this in a CTA's range -> warp/CTA-per-row path
 constexpr int SPMV_LONG_IN_STREAM = 192;   // rows longer than this inside a streamed range are summed by a warp
+constexpr int SPMV_PERM_MAX_ROWS = 2048;   // chunks of at most this many rows have their rows ordered by length (row_perm)
 constexpr int SPMV_CTA_ROW = 4096;         // rows longer than this are reduced by the whole CTA
 constexpr int SPMV_ROWS_CAP = 2560;        // rows kernel: upper bound of the entries per TMA stage
 
@@ -73,6 +74,7 @@ struct smm_csr {
     // SpMV analysis: CTA q handles rows [block_row[q], block_row[q+1])
     int num_blocks = 0;
     int32_t* block_row = nullptr;   // [num_blocks+1]
+    int32_t* row_perm = nullptr;    // [rows] or null: the rows of every chunk, longest first (irregular-row kernels; spmv.cu)
     int max_row_len = 0;
     int rows_kernel_lanes = 0;      // 0: product-staging kernel; V > 0: TMA rows kernel with V lanes per row
     int sm_count = 148;

@@ -42,6 +42,7 @@ struct SpmvParams {
     const int32_t* __restrict__ positions;
     const float* __restrict__ values;
     const int32_t* __restrict__ block_row;
+    const int32_t* __restrict__ row_perm;   // rows of every chunk, longest first (null: in index order)
     int rows;
     int nnz;
     int nnz_alloc;        // entries readable in positions/values (TMA windows are rounded up to 16 bytes)
@@ -254,8 +255,12 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const SpmvParams P) 
                 if (k < k1) prod[k - a0] = __fmul_rn(ldg_stream_f(P.values + k), __ldg(P.mult + ldg_stream_i(P.positions + k)));
             }
             __syncthreads();
+            // One thread per row, left to right.  With row_perm the rows of the range come longest first: the 32 rows of a
+            // warp have similar lengths (a warp costs its longest row), and the rows too long for one thread lead the list.
+            const bool sorted = P.row_perm != nullptr && nrows <= SPMV_PERM_MAX_ROWS;
             bool saw_long = false;
-            for (int r = r0 + tid; r < r1; r += SPMV_THREADS) {
+            for (int i = tid; i < nrows; i += SPMV_THREADS) {
+                const int r = sorted ? P.row_perm[r0 + i] : r0 + i;
                 const int s = P.start[r] - a0, e = P.start[r + 1] - a0;
                 if (!P.exact && e - s > SPMV_LONG_IN_STREAM) { saw_long = true; continue; }
                 float dot = 0.0f;                             // H:1484 ; empty row -> op(lhs, 0), H:1479-1483
@@ -265,9 +270,10 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const SpmvParams P) 
             if (saw_long) sh_long = 1;
             __syncthreads();
             if (sh_long) {
-                for (int r = r0 + warp; r < r1; r += NWARPS) {
+                for (int i = warp; i < nrows; i += NWARPS) {
+                    const int r = sorted ? P.row_perm[r0 + i] : r0 + i;
                     const int s = P.start[r] - a0, e = P.start[r + 1] - a0;
-                    if (e - s <= SPMV_LONG_IN_STREAM) continue;
+                    if (e - s <= SPMV_LONG_IN_STREAM) { if (sorted) break; continue; }
                     float acc = 0.0f;
                     for (int j = s + lane; j < e; j += 32) acc += prod[j];
                     acc = warp_sum(acc);
@@ -732,6 +738,28 @@ __global__ void block_row_kernel(const int32_t* __restrict__ start, int rows, in
     block_row[q] = lo;
 }
 
+// row_perm: the rows of chunk q (one CTA each) ordered by length, longest first, ties in index order -- a rank by counting
+// (chunks hold ~ SPMV_CHUNK / mean-row-length rows; chunks of more than SPMV_PERM_MAX_ROWS rows, i.e. mostly empty rows,
+// keep the index order and the kernels do not read row_perm for them)
+__global__ void __launch_bounds__(256) row_perm_kernel(const int32_t* __restrict__ start, const int32_t* __restrict__ block_row, int32_t* __restrict__ row_perm) {
+    __shared__ int len[SPMV_PERM_MAX_ROWS];
+    const int r0 = block_row[blockIdx.x], r1 = block_row[blockIdx.x + 1];
+    const int n = r1 - r0;
+    if (n <= 0) return;
+    if (n > SPMV_PERM_MAX_ROWS) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) row_perm[r0 + i] = r0 + i;
+        return;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) len[i] = start[r0 + i + 1] - start[r0 + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int mine = len[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (len[j] > mine) || (len[j] == mine && j < i);
+        row_perm[r0 + rank] = r0 + i;
+    }
+}
+
 __global__ void first_active_kernel(const int32_t* __restrict__ start, int rows, int* out) {
     // firstActiveStart (H:1622-1628): first row i with start[i+1] != 0, or rows
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -779,6 +807,13 @@ int smm_csr_analyse(smm_csr* m, cudaStream_t s) {
     const int threads = 256;
     block_row_kernel<<<(m->num_blocks + 1 + threads - 1) / threads, threads, 0, s>>>(m->start, m->rows, m->num_blocks, m->block_row);
     SMM_COUNT_LAUNCH(1);
+    if (m->row_perm) { cudaFree(m->row_perm); m->row_perm = nullptr; }
+    static const bool perm_on = [] { const char* e = getenv("SMM_B200_SPMV_PERM"); return !e || atoi(e) != 0; }();
+    if (m->rows_kernel_lanes != 1 && m->rows > 0 && perm_on) {      // the product-staging kernels run for this matrix (always, or in exact mode)
+        SMM_CUDA(cudaMalloc(&m->row_perm, sizeof(int32_t) * (size_t)m->rows));
+        row_perm_kernel<<<m->num_blocks, 256, 0, s>>>(m->start, m->block_row, m->row_perm);
+        SMM_COUNT_LAUNCH(1);
+    }
     SMM_CUDA(cudaGetLastError());
     return SMM_OK;
 }
@@ -837,7 +872,7 @@ int smm_launch_cg_persistent(const smm_csr* m, SolveState* state, float* x, floa
     const RowsConfig rc = rows_config(m, 1);
     PersistParams A;
     SpmvParams& P = A.sp;
-    P.start = m->start; P.positions = m->positions; P.values = m->values; P.block_row = m->block_row;
+    P.start = m->start; P.positions = m->positions; P.values = m->values; P.block_row = m->block_row; P.row_perm = m->row_perm;
     P.rows = m->rows; P.nnz = (int)m->nnz; P.nnz_alloc = (int)m->nnz_alloc; P.op = SMM_OP_ASSIGN; P.exact = 0;
     P.lhs = nullptr; P.mult = p; P.out = ap; P.copy1 = P.copy2 = P.copy3 = nullptr;
     P.aux = p; P.reduce = RED_OUT_AUX; P.finish = FIN_CG_ALPHA; P.state = state;
@@ -885,7 +920,7 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
     const smm_csr* m = a.m;
     if (m->rows == 0) return SMM_OK;
     SpmvParams P;
-    P.start = m->start; P.positions = m->positions; P.values = m->values; P.block_row = m->block_row;
+    P.start = m->start; P.positions = m->positions; P.values = m->values; P.block_row = m->block_row; P.row_perm = m->row_perm;
     P.rows = m->rows; P.nnz = (int)m->nnz; P.nnz_alloc = (int)m->nnz_alloc; P.op = a.op; P.exact = a.exact;
     P.lhs = a.lhs; P.mult = a.mult; P.out = a.out;
     P.copy1 = a.copy1; P.copy2 = a.copy2; P.copy3 = a.copy3;
