@@ -136,6 +136,10 @@ int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backwar
  * 2D / 3D grid stencil: rows are grouped into tiles of <= 64 that one warp solves in shared memory), 0 / 0 when the
  * row-level schedule is in use.  Diagnostic; additive. */
 int smm_precond_tile_levels(const smm_precond_t* p, int* forward_levels, int* backward_levels);
+/* Which schedule the sweeps of this handle run: 0 = row by row in level order (any matrix), 1 = tiles, 2 = lines (grid
+ * stencils: a lane per grid line, a warp per patch of 32 lines, sgs_lines.cu; smm_precond_tile_levels then reports the
+ * number of patch offsets).  The result of apply is bit-identical whatever the schedule.  Diagnostic; additive. */
+int smm_precond_schedule(const smm_precond_t* p);
 /* CSRMatrix::IC0Preconditioner (H:1214-1235): construction + init() (factorize, H:1839-1928; *rc = its return code) and
  * apply (H:1802-1837, through smm_precond_apply[_dev]).  The factorisation is set-up code and runs on the host, row by
  * row instead of the reference's O(rows^2) scan, with bit-identical values; the two triangular solves of every apply

@@ -118,6 +118,7 @@ def lib():
         L.smm_precond_apply_dev.argtypes = [_vp, _vp, _vp, C.POINTER(_i32), _vp]
         L.smm_precond_levels.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_i32)]
         L.smm_precond_tile_levels.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_i32)]
+        L.smm_precond_schedule.argtypes = [_vp]
         L.smm_precond_destroy.argtypes = [_vp]
         L.smm_precond_ic0_create.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_vp)]
         L.smm_precond_ic0_factor.argtypes = [_vp, _vp]
@@ -309,6 +310,10 @@ class SGSPreconditioner:
         f, b = _i32(), _i32()
         _check(lib().smm_precond_tile_levels(self.handle, C.byref(f), C.byref(b)), "smm_precond_tile_levels")
         return f.value, b.value
+
+    def schedule(self):
+        """0: rows in level order, 1: tiles, 2: lines (which schedule the triangular sweeps of this handle run)."""
+        return int(lib().smm_precond_schedule(self.handle))
 
     def __del__(self):
         try:

@@ -424,6 +424,10 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
     static const int ctas_per_sm = [] { const char* e = getenv("SMM_B200_SGS_CTAS_PER_SM"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : v; }();
     // SGS reads A's current values; an IC(0) factor is frozen at init() like the reference's ic0Val
     const unsigned long long want_version = p->kind != 0 ? 0ull : m->values_version;
+    if (p->values_version != want_version && p->lined) {
+        SMM_TRY(smm_sgs_lines_gather(p, s));
+        const_cast<smm_precond*>(p)->values_version = want_version;
+    }
     if (p->values_version != want_version) {                   // matrix values changed since the packed copies were gathered
         smm_precond* pm = const_cast<smm_precond*>(p);
         for (int w = 0; w < 2; ++w) {
@@ -439,7 +443,9 @@ int smm_sgs_apply_async_rc(const smm_precond* p, const float* rhs_dev, float* x_
     // tuning knobs (tools/sgs_bench.py), read once
     static const unsigned int sleep_first = [] { const char* e = getenv("SMM_B200_SGS_SLEEP_FIRST"); return e ? (unsigned int)atoi(e) : 0u; }();
     static const unsigned int sleep_later = [] { const char* e = getenv("SMM_B200_SGS_SLEEP_LATER"); return e ? (unsigned int)atoi(e) : 64u; }();
-    if (p->tiled) {
+    if (p->lined) {
+        SMM_TRY(smm_sgs_lines_launch(p, rhs_dev, x_dev, state, sleep_first, sleep_later, s));
+    } else if (p->tiled) {
         SMM_TRY(smm_sgs_tiles_launch(p, rhs_dev, x_dev, state, ctas_per_sm, sleep_first, sleep_later, s));
     } else {
         const long long cap = (long long)m->sm_count * ctas_per_sm;
@@ -510,10 +516,12 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
         SMM_CUDA(cudaMalloc(&p->diag_pos, sizeof(int32_t) * diag.size()));
         SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
     }
-    // tile-level schedule when the matrix admits one (sgs_tiles.cu), else the row-level schedule below
     clock.mark("factorisation, diagonal upload");
-    const bool tiles = kind != 3 && p->valid && m->rows > 0 && smm_sgs_tiles_build(p, m->rows, start, pos, diag);
-    clock.mark(tiles ? "tile schedule: layout + upload" : "tile schedule: not applicable");
+    // line schedule when the matrix admits one (sgs_lines.cu), else the tile-level schedule (sgs_tiles.cu), else the row-level schedule below
+    const bool lines = kind != 3 && p->valid && m->rows > 0 && smm_sgs_lines_build(p, m->rows, start, pos);
+    clock.mark(lines ? "line schedule: layout on the device" : "line schedule: not applicable");
+    const bool tiles = lines || (kind != 3 && p->valid && m->rows > 0 && smm_sgs_tiles_build(p, m->rows, start, pos, diag));
+    if (!lines) clock.mark(tiles ? "tile schedule: layout + upload" : "tile schedule: not applicable");
     if (levels.valid()) levels.get();
     clock.mark("row levels (ran beside the above)");
     if (kind != 3 && p->valid && m->rows > 0 && !tiles) {
@@ -625,15 +633,19 @@ int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backwar
 // levels of the tile graph when the tile-level schedule is in use (sgs_tiles.cu), 0 / 0 otherwise
 int smm_precond_tile_levels(const smm_precond_t* p, int* forward_levels, int* backward_levels) {
     if (!p) return SMM_E_INVALID;
-    if (forward_levels) *forward_levels = p->tiled ? p->tile_levels[0] : 0;
-    if (backward_levels) *backward_levels = p->tiled ? p->tile_levels[1] : 0;
+    if (forward_levels) *forward_levels = p->lined ? p->line_levels : p->tiled ? p->tile_levels[0] : 0;
+    if (backward_levels) *backward_levels = p->lined ? p->line_levels : p->tiled ? p->tile_levels[1] : 0;
     return SMM_OK;
 }
+
+// which schedule the sweeps of this handle run: 0 = row by row in level order, 1 = tiles, 2 = lines
+int smm_precond_schedule(const smm_precond_t* p) { return !p ? -1 : p->lined ? 2 : p->tiled ? 1 : 0; }
 
 int smm_precond_destroy(smm_precond_t* p) {
     if (!p) return SMM_OK;
     cudaFree(p->tile_steps[0]); cudaFree(p->tile_steps[1]); cudaFree(p->tile_push[0]); cudaFree(p->tile_push[1]);
     cudaFree(p->tile_push2[0]); cudaFree(p->tile_push2[1]);
+    for (int w = 0; w < 2; ++w) { cudaFree(p->line_pack[w]); cudaFree(p->line_eidx[w]); }
     cudaFree(p->order_fwd); cudaFree(p->order_bwd); cudaFree(p->diag_pos); cudaFree(p->yperm); cudaFree(p->xperm); cudaFree(p->ypos); cudaFree(p->tickets); cudaFree(p->factor);
     for (int w = 0; w < 2; ++w) { cudaFree(p->slice_ptr[w]); cudaFree(p->ecol[w]); cudaFree(p->eidx[w]); cudaFree(p->eval[w]); cudaFree(p->dval[w]); }
     cudaFree(p->io[0]); cudaFree(p->io[1]);

@@ -1,4 +1,4 @@
-// sgs_internal.cuh -- shared between sgs.cu (row-level schedule) and sgs_tiles.cu (tile-level schedule)
+// sgs_internal.cuh -- shared between sgs.cu (row-level schedule), sgs_tiles.cu (tile-level schedule) and sgs_lines.cu (line schedule)
 #pragma once
 #include <stdint.h>
 
@@ -41,9 +41,24 @@ struct smm_precond {
     int tile_chain[2] = {1, 1};      // tiles per chain (one warp solves a chain from end to end), per sweep
     int tile_blocks = 0;             // cluster schedule: blocks of 32 chains, one thread-block cluster per block at a time (0: off)
     uint32_t* tile_push2[2] = {nullptr, nullptr};  // cluster schedule: [tiles * 64] pushes that leave the tile (next tile of the chain, other chains of the block)
+    // line schedule (sgs_lines.cu): a lane per grid line, a warp per patch of 32 lines; when `lined`, yperm / xperm are ordered
+    // patch by patch, step by step (position = 32 * (patch * line_steps + step) + lane), the same positions for both sweeps
+    bool lined = false;
+    int line_w = 0;                  // operands per row and sweep
+    int line_steps = 0;              // steps per patch
+    int line_patches = 0;
+    int line_levels = 0;             // distinct patch offsets along j + along k - 1 (reported as the "tile levels")
+    uint32_t* line_pack[2] = {nullptr, nullptr};   // [patches * steps][2 w + 2][32] per sweep
+    int32_t* line_eidx[2] = {nullptr, nullptr};    // [patches * steps][w + 1][32] index of every packed coefficient / diagonal in the CSR values
 };
 
+// sgs_lines.cu
+bool smm_sgs_lines_build(smm_precond* p, int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos);
+int smm_sgs_lines_gather(const smm_precond* p, cudaStream_t s);
+int smm_sgs_lines_launch(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, unsigned int sleep_first, unsigned int sleep_later, cudaStream_t s);
+
 // sgs_tiles.cu
+bool smm_sgs_detect_grid(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, long long* nx, long long* ny, long long* nz);
 bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag);
 int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, int ctas_per_sm, unsigned int sleep_first,
                          unsigned int sleep_later, cudaStream_t s);

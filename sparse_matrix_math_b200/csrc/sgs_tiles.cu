@@ -547,10 +547,10 @@ struct ClusterPlan {                                  // proposal: which block a
     std::vector<int32_t> block_of_chain, warp_of_chain;
 };
 
-// cluster ids for a natural-order grid stencil, or empty when the column offsets are not of that kind
-// *chain_len: clusters [c * chain_len, (c + 1) * chain_len) are proposed as chain c (the tiles of one grid column along i)
-std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int* nclusters, int* chain_len = nullptr,
-                                        ClusterPlan* plan = nullptr) {
+}  // namespace
+
+// Natural-order grid stencil?  (column offsets {1, nx} or {1, nx, nx * ny} with the row count a multiple of the largest.)
+bool smm_sgs_detect_grid(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, long long* pnx, long long* pny, long long* pnz) {
     // distinct |col - row| > 0 over a sample of the rows (head, middle, tail): this is only a proposal, what it leads to
     // is verified on every row by layout_sweep
     std::vector<long long> offs;
@@ -562,22 +562,34 @@ std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& st
             if (d < 0) d = -d;
             if (d == 0) continue;
             if (std::find(offs.begin(), offs.end(), d) == offs.end()) {
-                if (offs.size() == 3) return {};
+                if (offs.size() == 3) return false;
                 offs.push_back(d);
             }
         }
     }
     std::sort(offs.begin(), offs.end());
-    if (offs.size() < 2 || offs[0] != 1) return {};
+    if (offs.size() < 2 || offs[0] != 1) return false;
     long long nx = offs[1], ny = 0, nz = 1;
     if (offs.size() == 2) {
-        if (rows % nx) return {};
+        if (rows % nx) return false;
         ny = rows / nx;
     } else {
-        if (offs[2] % nx || rows % offs[2]) return {};
+        if (offs[2] % nx || rows % offs[2]) return false;
         ny = offs[2] / nx;
         nz = rows / offs[2];
     }
+    *pnx = nx; *pny = ny; *pnz = nz;
+    return true;
+}
+
+namespace {
+
+// cluster ids for a natural-order grid stencil, or empty when the column offsets are not of that kind
+// *chain_len: clusters [c * chain_len, (c + 1) * chain_len) are proposed as chain c (the tiles of one grid column along i)
+std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, int* nclusters, int* chain_len = nullptr,
+                                        ClusterPlan* plan = nullptr) {
+    long long nx = 0, ny = 0, nz = 1;
+    if (!smm_sgs_detect_grid(rows, start, pos, &nx, &ny, &nz)) return {};
     const int ti = nz > 1 ? 4 : 8, tj = nz > 1 ? 4 : 8, tk = nz > 1 ? 4 : 1;
     const long long TI = (nx + ti - 1) / ti, TJ = (ny + tj - 1) / tj, TK = (nz + tk - 1) / tk;
     if (TI * TJ * TK >= (1ll << 25)) return {};                // positions are int32: 64 * tiles < 2^31

@@ -24,4 +24,11 @@ for _ in range(reps):
 smm.lib().smm_sync()
 dt = (time.perf_counter() - t) / reps
 bytes_apply = 8 * A.nnz + 44 * n
+try:
+    import ctypes
+    st = (ctypes.c_ulonglong * 4)()
+    smm.lib().smm_debug_line_stats(st)
+    print(f"line schedule over {reps + 1} applies: lane-steps that missed an operand {st[0]}, their polls {st[1]}, gate polls {st[2]}")
+except AttributeError:
+    pass
 print(f"grid {grid}x{ny}x{nz} levels {M.levels()} tile levels {M.tile_levels()} apply {dt*1e3:.3f} ms  ({dt*1e6/(2*M.levels()[0]):.2f} us per level)  {bytes_apply/dt/1e9:.0f} GB/s  ctas_per_sm={os.environ.get('SMM_B200_SGS_CTAS_PER_SM','4')}")
