@@ -44,9 +44,8 @@ constexpr int LINE_RING = 8;          // steps of results a warp keeps in shared
 constexpr int LINE_BLOCK = 8;         // steps per bulk copy of packed rows (the unrolled body of the step loop)
 constexpr int LINE_NBLK = 3;          // blocks of packed rows in shared memory
 constexpr int LINE_AHEAD = 8;         // steps between reading a row's packed data (and requesting its right-hand side) and solving it
-constexpr int LINE_EXT = 4;           // steps between requesting a row's out-of-patch operands and solving it (covers an L2 round trip)
-constexpr int LINE_GATE = 6;          // a patch starts when the out-of-patch operands of its first LINE_GATE steps are there: its producers
-                                      // are then LINE_GATE - LINE_EXT steps further than the requests that follow need them to be
+constexpr int LINE_NW = 4;            // warps per CTA: they share a patch and take turns step by step
+constexpr int LINE_MARGIN = 2;        // a patch starts when the out-of-patch operands of its first LINE_AHEAD + LINE_MARGIN steps are there
 constexpr int LINE_WORDS = 8;         // packed words per row: 3 operand sources, 3 coefficients, diagonal, row index
 constexpr int LINE_MAX_W = 3;
 constexpr int LINE_NONE = -1;         // operand slot not used
@@ -176,6 +175,7 @@ __device__ __forceinline__ void lcp_wait() { asm volatile("cp.async.wait_group %
 
 // diagnostics (smm_debug_line_stats): steps that found an out-of-patch operand missing, their polls, polls at the gate
 __device__ unsigned long long g_line_stats[4];
+static_assert(LINE_MARGIN <= LINE_NW && LINE_BLOCK % LINE_NW == 0 && LINE_NW == 4, "the warps' turns");
 
 constexpr int LINE_BLOCK_WORDS = LINE_BLOCK * 32 * LINE_WORDS;                    // 2048 words = 8 KB
 constexpr size_t LINE_SMEM = (size_t)LINE_NBLK * LINE_BLOCK_WORDS * 4 + LINE_RING * 128 + 64;
@@ -184,38 +184,34 @@ constexpr size_t LINE_SMEM = (size_t)LINE_NBLK * LINE_BLOCK_WORDS * 4 + LINE_RIN
 template <int W>
 struct LineRow { int c[W]; float v[W]; float d; int row; float init; unsigned int xb[W]; };
 
-// One warp per CTA; warps claim patches in time order (forward: ascending rank, backward: descending -- the packed rows of the
-// backward sweep are stored in that order).  IC0 = false: SGS sweeps.  IC0 = true: `sum -= f * x; x = sum / d` in both
-// directions (IC(0), ILU(0)).
-template <bool FORWARD, bool IC0, int W>
-__global__ void __launch_bounds__(32) sgs_line_kernel(const LineArgs A, const float* __restrict__ rhs, float* yperm, float* xperm, float* __restrict__ x,
-                                                      unsigned int* tickets, const SolveState* st) {
-    if (st != nullptr && st->done) return;
-    extern __shared__ __align__(128) uint32_t line_sm[];
-    uint32_t* const blocks = line_sm;                                                     // [LINE_NBLK][LINE_BLOCK][32][LINE_WORDS]
-    float* const res = reinterpret_cast<float*>(blocks + LINE_NBLK * LINE_BLOCK_WORDS);   // [LINE_RING][32] results of the last steps
-    uint64_t* const full = reinterpret_cast<uint64_t*>(res + LINE_RING * 32);             // [LINE_NBLK]
-    const int lane = threadIdx.x;
+// LINE_NW warps per CTA share a patch and take turns step by step: warp w solves the steps k = w (mod LINE_NW).  A step's
+// dependency chain (operands out of the ring -> three multiply-adds -> division -> result into the ring) is what the sweep
+// waits for; everything else a step needs (reading the packed row, requesting its right-hand side and its out-of-patch
+// operands LINE_AHEAD steps early, publishing) is done by its warp while the other warps solve the steps in between, so
+// the chain sees one CTA barrier per step instead of a whole step's worth of one warp's instructions.
+// CTAs claim patches in time order (forward: ascending rank, backward: descending -- the packed rows of the backward sweep
+// are stored in that order).  IC0 = false: SGS sweeps.  IC0 = true: `sum -= f * x; x = sum / d` in both directions (IC(0), ILU(0)).
+template <bool FORWARD, bool IC0, int W, int WID>
+__device__ __forceinline__ void line_run(const LineArgs& A, const float* __restrict__ rhs, float* yperm, float* xperm, float* __restrict__ x,
+                                         unsigned int* tickets, uint32_t* const blocks, float* const res, uint64_t* const full, unsigned int* const sh_q) {
+    constexpr int MINE = LINE_BLOCK / LINE_NW;                                            // rows of a block this warp solves
+    const int lane = threadIdx.x & 31;
     unsigned int* const abort_flag = tickets + 2;
     unsigned int* const ticket = tickets + (FORWARD ? 0 : 1);
     const float* const src = FORWARD ? yperm : xperm;                                     // operands are addressed by position
     float* const dst = FORWARD ? yperm : xperm;
-    if (lane == 0) {
-        for (int i = 0; i < LINE_NBLK; ++i) lbar_init(&full[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
     const int S = A.S, nblk = S / LINE_BLOCK;
     uint32_t gb = 0;                                                                      // blocks consumed so far: ring slot and phase of the next one
-    for (;;) {
-        unsigned int q = 0;
-        if (lane == 0) q = atomicAdd(ticket, 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
+    for (unsigned int turn = 0;; ++turn) {
+        if (threadIdx.x == 0) sh_q[turn & 1u] = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const unsigned int q = sh_q[turn & 1u];
         if (q >= (unsigned int)A.npatch) break;
         const uint32_t* const pk = A.pack + (size_t)q * S * (32 * LINE_WORDS);
         // position of this lane's row at processing step k: 32 * (patch * S + s) + lane with s = k (forward) / S - 1 - k (backward)
         const size_t pos0 = ((size_t)(FORWARD ? (int)q : A.npatch - 1 - (int)q) * S + (FORWARD ? 0 : S - 1)) * 32 + lane;
-        auto issue = [&](int b) {                                                         // lane 0: block b of this patch -> ring
+        auto pos_of = [&](int k) { return FORWARD ? pos0 + (size_t)k * 32 : pos0 - (size_t)k * 32; };
+        auto issue = [&](int b) {                                                         // thread 0: block b of this patch -> ring
             const uint32_t n = gb + (uint32_t)b, slot = n % LINE_NBLK;
             lbar_expect_tx(&full[slot], LINE_BLOCK_WORDS * 4);
             lbulk_load(blocks + slot * LINE_BLOCK_WORDS, pk + (size_t)b * LINE_BLOCK_WORDS, LINE_BLOCK_WORDS * 4, &full[slot]);
@@ -227,7 +223,7 @@ __global__ void __launch_bounds__(32) sgs_line_kernel(const LineArgs A, const fl
         auto block_ptr = [&](int b) { return blocks + ((gb + (uint32_t)b) % LINE_NBLK) * LINE_BLOCK_WORDS + lane * LINE_WORDS; };
         // a row's packed data out of shared memory, and its requests to global memory: the right-hand side (backward: the row's
         // own forward result, at the row's position) and, unless the gate below polls for them, the out-of-patch operands
-        auto load_row = [&](const uint32_t* line, const float* own) {
+        auto load_row = [&](const uint32_t* line, const int k, const bool with_operands) {
             const uint4 lo = *reinterpret_cast<const uint4*>(line), hi = *reinterpret_cast<const uint4*>(line + 4);
             const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
             LineRow<W> r;
@@ -241,51 +237,75 @@ __global__ void __launch_bounds__(32) sgs_line_kernel(const LineArgs A, const fl
                     r.init = __ldg(rhs + r.row);                                          // H:1683 / H:1807
                     if (r.row + 16 < A.rows) lprefetch_l1(rhs + r.row + 16);              // the lane walks its line: the sector after the next one
                 } else {
-                    r.init = __ldg(own);                                                  // H:1710, H:1823 (written by the forward launch)
+                    r.init = __ldg(yperm + pos_of(k));                                    // H:1710, H:1823 (written by the forward launch)
                 }
+            }
+            if (with_operands) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) if (r.c[j] >= 0) r.xb[j] = peek(src + r.c[j]);
             }
             return r;
         };
         int issued = 0;
-        if (lane == 0) {
-            for (; issued < LINE_NBLK && issued < nblk; ++issued) issue(issued);
-            if (LINE_NBLK < nblk) lbulk_prefetch_l2(pk + (size_t)LINE_NBLK * LINE_BLOCK_WORDS, LINE_BLOCK_WORDS * 4);
-        }
-        issued = __shfl_sync(0xffffffffu, issued, 0);
+        for (; issued < LINE_NBLK && issued < nblk; ++issued) if (threadIdx.x == 0) issue(issued);
+        if (threadIdx.x == 0 && LINE_NBLK < nblk) lbulk_prefetch_l2(pk + (size_t)LINE_NBLK * LINE_BLOCK_WORDS, LINE_BLOCK_WORDS * 4);
         wait_block(0);
-        LineRow<W> R[LINE_AHEAD];
-        const float* ownp = yperm + pos0;                                                 // backward: the position of the row being loaded
+        LineRow<W> R[MINE];
 #pragma unroll
-        for (int u = 0; u < LINE_AHEAD; ++u) { R[u] = load_row(block_ptr(0) + u * 32 * LINE_WORDS, ownp); ownp -= 32; }
-        // Gate: the out-of-patch operands of the first LINE_GATE steps are polled here, all at once -- this is where a patch waits
-        // for its turn.  Once they are there the producers are far enough ahead for the requests of the steps that follow (issued
-        // LINE_EXT steps early) to find their operands published; without the margin every one of the first requests comes
-        // back empty and costs its step an L2 round trip.
+        for (int m = 0; m < MINE; ++m) R[m] = load_row(block_ptr(0) + (WID + m * LINE_NW) * 32 * LINE_WORDS, WID + m * LINE_NW, false);
+        // Gate: the out-of-patch operands of the first LINE_BLOCK + LINE_MARGIN steps are polled here, all at once -- this is where
+        // a patch waits for its turn.  Once they are there the producers are LINE_MARGIN steps further than the requests of the steps
+        // that follow (issued LINE_AHEAD steps early) need them to be; without the margin every one of the first requests comes back
+        // empty and costs its step an L2 round trip.
         bool aborted = false;
         {
+            int gc[W];                                                                    // operand sources of this warp's margin row (warps 0 .. LINE_MARGIN-1)
+            unsigned int gx[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) { gc[j] = LINE_NONE; gx[j] = 0u; }
+            if (WID < LINE_MARGIN && nblk > 1) {
+                wait_block(1);
+                const uint32_t* line = block_ptr(1) + WID * 32 * LINE_WORDS;
+#pragma unroll
+                for (int j = 0; j < W; ++j) { gc[j] = (int)line[j]; gx[j] = SENTINEL; }
+            }
             unsigned int polls = 0;
+            // first the cheap wait: one warp asks for the operands of the LAST of these steps (its producers publish in step
+            // order) and sleeps between polls, the other warps sit in the barrier -- a patch may wait here for most of the sweep,
+            // next to CTAs that are solving, and must not take their issue slots
+            if (WID == LINE_MARGIN - 1) {
+                for (;;) {
+                    bool miss = false;
+#pragma unroll
+                    for (int j = 0; j < W; ++j) if (gc[j] >= 0 && gx[j] == SENTINEL) { gx[j] = peek(src + gc[j]); miss |= gx[j] == SENTINEL; }
+                    if (!__any_sync(0xffffffffu, miss)) break;
+                    if (!poll_pause(&polls, abort_flag, 200u, 400u)) break;             // (the full check below notices an abort)
+                }
+            }
+            __syncthreads();
             for (;;) {
                 bool miss = false;
 #pragma unroll
-                for (int u = 0; u < LINE_GATE; ++u)
+                for (int m = 0; m < MINE; ++m)
 #pragma unroll
                     for (int j = 0; j < W; ++j)
-                        if (R[u].c[j] >= 0 && R[u].xb[j] == SENTINEL) { R[u].xb[j] = peek(src + R[u].c[j]); miss |= R[u].xb[j] == SENTINEL; }
-                if (!__any_sync(0xffffffffu, miss)) break;
-                if (lane == 0) atomicAdd(&g_line_stats[2], 1ull);
+                        if (R[m].c[j] >= 0 && R[m].xb[j] == SENTINEL) { R[m].xb[j] = peek(src + R[m].c[j]); miss |= R[m].xb[j] == SENTINEL; }
+#pragma unroll
+                for (int j = 0; j < W; ++j) if (gc[j] >= 0 && gx[j] == SENTINEL) { gx[j] = peek(src + gc[j]); miss |= gx[j] == SENTINEL; }
+                if (!__syncthreads_or(miss)) break;
                 if (!poll_pause(&polls, abort_flag, A.sleep_first, A.sleep_later)) aborted = true;
-                if (__any_sync(0xffffffffu, aborted)) { aborted = true; break; }
+                if (__syncthreads_or(aborted)) { aborted = true; break; }
             }
         }
         int blk = 0;
-        float* dstp = dst + pos0;
+        unsigned int n_miss = 0, n_polls = 0;                                             // diagnostics: steps of this warp that waited, their polls
         for (; blk < nblk && !aborted; ++blk) {
             // this block's rows are in registers; the next block's are read while it is solved, and the slot this block came from is free
+            // (every warp read its rows out of it before the step barriers of the previous block)
             const bool more = blk + 1 < nblk;
             if (more) wait_block(blk + 1);
-            __syncwarp();                                                                 // every lane has read its rows of this block out of the slot
             if (blk + LINE_NBLK < nblk) {
-                if (lane == 0) {
+                if (threadIdx.x == 0) {
                     issue(blk + LINE_NBLK);
                     if (blk + LINE_NBLK + 1 < nblk) lbulk_prefetch_l2(pk + (size_t)(blk + LINE_NBLK + 1) * LINE_BLOCK_WORDS, LINE_BLOCK_WORDS * 4);
                 }
@@ -294,61 +314,85 @@ __global__ void __launch_bounds__(32) sgs_line_kernel(const LineArgs A, const fl
             const uint32_t* const nxt = block_ptr(blk + 1);
 #pragma unroll
             for (int u = 0; u < LINE_BLOCK; ++u) {
-                const LineRow<W> r = R[u];
-                unsigned int xb[W];
-                bool miss = false;
+                if ((u & (LINE_NW - 1)) == WID) {
+                    const int k = blk * LINE_BLOCK + u;
+                    const LineRow<W> r = R[u / LINE_NW];
+                    unsigned int xb[W];
+                    bool miss = false;
 #pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    xb[j] = r.c[j] >= 0 ? r.xb[j] : __float_as_uint(res[(LINE_LOCAL - r.c[j]) & (LINE_RING * 32 - 1)]);
-                    miss |= r.c[j] >= 0 && xb[j] == SENTINEL;
-                }
-                if (miss) {                                                               // the producer patch is not far enough ahead: ask L2 until it is
-                    unsigned int polls = 0;
-                    atomicAdd(&g_line_stats[0], 1ull);
-                    for (;;) {
-                        atomicAdd(&g_line_stats[1], 1ull);
-                        miss = false;
-#pragma unroll
-                        for (int j = 0; j < W; ++j) if (r.c[j] >= 0 && xb[j] == SENTINEL) { xb[j] = peek(src + r.c[j]); miss |= xb[j] == SENTINEL; }
-                        if (!miss) break;
-                        if (!poll_pause(&polls, abort_flag, A.sleep_first, A.sleep_later)) { aborted = true; break; }
+                    for (int j = 0; j < W; ++j) {
+                        xb[j] = r.c[j] >= 0 ? r.xb[j] : __float_as_uint(res[(LINE_LOCAL - r.c[j]) & (LINE_RING * 32 - 1)]);
+                        miss |= r.c[j] >= 0 && xb[j] == SENTINEL;
                     }
-                }
-                float acc = (FORWARD || IC0) ? r.init : 0.0f;
+                    if (miss) {                                                           // the producer patch is not far enough ahead: ask L2 until it is
+                        unsigned int polls = 0;
+                        ++n_miss;
+                        for (;;) {
+                            ++n_polls;
+                            miss = false;
 #pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    if (r.c[j] != LINE_NONE) {
-                        const float xv = __uint_as_float(xb[j]);
-                        // forward: _smm_fma(-value, x[col], lhs), cols ascending (H:1685); backward: _smm_fma(value, x[col], lhs), cols descending
-                        // (H:1704); IC0: sum -= ic0[j] * x[col] (H:1813, H:1829)
-                        acc = (FORWARD || IC0) ? __fsub_rn(acc, __fmul_rn(r.v[j], xv)) : __fadd_rn(__fmul_rn(r.v[j], xv), acc);
+                            for (int j = 0; j < W; ++j) if (r.c[j] >= 0 && xb[j] == SENTINEL) { xb[j] = peek(src + r.c[j]); miss |= xb[j] == SENTINEL; }
+                            if (!miss) break;
+                            if (!poll_pause(&polls, abort_flag, A.sleep_first, A.sleep_later)) { aborted = true; break; }
+                        }
                     }
-                }
-                const float o = (FORWARD || IC0) ? __fdiv_rn(acc, r.d)                    // H:1694 / H:1818, H:1834
-                                                 : __fsub_rn(r.init, __fdiv_rn(acc, r.d));     // H:1710
-                if (r.row >= 0) {
-                    // H:1691-1693 `abs(diagonal) < 1e-5` with the float promoted to double: true exactly for the floats <= 1e-5f
-                    if (FORWARD && !IC0 && fabsf(r.d) <= 1e-5f) atomicOr(tickets + 3, 1u);     // (reported, not fatal here)
-                    res[(FORWARD ? u : LINE_BLOCK - 1 - u) * 32 + lane] = o;              // S is a multiple of the ring: step % ring = index in the block
-                    publish(dstp, o);
-                    if (!FORWARD) x[r.row] = o;                                           // the caller's vector, natural order
-                }
-                dstp += FORWARD ? 32 : -32;
-                __syncwarp();
-                if (more) { R[u] = load_row(nxt + u * 32 * LINE_WORDS, ownp); ownp -= 32; }
-                {   // out-of-patch operands of the step LINE_EXT ahead (its packed data have been in registers for a while)
-                    LineRow<W>& n = R[(u + LINE_EXT) & (LINE_AHEAD - 1)];
+                    float acc = (FORWARD || IC0) ? r.init : 0.0f;
 #pragma unroll
-                    for (int j = 0; j < W; ++j) if (n.c[j] >= 0) n.xb[j] = peek(src + n.c[j]);
+                    for (int j = 0; j < W; ++j) {
+                        if (r.c[j] != LINE_NONE) {
+                            const float xv = __uint_as_float(xb[j]);
+                            // forward: _smm_fma(-value, x[col], lhs), cols ascending (H:1685); backward: _smm_fma(value, x[col], lhs), cols
+                            // descending (H:1704); IC0: sum -= ic0[j] * x[col] (H:1813, H:1829)
+                            acc = (FORWARD || IC0) ? __fsub_rn(acc, __fmul_rn(r.v[j], xv)) : __fadd_rn(__fmul_rn(r.v[j], xv), acc);
+                        }
+                    }
+                    const float o = (FORWARD || IC0) ? __fdiv_rn(acc, r.d)                // H:1694 / H:1818, H:1834
+                                                     : __fsub_rn(r.init, __fdiv_rn(acc, r.d));   // H:1710
+                    if (r.row >= 0) {
+                        // H:1691-1693 `abs(diagonal) < 1e-5` with the float promoted to double: true exactly for the floats <= 1e-5f
+                        if (FORWARD && !IC0 && fabsf(r.d) <= 1e-5f) atomicOr(tickets + 3, 1u);   // (reported, not fatal here)
+                        res[(FORWARD ? u : LINE_BLOCK - 1 - u) * 32 + lane] = o;          // S is a multiple of the ring: step % ring = index in the block
+                    }
+                    __syncthreads();                                                      // the step's results are in the ring: the next warp may go
+                    if (r.row >= 0) {
+                        publish(dst + pos_of(k), o);
+                        if (!FORWARD) x[r.row] = o;                                       // the caller's vector, natural order
+                    }
+                    if (more) R[u / LINE_NW] = load_row(nxt + u * 32 * LINE_WORDS, k + LINE_BLOCK, true);
+                } else {
+                    __syncthreads();
                 }
             }
-            if (__any_sync(0xffffffffu, aborted)) { aborted = true; break; }
+            if (__syncthreads_or(aborted)) { aborted = true; break; }
         }
         if (aborted) {                                                                    // leave only when no bulk copy into this CTA's memory is in flight
             for (int b = blk + 1; b < issued && b < nblk; ++b) wait_block(b);
             return;
         }
         gb += (uint32_t)nblk;
+        if (n_miss) { atomicAdd(&g_line_stats[0], (unsigned long long)n_miss); atomicAdd(&g_line_stats[1], (unsigned long long)n_polls); }
+    }
+}
+
+template <bool FORWARD, bool IC0, int W>
+__global__ void __launch_bounds__(LINE_NW * 32) sgs_line_kernel(const LineArgs A, const float* __restrict__ rhs, float* yperm, float* xperm, float* __restrict__ x,
+                                                                unsigned int* tickets, const SolveState* st) {
+    if (st != nullptr && st->done) return;
+    extern __shared__ __align__(128) uint32_t line_sm[];
+    uint32_t* const blocks = line_sm;                                                     // [LINE_NBLK][LINE_BLOCK][32][LINE_WORDS]
+    float* const res = reinterpret_cast<float*>(blocks + LINE_NBLK * LINE_BLOCK_WORDS);   // [LINE_RING][32] results of the last steps
+    uint64_t* const full = reinterpret_cast<uint64_t*>(res + LINE_RING * 32);             // [LINE_NBLK]
+    unsigned int* const sh_q = reinterpret_cast<unsigned int*>(full + LINE_NBLK);         // [2] the patch claimed for this / the next turn
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < LINE_NBLK; ++i) lbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    switch (threadIdx.x >> 5) {
+        case 0: line_run<FORWARD, IC0, W, 0>(A, rhs, yperm, xperm, x, tickets, blocks, res, full, sh_q); break;
+        case 1: line_run<FORWARD, IC0, W, 1>(A, rhs, yperm, xperm, x, tickets, blocks, res, full, sh_q); break;
+        case 2: line_run<FORWARD, IC0, W, 2>(A, rhs, yperm, xperm, x, tickets, blocks, res, full, sh_q); break;
+        default: line_run<FORWARD, IC0, W, 3>(A, rhs, yperm, xperm, x, tickets, blocks, res, full, sh_q); break;
     }
 }
 
@@ -376,13 +420,13 @@ int line_launch_one(const smm_precond* p, const LineArgs& A, const float* rhs_de
         int& r = per_sm_dev[p->m->device % SMM_MAX_DEVICES];
         if (!r) {
             SMM_CUDA(cudaFuncSetAttribute(sgs_line_kernel<FORWARD, IC0, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINE_SMEM));
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, sgs_line_kernel<FORWARD, IC0, W>, 32, LINE_SMEM) != cudaSuccess || r < 1) r = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, sgs_line_kernel<FORWARD, IC0, W>, LINE_NW * 32, LINE_SMEM) != cudaSuccess || r < 1) r = 1;
         }
         per_sm = r;
     }
     long long grid = (long long)p->m->sm_count * per_sm;
     if (grid > A.npatch) grid = A.npatch;
-    sgs_line_kernel<FORWARD, IC0, W><<<(unsigned)grid, 32, LINE_SMEM, s>>>(A, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
+    sgs_line_kernel<FORWARD, IC0, W><<<(unsigned)grid, LINE_NW * 32, LINE_SMEM, s>>>(A, rhs_dev, p->yperm, p->xperm, x_dev, p->tickets, state);
     return SMM_OK;
 }
 

@@ -661,6 +661,25 @@ def test_sweep_schedules_bit_exact(smm, case):
     assert I.validate() == 0
     lu = ol.ilu0_factorize(g)[1]
     assert I.apply(rhs)[1].tobytes() == ol.ilu0_apply(g, lu, rhs).tobytes()
+    # the line schedule (opt-in: a lane per grid line, a warp team per patch of 32 lines; layout built and verified on the device):
+    # taken for the grids, refused for everything else, same bits
+    os.environ["SMM_B200_SGS_LINES"] = "1"
+    try:
+        M2 = m.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
+        assert (M2.schedule() == 2) == tiled, M2.schedule()
+        rc2, x2 = M2.apply(rhs)
+        assert rc2 == 0 and x2.tobytes() == ox.tobytes()
+        rc3, x3 = M2.apply(rhs)                                          # reusable
+        assert rc3 == 0 and x3.tobytes() == ox.tobytes()
+        I2 = smm.ILU0Preconditioner(m)
+        assert I2.validate() == 0 and I2.apply(rhs)[1].tobytes() == ol.ilu0_apply(g, lu, rhs).tobytes()
+        if case in ("poisson2d_50x37", "poisson3d_8x12x20"):            # symmetric positive definite: IC(0) exists
+            C2 = smm.IC0Preconditioner(m)
+            assert C2.init() == 0 and C2.schedule() == 2
+            assert C2.apply(rhs)[1].tobytes() == ol.ic0_apply(g, ol.ic0_factorize(g)[1], rhs).tobytes()
+    finally:
+        del os.environ["SMM_B200_SGS_LINES"]
+    assert M.schedule() == (1 if tiled else 0)
 
 
 # ---------------------------------------------------------------------------------------------
