@@ -66,6 +66,7 @@ struct LineArgs {
     const uint32_t* pack;             // [patch in claim order][step in processing order][lane][LINE_WORDS]
     int npatch, S, rows;
     unsigned int sleep_first, sleep_later;
+    unsigned long long* trace;        // debug (SMM_B200_SGS_TRACE): [patch in claim order][4] globaltimer at claim / start / end, and the SM
 };
 
 __host__ __device__ __forceinline__ void line_where(const LineGeom& G, const int32_t* __restrict__ rank_of, const int r, int* q, int* s, int* lane) {
@@ -181,6 +182,12 @@ constexpr int LINE_BLOCK_WORDS = LINE_BLOCK * 32 * LINE_WORDS;                  
 constexpr size_t LINE_SMEM = (size_t)LINE_NBLK * LINE_BLOCK_WORDS * 4 + LINE_RING * 128 + 64;
 
 // a row on its way through the register pipeline: packed data, right-hand side and out-of-patch operands as requested
+__device__ __forceinline__ unsigned long long line_clock() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <int W>
 struct LineRow { int c[W]; float v[W]; float d; int row; float init; unsigned int xb[W]; };
 
@@ -207,6 +214,7 @@ __device__ __forceinline__ void line_run(const LineArgs& A, const float* __restr
         __syncthreads();
         const unsigned int q = sh_q[turn & 1u];
         if (q >= (unsigned int)A.npatch) break;
+        const unsigned long long t_claim = A.trace ? line_clock() : 0ull;
         const uint32_t* const pk = A.pack + (size_t)q * S * (32 * LINE_WORDS);
         // position of this lane's row at processing step k: 32 * (patch * S + s) + lane with s = k (forward) / S - 1 - k (backward)
         const size_t pos0 = ((size_t)(FORWARD ? (int)q : A.npatch - 1 - (int)q) * S + (FORWARD ? 0 : S - 1)) * 32 + lane;
@@ -297,6 +305,7 @@ __device__ __forceinline__ void line_run(const LineArgs& A, const float* __restr
                 if (__syncthreads_or(aborted)) { aborted = true; break; }
             }
         }
+        if (A.trace && threadIdx.x == 0) { A.trace[4ull * q] = t_claim; A.trace[4ull * q + 1] = line_clock(); }
         int blk = 0;
         unsigned int n_miss = 0, n_polls = 0;                                             // diagnostics: steps of this warp that waited, their polls
         for (; blk < nblk && !aborted; ++blk) {
@@ -370,6 +379,11 @@ __device__ __forceinline__ void line_run(const LineArgs& A, const float* __restr
             return;
         }
         gb += (uint32_t)nblk;
+        if (A.trace && threadIdx.x == 0) {
+            unsigned int sm;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+            A.trace[4ull * q + 2] = line_clock(); A.trace[4ull * q + 3] = sm;
+        }
         if (n_miss) { atomicAdd(&g_line_stats[0], (unsigned long long)n_miss); atomicAdd(&g_line_stats[1], (unsigned long long)n_polls); }
     }
 }
@@ -523,8 +537,24 @@ extern "C" int smm_debug_line_stats(unsigned long long* out4) {
 }
 
 int smm_sgs_lines_launch(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, unsigned int sleep_first, unsigned int sleep_later, cudaStream_t s) {
-    LineArgs F{p->line_pack[0], p->line_patches, p->line_steps, p->rows, sleep_first, sleep_later};
-    LineArgs B{p->line_pack[1], p->line_patches, p->line_steps, p->rows, sleep_first, sleep_later};
-    if (p->line_w == 2) return line_launch_w<2>(p, F, B, rhs_dev, x_dev, state, s);
-    return line_launch_w<3>(p, F, B, rhs_dev, x_dev, state, s);
+    // debug: SMM_B200_SGS_TRACE=<file> records per-patch timestamps of the forward sweep of every apply (last one kept)
+    static const char* trace_path = getenv("SMM_B200_SGS_TRACE");
+    static unsigned long long* trace = nullptr;
+    static long long trace_cap = 0;
+    if (trace_path && trace_cap < p->line_patches) {
+        cudaFree(trace);
+        trace = nullptr;
+        SMM_CUDA(cudaMalloc(&trace, sizeof(unsigned long long) * 4 * (size_t)p->line_patches));
+        trace_cap = p->line_patches;
+    }
+    LineArgs F{p->line_pack[0], p->line_patches, p->line_steps, p->rows, sleep_first, sleep_later, trace};
+    LineArgs B{p->line_pack[1], p->line_patches, p->line_steps, p->rows, sleep_first, sleep_later, nullptr};
+    SMM_TRY(p->line_w == 2 ? line_launch_w<2>(p, F, B, rhs_dev, x_dev, state, s) : line_launch_w<3>(p, F, B, rhs_dev, x_dev, state, s));
+    if (trace) {
+        std::vector<unsigned long long> h(4 * (size_t)p->line_patches);
+        SMM_CUDA(cudaStreamSynchronize(s));
+        SMM_CUDA(cudaMemcpy(h.data(), trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
+    }
+    return SMM_OK;
 }

@@ -9,6 +9,9 @@ void smm_set_error(const char*, ...) {}
 cudaStream_t smm_default_stream() { return nullptr; }
 bool smm_sgs_tiles_build(smm_precond*, int, const std::vector<int32_t>&, const std::vector<int32_t>&, const std::vector<int32_t>&) { return false; }
 int smm_sgs_tiles_launch(const smm_precond*, const float*, float*, SolveState*, int, unsigned int, unsigned int, cudaStream_t) { return 0; }
+bool smm_sgs_lines_build(smm_precond*, int, const std::vector<int32_t>&, const std::vector<int32_t>&) { return false; }
+int smm_sgs_lines_gather(const smm_precond*, cudaStream_t) { return 0; }
+int smm_sgs_lines_launch(const smm_precond*, const float*, float*, SolveState*, unsigned int, unsigned int, cudaStream_t) { return 0; }
 std::atomic<long long> g_smm_launches{0};
 thread_local long long t_smm_launches = 0;
 thread_local bool t_smm_capturing = false;
