@@ -140,6 +140,12 @@ int smm_precond_tile_levels(const smm_precond_t* p, int* forward_levels, int* ba
  * stencils: a lane per grid line, a warp per patch of 32 lines, sgs_lines.cu; smm_precond_tile_levels then reports the
  * number of patch offsets).  The result of apply is bit-identical whatever the schedule.  Diagnostic; additive. */
 int smm_precond_schedule(const smm_precond_t* p);
+/* Fingerprints (FNV-1a, 64 bit) of the layout arrays the sweep kernels of this handle read, for checking that two ways of
+ * building a handle (the set-up kernels of sgs_tiles_setup.cu and the host code of sgs_tiles.cu; SMM_B200_SGS_SETUP=host)
+ * produce the same arrays bit for bit: out[0..11] = diagonal positions, forward / backward row order, backward-to-forward
+ * positions, then per sweep operand positions, operand value indices, steps, push lists; out[12] = sizes and level counts.
+ * Downloads the arrays: a test / diagnostic call.  Diagnostic; additive. */
+int smm_precond_layout_fingerprint(const smm_precond_t* p, uint64_t out[13]);
 /* CSRMatrix::IC0Preconditioner (H:1214-1235): construction + init() (factorize, H:1839-1928; *rc = its return code) and
  * apply (H:1802-1837, through smm_precond_apply[_dev]).  The factorisation is set-up code and runs on the host, row by
  * row instead of the reference's O(rows^2) scan, with bit-identical values; the two triangular solves of every apply

@@ -119,6 +119,7 @@ def lib():
         L.smm_precond_levels.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_i32)]
         L.smm_precond_tile_levels.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_i32)]
         L.smm_precond_schedule.argtypes = [_vp]
+        L.smm_precond_layout_fingerprint.argtypes = [_vp, C.POINTER(C.c_uint64)]
         L.smm_precond_destroy.argtypes = [_vp]
         L.smm_precond_ic0_create.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_vp)]
         L.smm_precond_ic0_factor.argtypes = [_vp, _vp]
@@ -314,6 +315,12 @@ class SGSPreconditioner:
     def schedule(self):
         """0: rows in level order, 1: tiles, 2: lines (which schedule the triangular sweeps of this handle run)."""
         return int(lib().smm_precond_schedule(self.handle))
+
+    def layout_fingerprint(self):
+        """FNV-1a fingerprints of the layout arrays the sweep kernels read (smm_precond_layout_fingerprint): a tuple of 13."""
+        out = (C.c_uint64 * 13)()
+        _check(lib().smm_precond_layout_fingerprint(self.handle, out), "smm_precond_layout_fingerprint")
+        return tuple(int(v) for v in out)
 
     def __del__(self):
         try:

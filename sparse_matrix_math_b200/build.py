@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsmm_b200.so")
-SOURCES = ["core.cu", "spmv.cu", "vecops.cu", "dots.cu", "solvers.cu", "sgs.cu", "sgs_tiles.cu", "sgs_lines.cu", "gen.cu", "dist.cu", "group.cu"]
+SOURCES = ["core.cu", "spmv.cu", "vecops.cu", "dots.cu", "solvers.cu", "sgs.cu", "sgs_tiles.cu", "sgs_tiles_setup.cu", "sgs_lines.cu", "gen.cu", "dist.cu", "group.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -28,6 +28,7 @@
 // (about 24 n) + rhs, y, x traffic (about 20 n).
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <time.h>
 
 #include <algorithm>
@@ -483,22 +484,43 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
     p->kind = kind;
     p->rows = m->rows;
     SetupClock clock;
-    std::vector<int32_t> start((size_t)m->rows + 1), pos((size_t)m->nnz);
     SMM_CUDA(cudaDeviceSynchronize());
-    SMM_CUDA(cudaMemcpy(start.data(), m->start, sizeof(int32_t) * start.size(), cudaMemcpyDeviceToHost));
-    if (m->nnz) SMM_CUDA(cudaMemcpy(pos.data(), m->positions, sizeof(int32_t) * pos.size(), cudaMemcpyDeviceToHost));
-    clock.mark("download start / positions");
-    std::vector<int32_t> diag, of, ob, lev_f, lev_b;
-    p->valid = find_diagonals(m->rows, start, pos, m->first_active_start, &diag);
-    clock.mark("find diagonals");
-    // the level analysis (the level counts smm_precond_levels reports, and the row-level schedule when no tile schedule is
-    // found) runs beside the factorisation and the tile layout below: all of it is set-up time
-    std::future<void> levels;
-    if (p->valid && m->rows > 0 && kind != 3)
-        levels = std::async(std::launch::async, [&] { row_levels(m->rows, start, pos, diag, &lev_f, &lev_b, &p->levels_fwd, &p->levels_bwd); });
-    struct Join { std::future<void>& f; ~Join() { if (f.valid()) f.wait(); } } join{levels};   // never leave with the task running
+    // Host copies of the pattern are fetched only by what still needs them: the IC(0) / ILU(0) factorisations, the opt-in
+    // schedules and the row-level schedule.  The default path for SGS on a grid stencil -- diagonals, tile layout -- runs on
+    // the device from the arrays where they lie (sgs_tiles_setup.cu); SMM_B200_SGS_SETUP=host forces the host code.
+    const bool host_setup = [] { const char* e = getenv("SMM_B200_SGS_SETUP"); return e && strcmp(e, "host") == 0; }();   // read per call: the tests build both ways
+    const bool opt_in_layout = [] {
+        for (const char* name : {"SMM_B200_SGS_CHAINS", "SMM_B200_SGS_CLUSTERS", "SMM_B200_SGS_LINES"}) { const char* e = getenv(name); if (e && atoi(e) != 0) return true; }
+        return false;
+    }();
+    std::vector<int32_t> start, pos, diag, of, ob, lev_f, lev_b;
+    bool on_host = false;
+    auto fetch = [&]() -> int {                                // start / positions / diagonals on the host
+        if (on_host) return SMM_OK;
+        start.resize((size_t)m->rows + 1);
+        pos.resize((size_t)m->nnz);
+        SMM_CUDA(cudaMemcpy(start.data(), m->start, sizeof(int32_t) * start.size(), cudaMemcpyDeviceToHost));
+        if (m->nnz) SMM_CUDA(cudaMemcpy(pos.data(), m->positions, sizeof(int32_t) * pos.size(), cudaMemcpyDeviceToHost));
+        clock.mark("download start / positions");
+        const bool valid = find_diagonals(m->rows, start, pos, m->first_active_start, &diag);
+        clock.mark("find diagonals (host)");
+        if (valid != p->valid && p->diag_pos) { smm_set_error("preconditioner: host and device disagree on the diagonal"); return SMM_E_STATE; }
+        p->valid = valid;
+        on_host = true;
+        return SMM_OK;
+    };
+    int width_dev = -1;
+    if (!host_setup && m->rows > 0 && kind != 3) {
+        SMM_CUDA(cudaMalloc(&p->diag_pos, sizeof(int32_t) * (size_t)m->rows));
+        SMM_TRY(smm_sgs_diagonals_dev(m, p->diag_pos, &p->valid, &width_dev));
+        if (!p->valid) { cudaFree(p->diag_pos); p->diag_pos = nullptr; }
+        clock.mark("find diagonals (device)");
+    } else {
+        SMM_TRY(fetch());
+    }
     if (rc_out) *rc_out = p->valid ? 0 : 1;
     if (kind != 0 && kind != 3 && p->valid && m->nnz > 0) {
+        SMM_TRY(fetch());
         std::vector<float> a((size_t)m->nnz), l;
         SMM_CUDA(cudaMemcpy(a.data(), m->values, sizeof(float) * a.size(), cudaMemcpyDeviceToHost));
         if (kind == 1) {
@@ -509,21 +531,40 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
         }
         SMM_CUDA(cudaMalloc(&p->factor, sizeof(float) * l.size()));
         SMM_CUDA(cudaMemcpy(p->factor, l.data(), sizeof(float) * l.size(), cudaMemcpyHostToDevice));
+        clock.mark("factorisation (host)");
     }
     SMM_CUDA(cudaMalloc(&p->tickets, 4 * sizeof(unsigned int)));
     SMM_CUDA(cudaMemset(p->tickets, 0, 4 * sizeof(unsigned int)));
-    if (p->valid && m->rows > 0) {
+    if (p->valid && m->rows > 0 && !p->diag_pos) {
         SMM_CUDA(cudaMalloc(&p->diag_pos, sizeof(int32_t) * diag.size()));
         SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
     }
-    clock.mark("factorisation, diagonal upload");
-    // line schedule when the matrix admits one (sgs_lines.cu), else the tile-level schedule (sgs_tiles.cu), else the row-level schedule below
-    const bool lines = kind != 3 && p->valid && m->rows > 0 && smm_sgs_lines_build(p, m->rows, start, pos);
-    clock.mark(lines ? "line schedule: layout on the device" : "line schedule: not applicable");
-    const bool tiles = lines || (kind != 3 && p->valid && m->rows > 0 && smm_sgs_tiles_build(p, m->rows, start, pos, diag));
-    if (!lines) clock.mark(tiles ? "tile schedule: layout + upload" : "tile schedule: not applicable");
-    if (levels.valid()) levels.get();
-    clock.mark("row levels (ran beside the above)");
+    const bool sweeps = kind != 3 && p->valid && m->rows > 0;
+    // line schedule when asked for and admitted (sgs_lines.cu), else the tile-level schedule (sgs_tiles.cu / sgs_tiles_setup.cu),
+    // else the row-level schedule below
+    bool tiles = false;
+    if (sweeps && opt_in_layout) {
+        SMM_TRY(fetch());
+        tiles = smm_sgs_lines_build(p, m->rows, start, pos);
+        clock.mark(tiles ? "line schedule: layout on the device" : "line schedule: not applicable");
+    }
+    if (sweeps && !tiles && !host_setup && !opt_in_layout && width_dev >= 0) {
+        tiles = smm_sgs_tiles_build_dev(p, m, p->diag_pos, width_dev);
+        clock.mark(tiles ? "tile schedule: layout on the device" : "tile schedule: device layout not applicable");
+    }
+    if (sweeps && !tiles) {
+        SMM_TRY(fetch());
+        tiles = smm_sgs_tiles_build(p, m->rows, start, pos, diag);
+        clock.mark(tiles ? "tile schedule: host layout + upload" : "tile schedule: not applicable");
+    }
+    // row levels: what smm_precond_levels reports, and the row-level schedule when no tile schedule was found.  With a tile
+    // schedule in place they are only computed when asked for (smm_precond_levels).
+    if (sweeps && !tiles) {
+        SMM_TRY(fetch());
+        row_levels(m->rows, start, pos, diag, &lev_f, &lev_b, &p->levels_fwd, &p->levels_bwd);
+        p->levels_known = true;
+        clock.mark("row levels");
+    }
     if (kind != 3 && p->valid && m->rows > 0 && !tiles) {
         level_orders(m->rows, lev_f, lev_b, p->levels_fwd, p->levels_bwd, &of, &ob);
         p->threads_fwd = (long long)of.size();
@@ -623,8 +664,20 @@ int smm_precond_apply(const smm_precond_t* pc, const float* rhs, float* x, int* 
     return SMM_OK;
 }
 
-int smm_precond_levels(const smm_precond_t* p, int* forward_levels, int* backward_levels) {
-    if (!p) return SMM_E_INVALID;
+int smm_precond_levels(const smm_precond_t* pc, int* forward_levels, int* backward_levels) {
+    if (!pc) return SMM_E_INVALID;
+    smm_precond* p = const_cast<smm_precond*>(pc);
+    if (!p->levels_known && p->valid && p->rows > 0 && p->kind != 3) {       // a report, not needed by the tile schedule: computed on demand
+        const smm_csr* m = p->m;
+        SMM_CUDA(cudaSetDevice(m->device));
+        SMM_CUDA(cudaDeviceSynchronize());
+        std::vector<int32_t> start((size_t)m->rows + 1), pos((size_t)m->nnz), diag, lev_f, lev_b;
+        SMM_CUDA(cudaMemcpy(start.data(), m->start, sizeof(int32_t) * start.size(), cudaMemcpyDeviceToHost));
+        if (m->nnz) SMM_CUDA(cudaMemcpy(pos.data(), m->positions, sizeof(int32_t) * pos.size(), cudaMemcpyDeviceToHost));
+        if (!find_diagonals(m->rows, start, pos, m->first_active_start, &diag)) return SMM_E_STATE;
+        row_levels(m->rows, start, pos, diag, &lev_f, &lev_b, &p->levels_fwd, &p->levels_bwd);
+        p->levels_known = true;
+    }
     if (forward_levels) *forward_levels = p->levels_fwd;
     if (backward_levels) *backward_levels = p->levels_bwd;
     return SMM_OK;
@@ -635,6 +688,41 @@ int smm_precond_tile_levels(const smm_precond_t* p, int* forward_levels, int* ba
     if (!p) return SMM_E_INVALID;
     if (forward_levels) *forward_levels = p->lined ? p->line_levels : p->tiled ? p->tile_levels[0] : 0;
     if (backward_levels) *backward_levels = p->lined ? p->line_levels : p->tiled ? p->tile_levels[1] : 0;
+    return SMM_OK;
+}
+
+int smm_precond_layout_fingerprint(const smm_precond_t* p, uint64_t out[13]) {
+    if (!p || !out) return SMM_E_INVALID;
+    SMM_CUDA(cudaSetDevice(p->m->device));
+    SMM_CUDA(cudaDeviceSynchronize());
+    std::vector<unsigned char> h;
+    auto fp = [&](const void* dev, size_t bytes, uint64_t* to) -> int {
+        uint64_t x = 1469598103934665603ull;
+        if (dev && bytes) {
+            h.resize(bytes);
+            SMM_CUDA(cudaMemcpy(h.data(), dev, bytes, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < bytes; ++i) { x ^= h[i]; x *= 1099511628211ull; }
+        }
+        *to = x;
+        return SMM_OK;
+    };
+    const size_t nf = (size_t)p->threads_fwd, nb = (size_t)p->threads_bwd;
+    SMM_TRY(fp(p->diag_pos, sizeof(int32_t) * (size_t)p->rows, &out[0]));
+    SMM_TRY(fp(p->order_fwd, sizeof(int32_t) * nf, &out[1]));
+    SMM_TRY(fp(p->order_bwd, sizeof(int32_t) * nb, &out[2]));
+    SMM_TRY(fp(p->ypos, sizeof(int32_t) * nb, &out[3]));
+    for (int w = 0; w < 2; ++w) {
+        const size_t nt = w == 0 ? nf : nb;
+        SMM_TRY(fp(p->ecol[w], sizeof(int32_t) * (size_t)p->esize[w], &out[4 + 4 * w]));
+        SMM_TRY(fp(p->eidx[w], sizeof(int32_t) * (size_t)p->esize[w], &out[5 + 4 * w]));
+        SMM_TRY(fp(p->tiled ? p->tile_steps[w] : nullptr, nt + nt / 64, &out[6 + 4 * w]));
+        SMM_TRY(fp(p->tiled ? p->tile_push[w] : nullptr, sizeof(uint32_t) * nt, &out[7 + 4 * w]));
+    }
+    const long long meta[10] = {p->threads_fwd, p->threads_bwd, p->esize[0], p->esize[1], p->tile_width, p->tile_levels[0], p->tile_levels[1],
+                                p->tile_chain[0], p->tile_chain[1], (long long)p->tiled + 2 * (long long)p->lined + 4 * (long long)p->valid};
+    uint64_t x = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(meta); ++i) { x ^= reinterpret_cast<const unsigned char*>(meta)[i]; x *= 1099511628211ull; }
+    out[12] = x;
     return SMM_OK;
 }
 

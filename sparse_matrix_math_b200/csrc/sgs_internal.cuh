@@ -13,7 +13,8 @@ struct smm_precond {
     const smm_csr* m = nullptr;
     int rows = 0;
     bool valid = true;               // structure admits the sweeps (else apply returns the reference's code 1)
-    int levels_fwd = 0, levels_bwd = 0;
+    int levels_fwd = 0, levels_bwd = 0;   // row levels of the two triangles (smm_precond_levels)
+    bool levels_known = false;       // computed at create time only when the row-level schedule needs them, else on demand
     long long threads_fwd = 0, threads_bwd = 0;   // padded launch sizes
     int32_t* order_fwd = nullptr;    // [threads_fwd] row index or -1 (padding)
     int32_t* order_bwd = nullptr;    // [threads_bwd]
@@ -59,11 +60,30 @@ int smm_sgs_lines_launch(const smm_precond* p, const float* rhs_dev, float* x_de
 
 // sgs_tiles.cu
 bool smm_sgs_detect_grid(int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, long long* nx, long long* ny, long long* nz);
+bool smm_sgs_grid_from_offsets(int rows, std::vector<long long> offs, long long* nx, long long* ny, long long* nz);
 bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& start, const std::vector<int32_t>& pos, const std::vector<int32_t>& diag);
 int smm_sgs_tiles_launch(const smm_precond* p, const float* rhs_dev, float* x_dev, SolveState* state, int ctas_per_sm, unsigned int sleep_first,
                          unsigned int sleep_later, cudaStream_t s);
 
+// sgs_tiles_setup.cu: the same tile layout built by kernels from the CSR arrays in HBM (no download, no upload).
+// diag_dev: [rows] index of a_ii (device).  Returns false when the device path does not apply or does not verify -- the
+// caller then runs smm_sgs_tiles_build on host copies, which decides for good.
+bool smm_sgs_tiles_build_dev(smm_precond* p, const smm_csr* m, const int32_t* diag_dev, int width);
+// diagonal positions and structural validity (find_diagonals of sgs.cu) on the device: *valid, *width = most entries a row
+// keeps on one side of its diagonal
+int smm_sgs_diagonals_dev(const smm_csr* m, int32_t* diag_dev, bool* valid, int* width);
+
 namespace {
+
+constexpr int TILE = 64;         // rows per tile (sgs_tiles.cu)
+constexpr int TILE_MAX_W = 4;    // stored operands per row and sweep
+constexpr int MAX_STEPS = 64;    // internal levels of a tile
+constexpr int MAX_PREDS = 8;     // distinct predecessor tiles of a tile
+
+// proposed tile of a natural-order grid: 4 x 4 x 4 grid points in 3D, 8 x 8 in 2D
+inline void smm_sgs_tile_shape(long long nz, int* ti, int* tj, int* tk) {
+    *ti = nz > 1 ? 4 : 8; *tj = nz > 1 ? 4 : 8; *tk = nz > 1 ? 4 : 1;
+}
 
 constexpr unsigned int SENTINEL = 0x7FC0DEADu;   // quiet NaN with a payload; GPU arithmetic only produces 0x7FFFFFFF
 constexpr int SGS_THREADS = 128;

@@ -48,8 +48,6 @@ namespace {
 #ifndef SMM_TILE_MIN_CTAS
 #define SMM_TILE_MIN_CTAS 4      // resident 4-warp CTAs per SM the register allocation must allow
 #endif
-constexpr int TILE = 64;
-constexpr int TILE_MAX_W = 4;
 // Cluster schedule: a BLOCK of CLUSTER_CHAINS neighbouring chains is solved by one thread-block cluster (8 CTAs x 4 warps,
 // one warp per chain); operands that cross from one chain of the block to another travel through distributed shared memory.
 constexpr int CLUSTER_CTAS = 8;
@@ -64,9 +62,6 @@ constexpr int E_INBOX = -16;                         // -16 - slot: arrives in t
 // push2 word of a producer row: [7:0] staging slot of the consumer in the NEXT tile of the chain (0xFF: none),
 // [18:8] and [29:19]: (target warp of the cluster block << 5 | inbox slot) (0x7FF: none)
 constexpr uint32_t PUSH2_NONE = 0xFFu | (0x7FFu << 8) | (0x7FFu << 19);
-
-constexpr int MAX_STEPS = 64;
-constexpr int MAX_PREDS = 8;
 
 struct TileArgs {
     const uint8_t* nsteps;      // [tiles]
@@ -567,8 +562,13 @@ bool smm_sgs_detect_grid(int rows, const std::vector<int32_t>& start, const std:
             }
         }
     }
+    return smm_sgs_grid_from_offsets(rows, offs, pnx, pny, pnz);
+}
+
+// the grid a set of distinct |col - row| > 0 offsets suggests: {1, nx} or {1, nx, nx * ny}
+bool smm_sgs_grid_from_offsets(int rows, std::vector<long long> offs, long long* pnx, long long* pny, long long* pnz) {
     std::sort(offs.begin(), offs.end());
-    if (offs.size() < 2 || offs[0] != 1) return false;
+    if (offs.size() < 2 || offs.size() > 3 || offs[0] != 1) return false;
     long long nx = offs[1], ny = 0, nz = 1;
     if (offs.size() == 2) {
         if (rows % nx) return false;
@@ -590,7 +590,8 @@ std::vector<int32_t> propose_grid_tiles(int rows, const std::vector<int32_t>& st
                                         ClusterPlan* plan = nullptr) {
     long long nx = 0, ny = 0, nz = 1;
     if (!smm_sgs_detect_grid(rows, start, pos, &nx, &ny, &nz)) return {};
-    const int ti = nz > 1 ? 4 : 8, tj = nz > 1 ? 4 : 8, tk = nz > 1 ? 4 : 1;
+    int ti, tj, tk;
+    smm_sgs_tile_shape(nz, &ti, &tj, &tk);
     const long long TI = (nx + ti - 1) / ti, TJ = (ny + tj - 1) / tj, TK = (nz + tk - 1) / tk;
     if (TI * TJ * TK >= (1ll << 25)) return {};                // positions are int32: 64 * tiles < 2^31
     std::vector<int32_t> cl((size_t)rows);

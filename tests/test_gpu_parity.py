@@ -618,6 +618,70 @@ def test_bicgstab_factor_preconditioners_parity(smm, precond):
 
 
 # ---------------------------------------------------------------------------------------------
+# set-up of the tile schedule on the device (sgs_tiles_setup.cu): the same arrays as the host code, bit for bit
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["convdiff3d_23", "poisson2d_50x37", "poisson3d_8x12x20", "poisson3d_64", "poisson3d_70x45x33", "poisson2d_200x150",
+                                  "periodic_ring", "powerlaw", "missing_diagonal"])
+def test_tile_layout_device_equals_host(smm, case):
+    tiled = True
+    if case == "convdiff3d_23":
+        g = matgen.convdiff3d(23, 0.5)
+    elif case == "poisson2d_50x37":
+        g = matgen.poisson2d(50, 37)
+    elif case == "poisson3d_8x12x20":
+        g = matgen.convdiff3d(8, 0.0, ny=12, nz=20)
+    elif case == "poisson3d_64":
+        g = matgen.convdiff3d(64, 0.0)
+    elif case == "poisson3d_70x45x33":
+        g = matgen.convdiff3d(70, 0.0, ny=45, nz=33)
+    elif case == "poisson2d_200x150":
+        g = matgen.poisson2d(200, 150)
+    elif case == "periodic_ring":                                    # grid-like offsets, cyclic tile graph: both paths must refuse the tiles
+        n = 256
+        r = np.arange(n)
+        trow = np.concatenate([r, r, r, r, r]); tcol = np.concatenate([r, (r + 1) % n, (r - 1) % n, (r + 16) % n, (r - 16) % n])
+        keep = np.abs(trow - tcol) <= 16
+        tval = np.where(trow == tcol, 4.5, -1.0).astype(np.float32)
+        g, tiled = ol.triplets_to_csr(n, n, trow[keep], tcol[keep], tval[keep]), False
+    elif case == "powerlaw":
+        g, tiled = matgen.powerlaw(4000), False
+    else:                                                            # a row without its diagonal: apply() returns the reference's code 1 either way
+        g0 = matgen.poisson2d(20, 20)
+        r = np.repeat(np.arange(g0.rows), np.diff(g0.start))
+        c, v = g0.positions[: g0.nnz], g0.values[: g0.nnz]
+        keep = ~((r == 137) & (c == 137))
+        g, tiled = ol.triplets_to_csr(g0.rows, g0.rows, r[keep], c[keep], v[keep]), False
+    m = upload(smm, g)
+    rhs = matgen.xstar(g.rows)
+
+    def build(host):
+        if host:
+            os.environ["SMM_B200_SGS_SETUP"] = "host"
+        try:
+            M = m.getPreconditioner(smm.SolverPreconditioner.SYMMETRIC_GAUS_SEIDEL)
+            I = smm.ILU0Preconditioner(m)
+            code = I.validate()
+            return M, M.layout_fingerprint(), M.schedule(), M.tile_levels(), M.apply(rhs), I, code, I.layout_fingerprint()
+        finally:
+            os.environ.pop("SMM_B200_SGS_SETUP", None)
+
+    Md, fd, sd, tld, (rcd, xd), Id, cd, fid = build(False)
+    Mh, fh, sh, tlh, (rch, xh), Ih, ch, fih = build(True)
+    assert sd == sh == (1 if tiled else 0)
+    assert tld == tlh and (tld != (0, 0)) == tiled
+    assert fd == fh, [i for i in range(13) if fd[i] != fh[i]]
+    assert fid == fih and cd == ch
+    assert rcd == rch and xd.tobytes() == xh.tobytes()
+    if case != "missing_diagonal":
+        orc, ox = ol.sgs_apply(g, rhs)
+        assert rcd == orc == 0 and xd.tobytes() == ox.tobytes()
+        assert Md.levels() == Mh.levels()                            # row levels: computed on demand after a device set-up
+        assert Id.apply(rhs)[1].tobytes() == Ih.apply(rhs)[1].tobytes()
+    else:
+        assert rcd == 1 and cd == 1
+
+
+# ---------------------------------------------------------------------------------------------
 # schedule selection of the triangular sweeps: tile-level for grid stencils, row-level otherwise -- same bits either way
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("case", ["convdiff3d_23", "poisson2d_50x37", "poisson3d_8x12x20", "powerlaw", "periodic_ring", "wide_offsets"])
