@@ -519,7 +519,29 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
         SMM_TRY(fetch());
     }
     if (rc_out) *rc_out = p->valid ? 0 : 1;
-    if (kind != 0 && kind != 3 && p->valid && m->nnz > 0) {
+    SMM_CUDA(cudaMalloc(&p->tickets, 4 * sizeof(unsigned int)));
+    SMM_CUDA(cudaMemset(p->tickets, 0, 4 * sizeof(unsigned int)));
+    if (p->valid && m->rows > 0 && !p->diag_pos) {
+        SMM_CUDA(cudaMalloc(&p->diag_pos, sizeof(int32_t) * diag.size()));
+        SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
+    }
+    bool sweeps = kind != 3 && p->valid && m->rows > 0;
+    // line schedule when asked for and admitted (sgs_lines.cu), else the tile-level schedule (sgs_tiles.cu / sgs_tiles_setup.cu),
+    // else the row-level schedule below.  The layout depends on the pattern only, so it comes before the factorisation, which
+    // then runs on the device in the order of the forward tile schedule when there is one.
+    bool tiles = false, factored = !(kind == 1 || kind == 2) || m->nnz == 0;
+    if (sweeps && !host_setup && !opt_in_layout && width_dev >= 0) {
+        tiles = smm_sgs_tiles_build_dev(p, m, p->diag_pos, width_dev);
+        clock.mark(tiles ? "tile schedule: layout on the device" : "tile schedule: device layout not applicable");
+        if (tiles && !factored) {
+            int code = 0;
+            const int rc = smm_sgs_factorize_dev(p, &code);
+            if (rc == SMM_OK) factored = true;
+            else cudaGetLastError();                           // the host code below decides (and reproduces a failed factorisation's state)
+            clock.mark(factored ? "factorisation on the device" : "factorisation on the device: left to the host");
+        }
+    }
+    if (!factored && p->valid) {
         SMM_TRY(fetch());
         std::vector<float> a((size_t)m->nnz), l;
         SMM_CUDA(cudaMemcpy(a.data(), m->values, sizeof(float) * a.size(), cudaMemcpyDeviceToHost));
@@ -528,29 +550,17 @@ static int precond_create(const smm_csr_t* m, int kind, int* rc_out, smm_precond
         } else if (ilu0_factorize_host(m->rows, start, pos, diag, a, &l) != 0) {
             p->valid = false;                                  // no usable pivot: apply() reports an error instead of dividing by ~0
             if (rc_out) *rc_out = 2;
+            sweeps = false;
+            if (tiles) { smm_sgs_tiles_release(p); tiles = false; }   // the state the host-only path leaves: no schedule for an unusable factor
         }
         SMM_CUDA(cudaMalloc(&p->factor, sizeof(float) * l.size()));
         SMM_CUDA(cudaMemcpy(p->factor, l.data(), sizeof(float) * l.size(), cudaMemcpyHostToDevice));
         clock.mark("factorisation (host)");
     }
-    SMM_CUDA(cudaMalloc(&p->tickets, 4 * sizeof(unsigned int)));
-    SMM_CUDA(cudaMemset(p->tickets, 0, 4 * sizeof(unsigned int)));
-    if (p->valid && m->rows > 0 && !p->diag_pos) {
-        SMM_CUDA(cudaMalloc(&p->diag_pos, sizeof(int32_t) * diag.size()));
-        SMM_CUDA(cudaMemcpy(p->diag_pos, diag.data(), sizeof(int32_t) * diag.size(), cudaMemcpyHostToDevice));
-    }
-    const bool sweeps = kind != 3 && p->valid && m->rows > 0;
-    // line schedule when asked for and admitted (sgs_lines.cu), else the tile-level schedule (sgs_tiles.cu / sgs_tiles_setup.cu),
-    // else the row-level schedule below
-    bool tiles = false;
-    if (sweeps && opt_in_layout) {
+    if (sweeps && !tiles && opt_in_layout) {
         SMM_TRY(fetch());
         tiles = smm_sgs_lines_build(p, m->rows, start, pos);
         clock.mark(tiles ? "line schedule: layout on the device" : "line schedule: not applicable");
-    }
-    if (sweeps && !tiles && !host_setup && !opt_in_layout && width_dev >= 0) {
-        tiles = smm_sgs_tiles_build_dev(p, m, p->diag_pos, width_dev);
-        clock.mark(tiles ? "tile schedule: layout on the device" : "tile schedule: device layout not applicable");
     }
     if (sweeps && !tiles) {
         SMM_TRY(fetch());

@@ -39,6 +39,7 @@ struct smm_precond {
     uint8_t* tile_steps[2] = {nullptr, nullptr};   // [tiles * 64] step of every row, then [tiles] number of steps
     uint32_t* tile_push[2] = {nullptr, nullptr};   // [tiles * 64] operand slots inside the tile that consume the row's result
     int tile_levels[2] = {0, 0};
+    std::vector<int32_t> tile_level_ptr;   // forward sweep, tiles in tile-level order: level l = tiles [ptr[l], ptr[l + 1]) (host copy; the device factorisations walk it)
     int tile_chain[2] = {1, 1};      // tiles per chain (one warp solves a chain from end to end), per sweep
     int tile_blocks = 0;             // cluster schedule: blocks of 32 chains, one thread-block cluster per block at a time (0: off)
     uint32_t* tile_push2[2] = {nullptr, nullptr};  // cluster schedule: [tiles * 64] pushes that leave the tile (next tile of the chain, other chains of the block)
@@ -72,6 +73,12 @@ bool smm_sgs_tiles_build_dev(smm_precond* p, const smm_csr* m, const int32_t* di
 // diagonal positions and structural validity (find_diagonals of sgs.cu) on the device: *valid, *width = most entries a row
 // keeps on one side of its diagonal
 int smm_sgs_diagonals_dev(const smm_csr* m, int32_t* diag_dev, bool* valid, int* width);
+
+// IC(0) (kind 1) / ILU(0) (kind 2) factorisation on the device, in the order of the forward tile schedule: needs p->tiled with
+// single-tile chains and p->tile_level_ptr.  *code: 0 ok, 2 = ILU(0) pivot not > 1e-6 in magnitude; returns SMM_E_STATE when
+// the result must come from the host code instead (no tile schedule, a non-finite IC(0) pivot).
+int smm_sgs_factorize_dev(smm_precond* p, int* code);
+void smm_sgs_tiles_release(smm_precond* p);   // drops a tile schedule built by either path
 
 namespace {
 

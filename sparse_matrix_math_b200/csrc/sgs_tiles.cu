@@ -526,6 +526,7 @@ void fill_parallel(V& v, size_t n, T value) {
 }
 
 struct SweepLayout {
+    std::vector<int32_t> level_ptr;                  // tiles in tile-level order: level l = tiles [level_ptr[l], level_ptr[l + 1])
     raw_vector<int32_t> order, ecol, eidx, where;    // where[row] = position
     raw_vector<uint8_t> steps;
     raw_vector<uint32_t> push;
@@ -836,6 +837,7 @@ bool layout_sweep(bool forward, int rows, const std::vector<int32_t>& start, con
         for (int a = 0; a < ncl; ++a) lptr[(size_t)level[a] + 1]++;
         for (int l = 0; l < out->levels; ++l) lptr[(size_t)l + 1] += lptr[l];
         std::vector<int32_t> cur(lptr.begin(), lptr.end() - 1);
+        out->level_ptr = lptr;
         if (forward) { for (int a = 0; a < ncl; ++a) tile_of[a] = cur[level[a]]++; }
         else { for (int a = ncl - 1; a >= 0; --a) tile_of[a] = cur[level[a]]++; }
     }
@@ -991,6 +993,7 @@ bool smm_sgs_tiles_build(smm_precond* p, int rows, const std::vector<int32_t>& s
     p->tile_levels[1] = L[1].levels;
     p->tile_chain[0] = L[0].chain_len;
     p->tile_chain[1] = L[1].chain_len;
+    p->tile_level_ptr = L[0].level_ptr;
     bool ok = upload(L[0].order, &p->order_fwd) == SMM_OK && upload(L[1].order, &p->order_bwd) == SMM_OK && upload(yp, &p->ypos) == SMM_OK &&
               cudaMalloc(&p->yperm, sizeof(float) * npos) == cudaSuccess && cudaMalloc(&p->xperm, sizeof(float) * npos) == cudaSuccess;
     for (int w = 0; w < 2 && ok; ++w) {

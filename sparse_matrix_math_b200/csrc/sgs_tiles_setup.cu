@@ -329,9 +329,146 @@ void release_tiles(smm_precond* p) {
         p->esize[w] = 0;
     }
     p->threads_fwd = p->threads_bwd = 0;
+    p->tile_level_ptr.clear();
+}
+
+// ---- IC(0) / ILU(0) factorisation in the order of the forward tile schedule ------------------------------------------------
+// A row's factor entries depend on the rows its strict lower triangle points to -- the forward sweep's dependencies -- so the
+// factorisation runs tile level by tile level (one launch per level, a warp per tile, the tile's rows step by step), every row
+// by ONE thread that performs the host code's operations in the host code's order (sgs.cu: ic0_factorize_host /
+// ilu0_factorize_host, which restate H:1839-1928 / H:1723-1790): the factor has the same bits.
+struct FactorArgs {
+    const int32_t* order;        // forward sweep: [tiles * 64] row or -1
+    const uint8_t* steps;        // [tiles * 64] step of the row, then [tiles] steps of the tile
+    long long ntl;
+    const int32_t* start;
+    const int32_t* pos;
+    const int32_t* diag;
+    const float* a;
+    float* f;                    // factor, A's pattern
+    float* dinv;                 // [rows] reciprocal pivots
+    int* flags;                  // [0] ILU(0): pivot not > 1e-6 ; [1] IC(0): non-finite pivot (left to the host code)
+};
+
+__device__ __forceinline__ void ic0_row(const FactorArgs& A, const int j) {
+    const int rs = A.start[j], dj = A.diag[j];
+    float* l = A.f;
+    for (int e = rs; e < dj; ++e) {
+        const int i = A.pos[e];                                // entry (j, i), i < j
+        float sum = 0.0f;
+        int ki = A.start[i];
+        const int di = A.diag[i];
+        for (int ek = rs; ek < e; ++ek) {                      // row j's columns k < i, ascending (H:1900-1907)
+            const int k = A.pos[ek];
+            while (ki < di && A.pos[ki] < k) ++ki;
+            if (ki < di && A.pos[ki] == k) sum = __fadd_rn(sum, __fmul_rn(l[ki], l[ek]));
+        }
+        l[e] = __fmul_rn(__fsub_rn(A.a[e], sum), A.dinv[i]);   // H:1914
+    }
+    float dsum = 0.0f;
+    for (int e = rs; e < dj; ++e) dsum = __fadd_rn(dsum, __fmul_rn(l[e], l[e]));   // H:1868-1872
+    const float d = __fsqrt_rn(__fsub_rn(A.a[dj], dsum));      // H:1879
+    l[dj] = d;
+    A.dinv[j] = __fdiv_rn(1.0f, d);                            // H:1883
+    if (!(fabsf(d) <= 3.4028234e38f)) A.flags[1] = 1;          // NaN / inf: the sign and payload of a host NaN are not reproduced here
+}
+
+__device__ __forceinline__ void ilu0_row(const FactorArgs& A, const int row) {
+    const int rs = A.start[row], re = A.start[row + 1], dg = A.diag[row];
+    float* lu = A.f;
+    for (int kp = rs; kp < dg; ++kp) {                         // columns k < row, ascending
+        const int k = A.pos[kp];
+        const float alpha = __fmul_rn(lu[kp], A.dinv[k]);      // H:1762
+        lu[kp] = alpha;
+        for (int cp = A.start[k + 1] - 1; cp > A.diag[k]; --cp) {              // row k of U, strictly right of its diagonal
+            const int c = A.pos[cp];
+            int ci = rs;
+            while (ci < re && A.pos[ci] < c) ++ci;             // the host's column_index lookup: columns are ascending and distinct
+            if (ci < re && A.pos[ci] == c) lu[ci] = __fsub_rn(lu[ci], __fmul_rn(alpha, lu[cp]));   // H:1766-1768, two roundings
+        }
+    }
+    const float pivot = lu[dg];
+    if (!(fabsf(pivot) > 1e-6f)) A.flags[0] = 1;               // H:1774
+    A.dinv[row] = __fdiv_rn(1.0f, pivot);                      // H:1778
+}
+
+template <int KIND>
+__global__ void factor_level_kernel(const FactorArgs A, const int tile0, const int tile1) {
+    const int t = tile0 + (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (t >= tile1) return;
+    const int nsteps = A.steps[A.ntl * TILE + t];
+    int row[2], step[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { row[k] = A.order[(long long)t * TILE + k * 32 + lane]; step[k] = A.steps[(long long)t * TILE + k * 32 + lane]; }
+    for (int s = 0; s < nsteps; ++s) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (row[k] >= 0 && step[k] == s) { if (KIND == 1) ic0_row(A, row[k]); else ilu0_row(A, row[k]); }
+        }
+        __threadfence_block();
+        __syncwarp();
+    }
+}
+
+// IC(0): the transpose goes into the upper triangle of the same pattern (H:1916-1917)
+__global__ void ic0_transpose_kernel(int rows, const int32_t* __restrict__ start, const int32_t* __restrict__ pos, const int32_t* __restrict__ diag, float* l) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rows) return;
+    for (int e = start[j]; e < diag[j]; ++e) {
+        const int i = pos[e];
+        int lo = diag[i] + 1, hi = start[i + 1];               // first position in row i's upper part with column >= j
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (pos[mid] < j) lo = mid + 1; else hi = mid; }
+        if (lo < start[i + 1] && pos[lo] == j) l[lo] = l[e];
+    }
 }
 
 }  // namespace
+
+void smm_sgs_tiles_release(smm_precond* p) {
+    release_tiles(p);
+    cudaFree(p->tile_push2[0]); cudaFree(p->tile_push2[1]);
+    p->tile_push2[0] = p->tile_push2[1] = nullptr;
+    p->tiled = false;
+    p->tile_blocks = 0;
+    p->tile_width = 0;
+    p->tile_levels[0] = p->tile_levels[1] = 0;
+}
+
+int smm_sgs_factorize_dev(smm_precond* p, int* code) {
+    const smm_csr* m = p->m;
+    if (!p->tiled || p->lined || p->tile_chain[0] != 1 || p->tile_level_ptr.size() != (size_t)p->tile_levels[0] + 1 || !p->diag_pos || m->nnz <= 0) return SMM_E_STATE;
+    if (p->kind != 1 && p->kind != 2) return SMM_E_INVALID;
+    cudaStream_t s = smm_default_stream();
+    DevMem mem;
+    float* dinv = mem.get<float>((size_t)m->rows);
+    int* flags = mem.get<int>(2);
+    if (!dinv || !flags) return SMM_E_STATE;
+    SMM_CUDA(cudaMalloc(&p->factor, sizeof(float) * (size_t)m->nnz));
+    auto fail = [&](int rc) { cudaFree(p->factor); p->factor = nullptr; return rc; };
+    cudaError_t e = cudaMemsetAsync(flags, 0, 2 * sizeof(int), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dinv, 0, sizeof(float) * (size_t)m->rows, s);
+    if (e == cudaSuccess) e = p->kind == 1 ? cudaMemsetAsync(p->factor, 0, sizeof(float) * (size_t)m->nnz, s)          // l.assign(nnz, 0)
+                                           : cudaMemcpyAsync(p->factor, m->values, sizeof(float) * (size_t)m->nnz, cudaMemcpyDeviceToDevice, s);   // lu = a, H:1732
+    if (e != cudaSuccess) return fail(smm_cuda_fail(e, "factorisation set-up", __FILE__, __LINE__));
+    const FactorArgs A{p->order_fwd, p->tile_steps[0], p->threads_fwd / TILE, m->start, m->positions, p->diag_pos, m->values, p->factor, dinv, flags};
+    for (int l = 0; l < p->tile_levels[0]; ++l) {
+        const int t0 = p->tile_level_ptr[(size_t)l], t1 = p->tile_level_ptr[(size_t)l + 1];
+        if (t1 <= t0) continue;
+        const unsigned int grid = blocks_for(32ll * (t1 - t0), 128);
+        if (p->kind == 1) factor_level_kernel<1><<<grid, 128, 0, s>>>(A, t0, t1);
+        else factor_level_kernel<2><<<grid, 128, 0, s>>>(A, t0, t1);
+    }
+    if (p->kind == 1) ic0_transpose_kernel<<<blocks_for(m->rows), SETUP_T, 0, s>>>(m->rows, m->start, m->positions, p->diag_pos, p->factor);
+    int h[2] = {0, 0};
+    e = cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(smm_cuda_fail(e, "factorisation", __FILE__, __LINE__));
+    if (h[1] || h[0]) return fail(SMM_E_STATE);                 // a failed factorisation is reproduced by the host code (which rows it still wrote, its NaN bits)
+    *code = 0;
+    return SMM_OK;
+}
+
 
 int smm_sgs_diagonals_dev(const smm_csr* m, int32_t* diag_dev, bool* valid, int* width) {
     *valid = false;
@@ -443,6 +580,11 @@ bool smm_sgs_tiles_build_dev(smm_precond* p, const smm_csr* m, const int32_t* di
         setup_level_colscan_kernel<<<blocks_for(nlev), SETUP_T, 0, s>>>(nb, nlev, H, total);
         setup_exclusive_small_kernel<<<1, 32, 0, s>>>(nlev, total, lptr);
         setup_tile_order_kernel<<<(unsigned)nb, HIST_BLOCK, 0, s>>>(ncl, forward, level, nlev, H, lptr, tile_of);
+        if (forward) {                                         // host copy of the level boundaries (the device factorisations walk them)
+            p->tile_level_ptr.assign((size_t)nlev + 1, ncl);
+            ok = cudaMemcpyAsync(p->tile_level_ptr.data(), lptr, sizeof(int) * (size_t)nlev, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+            if (!ok) break;
+        }
         // 4. inside the tiles
         ok = cudaMemsetAsync(order, 0xFF, sizeof(int32_t) * npos, s) == cudaSuccess &&                       // -1: padding
              cudaMemsetAsync(p->tile_steps[w], 0xFF, (size_t)npos + (size_t)ntl, s) == cudaSuccess &&        // 255: padding

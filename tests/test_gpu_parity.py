@@ -677,6 +677,20 @@ def test_tile_layout_device_equals_host(smm, case):
         assert rcd == orc == 0 and xd.tobytes() == ox.tobytes()
         assert Md.levels() == Mh.levels()                            # row levels: computed on demand after a device set-up
         assert Id.apply(rhs)[1].tobytes() == Ih.apply(rhs)[1].tobytes()
+        # the factorisations: on the device in the order of the forward tile schedule, on the host row by row -- same bits
+        assert Id.factor().tobytes() == Ih.factor().tobytes() == ol.ilu0_factorize(g)[1][: g.nnz].tobytes()
+        if case.startswith("poisson"):                               # symmetric positive definite: IC(0) exists
+            Cd = smm.IC0Preconditioner(m)
+            assert Cd.init() == 0
+            os.environ["SMM_B200_SGS_SETUP"] = "host"
+            try:
+                Ch = smm.IC0Preconditioner(m)
+                assert Ch.init() == 0
+            finally:
+                os.environ.pop("SMM_B200_SGS_SETUP", None)
+            assert Cd.factor().tobytes() == Ch.factor().tobytes()
+            assert Cd.layout_fingerprint() == Ch.layout_fingerprint()
+            assert Cd.apply(rhs)[1].tobytes() == Ch.apply(rhs)[1].tobytes()
     else:
         assert rcd == 1 and cd == 1
 
