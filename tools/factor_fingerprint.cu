@@ -9,6 +9,10 @@ void smm_set_error(const char*, ...) {}
 cudaStream_t smm_default_stream() { return nullptr; }
 bool smm_sgs_tiles_build(smm_precond*, int, const std::vector<int32_t>&, const std::vector<int32_t>&, const std::vector<int32_t>&) { return false; }
 int smm_sgs_tiles_launch(const smm_precond*, const float*, float*, SolveState*, int, unsigned int, unsigned int, cudaStream_t) { return 0; }
+bool smm_sgs_tiles_build_dev(smm_precond*, const smm_csr*, const int32_t*, int) { return false; }
+int smm_sgs_diagonals_dev(const smm_csr*, int32_t*, bool*, int*) { return 1; }
+int smm_sgs_factorize_dev(smm_precond*, int*) { return 1; }
+void smm_sgs_tiles_release(smm_precond*) {}
 bool smm_sgs_lines_build(smm_precond*, int, const std::vector<int32_t>&, const std::vector<int32_t>&) { return false; }
 int smm_sgs_lines_gather(const smm_precond*, cudaStream_t) { return 0; }
 int smm_sgs_lines_launch(const smm_precond*, const float*, float*, SolveState*, unsigned int, unsigned int, cudaStream_t) { return 0; }
