@@ -68,8 +68,13 @@ def stencil_nnz(n):
 
 
 def bytes_cg_iteration(rows, nnz):
-    """fused minimum of one CG iteration."""
+    """fused minimum of one CG iteration (SpMV + dot | x,r update | p update)."""
     return 8 * nnz + 48 * rows + 4
+
+
+def bytes_cg_iteration_two_pass(rows, nnz):
+    """What the iteration moves since round 2: SpMV + dot (8 nnz + 12 n) | r update + r.r (12 n) | x and p update, p read once (20 n)."""
+    return 8 * nnz + 44 * rows + 4
 
 
 def bytes_spmv_dot(rows, nnz):
@@ -597,7 +602,10 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": ms_spmv,
                      "share_of_iteration": ms_spmv / kernel_sum if kernel_sum > 0 else None},
         "iteration": {"algorithmic_bytes": iter_bytes, "achieved_gbs": iter_gbs, "frac_of_peak": iter_gbs / peak,
-                      "ms_spmv_dot": ms_spmv, "ms_xr_update": ms_xr, "ms_p_update": ms_p,
+                      "bytes_moved_two_pass": bytes_cg_iteration_two_pass(rows, nnz),
+                      "frac_of_peak_bytes_moved": bytes_cg_iteration_two_pass(rows, nnz) * value / 1e9 / peak,
+                      "note": "algorithmic_bytes is SURVEY 8(d)'s 8 nnz + 48 n; the vector passes now read p once (r update | x and p update): 8 nnz + 44 n are moved",
+                      "ms_spmv_dot": ms_spmv, "ms_r_update": ms_xr, "ms_px_update": ms_p,
                       "ms_per_iteration": solve_ms / iters, "final_rr": final_rr, "x_mid": x_host_check},
         "spmv_effective_gbs": achieved,
         "parity": parity,

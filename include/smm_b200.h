@@ -270,7 +270,8 @@ int smm_group_solve(smm_group_t* g, int solver, const float* b, const float* x0,
 int smm_group_destroy(smm_group_t* g);
 
 /* ---- measurement hook (bench.py): average device time, in ms, of each of the three kernels of one fused CG
- * iteration (SpMV + p.Ap | x,r update + r.r | p update), `reps` launches each, CUDA events on `stream` ---- */
+ * iteration (SpMV + p.Ap | r update + r.r | x and p update, p read once), `reps` launches each, CUDA events on `stream`;
+ * ms_xr receives the r update's time, ms_p the x and p update's ---- */
 int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_spmv, float* ms_xr, float* ms_p, void* stream);
 
 /* ---- device memory helpers for hosts without their own allocator ---- */

@@ -76,10 +76,12 @@ __device__ __forceinline__ void smm_finish(int kind, SolveState* st, float t0, f
             smm_push_history(st, new_rr);
             st->iterations += 1;
             st->residual = new_rr;
-            if (st->eps2 > new_rr) { st->done = 1; st->status = SMM_SOLVER_SUCCESS; break; }  // H:2377-2379
+            // x_owed: with the two-pass iteration (VEC_CG_R / VEC_CG_PX) the x update of this iteration comes after this test;
+            // the flag lets that one kernel run although the solve is over (harmless for VEC_CG_XR, which has updated x already)
+            if (st->eps2 > new_rr) { st->done = 1; st->x_owed = 1; st->status = SMM_SOLVER_SUCCESS; break; }  // H:2377-2379
             st->beta = __fdiv_rn(new_rr, st->rr);              // H:2381
             st->rr = new_rr;
-            if (st->iterations >= st->max_iterations) { st->done = 1; st->status = SMM_SOLVER_MAX_ITERATIONS_REACHED; }  // H:2397
+            if (st->iterations >= st->max_iterations) { st->done = 1; st->x_owed = 1; st->status = SMM_SOLVER_MAX_ITERATIONS_REACHED; }  // H:2397
             break;
         }
         case FIN_BICGSYM_ALPHA:

@@ -104,7 +104,8 @@ struct SolveState {
     float* history;      // device residual history (may be null)
     unsigned long long cond_handle;   // cudaGraphConditionalHandle of the WHILE driver (0 = none)
     struct DistComm* comm;            // multi-GPU: reductions are summed over ranks before the scalar step (null: one GPU)
-    int pad[6];
+    int x_owed;          // ConjugateGradient: the stopping test fired in the r update, the x update of that iteration is still to come (VEC_CG_PX)
+    int pad[5];
 };
 
 // scratch of the reference-order dot products (dots.cu): per handle, so that two handles solving on different streams of
@@ -178,9 +179,11 @@ enum VecKind {
     VEC_STAB_P,        // in: p ap r          out: p
     VEC_DOT2,          // in: a b                          t0 = a.b, t1 = a.a
     VEC_COPY3,         // in: a               out: o0 o1 o2
+    VEC_CG_R,          // in: r Ap            out: r       t0 = r.r
+    VEC_CG_PX,         // in: p r x           out: p x     (x += alpha p with the OLD p, then p = beta p + r)
 };
 struct VecArgs {
-    const void* halo_push = nullptr;   // HaloPushDev* (device): out[0]'s boundary entries also go to the peers (VEC_CG_P / VEC_COPY3)
+    const void* halo_push = nullptr;   // HaloPushDev* (device): out[0]'s boundary entries also go to the peers (VEC_CG_P / VEC_CG_PX / VEC_COPY3)
     long long n = 0;
     const float* in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float* out[3] = {nullptr, nullptr, nullptr};

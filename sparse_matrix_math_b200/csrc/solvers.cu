@@ -132,16 +132,16 @@ int cg_iter_dist(Ctx& c) {
     if (c.exact) {
         SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, d->ext, c.ap, RED_NONE, FIN_NONE, nullptr));
         SMM_TRY(dots(c, FIN_CG_ALPHA, c.ap, c.p));
-        SMM_TRY(vec(c, VEC_CG_XR, FIN_NONE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
+        SMM_TRY(vec(c, VEC_CG_R, FIN_NONE, {c.r, c.ap}, {c.r}));
         SMM_TRY(dots(c, FIN_CG_UPDATE, c.r, c.r));
-        SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}, true));
+        SMM_TRY(vec(c, VEC_CG_PX, FIN_NONE, {c.p, c.r, c.x}, {c.p, c.x}, true));
         SMM_TRY(dist_after_p(c));
         c.kernels_per_iteration = 5 + extra;
         return SMM_OK;
     }
     SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, d->ext, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));
-    SMM_TRY(vec(c, VEC_CG_XR, FIN_CG_UPDATE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
-    SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}, true));
+    SMM_TRY(vec(c, VEC_CG_R, FIN_CG_UPDATE, {c.r, c.ap}, {c.r}));
+    SMM_TRY(vec(c, VEC_CG_PX, FIN_NONE, {c.p, c.r, c.x}, {c.p, c.x}, true));
     SMM_TRY(dist_after_p(c));
     c.kernels_per_iteration = 3 + extra;
     return SMM_OK;
@@ -156,16 +156,17 @@ int cg_init(Ctx& c, const float* x0) {
 int cg_iter(Ctx& c) {
     if (!c.exact) {
         SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));        // H:2353-2358
-        SMM_TRY(vec(c, VEC_CG_XR, FIN_CG_UPDATE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));              // H:2363-2382
-        SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}));                                    // H:2385-2393
+        // two passes that read p once: r and the stopping test first, then x (with this iteration's p) and the new p
+        SMM_TRY(vec(c, VEC_CG_R, FIN_CG_UPDATE, {c.r, c.ap}, {c.r}));                              // H:2366-2382
+        SMM_TRY(vec(c, VEC_CG_PX, FIN_NONE, {c.p, c.r, c.x}, {c.p, c.x}));                         // H:2363-2365, H:2385-2393
         c.kernels_per_iteration = 3;
         return SMM_OK;
     }
     SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_NONE, FIN_NONE, nullptr));
     SMM_TRY(dots(c, FIN_CG_ALPHA, c.ap, c.p));
-    SMM_TRY(vec(c, VEC_CG_XR, FIN_NONE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
+    SMM_TRY(vec(c, VEC_CG_R, FIN_NONE, {c.r, c.ap}, {c.r}));
     SMM_TRY(dots(c, FIN_CG_UPDATE, c.r, c.r));
-    SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}));
+    SMM_TRY(vec(c, VEC_CG_PX, FIN_NONE, {c.p, c.r, c.x}, {c.p, c.x}));
     c.kernels_per_iteration = 5;
     return SMM_OK;
 }
@@ -725,8 +726,8 @@ extern "C" int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_
         for (int rep = -2; rep < reps; ++rep) {                // two untimed warm-up launches
             if (rep == 0) SMM_CUDA(cudaEventRecord(ws->ev0, s));
             if (k == 0) SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));
-            else if (k == 1) SMM_TRY(vec(c, VEC_CG_XR, FIN_STORE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
-            else SMM_TRY(vec(c, VEC_CG_P, FIN_NONE, {c.p, c.r}, {c.p}));
+            else if (k == 1) SMM_TRY(vec(c, VEC_CG_R, FIN_STORE, {c.r, c.ap}, {c.r}));
+            else SMM_TRY(vec(c, VEC_CG_PX, FIN_NONE, {c.p, c.r, c.x}, {c.p, c.x}));
         }
         SMM_CUDA(cudaEventRecord(ws->ev1, s));
         SMM_CUDA(cudaEventSynchronize(ws->ev1));

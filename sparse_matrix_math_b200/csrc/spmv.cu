@@ -178,7 +178,11 @@ __device__ __forceinline__ void row_path(const SpmvParams& P, int r0, int r1, Wr
 template <int DEPTH, bool HINTS>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const SpmvParams P) {
     smm_pdl_wait();
-    if (P.state != nullptr && P.state->done) return;
+    if (P.state != nullptr && P.state->done) {
+        // an SpMV after the end of the solve: the x update a two-pass CG iteration still owed (VEC_CG_PX) has run by now
+        if (blockIdx.x == 0 && threadIdx.x == 0 && P.state->x_owed) P.state->x_owed = 0;
+        return;
+    }
 
     __shared__ __align__(16) float prod[SPMV_CAP];
     __shared__ float red_sh[96];
@@ -520,7 +524,11 @@ __global__ void __launch_bounds__(ROWS_THREADS) spmv_rows_kernel(const SpmvParam
     // everything above is independent of the previous kernel of the chain; the done flag, the operand vector and (for the
     // multi-GPU case) the exchange counter are not
     smm_pdl_wait();
-    if (P.state != nullptr && P.state->done) return;
+    if (P.state != nullptr && P.state->done) {
+        // an SpMV after the end of the solve: the x update a two-pass CG iteration still owed (VEC_CG_PX) has run by now
+        if (blockIdx.x == 0 && threadIdx.x == 0 && P.state->x_owed) P.state->x_owed = 0;
+        return;
+    }
 
     int ring_s = 0;
     uint32_t ring_k = 0;

@@ -2,6 +2,8 @@
 // parameter block of the kernels that run them, and the halo store of the multi-GPU CG.  Shared by vecops.cu (one kernel per
 // update) and the persistent CG iteration in spmv.cu.  Internal linkage: include inside the translation unit's own code.
 #pragma once
+#include <type_traits>
+
 #include "epilogue.cuh"
 #include "smm_internal.cuh"
 
@@ -37,6 +39,10 @@ __device__ __forceinline__ void halo_store(const HaloSeg* segs, const int nsegs,
     }
 }
 
+// F::OWED (optional): the kernel has work to do after the stopping test has fired (see FCgPX)
+template <class F, class = void> struct vec_owed : std::false_type {};
+template <class F> struct vec_owed<F, std::void_t<decltype(F::OWED)>> : std::integral_constant<bool, F::OWED> {};
+
 // ---- functors: NIN inputs, NOUT outputs, NRED reductions; sc = scalars read once per thread -------------------
 struct Scal { float a, b, c; };
 
@@ -58,6 +64,33 @@ struct FCgP {
     static constexpr int NIN = 2, NOUT = 1, NRED = 0;
     static __device__ Scal scal(const SolveState* s) { return {s->beta, 0.f, 0.f}; }
     static __device__ void apply(const Scal& sc, const float* in, float* out, float*) { out[0] = smm_fma2(sc.a, in[0], in[1]); }
+};
+// The same iteration in two passes that read p once instead of twice (32 n bytes instead of 36 n): the x update does not feed
+// the stopping test, so it waits for the pass that reads p anyway.
+// CG  r = fma(-alpha,Ap,r); t0 = r.r                                 (H:2366-2375)   in: r Ap  out: r
+struct FCgR {
+    static constexpr bool HALO_OK = false;
+    static constexpr int NIN = 2, NOUT = 1, NRED = 1;
+    static __device__ Scal scal(const SolveState* s) { return {s->alpha, 0.f, 0.f}; }
+    static __device__ void apply(const Scal& sc, const float* in, float* out, float* red) {
+        const float r = smm_fma2(-sc.a, in[1], in[0]);
+        out[0] = r;
+        red[0] = fmaf(r, r, red[0]);
+    }
+};
+// CG  x = fma(alpha,p,x) with the p of this iteration (H:2363-2365), then p = fma(beta,p,r) (H:2385-2393)
+//                                                                     in: p r x  out: p x
+// OWED: when the r update's stopping test has fired (state->done with state->x_owed) the kernel still runs once, for the x
+// update alone -- the reference updates x before it tests (H:2363-2379) -- and leaves p as it is (sc.c != 0).
+struct FCgPX {
+    static constexpr bool HALO_OK = true;
+    static constexpr bool OWED = true;
+    static constexpr int NIN = 3, NOUT = 2, NRED = 0;
+    static __device__ Scal scal(const SolveState* s) { return {s->beta, s->alpha, 0.f}; }
+    static __device__ void apply(const Scal& sc, const float* in, float* out, float*) {
+        out[1] = smm_fma2(sc.b, in[0], in[2]);
+        out[0] = sc.c != 0.f ? in[0] : smm_fma2(sc.a, in[0], in[1]);
+    }
 };
 // BiCGSymmetric  x += alpha*p; r -= alpha*ap; t0 = r.r               (H:2061-2075)   in: x p r ap  out: x r
 struct FBsXR {

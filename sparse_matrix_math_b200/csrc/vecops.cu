@@ -13,23 +13,28 @@
 
 namespace {
 
-// HALO (multi-GPU CG, F = FCgP / FCopy3): the kernel that produces the next SpMV operand also pushes its boundary entries
+// HALO (multi-GPU CG, F = FCgPX / FCgP / FCopy3): the kernel that produces the next SpMV operand also pushes its boundary entries
 // to the peers and, once every CTA is through, raises this rank's flag on them -- no separate push kernel.
 template <class F, bool VEC4, bool HALO>
 __global__ void __launch_bounds__(VEC_THREADS) vec_kernel(const VecParams P) {
     smm_pdl_wait();                                            // the scalars and vectors below come from the previous kernel
-    if (P.state != nullptr && P.state->done) return;
+    bool owed = false;                                         // the solve is over but this kernel's x update is still due (FCgPX)
+    if (P.state != nullptr && P.state->done) {
+        if (!vec_owed<F>::value || !P.state->x_owed) return;
+        owed = true;
+    }
     __shared__ float red_sh[96];
     __shared__ int sh_flag;
     __shared__ HaloSeg sh_segs[HALO ? SMM_MAX_RANKS : 1];
     int nsegs = 0;
     bool pushed = false;
     if (HALO) {
-        nsegs = P.halo->nsegs;
+        nsegs = owed ? 0 : P.halo->nsegs;                      // nothing is pushed once the solve is over (on any rank: the state is the same everywhere)
         if (threadIdx.x < nsegs) sh_segs[threadIdx.x] = P.halo->segs[threadIdx.x];
         __syncthreads();
     }
-    const Scal sc = F::scal(P.state);
+    Scal sc = F::scal(P.state);
+    if (vec_owed<F>::value && owed) sc.c = 1.f;
     float red[2] = {0.f, 0.f};
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,7 +81,7 @@ __global__ void __launch_bounds__(VEC_THREADS) vec_kernel(const VecParams P) {
     }
 
     smm_pdl_trigger();                                         // main loop done: the next kernel of the chain may start its prologue
-    if (HALO) {
+    if (HALO && !owed) {
         if (pushed) __threadfence_system();                    // my peer stores are visible before my CTA's ticket
         __syncthreads();
         if (threadIdx.x == 0 && atomicAdd(P.halo->ticket, 1u) == gridDim.x - 1) {
@@ -144,6 +149,8 @@ int smm_launch_vec(int kind, const VecArgs& a, cudaStream_t s) {
         case VEC_STAB_P: return launch<FStabP>(a, s);
         case VEC_DOT2: return launch<FDot2>(a, s);
         case VEC_COPY3: return launch<FCopy3>(a, s);
+        case VEC_CG_R: return launch<FCgR>(a, s);
+        case VEC_CG_PX: return launch<FCgPX>(a, s);
         default: smm_set_error("vecops: unknown kernel %d", kind); return SMM_E_INVALID;
     }
 }
