@@ -73,6 +73,7 @@ struct TreeParams {
     SolveState* state;
     int finish;
     float* out_dev;        // optional: totals written here too
+    float* upd;            // dot_tree_rows_kernel<R, true>: r (== a[0]) is first replaced by r - alpha * b[0], the dot is r.r of the new r
 };
 
 // every CTA has stored its depth-D' node values: the last one to arrive combines them by a perfect pairwise tree (ping-pong
@@ -155,7 +156,12 @@ __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, in
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
 }
 
-template <int R>
+// UPD (ConjugateGradient in the reference-order mode): the r update of H:2366-2368 rides on the dot that follows it -- the
+// lane that adds node l's squares first forms r_i = fma(-alpha, Ap_i, r_i) (two roundings, like vecops.cu's FCgR) from the
+// staged windows of r and Ap, leaves the new r in the staging buffer, and the warp stores the finished stage back with
+// coalesced 16-byte stores (only the elements of its own nodes: a window starts at the 16-byte boundary below its node).
+// One pass over r and Ap instead of an update kernel (12 n bytes) plus a dot (4 n).
+template <int R, bool UPD>
 __global__ void __launch_bounds__(TREE_WARPS * 32) dot_tree_rows_kernel(const TreeParams P) {
     if (P.state != nullptr && P.state->done) return;
     extern __shared__ __align__(16) float rows_smem[];
@@ -169,8 +175,9 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) dot_tree_rows_kernel(const Tr
     if (job < groups * P.ndots) {
         const int d = (int)(job / groups);
         const long long node = (job - (long long)d * groups) * R + (lane % R);
-        const float* __restrict__ a = P.a[d];
+        const float* a = P.a[d];                                               // UPD: also written (through P.upd)
         const float* __restrict__ b = P.b[d];
+        const float nalpha = UPD ? -P.state->alpha : 0.0f;
         long long lo = 0, hi = P.n;
         for (int level = P.depth - 1; level >= 0; --level) {
             const long long mid = lo + (hi - lo) / 2;
@@ -207,13 +214,20 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) dot_tree_rows_kernel(const Tr
             asm volatile("cp.async.wait_group 2;" ::: "memory");
             __syncwarp();
             if (lane < R) {
-                const float* sa = mine + (size_t)(t % ROWS_STAGES) * 2 * ARR + lane * CP;
+                float* sa = mine + (size_t)(t % ROWS_STAGES) * 2 * ARR + lane * CP;
                 const float* sb = sa + ARR;
                 const long long g0 = a4 + (long long)t * C;
                 if (g0 >= lo && g0 + C <= hi && !(split >= g0 && split < g0 + C)) {
 #pragma unroll 4
                     for (int c = 0; c < C; c += 4) {
-                        const float4 va = *reinterpret_cast<const float4*>(sa + c), vb = *reinterpret_cast<const float4*>(sb + c);
+                        float4 va = *reinterpret_cast<const float4*>(sa + c);
+                        float4 vb = *reinterpret_cast<const float4*>(sb + c);
+                        if (UPD) {                                                  // r = fma(-alpha, Ap, r), then r.r
+                            va.x = smm_fma2(nalpha, vb.x, va.x); va.y = smm_fma2(nalpha, vb.y, va.y);
+                            va.z = smm_fma2(nalpha, vb.z, va.z); va.w = smm_fma2(nalpha, vb.w, va.w);
+                            *reinterpret_cast<float4*>(sa + c) = va;
+                            vb = va;
+                        }
                         acc = __fadd_rn(acc, __fmul_rn(va.x, vb.x)); acc = __fadd_rn(acc, __fmul_rn(va.y, vb.y));   // H:314-316
                         acc = __fadd_rn(acc, __fmul_rn(va.z, vb.z)); acc = __fadd_rn(acc, __fmul_rn(va.w, vb.w));
                     }
@@ -222,11 +236,30 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) dot_tree_rows_kernel(const Tr
                         const long long g = g0 + c;
                         if (g < lo || g >= hi) continue;
                         if (g == split) { first = acc; acc = 0.0f; }
-                        acc = __fadd_rn(acc, __fmul_rn(sa[c], sb[c]));
+                        float va = sa[c], vb = sb[c];
+                        if (UPD) { va = smm_fma2(nalpha, vb, va); sa[c] = va; vb = va; }
+                        acc = __fadd_rn(acc, __fmul_rn(va, vb));
                     }
                 }
             }
             __syncwarp();
+            if (UPD) {                                                              // the finished stage of r goes back, every node its own elements
+                const float* sa = mine + (size_t)(t % ROWS_STAGES) * 2 * ARR;
+#pragma unroll
+                for (int k = 0; k < (R * CHUNKS_PER_ROW) / 32; ++k) {
+                    const int q = lane + 32 * k, row = q / CHUNKS_PER_ROW, col = (q % CHUNKS_PER_ROW) * 4;
+                    const long long g0 = __shfl_sync(0xFFFFFFFFu, a4, row) + (long long)t * C + col;
+                    const long long rlo = __shfl_sync(0xFFFFFFFFu, lo, row), rhi = __shfl_sync(0xFFFFFFFFu, hi, row);
+                    const float4 v = *reinterpret_cast<const float4*>(sa + row * CP + col);
+                    if (g0 >= rlo && g0 + 4 <= rhi) *reinterpret_cast<float4*>(P.upd + g0) = v;
+                    else {
+                        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) if (g0 + c >= rlo && g0 + c < rhi) P.upd[g0 + c] = e[c];
+                    }
+                }
+                __syncwarp();
+            }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (lane < R) P.nodes[(size_t)d * 2 * nn + node] = split >= 0 ? __fadd_rn(first, acc) : acc;
@@ -569,21 +602,44 @@ int smm_tree_depth(long long n) {
 
 // t0 = a0.b0 [, t1 = a1.b1] in the requested reference order; the totals go to smm_finish(finish, state, t0, t1)
 // and/or out_dev[0..1].  mode: SMM_REDUCE_REFERENCE_TREE or SMM_REDUCE_REFERENCE_SERIAL.
+namespace {
+// lanes-per-node variant of the tree dot for long, 16-byte aligned vectors: R nodes per warp, or 0 when it does not apply
+int tree_rows_R(long long n, int ndots, const float* a0, const float* b0, const float* a1, const float* b1) {
+    const int depth = smm_tree_depth(n);
+    const long long jobs = (1ll << depth) * ndots;
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(a0) | reinterpret_cast<uintptr_t>(b0) | reinterpret_cast<uintptr_t>(a1) | reinterpret_cast<uintptr_t>(b1)) & 15) == 0;
+    static const bool rows_off = [] { const char* e = getenv("SMM_B200_DOT_ROWS"); return e && atoi(e) == 0; }();
+    int R = 0;
+    if (aligned16 && !rows_off) for (int r = 16; r >= 2 && !R; r >>= 1) if ((1ll << depth) >= r && jobs / r >= 592) R = r;
+    return R;
+}
+}  // namespace
+
+// r = r - alpha * ap (alpha from the state) and t0 = r.r of the new r in the reference's tree order, in one pass: only in
+// the lane-per-node form of the tree dot
+bool smm_dot_ref_update_applies(int mode, long long n, const float* r, const float* ap) {
+    const char* e = getenv("SMM_B200_DOT_UPDATE");            // read per call: the tests run both forms
+    const bool off = e && atoi(e) == 0;
+    return !off && mode == SMM_REDUCE_REFERENCE_TREE && tree_rows_R(n, 1, r, ap, r, ap) != 0;
+}
+
 int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const float* b0, const float* a1, const float* b1,
-                       SolveState* state, int finish, float* out_dev, cudaStream_t s, smm_workspace* ws) {
+                       SolveState* state, int finish, float* out_dev, cudaStream_t s, smm_workspace* ws, float* update_r) {
+    if (update_r != nullptr && !(mode == SMM_REDUCE_REFERENCE_TREE && ndots == 1 && update_r == a0 && state != nullptr && tree_rows_R(n, 1, a0, b0, a0, b0) != 0)) {
+        smm_set_error("dot with a fused r update: not applicable here");
+        return SMM_E_INVALID;
+    }
     if (mode == SMM_REDUCE_REFERENCE_TREE) {
         TreeParams P;
         P.n = n; P.depth = smm_tree_depth(n); P.ndots = ndots;
+        P.upd = update_r;
         P.a[0] = a0; P.b[0] = b0; P.a[1] = a1; P.b[1] = b1;
         DotScratch* sc = nullptr;
         SMM_TRY(scratch_for(1ll << P.depth, ws, &sc));
         P.nodes = sc->nodes; P.ticket = sc->ticket; P.state = state; P.finish = finish; P.out_dev = out_dev;
         const long long jobs = (1ll << P.depth) * ndots;       // (dot, depth-D' node)
         // long vectors: a lane per node, R nodes per warp (as many as still leave four warps for every SM)
-        int R = 0;
-        const bool aligned16 = ((reinterpret_cast<uintptr_t>(a0) | reinterpret_cast<uintptr_t>(b0) | reinterpret_cast<uintptr_t>(a1) | reinterpret_cast<uintptr_t>(b1)) & 15) == 0;
-        static const bool rows_off = [] { const char* e = getenv("SMM_B200_DOT_ROWS"); return e && atoi(e) == 0; }();
-        if (aligned16 && !rows_off) for (int r = 16; r >= 2 && !R; r >>= 1) if ((1ll << P.depth) >= r && jobs / r >= 592) R = r;
+        const int R = tree_rows_R(n, ndots, a0, b0, a1, b1);
         if (R) {
             const size_t smem = (size_t)TREE_WARPS * ROWS_STAGES * 2 * (ROWS_TILE + 4 * R) * sizeof(float);
             {
@@ -593,19 +649,32 @@ int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const 
                 std::lock_guard<std::mutex> lk(g_smm_attr_mu);
                 if (!attr_done[dev % SMM_MAX_DEVICES]) {
                     const int most = (int)((size_t)TREE_WARPS * ROWS_STAGES * 2 * (ROWS_TILE + 4 * 16) * sizeof(float));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
                     attr_done[dev % SMM_MAX_DEVICES] = true;
                 }
             }
             const unsigned grid = (unsigned)((jobs / R + TREE_WARPS - 1) / TREE_WARPS);
-            switch (R) {
-                case 16: dot_tree_rows_kernel<16><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
-                case 8: dot_tree_rows_kernel<8><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
-                case 4: dot_tree_rows_kernel<4><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
-                default: dot_tree_rows_kernel<2><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+            if (update_r) {
+                switch (R) {
+                    case 16: dot_tree_rows_kernel<16, true><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+                    case 8: dot_tree_rows_kernel<8, true><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+                    case 4: dot_tree_rows_kernel<4, true><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+                    default: dot_tree_rows_kernel<2, true><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+                }
+            } else {
+                switch (R) {
+                    case 16: dot_tree_rows_kernel<16, false><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+                    case 8: dot_tree_rows_kernel<8, false><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+                    case 4: dot_tree_rows_kernel<4, false><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+                    default: dot_tree_rows_kernel<2, false><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
+                }
             }
         } else
         dot_tree_kernel<<<(unsigned)((jobs + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, 0, s>>>(P);

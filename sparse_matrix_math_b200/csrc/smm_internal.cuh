@@ -204,7 +204,10 @@ int smm_tree_depth(long long n);
 // ws: the handle's workspace (its own scratch); null: the stand-alone smm_dot's per-device scratch
 int smm_dot_ref_prepare(long long n, smm_workspace* ws);
 int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const float* b0, const float* a1, const float* b1,
-                       SolveState* state, int finish, float* out_dev, cudaStream_t s, smm_workspace* ws);
+                       SolveState* state, int finish, float* out_dev, cudaStream_t s, smm_workspace* ws, float* update_r = nullptr);
+// update_r (== a0, with b0 = Ap): r = r - state->alpha * Ap rides on the dot, which is then r.r of the new r (ConjugateGradient in
+// the reference-tree mode on long vectors; smm_dot_ref_update_applies says whether this form exists for the operands)
+bool smm_dot_ref_update_applies(int mode, long long n, const float* r, const float* ap);
 void smm_dot_scratch_free(smm_dot_scratch* sc);
 
 // SGS preconditioner (sgs.cu)

@@ -132,11 +132,15 @@ int cg_iter_dist(Ctx& c) {
     if (c.exact) {
         SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, d->ext, c.ap, RED_NONE, FIN_NONE, nullptr));
         SMM_TRY(dots(c, FIN_CG_ALPHA, c.ap, c.p));
-        SMM_TRY(vec(c, VEC_CG_R, FIN_NONE, {c.r, c.ap}, {c.r}));
-        SMM_TRY(dots(c, FIN_CG_UPDATE, c.r, c.r));
+        const bool fused_r = smm_dot_ref_update_applies(c.mode, c.n, c.r, c.ap);   // the r update rides on the tree dot that follows it
+        if (fused_r) SMM_TRY(smm_launch_dot_ref(c.mode, c.n, 1, c.r, c.ap, c.r, c.ap, c.st, FIN_CG_UPDATE, nullptr, c.s, c.ws, c.r));
+        else {
+            SMM_TRY(vec(c, VEC_CG_R, FIN_NONE, {c.r, c.ap}, {c.r}));
+            SMM_TRY(dots(c, FIN_CG_UPDATE, c.r, c.r));
+        }
         SMM_TRY(vec(c, VEC_CG_PX, FIN_NONE, {c.p, c.r, c.x}, {c.p, c.x}, true));
         SMM_TRY(dist_after_p(c));
-        c.kernels_per_iteration = 5 + extra;
+        c.kernels_per_iteration = (fused_r ? 4 : 5) + extra;
         return SMM_OK;
     }
     SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, d->ext, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));
@@ -164,10 +168,14 @@ int cg_iter(Ctx& c) {
     }
     SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_NONE, FIN_NONE, nullptr));
     SMM_TRY(dots(c, FIN_CG_ALPHA, c.ap, c.p));
-    SMM_TRY(vec(c, VEC_CG_R, FIN_NONE, {c.r, c.ap}, {c.r}));
-    SMM_TRY(dots(c, FIN_CG_UPDATE, c.r, c.r));
+    const bool fused_r = smm_dot_ref_update_applies(c.mode, c.n, c.r, c.ap);       // the r update rides on the tree dot that follows it
+    if (fused_r) SMM_TRY(smm_launch_dot_ref(c.mode, c.n, 1, c.r, c.ap, c.r, c.ap, c.st, FIN_CG_UPDATE, nullptr, c.s, c.ws, c.r));
+    else {
+        SMM_TRY(vec(c, VEC_CG_R, FIN_NONE, {c.r, c.ap}, {c.r}));
+        SMM_TRY(dots(c, FIN_CG_UPDATE, c.r, c.r));
+    }
     SMM_TRY(vec(c, VEC_CG_PX, FIN_NONE, {c.p, c.r, c.x}, {c.p, c.x}));
-    c.kernels_per_iteration = 5;
+    c.kernels_per_iteration = fused_r ? 4 : 5;
     return SMM_OK;
 }
 

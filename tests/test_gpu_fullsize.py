@@ -98,6 +98,36 @@ def test_fullsize_reference_order_is_bit_exact_and_fast_mode_converges(smm, key)
     assert float(np.max(np.abs(x - xs))) <= max(2.0 * ref["max_abs_error"], 5e-5)
 
 
+@pytest.mark.parametrize("grid", [(219, 219, 219), (343, 343, 343), (401, 397, 263)])
+def test_tree_mode_cg_r_update_fused_into_the_dot(smm, grid):
+    """ConjugateGradient in the reference-tree mode on long vectors: the r update (H:2366-2368) rides on the tree dot that follows
+    it (dot_tree_rows_kernel<R, true>).  Same bits as the separate update kernel + dot (SMM_B200_DOT_UPDATE=0), for 2 / 8 / 16
+    nodes per warp and node boundaries that are not multiples of four elements; the 512^3 golden run covers aligned nodes."""
+    from sparse_matrix_math_b200 import binding as B
+    A = smm.CSRMatrix.generate(B.GEN_CONVDIFF3D, *grid, 0.0)
+    n = A.rows
+    xs = smm.DeviceVector(n)
+    B._check(smm.lib().smm_gen_xstar_dev(n, 0, 0xB200, xs.ptr, None), "xstar")
+    b = smm.DeviceVector(n)
+    A.spmv_dev(B.OP_ASSIGN, None, xs.ptr, b.ptr)
+    got = []
+    for fused in (True, False):
+        if not fused:
+            os.environ["SMM_B200_DOT_UPDATE"] = "0"
+        try:
+            x = smm.DeviceVector(n)
+            x.zero()
+            o, _ = B._options(smm.REDUCE_REFERENCE_TREE, B.DRIVER_AUTO, 0, 0)
+            info = B._Info()
+            B._check(smm.lib().smm_solve_cg_dev(A.handle, b.ptr, x.ptr, x.ptr, 12, 0.0, C.byref(o), C.byref(info), None), "solve")
+            got.append((info.iterations, int(np.float32(info.residual).view(np.uint32)), info.kernel_launches, checksum(x.download())))
+        finally:
+            os.environ.pop("SMM_B200_DOT_UPDATE", None)
+    assert got[0][0] == got[1][0] == 12
+    assert got[0][1] == got[1][1] and got[0][3] == got[1][3]
+    assert got[0][2] < got[1][2]                                      # one kernel fewer per iteration
+
+
 def test_config4_powerlaw_properties(smm):
     from sparse_matrix_math_b200 import binding as B
     n = 8388608
