@@ -277,6 +277,7 @@ static int dist_finish_connect(smm_dist_t* d, const int64_t* all_ranges) {
     SMM_CUDA(cudaMalloc(&d->sources_dev, sizeof(int) * SMM_MAX_RANKS));
     if (!d->dests.empty()) SMM_CUDA(cudaMemcpy(d->dests_dev, d->dests.data(), sizeof(int) * d->dests.size(), cudaMemcpyHostToDevice));
     if (!d->sources.empty()) SMM_CUDA(cudaMemcpy(d->sources_dev, d->sources.data(), sizeof(int) * d->sources.size(), cudaMemcpyHostToDevice));
+    if (const char* e = getenv("SMM_B200_DIST_DEBUG")) c.debug = atoi(e);   // measurement only: see DistComm::debug
     SMM_CUDA(cudaMemcpy(d->comm_dev, &c, sizeof c, cudaMemcpyHostToDevice));
     // rows [0, halo_row_lo) and [halo_row_hi, rows) read halo entries: the SpMV multiplies the others while the pushes travel
     const int rows = d->local->rows;
@@ -297,6 +298,7 @@ static int dist_finish_connect(smm_dist_t* d, const int64_t* all_ranges) {
     hw.nsources = (int)d->sources.size();
     for (int k = 0; k < hw.nsources; ++k) hw.sources[k] = d->sources[k];
     hw.row_lo = bounds[0]; hw.row_hi = bounds[1]; hw.comm = d->comm_dev;
+    hp.debug = c.debug;
     SMM_CUDA(cudaMalloc(&d->push_dev, sizeof hp));
     SMM_CUDA(cudaMalloc(&d->wait_dev, sizeof hw));
     SMM_CUDA(cudaMemcpy(d->push_dev, &hp, sizeof hp, cudaMemcpyHostToDevice));
@@ -402,6 +404,15 @@ int smm_dist_solve_cgs(smm_dist_t* d, const float* b_dev, float* x_dev, int maxI
 int smm_dist_solve_bicgstab(smm_dist_t* d, const float* b_dev, float* x_dev, int maxIterations, float eps,
                             const smm_solve_options* opts, smm_solve_info* info, void* stream) {
     return dist_solve_other(d, 3, b_dev, x_dev, maxIterations, eps, opts, info, stream);
+}
+
+// measurement hook (tools/dist_kernel_times.py): the three kernels of this rank's CG iteration, timed back to back; needs
+// SMM_B200_DIST_DEBUG=7 at create time (no waiting for peers, no pushes)
+int smm_dist_profile_cg_iteration(smm_dist_t* d, int reps, float* ms_spmv, float* ms_r, float* ms_px, void* stream) {
+    if (!d || !d->connected) return SMM_E_STATE;
+    const char* e = getenv("SMM_B200_DIST_DEBUG");
+    if (!e || (atoi(e) & 6) != 6) { smm_set_error("smm_dist_profile_cg_iteration: set SMM_B200_DIST_DEBUG=7 before creating the handle"); return SMM_E_STATE; }
+    return smm_profile_cg_iteration_impl(d->local, d, reps, ms_spmv, ms_r, ms_px, stream);
 }
 
 int smm_dist_error(const smm_dist_t* d, int* error) {

@@ -38,3 +38,5 @@ struct smm_dist {
 int smm_dist_exchange_async(smm_dist* d, SolveState* st, cudaStream_t s, bool wait_kernel = true);
 // the wait kernel alone (the push was done by the kernel that produced the operand)
 int smm_dist_wait_async(smm_dist* d, SolveState* st, cudaStream_t s);
+// solvers.cu: per-kernel times of a CG iteration (dist == nullptr: the single-GPU kernels)
+int smm_profile_cg_iteration_impl(const smm_csr_t* a, smm_dist* dist, int reps, float* ms_spmv, float* ms_xr, float* ms_p, void* stream);

@@ -40,6 +40,7 @@ struct DistComm {
     unsigned int ack_seq;                       // stand-alone SpMV calls completed
     unsigned long long* chain[SMM_MAX_RANKS];   // chain[d]: rank d's inbound word of a sum that is CHAINED through the ranks
     unsigned int chain_seq;                     // chained sums completed (same on every rank)
+    int debug;                                  // measurement only (SMM_B200_DIST_DEBUG, bit mask): 1 = no all-reduce (local sums), 2 = no halo wait, 4 = no halo push
 };
 
 // halo push fused into an element-wise kernel: segment s covers elements [begin, begin + len) of the kernel's first
@@ -47,6 +48,7 @@ struct DistComm {
 struct HaloSeg { float* dst; long long begin; long long len; };
 struct HaloPushDev {
     int nsegs, ndests;
+    int debug;                                  // copy of DistComm::debug (set at connect time)
     HaloSeg segs[SMM_MAX_RANKS];
     int dests[SMM_MAX_RANKS];
     DistComm* comm;
@@ -81,6 +83,7 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p
 // spin until every source rank has raised its flag for the current exchange; false when the bounded wait expired
 __device__ __forceinline__ bool dist_halo_wait(const HaloWaitDev* w) {
     DistComm* c = w->comm;
+    if (c->debug & 2) return true;
     const unsigned int want = c->push_seq;                  // my own push of this exchange is already counted
     const unsigned int* f = c->flags[c->rank];
     for (int k = 0; k < w->nsources; ++k) {
@@ -95,6 +98,7 @@ __device__ __forceinline__ bool dist_halo_wait(const HaloWaitDev* w) {
 // Called by ONE thread per rank.  Sums t0 and t1 over all ranks: in rank order, or pairwise in reference-tree mode.
 __device__ __forceinline__ void dist_allreduce2(DistComm* c, float& t0, float& t1) {
     const unsigned int seq = c->red_seq + 1u;
+    if (c->debug & 1) { c->red_seq = seq; return; }
     const int P = c->nranks, me = c->rank;
     const size_t set = (size_t)(seq & 3u) * P * 2;
     const unsigned long long w0 = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(t0);

@@ -713,7 +713,10 @@ int smm_solve_bicgstab_dev(const smm_csr_t* a, const smm_precond_t* precond, con
 // Launches the SAME three kernels the solver's iteration graph holds, `reps` times each, on `stream`, bracketed
 // by CUDA events.  Vectors are the handle's own work vectors (contents irrelevant for timing, kept finite).
 // ---------------------------------------------------------------------------------------------------
-extern "C" int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_spmv, float* ms_xr, float* ms_p, void* stream) {
+// dist != null: the kernels of the multi-GPU iteration on this rank's rows (p inside the extended vector, halo stores fused into
+// the x,p update, interior rows first in the SpMV).  Only meaningful with SMM_B200_DIST_DEBUG=7 set when the handle was created:
+// the timed launches of one kernel follow each other without the peers taking part, so nothing may wait for them.
+int smm_profile_cg_iteration_impl(const smm_csr_t* a, smm_dist* dist, int reps, float* ms_spmv, float* ms_xr, float* ms_p, void* stream) {
     if (!a || reps < 1) return SMM_E_INVALID;
     SMM_CUDA(cudaSetDevice(a->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : smm_default_stream();
@@ -722,8 +725,10 @@ extern "C" int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_
     SMM_TRY(smm_workspace_vectors(ws, 7, (size_t)a->rows));
     Ctx c;
     c.a = a; c.ws = ws; c.s = s; c.st = ws->state; c.n = a->rows;
+    c.dist = dist;
     float** w = ws->vec + 3;
     c.x = ws->vec[1]; c.r = w[0]; c.p = w[1]; c.ap = w[2];
+    if (dist) c.p = dist->ext + dist->own_off;
     const size_t bytes = sizeof(float) * (size_t)a->rows;
     SMM_CUDA(cudaMemsetAsync(c.x, 0, bytes, s));
     SMM_CUDA(cudaMemsetAsync(c.r, 0, bytes, s));
@@ -733,9 +738,9 @@ extern "C" int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_
     for (int k = 0; k < 3; ++k) {
         for (int rep = -2; rep < reps; ++rep) {                // two untimed warm-up launches
             if (rep == 0) SMM_CUDA(cudaEventRecord(ws->ev0, s));
-            if (k == 0) SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));
+            if (k == 0) SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, dist ? dist->ext : c.p, c.ap, RED_OUT_AUX, FIN_CG_ALPHA, c.p));
             else if (k == 1) SMM_TRY(vec(c, VEC_CG_R, FIN_STORE, {c.r, c.ap}, {c.r}));
-            else SMM_TRY(vec(c, VEC_CG_PX, FIN_NONE, {c.p, c.r, c.x}, {c.p, c.x}));
+            else { SMM_TRY(vec(c, VEC_CG_PX, FIN_NONE, {c.p, c.r, c.x}, {c.p, c.x}, dist != nullptr)); if (dist) SMM_TRY(dist_after_p(c)); }
         }
         SMM_CUDA(cudaEventRecord(ws->ev1, s));
         SMM_CUDA(cudaEventSynchronize(ws->ev1));
@@ -744,4 +749,8 @@ extern "C" int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_
         if (outs[k]) *outs[k] = ms / reps;
     }
     return SMM_OK;
+}
+
+extern "C" int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_spmv, float* ms_xr, float* ms_p, void* stream) {
+    return smm_profile_cg_iteration_impl(a, nullptr, reps, ms_spmv, ms_xr, ms_p, stream);
 }

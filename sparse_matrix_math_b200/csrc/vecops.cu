@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(VEC_THREADS) vec_kernel(const VecParams P) {
     int nsegs = 0;
     bool pushed = false;
     if (HALO) {
-        nsegs = owed ? 0 : P.halo->nsegs;                      // nothing is pushed once the solve is over (on any rank: the state is the same everywhere)
+        nsegs = (owed || (P.halo->debug & 4)) ? 0 : P.halo->nsegs;                      // nothing is pushed once the solve is over (on any rank: the state is the same everywhere)
         if (threadIdx.x < nsegs) sh_segs[threadIdx.x] = P.halo->segs[threadIdx.x];
         __syncthreads();
     }
