@@ -58,7 +58,13 @@ struct Ctx {
 // multi-GPU: can the SpMV wait for the halo itself (rows kernel), or does it need the wait kernel in front of it?
 // (SMM_B200_DIST_FUSED=0: separate push and wait kernels around every exchange, for A/B measurements)
 bool dist_fused() { static const bool on = [] { const char* e = getenv("SMM_B200_DIST_FUSED"); return !e || atoi(e) != 0; }(); return on; }
-bool fused_wait(const Ctx& c) { return dist_fused() && c.dist && c.dist->nranks > 1 && c.dist->wait_dev && smm_spmv_rows_lanes(c.a, c.exact ? 1 : 0) > 0; }
+// The halo stores are fused into the kernel that writes p; the wait for the peers' flags is a one-warp kernel in front of the
+// SpMV, which is then the plain instance of the rows kernel.  Waiting inside the SpMV (boundary row groups last, interior rows
+// overlapping the pushes; SMM_B200_DIST_FUSED_WAIT=1) saves that launch but its HALO instance of the rows kernel is 3 % slower
+// than the plain one on the same rows: measured 1086 vs 1071 us per iteration on 2 GPUs, 306.4 vs 301.6 us on 8
+// (profiles/r02_dist_overhead.txt).
+bool dist_fused_wait_on() { static const bool on = [] { const char* e = getenv("SMM_B200_DIST_FUSED_WAIT"); return e && atoi(e) != 0; }(); return on; }
+bool fused_wait(const Ctx& c) { return dist_fused() && dist_fused_wait_on() && c.dist && c.dist->nranks > 1 && c.dist->wait_dev && smm_spmv_rows_lanes(c.a, c.exact ? 1 : 0) > 0; }
 
 int spmv(Ctx& c, int op, const float* lhs, const float* mult, float* out, int reduce, int finish, const float* aux,
          float* c1 = nullptr, float* c2 = nullptr, float* c3 = nullptr) {
