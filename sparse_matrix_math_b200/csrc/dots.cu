@@ -148,8 +148,11 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) dot_tree_kernel(const TreePar
 // one, about 0.2 warp instructions per element for R = 16.  A node of 8193 elements is two leaves (H:308-320: the range is
 // halved while it exceeds the grain): the lane restarts from 0 at the split point and joins left + right at the end.
 // ---------------------------------------------------------------------------------------------------
-constexpr int ROWS_TILE = 1024;        // elements per stage and array, all R rows together
+constexpr int ROWS_TILE = 1024;        // elements per stage and array, all R rows together (the wide form; the narrow forms stage 64 per row)
 constexpr int ROWS_STAGES = 3;
+#ifndef SMM_DOT_NARROW_DEFAULT
+#define SMM_DOT_NARROW_DEFAULT 0     // 0: wide form; 8 / 4: narrow form on long vectors (see tree_rows_narrow)
+#endif
 
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, int src_bytes) {
     const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst_smem);
@@ -161,11 +164,11 @@ __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, in
 // staged windows of r and Ap, leaves the new r in the staging buffer, and the warp stores the finished stage back with
 // coalesced 16-byte stores (only the elements of its own nodes: a window starts at the 16-byte boundary below its node).
 // One pass over r and Ap instead of an update kernel (12 n bytes) plus a dot (4 n).
-template <int R, bool UPD>
+template <int R, int TILE, bool UPD>
 __global__ void __launch_bounds__(TREE_WARPS * 32) dot_tree_rows_kernel(const TreeParams P) {
     if (P.state != nullptr && P.state->done) return;
     extern __shared__ __align__(16) float rows_smem[];
-    constexpr int C = ROWS_TILE / R, CP = C + 4, ARR = R * CP;               // elements per row, padded row, one array of a stage
+    constexpr int C = TILE / R, CP = C + 4, ARR = R * CP;                    // elements per row, padded row, one array of a stage
     constexpr int CHUNKS_PER_ROW = C / 4;
     const long long nn = 1ll << P.depth;
     const long long groups = nn / R;
@@ -613,6 +616,34 @@ int tree_rows_R(long long n, int ndots, const float* a0, const float* b0, const 
     if (aligned16 && !rows_off) for (int r = 16; r >= 2 && !R; r >>= 1) if ((1ll << depth) >= r && jobs / r >= 592) R = r;
     return R;
 }
+
+// 0: the wide form with R rows; 8 / 4: the narrow form with that many rows per warp (long vectors only: every resident warp slot
+// must still find a job).  SMM_B200_DOT_NARROW=0 / 8 / 4 forces the choice (measurements).
+int tree_rows_narrow(int R, long long jobs) {
+    static const int forced = [] { const char* e = getenv("SMM_B200_DOT_NARROW"); return e ? atoi(e) : -1; }();
+    if (R != 16) return 0;
+    if (forced == 0) return 0;
+    if (forced == 8 || forced == 4) return jobs / forced >= 592 ? forced : 0;
+    return SMM_DOT_NARROW_DEFAULT;
+}
+
+template <int R, int TILE, bool UPD>
+int launch_rows(const TreeParams& P, long long jobs, cudaStream_t s) {
+    const size_t smem = (size_t)TREE_WARPS * ROWS_STAGES * 2 * (TILE + 4 * R) * sizeof(float);
+    {
+        static bool attr_done[SMM_MAX_DEVICES] = {false};              // per instantiation and device
+        int dev = 0;
+        SMM_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(g_smm_attr_mu);
+        if (!attr_done[dev % SMM_MAX_DEVICES]) {
+            SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<R, TILE, UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done[dev % SMM_MAX_DEVICES] = true;
+        }
+    }
+    const unsigned grid = (unsigned)((jobs / R + TREE_WARPS - 1) / TREE_WARPS);
+    dot_tree_rows_kernel<R, TILE, UPD><<<grid, TREE_WARPS * 32, smem, s>>>(P);
+    return SMM_OK;
+}
 }  // namespace
 
 // r = r - alpha * ap (alpha from the state) and t0 = r.r of the new r in the reference's tree order, in one pass: only in
@@ -641,41 +672,27 @@ int smm_launch_dot_ref(int mode, long long n, int ndots, const float* a0, const 
         // long vectors: a lane per node, R nodes per warp (as many as still leave four warps for every SM)
         const int R = tree_rows_R(n, ndots, a0, b0, a1, b1);
         if (R) {
-            const size_t smem = (size_t)TREE_WARPS * ROWS_STAGES * 2 * (ROWS_TILE + 4 * R) * sizeof(float);
-            {
-                static bool attr_done[SMM_MAX_DEVICES] = {false};
-                int dev = 0;
-                SMM_CUDA(cudaGetDevice(&dev));
-                std::lock_guard<std::mutex> lk(g_smm_attr_mu);
-                if (!attr_done[dev % SMM_MAX_DEVICES]) {
-                    const int most = (int)((size_t)TREE_WARPS * ROWS_STAGES * 2 * (ROWS_TILE + 4 * 16) * sizeof(float));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-                    SMM_CUDA(cudaFuncSetAttribute(dot_tree_rows_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-                    attr_done[dev % SMM_MAX_DEVICES] = true;
-                }
-            }
-            const unsigned grid = (unsigned)((jobs / R + TREE_WARPS - 1) / TREE_WARPS);
+            // narrow form (64 elements per row and stage instead of 1024 / R): a quarter / half of the shared memory per warp, so
+            // two / four times the resident warps -- the lane that adds a node's products issues ~5 instructions per element
+            // and a warp is bound by that chain, not by the loads (ncu: 7 warps per SM, 0.21 instructions per cycle and warp)
+            const int narrow = tree_rows_narrow(R, jobs);
+            int rc = SMM_OK;
             if (update_r) {
-                switch (R) {
-                    case 16: dot_tree_rows_kernel<16, true><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
-                    case 8: dot_tree_rows_kernel<8, true><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
-                    case 4: dot_tree_rows_kernel<4, true><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
-                    default: dot_tree_rows_kernel<2, true><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
-                }
+                if (narrow == 8) rc = launch_rows<8, 512, true>(P, jobs, s);
+                else if (narrow == 4) rc = launch_rows<4, 256, true>(P, jobs, s);
+                else if (R == 16) rc = launch_rows<16, ROWS_TILE, true>(P, jobs, s);
+                else if (R == 8) rc = launch_rows<8, ROWS_TILE, true>(P, jobs, s);
+                else if (R == 4) rc = launch_rows<4, ROWS_TILE, true>(P, jobs, s);
+                else rc = launch_rows<2, ROWS_TILE, true>(P, jobs, s);
             } else {
-                switch (R) {
-                    case 16: dot_tree_rows_kernel<16, false><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
-                    case 8: dot_tree_rows_kernel<8, false><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
-                    case 4: dot_tree_rows_kernel<4, false><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
-                    default: dot_tree_rows_kernel<2, false><<<grid, TREE_WARPS * 32, smem, s>>>(P); break;
-                }
+                if (narrow == 8) rc = launch_rows<8, 512, false>(P, jobs, s);
+                else if (narrow == 4) rc = launch_rows<4, 256, false>(P, jobs, s);
+                else if (R == 16) rc = launch_rows<16, ROWS_TILE, false>(P, jobs, s);
+                else if (R == 8) rc = launch_rows<8, ROWS_TILE, false>(P, jobs, s);
+                else if (R == 4) rc = launch_rows<4, ROWS_TILE, false>(P, jobs, s);
+                else rc = launch_rows<2, ROWS_TILE, false>(P, jobs, s);
             }
+            SMM_TRY(rc);
         } else
         dot_tree_kernel<<<(unsigned)((jobs + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, 0, s>>>(P);
     } else {
