@@ -273,6 +273,9 @@ int smm_group_destroy(smm_group_t* g);
  * iteration (SpMV + p.Ap | r update + r.r | x and p update, p read once), `reps` launches each, CUDA events on `stream`;
  * ms_xr receives the r update's time, ms_p the x and p update's ---- */
 int smm_profile_cg_iteration(const smm_csr_t* a, int reps, float* ms_spmv, float* ms_xr, float* ms_p, void* stream);
+/* The same for this rank's kernels of the multi-GPU iteration (halo stores fused into the x,p update, halo wait), timed without
+ * the peers taking part: needs SMM_B200_DIST_DEBUG=7 in the environment when the handle is created (tools/dist_kernel_times.py). */
+int smm_dist_profile_cg_iteration(smm_dist_t* d, int reps, float* ms_spmv, float* ms_r, float* ms_px, void* stream);
 
 /* ---- device memory helpers for hosts without their own allocator ---- */
 int smm_malloc_dev(size_t bytes, void** ptr_dev);
