@@ -126,8 +126,10 @@ int smm_dot(int64_t n, const float* a, const float* b, int reduction_mode, float
 int smm_dot_dev(int64_t n, const float* a_dev, const float* b_dev, int reduction_mode, float* out_host, void* stream);
 
 /* ---- CSRMatrix::getPreconditioner<SYMMETRIC_GAUS_SEIDEL>() H:1643-1651; SGSPreconditioner::apply H:1658-1713 ----
- * create analyses the dependency levels of the lower and upper triangles once; apply returns the reference's
- * int code through *rc (0 ok, 1 = empty row / missing or tiny diagonal / leading empty rows). */
+ * create builds the schedule of the two triangular sweeps once -- on the device from the resident CSR arrays for grid
+ * stencils (tile schedule, ~0.03-0.16 s at 16.8 M rows), on the host for everything else (row levels); the reference has no
+ * set-up.  apply returns the reference's int code through *rc (0 ok, 1 = empty row / missing or tiny diagonal / leading
+ * empty rows). */
 int smm_precond_sgs_create(const smm_csr_t* m, smm_precond_t** out);
 int smm_precond_apply(const smm_precond_t* p, const float* rhs, float* x, int* rc);
 int smm_precond_apply_dev(const smm_precond_t* p, const float* rhs_dev, float* x_dev, int* rc, void* stream);
@@ -147,15 +149,16 @@ int smm_precond_schedule(const smm_precond_t* p);
  * Downloads the arrays: a test / diagnostic call.  Diagnostic; additive. */
 int smm_precond_layout_fingerprint(const smm_precond_t* p, uint64_t out[13]);
 /* CSRMatrix::IC0Preconditioner (H:1214-1235): construction + init() (factorize, H:1839-1928; *rc = its return code) and
- * apply (H:1802-1837, through smm_precond_apply[_dev]).  The factorisation is set-up code and runs on the host, row by
- * row instead of the reference's O(rows^2) scan, with bit-identical values; the two triangular solves of every apply
- * run on the GPU with the same level-scheduled sweeps as SGS. */
+ * apply (H:1802-1837, through smm_precond_apply[_dev]).  The factorisation is set-up code: row by row instead of the
+ * reference's O(rows^2) scan, with bit-identical values -- on the device in the order of the forward tile schedule when the
+ * matrix has one, else on the host; the two triangular solves of every apply run on the GPU with the same level-scheduled
+ * sweeps as SGS. */
 int smm_precond_ic0_create(const smm_csr_t* m, int* rc, smm_precond_t** out);
 int smm_precond_ic0_factor(const smm_precond_t* p, float* factor_host);
 /* EXTENSION -- CSRMatrix::ILU0Preconditioner (H:1188-1212, 1715-1790).  The reference declares it but its factorize()
  * cannot succeed and apply() is never defined (dead code), so there is nothing to be bit-identical to: this is the
  * zero-fill LU that code describes (row-wise IKJ in A's pattern, unit lower factor, multipliers formed with the
- * reciprocal pivot), factorised on the host at create time; apply = L y = rhs, U x = y on the GPU with the level-scheduled
+ * reciprocal pivot), factorised at create time (on the device for grid stencils, else on the host); apply = L y = rhs, U x = y on the GPU with the level-scheduled
  * sweeps.  *rc: 0 ok, 1 structurally unusable, 2 pivot not > 1e-6 in magnitude.  smm_precond_ic0_factor returns the
  * factor of either kind (strict L and U in A's pattern).  smm_solve_bicgstab accepts it as `precond`. */
 int smm_precond_ilu0_create(const smm_csr_t* m, int* rc, smm_precond_t** out);
