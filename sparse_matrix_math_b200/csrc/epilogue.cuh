@@ -92,7 +92,7 @@ __device__ __forceinline__ void smm_finish(int kind, SolveState* st, float t0, f
         case FIN_BICGSYM_UPDATE: {
             const float new_rr = t0;                           // H:2075
             if (new_rr > 1.0f && st->rr < st->eps) {           // H:2079-2081
-                st->done = 1; st->status = SMM_SOLVER_DIVERGED; st->residual = new_rr; break;
+                st->done = 1; st->x_owed = 1; st->status = SMM_SOLVER_DIVERGED; st->residual = new_rr; break;   // x has been updated by then (H:2061-2067)
             }
             st->beta = __fdiv_rn(new_rr, st->rr);              // H:2082
             st->rr = new_rr;                                   // H:2094
@@ -100,7 +100,7 @@ __device__ __forceinline__ void smm_finish(int kind, SolveState* st, float t0, f
             st->iterations += 1;                               // H:2095
             st->residual = new_rr;
             if (!(new_rr > st->eps2 && st->iterations < st->max_iterations)) {                 // H:2096
-                st->done = 1; st->status = smm_do_while_status(st);                            // H:2098-2101
+                st->done = 1; st->x_owed = 1; st->status = smm_do_while_status(st);            // H:2098-2101
             }
             break;
         }

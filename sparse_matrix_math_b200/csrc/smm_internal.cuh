@@ -104,7 +104,7 @@ struct SolveState {
     float* history;      // device residual history (may be null)
     unsigned long long cond_handle;   // cudaGraphConditionalHandle of the WHILE driver (0 = none)
     struct DistComm* comm;            // multi-GPU: reductions are summed over ranks before the scalar step (null: one GPU)
-    int x_owed;          // ConjugateGradient: the stopping test fired in the r update, the x update of that iteration is still to come (VEC_CG_PX)
+    int x_owed;          // ConjugateGradient / BiCGSymmetric: the stopping test fired in the r update, the x update of that iteration is still to come (VEC_CG_PX / VEC_BICGSYM_PX)
     int pad[5];
 };
 
@@ -181,6 +181,8 @@ enum VecKind {
     VEC_COPY3,         // in: a               out: o0 o1 o2
     VEC_CG_R,          // in: r Ap            out: r       t0 = r.r
     VEC_CG_PX,         // in: p r x           out: p x     (x += alpha p with the OLD p, then p = beta p + r)
+    VEC_BICGSYM_R,     // in: r ap            out: r       t0 = r.r
+    VEC_BICGSYM_PX,    // in: p r x           out: p x
 };
 struct VecArgs {
     const void* halo_push = nullptr;   // HaloPushDev* (device): out[0]'s boundary entries also go to the peers (VEC_CG_P / VEC_CG_PX / VEC_COPY3)

@@ -218,16 +218,16 @@ int bicgsym_init(Ctx& c) {
 int bicgsym_iter(Ctx& c) {
     if (!c.exact) {
         SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_OUT_AUX, FIN_BICGSYM_ALPHA, c.p));   // H:2048-2059
-        SMM_TRY(vec(c, VEC_BICGSYM_XR, FIN_BICGSYM_UPDATE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));    // H:2061-2082, 2094-2096
-        SMM_TRY(vec(c, VEC_BICGSYM_P, FIN_NONE, {c.p, c.r}, {c.p}));                               // H:2084-2092
+        SMM_TRY(vec(c, VEC_BICGSYM_R, FIN_BICGSYM_UPDATE, {c.r, c.ap}, {c.r}));                    // H:2068-2082, 2094-2096
+        SMM_TRY(vec(c, VEC_BICGSYM_PX, FIN_NONE, {c.p, c.r, c.x}, {c.p, c.x}));                    // H:2061-2067, H:2084-2092 (p read once)
         c.kernels_per_iteration = 3;
         return SMM_OK;
     }
     SMM_TRY(spmv(c, SMM_OP_ASSIGN, nullptr, c.p, c.ap, RED_NONE, FIN_NONE, nullptr));
     SMM_TRY(dots(c, FIN_BICGSYM_ALPHA, c.ap, c.p));
-    SMM_TRY(vec(c, VEC_BICGSYM_XR, FIN_NONE, {c.x, c.p, c.r, c.ap}, {c.x, c.r}));
+    SMM_TRY(vec(c, VEC_BICGSYM_R, FIN_NONE, {c.r, c.ap}, {c.r}));
     SMM_TRY(dots(c, FIN_BICGSYM_UPDATE, c.r, c.r));
-    SMM_TRY(vec(c, VEC_BICGSYM_P, FIN_NONE, {c.p, c.r}, {c.p}));
+    SMM_TRY(vec(c, VEC_BICGSYM_PX, FIN_NONE, {c.p, c.r, c.x}, {c.p, c.x}));
     c.kernels_per_iteration = 5;
     return SMM_OK;
 }

@@ -104,6 +104,28 @@ struct FBsXR {
         red[0] = fmaf(r, r, red[0]);
     }
 };
+// BiCGSymmetric in two passes that read p once, like FCgR / FCgPX:  r -= alpha*ap; t0 = r.r   (H:2068-2075)   in: r ap  out: r
+struct FBsR {
+    static constexpr bool HALO_OK = false;
+    static constexpr int NIN = 2, NOUT = 1, NRED = 1;
+    static __device__ Scal scal(const SolveState* s) { return {s->alpha, 0.f, 0.f}; }
+    static __device__ void apply(const Scal& sc, const float* in, float* out, float* red) {
+        const float r = __fsub_rn(in[0], __fmul_rn(sc.a, in[1]));
+        out[0] = r;
+        red[0] = fmaf(r, r, red[0]);
+    }
+};
+// BiCGSymmetric  x += alpha*p (H:2061-2067), then p = r + beta*p (H:2084-2092)        in: p r x  out: p x   (OWED: see FCgPX)
+struct FBsPX {
+    static constexpr bool HALO_OK = false;
+    static constexpr bool OWED = true;
+    static constexpr int NIN = 3, NOUT = 2, NRED = 0;
+    static __device__ Scal scal(const SolveState* s) { return {s->beta, s->alpha, 0.f}; }
+    static __device__ void apply(const Scal& sc, const float* in, float* out, float*) {
+        out[1] = __fadd_rn(in[2], __fmul_rn(sc.b, in[0]));
+        out[0] = sc.c != 0.f ? in[0] : __fadd_rn(in[1], __fmul_rn(sc.a, in[0]));
+    }
+};
 // BiCGSymmetric  p = r + beta*p                                      (H:2084-2092)   in: p r  out: p
 struct FBsP {
     static constexpr bool HALO_OK = false;

@@ -151,6 +151,8 @@ int smm_launch_vec(int kind, const VecArgs& a, cudaStream_t s) {
         case VEC_COPY3: return launch<FCopy3>(a, s);
         case VEC_CG_R: return launch<FCgR>(a, s);
         case VEC_CG_PX: return launch<FCgPX>(a, s);
+        case VEC_BICGSYM_R: return launch<FBsR>(a, s);
+        case VEC_BICGSYM_PX: return launch<FBsPX>(a, s);
         default: smm_set_error("vecops: unknown kernel %d", kind); return SMM_E_INVALID;
     }
 }
