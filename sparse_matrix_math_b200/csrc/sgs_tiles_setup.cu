@@ -20,6 +20,10 @@
 // Every "does not verify" of the host code (a tile with more than 64 rows, more than 8 predecessor tiles, 64 internal levels,
 // a row with more than three consumers inside its tile) raises a flag here and returns false; the caller then runs the host
 // path, which decides.  The opt-in chain / cluster layouts are only built on the host.
+//
+// The IC(0) / ILU(0) factorisations run here too (smm_sgs_factorize_dev, further down): level by level along the forward tile
+// schedule, one thread per row doing the host code's operations in the host code's order -- the same factor bits, without
+// the download / host factorisation / upload that cost 1.1 s at 256^3.
 #include <stdio.h>
 #include <stdlib.h>
 
