@@ -41,16 +41,23 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-TRAFFIC_SOURCE = "profiles/r02_spmv_rows_kernel_full.txt: committed ncu --set full capture of this kernel in this command (a constant, not re-measured in this run)"
+TRAFFIC_FILES = ("r02e_spmv_rows_kernel_full.txt", "r02_spmv_rows_kernel_full.txt", "r01h_spmv_rows_kernel_full.txt")
+TRAFFIC_SOURCE = "profiles/%s: committed ncu --set full capture of this kernel in this command (a constant, not re-measured in this run)"
+
+
+def traffic_file():
+    for name in TRAFFIC_FILES:
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return p
+    return None
 
 
 def ncu_traffic_bytes(kernel_prefix, grid):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
     same command (profiles/r02_spmv_rows_kernel_full.txt, 512^3); None for any other problem size."""
-    p = os.path.join(ROOT, "profiles", "r02_spmv_rows_kernel_full.txt")
-    if not os.path.exists(p):
-        p = os.path.join(ROOT, "profiles", "r01h_spmv_rows_kernel_full.txt")
-    if grid != 512 or not os.path.exists(p):
+    p = traffic_file()
+    if grid != 512 or p is None:
         return None
     rd = wr = None
     unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
@@ -73,13 +80,20 @@ def bytes_cg_iteration(rows, nnz):
 
 
 def bytes_cg_iteration_two_pass(rows, nnz):
-    """What the iteration moves since round 2: SpMV + dot (8 nnz + 12 n) | r update + r.r (12 n) | x and p update, p read once (20 n)."""
-    return 8 * nnz + 44 * rows + 4
+    """What the iteration moves since round 2: SpMV + dot (8 nnz + 10 n: 16-bit row starts) | r update + r.r (12 n) | x and p update,
+    p read once (20 n)."""
+    return bytes_spmv_dot_moved(rows, nnz) + 32 * rows
 
 
 def bytes_spmv_dot(rows, nnz):
-    """The dominant kernel: Ap = A p with p.Ap in its epilogue: values+positions, start, p (gathered once), Ap."""
+    """The dominant kernel: Ap = A p with p.Ap in its epilogue: values+positions, start, p (gathered once), Ap (SURVEY 8(d))."""
     return 8 * nnz + 4 * (rows + 1) + 4 * rows + 4 * rows
+
+
+def bytes_spmv_dot_moved(rows, nnz):
+    """What the rows kernel reads and writes since it takes the row starts from start16 (2 bytes per row, 257 entries per group of
+    256 rows, relative to the group's staging window) instead of start[] (4 bytes per row)."""
+    return 8 * nnz + 2 * (rows + rows // 256 + 1) + 4 * rows + 4 * rows
 
 
 class ClockSampler:
@@ -598,13 +612,18 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "spmv_rows_kernel<1> (Ap = A p, p.Ap fused; TMA-staged, 1 lane per row)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes("spmv_rows", grid),
-                     "traffic_source": TRAFFIC_SOURCE if grid == 512 else None, "peak_source": peak_src,
+                     "traffic_source": (TRAFFIC_SOURCE % os.path.basename(traffic_file())) if grid == 512 and traffic_file() else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": ms_spmv,
+                     "bytes_moved_per_launch": bytes_spmv_dot_moved(rows, nnz),
+                     "frac_bytes_moved": bytes_spmv_dot_moved(rows, nnz) / (ms_spmv * 1e-3) / 1e9 / peak,
+                     "note": "achieved / frac use SURVEY 8(d)'s 8 nnz + 4 (rows + 1) + 8 rows; the kernel reads its row starts as 16-bit offsets "
+                             "(2 bytes per row), so it moves 2 bytes per row less than that; peak is the measured COPY bandwidth (reads + writes), "
+                             "which a read-dominated stream can exceed",
                      "share_of_iteration": ms_spmv / kernel_sum if kernel_sum > 0 else None},
         "iteration": {"algorithmic_bytes": iter_bytes, "achieved_gbs": iter_gbs, "frac_of_peak": iter_gbs / peak,
                       "bytes_moved_two_pass": bytes_cg_iteration_two_pass(rows, nnz),
                       "frac_of_peak_bytes_moved": bytes_cg_iteration_two_pass(rows, nnz) * value / 1e9 / peak,
-                      "note": "algorithmic_bytes is SURVEY 8(d)'s 8 nnz + 48 n; the vector passes now read p once (r update | x and p update): 8 nnz + 44 n are moved",
+                      "note": "algorithmic_bytes is SURVEY 8(d)'s 8 nnz + 48 n; the vector passes read p once (r update | x and p update) and the SpMV reads 16-bit row starts: 8 nnz + 42 n are moved",
                       "ms_spmv_dot": ms_spmv, "ms_r_update": ms_xr, "ms_px_update": ms_p,
                       "ms_per_iteration": solve_ms / iters, "final_rr": final_rr, "x_mid": x_host_check},
         "spmv_effective_gbs": achieved,

@@ -273,6 +273,7 @@ int smm_csr_destroy(smm_csr_t* m) {
     if (m->owns_arrays) { cudaFree(m->start); cudaFree(m->positions); cudaFree(m->values); }
     cudaFree(m->block_row);
     cudaFree(m->row_perm);
+    cudaFree(m->start16);
     smm_workspace_free(m->ws);
     delete m;
     return SMM_OK;

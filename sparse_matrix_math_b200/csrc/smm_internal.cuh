@@ -75,6 +75,7 @@ struct smm_csr {
     int num_blocks = 0;
     int32_t* block_row = nullptr;   // [num_blocks+1]
     int32_t* row_perm = nullptr;    // [rows] or null: the rows of every chunk, longest first (irregular-row kernels; spmv.cu)
+    uint16_t* start16 = nullptr;    // rows kernel: [groups][R + 1] row starts relative to the group's staging window (2 B per row instead of 4)
     int max_row_len = 0;
     int rows_kernel_lanes = 0;      // 0: product-staging kernel; V > 0: TMA rows kernel with V lanes per row
     int sm_count = 148;

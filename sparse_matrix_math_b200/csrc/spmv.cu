@@ -43,6 +43,7 @@ struct SpmvParams {
     const float* __restrict__ values;
     const int32_t* __restrict__ block_row;
     const int32_t* __restrict__ row_perm;   // rows of every chunk, longest first (null: in index order)
+    const uint16_t* __restrict__ start16;   // rows kernel: [groups][R + 1] row starts relative to the group's window start (a0)
     int rows;
     int nnz;
     int nnz_alloc;        // entries readable in positions/values (TMA windows are rounded up to 16 bytes)
@@ -456,8 +457,8 @@ __device__ __forceinline__ void rows_sweep(const SpmvParams& P, const int cap, c
         const int rloc = tid / V;                                 // row inside the group
         int my_s = 0, my_e = 0;
         if (my_chunks > 0) {
-            const int r = group_of(first) * R + rloc;
-            if (r < P.rows) { my_s = P.start[r]; my_e = P.start[r + 1]; }
+            const uint16_t* s16 = P.start16 + (size_t)group_of(first) * (R + 1) + rloc;    // relative to the group's window start
+            my_s = s16[0]; my_e = s16[1];
         }
         int s = ring_s;
         uint32_t phase = ring_k;
@@ -467,8 +468,8 @@ __device__ __forceinline__ void rows_sweep(const SpmvParams& P, const int cap, c
             const int q = group_of(j);
             int nx_s = 0, nx_e = 0;                               // next group's row bounds, fetched ahead
             if (it + 1 < my_chunks) {
-                const int rn = group_of(j + G) * R + rloc;
-                if (rn < P.rows) { nx_s = P.start[rn]; nx_e = P.start[rn + 1]; }
+                const uint16_t* s16 = P.start16 + (size_t)group_of(j + G) * (R + 1) + rloc;
+                nx_s = s16[0]; nx_e = s16[1];
             }
             const int row = q * R + rloc;
             const bool boundary = HALO && (q < c_lo || q >= c_hi);
@@ -480,12 +481,13 @@ __device__ __forceinline__ void rows_sweep(const SpmvParams& P, const int cap, c
             mbar_wait(&full[s], phase);
             const int a0 = win[2 * s];
             float dot;
-            // rows past the end have my_s == my_e == 0: their lanes fall through and only join the shuffles
+            // my_s / my_e are relative to a0, the start of the group's window (start16: 2 bytes per row instead of the 4 of start[]);
+            // rows past the end have my_s == my_e: their lanes fall through and only join the shuffles
             if (HALO && boundary) {
-                if (win[2 * s + 1]) dot = row_dot<V, true>(vals_s + (size_t)s * cap - a0, cols_s + (size_t)s * cap - a0, P.mult, my_s + sub, my_e);
-                else dot = row_dot<V, true>(P.values, P.positions, P.mult, my_s + sub, my_e);
-            } else if (win[2 * s + 1]) dot = row_dot<V, false>(vals_s + (size_t)s * cap - a0, cols_s + (size_t)s * cap - a0, P.mult, my_s + sub, my_e);
-            else dot = row_dot<V, false>(P.values, P.positions, P.mult, my_s + sub, my_e);
+                if (win[2 * s + 1]) dot = row_dot<V, true>(vals_s + (size_t)s * cap, cols_s + (size_t)s * cap, P.mult, my_s + sub, my_e);
+                else dot = row_dot<V, true>(P.values + a0, P.positions + a0, P.mult, my_s + sub, my_e);
+            } else if (win[2 * s + 1]) dot = row_dot<V, false>(vals_s + (size_t)s * cap, cols_s + (size_t)s * cap, P.mult, my_s + sub, my_e);
+            else dot = row_dot<V, false>(P.values + a0, P.positions + a0, P.mult, my_s + sub, my_e);
             if (V > 1) {
 #pragma unroll
                 for (int o = V / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
@@ -768,6 +770,18 @@ __global__ void __launch_bounds__(256) row_perm_kernel(const int32_t* __restrict
     }
 }
 
+// rows kernel: row starts of every group of R rows relative to the group's staging window (a0 = first entry rounded down to 16
+// bytes), R + 1 entries per group so that a row finds its end next to its start; rows past the end get the group's end (empty)
+__global__ void start16_kernel(const int32_t* __restrict__ start, const int rows, const int R, const long long total, uint16_t* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long long g = t / (R + 1);
+    const int i = (int)(t - g * (R + 1));
+    const long long r0 = g * R, r = r0 + i;
+    const int a0 = start[r0 < rows ? r0 : rows] & ~3;
+    out[t] = (uint16_t)(start[r < rows ? r : rows] - a0);
+}
+
 __global__ void first_active_kernel(const int32_t* __restrict__ start, int rows, int* out) {
     // firstActiveStart (H:1622-1628): first row i with start[i+1] != 0, or rows
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -805,6 +819,8 @@ int smm_csr_analyse(smm_csr* m, cudaStream_t s) {
         const char* env = getenv("SMM_B200_SPMV_KERNEL");           // benchmarking override: "stage" | "rows"
         if (env && !strcmp(env, "stage")) m->rows_kernel_lanes = 0;
         if (env && !strcmp(env, "rows") && m->rows_kernel_lanes == 0) m->rows_kernel_lanes = v;
+        // start16 holds row starts relative to their group's window in 16 bits
+        if (m->rows_kernel_lanes > 0 && (long long)m->max_row_len * (SPMV_THREADS / m->rows_kernel_lanes) >= 65536) m->rows_kernel_lanes = 0;
         cudaDeviceProp prop;
         SMM_CUDA(cudaGetDeviceProperties(&prop, m->device));
         m->sm_count = prop.multiProcessorCount;
@@ -820,6 +836,15 @@ int smm_csr_analyse(smm_csr* m, cudaStream_t s) {
     if (m->rows_kernel_lanes != 1 && m->rows > 0 && perm_on) {      // the product-staging kernels run for this matrix (always, or in exact mode)
         SMM_CUDA(cudaMalloc(&m->row_perm, sizeof(int32_t) * (size_t)m->rows));
         row_perm_kernel<<<m->num_blocks, 256, 0, s>>>(m->start, m->block_row, m->row_perm);
+        SMM_COUNT_LAUNCH(1);
+    }
+    if (m->start16) { cudaFree(m->start16); m->start16 = nullptr; }
+    if (m->rows_kernel_lanes > 0) {
+        // a regular matrix has rows of at most 64 entries: a group of up to 256 rows spans less than 2^16 entries
+        const int R = SPMV_THREADS / m->rows_kernel_lanes;
+        const long long total = (long long)((m->rows + R - 1) / R) * (R + 1);
+        SMM_CUDA(cudaMalloc(&m->start16, sizeof(uint16_t) * (size_t)(total > 0 ? total : 1)));
+        start16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->start, m->rows, R, total, m->start16);
         SMM_COUNT_LAUNCH(1);
     }
     SMM_CUDA(cudaGetLastError());
@@ -880,7 +905,7 @@ int smm_launch_cg_persistent(const smm_csr* m, SolveState* state, float* x, floa
     const RowsConfig rc = rows_config(m, 1);
     PersistParams A;
     SpmvParams& P = A.sp;
-    P.start = m->start; P.positions = m->positions; P.values = m->values; P.block_row = m->block_row; P.row_perm = m->row_perm;
+    P.start = m->start; P.positions = m->positions; P.values = m->values; P.block_row = m->block_row; P.row_perm = m->row_perm; P.start16 = m->start16;
     P.rows = m->rows; P.nnz = (int)m->nnz; P.nnz_alloc = (int)m->nnz_alloc; P.op = SMM_OP_ASSIGN; P.exact = 0;
     P.lhs = nullptr; P.mult = p; P.out = ap; P.copy1 = P.copy2 = P.copy3 = nullptr;
     P.aux = p; P.reduce = RED_OUT_AUX; P.finish = FIN_CG_ALPHA; P.state = state;
@@ -928,7 +953,7 @@ int smm_launch_spmv(const SpmvArgs& a, cudaStream_t s) {
     const smm_csr* m = a.m;
     if (m->rows == 0) return SMM_OK;
     SpmvParams P;
-    P.start = m->start; P.positions = m->positions; P.values = m->values; P.block_row = m->block_row; P.row_perm = m->row_perm;
+    P.start = m->start; P.positions = m->positions; P.values = m->values; P.block_row = m->block_row; P.row_perm = m->row_perm; P.start16 = m->start16;
     P.rows = m->rows; P.nnz = (int)m->nnz; P.nnz_alloc = (int)m->nnz_alloc; P.op = a.op; P.exact = a.exact;
     P.lhs = a.lhs; P.mult = a.mult; P.out = a.out;
     P.copy1 = a.copy1; P.copy2 = a.copy2; P.copy3 = a.copy3;
