@@ -56,13 +56,14 @@ struct Ctx {
 };
 
 // multi-GPU: can the SpMV wait for the halo itself (rows kernel), or does it need the wait kernel in front of it?
-// (SMM_B200_DIST_FUSED=0: separate push and wait kernels around every exchange, for A/B measurements)
-bool dist_fused() { static const bool on = [] { const char* e = getenv("SMM_B200_DIST_FUSED"); return !e || atoi(e) != 0; }(); return on; }
-// The halo stores are fused into the kernel that writes p; the wait for the peers' flags is a one-warp kernel in front of the
-// SpMV, which is then the plain instance of the rows kernel.  Waiting inside the SpMV (boundary row groups last, interior rows
-// overlapping the pushes; SMM_B200_DIST_FUSED_WAIT=1) saves that launch but its HALO instance of the rows kernel is 3 % slower
-// than the plain one on the same rows: measured 1086 vs 1071 us per iteration on 2 GPUs, 306.4 vs 301.6 us on 8
-// (profiles/r02_dist_overhead.txt).
+// Default since the end of round 2: separate push and wait kernels.  Measured with the final kernels (profiles/r02_dist_overhead.txt
+// section 5): 2 GPUs 1042.9 us per iteration against 1114.4 (halo stores fused into the x,p update + wait kernel) and 1086.8 (fused
+// stores + wait inside the SpMV); 8 GPUs 309.3 against 308.4 -- never slower, and the x,p update and the SpMV stay the plain kernels
+// of the single-GPU solve.  SMM_B200_DIST_FUSED=1 selects the fused forms.
+bool dist_fused() { static const bool on = [] { const char* e = getenv("SMM_B200_DIST_FUSED"); return e && atoi(e) != 0; }(); return on; }
+// With the fused stores (SMM_B200_DIST_FUSED=1): the wait for the peers' flags is a one-warp kernel in front of the plain SpMV, or
+// (SMM_B200_DIST_FUSED_WAIT=1) happens inside the SpMV's HALO instance, which walks the interior row groups first -- that
+// instance is 3 % slower than the plain one on the same rows (profiles/r02_dist_overhead.txt).
 bool dist_fused_wait_on() { static const bool on = [] { const char* e = getenv("SMM_B200_DIST_FUSED_WAIT"); return e && atoi(e) != 0; }(); return on; }
 bool fused_wait(const Ctx& c) { return dist_fused() && dist_fused_wait_on() && c.dist && c.dist->nranks > 1 && c.dist->wait_dev && smm_spmv_rows_lanes(c.a, c.exact ? 1 : 0) > 0; }
 
@@ -112,10 +113,11 @@ int dots(Ctx& c, int finish, const float* a0, const float* b0, const float* a1 =
 // Multi-GPU CG: p lives inside the extended vector (owned part + halo); every SpMV operand is exchanged first.
 // The reductions are summed over the ranks inside the kernels' epilogues (dist_device.cuh), so the scalar state --
 // and with it every branch -- is bit-identical on all ranks.
-// p lives in the extended vector; the kernel that writes it (p = r at the start, the p update afterwards) stores its boundary
-// entries into the peers' extended vectors as well and raises the flags, and the next SpMV multiplies its interior rows while
-// those stores travel, waiting for the peers' flags only in the warps that reach a boundary row group: 3 launches per
-// iteration, like the single-GPU solve.
+// p lives in the extended vector.  Default: after the kernel that writes it (p = r at the start, the x,p update afterwards) a push
+// kernel stores its boundary entries into the peers' extended vectors and raises the flags, a wait kernel spins on the peers'
+// flags, and the SpMV is the plain kernel.  Fused forms (SMM_B200_DIST_FUSED=1): the writing kernel stores the boundary entries
+// itself, and (SMM_B200_DIST_FUSED_WAIT=1) the SpMV multiplies its interior rows while those stores travel, waiting for the
+// peers' flags only in the warps that reach a boundary row group.
 // after the kernel that wrote p: whatever part of the exchange that kernel and the next SpMV do not do themselves
 int dist_after_p(Ctx& c) {
     if (!dist_fused()) return smm_dist_exchange_async(c.dist, c.st, c.s, true);
