@@ -55,7 +55,7 @@ def traffic_file():
 
 def ncu_traffic_bytes(kernel_prefix, grid):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
-    same command (profiles/r02_spmv_rows_kernel_full.txt, 512^3); None for any other problem size."""
+    same command (the newest of TRAFFIC_FILES under profiles/, 512^3); None for any other problem size."""
     p = traffic_file()
     if grid != 512 or p is None:
         return None
