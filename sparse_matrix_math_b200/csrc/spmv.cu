@@ -820,7 +820,8 @@ int smm_csr_analyse(smm_csr* m, cudaStream_t s) {
         if (env && !strcmp(env, "stage")) m->rows_kernel_lanes = 0;
         if (env && !strcmp(env, "rows") && m->rows_kernel_lanes == 0) m->rows_kernel_lanes = v;
         // start16 holds row starts relative to their group's window in 16 bits
-        if (m->rows_kernel_lanes > 0 && (long long)m->max_row_len * (SPMV_THREADS / m->rows_kernel_lanes) >= 65536) m->rows_kernel_lanes = 0;
+        // (a group's entries + the up to 3 entries between the 16-byte window start and its first entry must stay below 2^16)
+        if (m->rows_kernel_lanes > 0 && (long long)m->max_row_len * (SPMV_THREADS / m->rows_kernel_lanes) + 3 >= 65536) m->rows_kernel_lanes = 0;
         cudaDeviceProp prop;
         SMM_CUDA(cudaGetDeviceProperties(&prop, m->device));
         m->sm_count = prop.multiProcessorCount;
